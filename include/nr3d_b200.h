@@ -1,0 +1,197 @@
+/* nr3d_b200.h -- C ABI of libnr3d_b200.so: the B200-native (sm_100a) replacement for the three
+ * native extensions on nr3d_lib's LoTD / occupancy-march / pack_ops hot path.
+ *
+ * Each entry point names the reference interface it replaces (file:line under the reference tree).
+ * Conventions
+ *   - plain C types only; every `const void*` / `void*` is a DEVICE pointer unless marked (host);
+ *   - the callee never allocates device memory: outputs are caller-allocated (the Python shim
+ *     allocates them through torch's caching allocator), two-pass ops expose a count + fill pair;
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and returns immediately;
+ *   - return value 0 = ok, negative = error; nr3d_last_error() returns a thread-local message.
+ *     The Python shim turns a non-zero status into RuntimeError (the reference throws
+ *     std::runtime_error / c10::Error, e.g. csrc/lotd/src/lotd_torch_api.cu:41,257).
+ *   - thread-safe and re-entrant: no global mutable state besides the thread-local error string.
+ */
+#ifndef NR3D_B200_H
+#define NR3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NR3D_MAX_LEVELS 32          /* csrc/lotd/include/lotd/lotd_cuda.h:26 */
+#define NR3D_MAX_DIMS 4             /* csrc/lotd/include/lotd/lotd_cuda.h:27 */
+#define NR3D_MAX_PSEUDO_LEVELS 256  /* csrc/lotd/include/lotd/lotd_cuda.h:37 (MAX_N_LEVELS * 8) */
+
+/* dtype codes used by every entry point */
+enum { NR3D_F32 = 0, NR3D_F16 = 1, NR3D_F64 = 2, NR3D_I32 = 3, NR3D_I64 = 4, NR3D_I16 = 5, NR3D_I8 = 6, NR3D_U8 = 7 };
+
+/* LoDType values follow the reference's C++ enum incl. the un-exported VecZMatXoY
+ * (csrc/lotd/include/lotd/lotd_types.h:16-26). */
+enum { NR3D_LOD_DENSE = 0, NR3D_LOD_VM = 1, NR3D_LOD_VECZMATXOY = 2, NR3D_LOD_CP = 3, NR3D_LOD_CPFAST = 4,
+       NR3D_LOD_NPLANEMUL = 5, NR3D_LOD_NPLANESUM = 6, NR3D_LOD_HASH = 7 };
+enum { NR3D_INTERP_LINEAR = 0, NR3D_INTERP_SMOOTHSTEP = 1 }; /* lotd_types.h:78-82 */
+
+/* Host-side POD mirror of LoDMeta / LoDMetaRef
+ * (csrc/lotd/include/lotd/lotd_torch_api.h:81-135, csrc/lotd/include/lotd/lotd_cuda.h:29-76). */
+typedef struct nr3d_lotd_meta {
+    uint32_t n_levels, n_pseudo_levels, n_feat_per_pseudo_lvl, n_dims_to_encode, n_encoded_dims, n_params;
+    uint32_t interpolation_type; /* NR3D_INTERP_* */
+    uint32_t hash_only;          /* 1 when every level is Dense or Hash (c_hash_only) */
+    uint32_t level_res[NR3D_MAX_LEVELS][NR3D_MAX_DIMS];
+    uint32_t level_n_feats[NR3D_MAX_LEVELS];
+    uint32_t level_types[NR3D_MAX_LEVELS];
+    uint32_t level_n_params[NR3D_MAX_LEVELS];
+    uint32_t level_sizes[NR3D_MAX_LEVELS];
+    uint32_t level_offsets[NR3D_MAX_LEVELS + 1];
+    uint32_t map_levels[NR3D_MAX_PSEUDO_LEVELS];
+    uint32_t map_cnt[NR3D_MAX_PSEUDO_LEVELS];
+} nr3d_lotd_meta;
+
+const char* nr3d_last_error(void);
+int nr3d_version(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+uint64_t nr3d_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * LoTD  (replaces nr3d_lib.bindings._lotd, csrc/lotd/src/lotd.cpp:23-110)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* == LoDMeta::create_meta, csrc/lotd/src/lotd_torch_api.cu:29-230.  Host only, no CUDA call.
+ * res: [n_levels * n_dims] (host), n_feats/types: [n_levels] (host). hashmap_size 0 = not given. */
+int nr3d_lotd_meta_create(int32_t n_dims, int32_t n_levels, const int32_t* res, const int32_t* n_feats,
+                          const int32_t* types, uint32_t hashmap_size, int32_t use_smooth_step,
+                          nr3d_lotd_meta* out /* host */);
+
+/* == lod_fwd, csrc/lotd/src/lotd_torch_api.cu:232-395 (kernels lotd_hash_only.h:15-378, lotd_encoding.h:113-428).
+ * x: [N, D] input_dtype contiguous.  params: [n_batches * n_params] param_dtype.
+ * batch_inds: int64 [N] or NULL; batch_offsets: int64 [B] or NULL; batch_data_size: 0 = unused.
+ * y element (n, j) is written at y + n*y_stride_n + j*y_stride_f (elements of param_dtype); EVERY element is
+ * written (zeros for skipped points / levels) so the caller may pass uninitialised memory.
+ * dy_dx (nullable): element (n, j, d) at dy_dx + n*dydx_stride_n + j*dydx_stride_f + d (input_dtype). */
+int nr3d_lotd_fwd(const nr3d_lotd_meta* meta, int32_t input_dtype, int32_t param_dtype, uint64_t N,
+                  const void* x, const void* params, const int64_t* batch_inds, const int64_t* batch_offsets,
+                  uint32_t batch_data_size, int32_t max_level,
+                  void* y, int64_t y_stride_n, int64_t y_stride_f,
+                  void* dy_dx, int64_t dydx_stride_n, int64_t dydx_stride_f, void* stream);
+
+/* == lod_bwd (dL/dparam part), csrc/lotd/src/lotd_torch_api.cu:397-573
+ * (kernels lotd_hash_only.h:380-470, lotd_encoding.h:467-711).
+ * dL_dy element (n, j) read at dL_dy + n*s_n + j*s_f (param_dtype, any strides).
+ * dL_dparam: [n_batches*n_params] param_dtype, MUST be zero-filled by the caller; gradients are accumulated. */
+int nr3d_lotd_bwd_param(const nr3d_lotd_meta* meta, int32_t input_dtype, int32_t param_dtype, uint64_t N,
+                        const void* dL_dy, int64_t dLdy_stride_n, int64_t dLdy_stride_f,
+                        const void* x, const void* params, const int64_t* batch_inds, const int64_t* batch_offsets,
+                        uint32_t batch_data_size, int32_t max_level, void* dL_dparam, void* stream);
+
+/* == lod_bwd (dL/dx part): dL_dx[n,d] = sum_j dL_dy[n,j] * dy_dx[n,j,d]
+ * (reference: at::mul + at::sum_out, lotd_hash_only.h:839-863, lotd_encoding.h:1562-1586), fused in one kernel.
+ * dL_dx: [N, D] input_dtype contiguous, fully written. */
+int nr3d_lotd_bwd_input(const nr3d_lotd_meta* meta, int32_t input_dtype, int32_t param_dtype, uint64_t N,
+                        const void* dL_dy, int64_t dLdy_stride_n, int64_t dLdy_stride_f,
+                        const void* dy_dx, int64_t dydx_stride_n, int64_t dydx_stride_f,
+                        void* dL_dx, void* stream);
+
+/* == lod_bwd_bwd_input, csrc/lotd/src/lotd_torch_api.cu:575-769 -- three independent outputs, each nullable:
+ *   dL_ddLdy [N, n_enc] param_dtype contiguous = sum_d dL_ddLdx[n,d]*dy_dx[n,j,d]   (lotd_hash_only.h:982-1006)
+ *   dL_dparam (zero-filled by caller) += d(dL/dx)/dparam . dL_ddLdx                (lotd_encoding.h:713-1041)
+ *   dL_dx [N, D] (zero-filled by caller) += d(dL/dx)/dx . dL_ddLdx                  (lotd_encoding.h:1043-1298) */
+int nr3d_lotd_bwd_bwd_input(const nr3d_lotd_meta* meta, int32_t input_dtype, int32_t param_dtype, uint64_t N,
+                            const void* dL_ddLdx, const void* dL_dy, int64_t dLdy_stride_n, int64_t dLdy_stride_f,
+                            const void* x, const void* params,
+                            const void* dy_dx, int64_t dydx_stride_n, int64_t dydx_stride_f,
+                            const int64_t* batch_inds, const int64_t* batch_offsets, uint32_t batch_data_size,
+                            int32_t max_level, void* dL_ddLdy, void* dL_dparam, void* dL_dx, void* stream);
+
+/* == lod_get_grid_index, csrc/lotd/src/lotd_torch_api.cu:771-855 (kernel lotd_encoding.h:1300-1433).
+ * out: int64 [N, n_enc, 2^D], MUST be zero-filled by the caller (skipped entries stay 0). Dense/Hash only. */
+int nr3d_lotd_grid_index(const nr3d_lotd_meta* meta, int32_t input_dtype, uint64_t N, const void* x,
+                         const int64_t* batch_inds, const int64_t* batch_offsets, uint32_t batch_data_size,
+                         int32_t max_level, int64_t* out, void* stream);
+
+/* B200-native fused training step for the Dense/Hash fast path (no reference counterpart; used by
+ * nr3d_lib_b200.lotd.LoTDFunction when permitted): bins the points by coarse cell once so that forward gathers
+ * and backward scatters of neighbouring points coalesce.  workspace_bytes may be queried with ws == NULL. */
+int nr3d_lotd_sort_points(uint64_t N, const float* x /*[N,3]*/, uint32_t bin_res, void* ws, uint64_t* ws_bytes,
+                          uint32_t* perm /*[N]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * occupancy-grid ray marching (replaces nr3d_lib.bindings._occ_grid, csrc/occ_grid/src/occ_grid.cpp:22-33)
+ * ---------------------------------------------------------------------------------------------- */
+enum { NR3D_CONTRACTION_AABB = 0, NR3D_CONTRACTION_TANH = 1, NR3D_CONTRACTION_SPHERE = 2 }; /* cpp_api.h:14-19 */
+
+/* Pass 1 of ray_marching / batched_ray_marching (csrc/occ_grid/src/ray_marching.cu:17-134,179-203,
+ * batched_marching.cu:18-148): writes num_steps[R] (int32) for every ray (0 for batch_inds<0).
+ * batch_inds (int32 [R]) and batch_data_size select the batched variant; pass NULL / 0 with n_batches=1 for single.
+ * roi: [n_batches, 6] float; grid: bool/uint8 [n_batches, rx, ry, rz]. */
+int nr3d_march_count(uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                     const int32_t* batch_inds, uint32_t batch_data_size, int32_t n_batches,
+                     const float* roi, const uint8_t* grid, int32_t rx, int32_t ry, int32_t rz, int32_t contraction,
+                     float step_size, float max_step_size, float dt_gamma, uint32_t max_steps,
+                     int32_t* num_steps, void* stream);
+/* On-device replacement of `cumsum` + `stack` + `.item()` (ray_marching.cu:205-209): packed_info[R,2] int32 =
+ * (exclusive offset, count); total[0] (int64, device) = number of samples. ws: scratch, query size with ws==NULL. */
+int nr3d_march_pack(uint64_t n_rays, const int32_t* num_steps, int32_t* packed_info, int64_t* total,
+                    void* ws, uint64_t* ws_bytes, void* stream);
+/* Pass 2 (ray_marching.cu:218-241): fills t_starts/t_ends [S] f32, ridx [S] i32, bidx (nullable), gidx (nullable). */
+int nr3d_march_fill(uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                    const int32_t* batch_inds, uint32_t batch_data_size, int32_t n_batches,
+                    const float* roi, const uint8_t* grid, int32_t rx, int32_t ry, int32_t rz, int32_t contraction,
+                    float step_size, float max_step_size, float dt_gamma, uint32_t max_steps,
+                    const int32_t* packed_info, float* t_starts, float* t_ends, int32_t* ridx, int32_t* bidx,
+                    int32_t* gidx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * pack_ops (replaces nr3d_lib.bindings._pack_ops, csrc/pack_ops/pack_ops.cpp:20-58)
+ * pack_infos: int64 [P, 2] = (first index, length).  feats: [S, C] contiguous (C = 1 for 1-D tensors).
+ * ---------------------------------------------------------------------------------------------- */
+/* == packed_sum, pack_ops_cuda.cu:798-861.  out [P, C] fully written (0 for empty packs). */
+int nr3d_pack_sum(int32_t dtype, uint64_t P, uint32_t C, const void* feats, const int64_t* pack_infos, void* out, void* stream);
+/* == packed_cumsum / packed_cumprod, pack_ops_cuda.cu:864-1095.  out [S, C] must be zero-filled where elements
+ * are not covered by any pack. exclusive cumprod implements the DOCUMENTED semantics (leading 1,
+ * nr3d_lib/graphics/pack_ops/pack_ops.py:149); bug_compat=1 reproduces the reference CUDA output (all zeros). */
+int nr3d_pack_cumsum(int32_t dtype, uint64_t P, uint32_t C, const void* feats, const int64_t* pack_infos,
+                     int32_t exclusive, int32_t reverse, void* out, void* stream);
+int nr3d_pack_cumprod(int32_t dtype, uint64_t P, uint32_t C, const void* feats, const int64_t* pack_infos,
+                      int32_t exclusive, int32_t reverse, int32_t bug_compat, void* out, void* stream);
+/* == packed_diff / packed_backward_diff, pack_ops_cuda.cu:1098-1334. edge / fill: [P, C] nullable, at most one. */
+int nr3d_pack_diff(int32_t dtype, uint64_t P, uint32_t C, const void* feats, const int64_t* pack_infos,
+                   const void* appends, const void* last_fill, void* out, void* stream);
+int nr3d_pack_backward_diff(int32_t dtype, uint64_t P, uint32_t C, const void* feats, const int64_t* pack_infos,
+                            const void* prepends, const void* first_fill, void* out, void* stream);
+/* == packed_{add,sub,mul,div,gt,geq,lt,leq,eq,neq}, pack_ops_cuda.cu:1960-2540. op: 0 add 1 sub 2 mul 3 div
+ * (out dtype = dtype), 5 gt 6 geq 7 lt 8 leq 9 eq 10 neq (out = uint8/bool). other: [P, C]. */
+int nr3d_pack_binary(int32_t op, int32_t dtype, uint64_t P, uint32_t C, const void* feats, const void* other,
+                     const int64_t* pack_infos, void* out, void* stream);
+/* == packed_alpha_to_vw_forward, pack_ops_cuda.cu:1735-1793,1850-1911.  weights (nullable) must be zero-filled;
+ * num_steps (nullable, int64 [P]) fully written; selector (nullable, bool [S]) must be zero-filled. */
+int nr3d_pack_alpha_to_vw_fwd(int32_t dtype, uint64_t P, const void* alphas, const int64_t* pack_infos,
+                              float early_stop_eps, float alpha_thre, void* weights, int64_t* num_steps,
+                              uint8_t* selector, void* stream);
+/* == packed_alpha_to_vw_backward, pack_ops_cuda.cu:1795-1848,1914-1958. grad_alphas must be zero-filled. */
+int nr3d_pack_alpha_to_vw_bwd(int32_t dtype, uint64_t P, const void* weights, const void* grad_weights,
+                              const void* alphas, const int64_t* pack_infos, float early_stop_eps, float alpha_thre,
+                              void* grad_alphas, void* stream);
+/* int64 exclusive scan helper: pack_infos[P,2] = (exclusive cumsum(n), n); total[0] = sum.  Replaces the
+ * `cumsum` + `stack` + `.item()` idiom (pack_ops_cuda.cu:579-581,1874-1875). */
+int nr3d_pack_infos_from_counts(uint64_t P, const int64_t* counts, int64_t* pack_infos, int64_t* total,
+                                void* ws, uint64_t* ws_bytes, void* stream);
+/* == interleave_arange / interleave_linstep, pack_ops_cuda.cu:47-218: out[begin_p + j] = start_p + j*step_p;
+ * nidx (nullable int64) = pack id.  starts / steps nullable -> scalar start / step (as double). */
+int nr3d_pack_interleave_linstep(int32_t dtype, uint64_t P, const int64_t* pack_infos, const void* starts,
+                                 const void* steps, double start, double step, void* out, int64_t* nidx, void* stream);
+/* == interleave_sample_step_wrt_depth_clamped, pack_ops_cuda.cu:480-604 (two passes). */
+int nr3d_pack_sample_step_count(int32_t dtype, uint64_t P, const void* nears, const void* fars, uint32_t max_steps,
+                                double dt_gamma, double min_step, double max_step, int64_t* n_per_pack, void* stream);
+int nr3d_pack_sample_step_fill(int32_t dtype, uint64_t P, const void* nears, const int64_t* pack_infos,
+                               double dt_gamma, double min_step, double max_step, void* t_samples, void* deltas,
+                               int64_t* nidx, void* stream);
+/* == mark_pack_boundaries_cuda, pack_ops_cuda.cu:2765-2805. ids dtype in {U8,I8,I16,I32,I64}; out int32 [S]. */
+int nr3d_pack_mark_boundaries(int32_t dtype, uint64_t S, const void* pack_ids, int32_t* boundaries, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NR3D_B200_H */

@@ -1,0 +1,403 @@
+// lotd_device.cuh -- device-side maths of the LoTD encoder (all level types), written for sm_100a.
+//
+// Parity notes (what each block reproduces in the reference):
+//   pos_fract            csrc/lotd/include/lotd/lotd_cuda.h:959-1077   (scale = res-2, +0.5, floor, smoothstep)
+//   index functions      csrc/lotd/include/lotd/lotd_cuda.h:92-296     (uint32 arithmetic, bit-exact)
+//   corner values        csrc/lotd/include/lotd/lotd_cuda.h:298-492
+//   n-linear weights     csrc/lotd/include/lotd/linear_interpolate.cuh:92-150
+//   gradient scatter     csrc/lotd/include/lotd/lotd_cuda.h:494-829
+#pragma once
+#include "common.cuh"
+
+namespace nr3d {
+
+struct LevelDesc {
+    uint32_t res[4];
+    uint32_t type, n_feat, size, offset;
+};
+// Kernel-parameter copy of the meta: 1.6 KB in the constant bank (the reference passes a 2.5 KB LoDMetaRef by value).
+struct LotdTable {
+    LevelDesc lv[NR3D_MAX_LEVELS];
+    uint8_t map_level[NR3D_MAX_PSEUDO_LEVELS];
+    uint8_t map_cnt[NR3D_MAX_PSEUDO_LEVELS];
+    uint32_t n_levels, n_pseudo, n_enc, n_params, interp, fpl, pad0, pad1;
+};
+
+struct LotdIn {
+    uint64_t N;
+    const float* x;
+    const void* params;
+    const int64_t* batch_inds;
+    const int64_t* batch_offsets;
+    uint32_t batch_data_size;
+    int32_t max_level;
+    uint32_t vec_ok;  // 1: level base pointers are 8-byte aligned (no user-supplied batch_offsets)
+};
+
+template <int D>
+struct Ctx {
+    uint32_t res[D];
+    uint32_t cell[D];
+    float scale[D], p[D], dp[D], d2p[D];
+    uint32_t type, n_feat, size, gfo;
+    uint64_t base;  // element offset of this level's table inside `params`
+};
+
+// returns false when the (point, pseudo level) pair is skipped (level > max_level or batch index < 0)
+template <int D, int F>
+__device__ __forceinline__ bool lotd_setup(const LotdTable& tab, const LotdIn& in, uint64_t i, uint32_t pl, Ctx<D>& c) {
+    const uint32_t level = tab.map_level[pl];
+    if ((int32_t)level > in.max_level) return false;
+    uint32_t batch_ind = 0;
+    if (in.batch_inds) {
+        const int64_t b = in.batch_inds[i];
+        if (b < 0) return false;
+        batch_ind = (uint32_t)b;
+    } else if (in.batch_data_size) {
+        batch_ind = (uint32_t)(i / in.batch_data_size);
+    }
+    const uint64_t batch_offset = in.batch_offsets ? (uint64_t)in.batch_offsets[batch_ind] : (uint64_t)batch_ind * tab.n_params;
+    const LevelDesc& L = tab.lv[level];
+    c.base = batch_offset + L.offset;
+    c.type = L.type;
+    c.n_feat = L.n_feat;
+    c.size = L.size;
+    c.gfo = (uint32_t)tab.map_cnt[pl] * F;
+    const float* xp = in.x + i * D;
+    const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        c.res[d] = L.res[d];
+        c.scale[d] = (float)(c.res[d] - 2u);
+        float v = xp[d] * c.scale[d] + 0.5f;
+        const float fl = floorf(v);
+        c.cell[d] = (uint32_t)fl;
+        v -= (float)c.cell[d];
+        if (smooth) {
+            c.p[d] = v * v * (3.0f - 2.0f * v);
+            c.dp[d] = 6.0f * v * (1.0f - v);
+            c.d2p[d] = 6.0f - 12.0f * v;
+        } else {
+            c.p[d] = v;
+            c.dp[d] = 1.0f;
+            c.d2p[d] = 0.0f;
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// index functions (all uint32, must be bit-exact)
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ uint32_t idx_dense(const uint32_t* res, const uint32_t* pos) {
+    uint32_t stride = 1, index = 0;
+#pragma unroll
+    for (int d = D - 1; d >= 0; --d) {  // last dim contiguous
+        index += pos[d] * stride;
+        stride *= res[d];
+    }
+    return index;
+}
+template <int D>
+__device__ __forceinline__ uint32_t idx_hash(const uint32_t* pos, uint32_t size) {
+    constexpr uint32_t primes[4] = {1u, 2654435761u, 805459861u, 3674653429u};
+    uint32_t h = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) h ^= pos[d] * primes[d];
+    return h % size;
+}
+// "N-plane" index of the plane that drops dimension `jump` (no per-plane offset: reference quirk Q3)
+template <int D>
+__device__ __forceinline__ uint32_t idx_nplane(const uint32_t* res, const uint32_t* pos, int jump) {
+    uint32_t stride = 1, index = 0;
+#pragma unroll
+    for (int d2 = 0; d2 < D - 1; ++d2) {
+        const int d3 = d2 >= jump ? d2 + 1 : d2;
+        index += pos[D - 1 - d3] * stride;
+        stride *= res[D - 1 - d3];
+    }
+    return index;
+}
+// NPlaneSum variant: plane-local coordinates + offset jump*stride (self-consistent for cubic res only)
+template <int D>
+__device__ __forceinline__ uint32_t idx_nplane_sub(const uint32_t* res, const uint32_t* pos_plane, int jump) {
+    uint32_t stride = 1, index = 0;
+#pragma unroll
+    for (int d2 = 0; d2 < D - 1; ++d2) {
+        const int d3 = d2 >= jump ? d2 + 1 : d2;
+        index += pos_plane[D - 2 - d2] * stride;
+        stride *= res[D - 1 - d3];
+    }
+    return (uint32_t)jump * stride + index;
+}
+template <int D>
+__device__ __forceinline__ uint32_t idx_cp_line(const uint32_t* res, uint32_t pos_line, int line_dim) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+        if (d < line_dim) acc += res[d];
+    return acc + pos_line;
+}
+// VM: lines [sum(res)] then planes; plane k drops dimension k
+template <int D>
+__device__ __forceinline__ void idx_vm(const uint32_t* res, const uint32_t* pos, uint32_t* plane, uint32_t* line) {
+    uint32_t acc_line = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        line[k] = acc_line + pos[k];
+        acc_line += res[k];
+    }
+    uint32_t acc_plane = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const int rev_jump = D - 1 - k;
+        uint32_t stride = 1, index = 0;
+#pragma unroll
+        for (int d2 = 0; d2 < D - 1; ++d2) {
+            const int d3 = d2 >= rev_jump ? d2 + 1 : d2;
+            index += pos[D - 1 - d3] * stride;
+            stride *= res[D - 1 - d3];
+        }
+        plane[k] = acc_line + acc_plane + index;
+        acc_plane += stride;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameter loads
+// ------------------------------------------------------------------------------------------------
+template <int F>
+__device__ __forceinline__ void load_feats(const float* g, float* v, bool vec_ok) {
+    if (vec_ok) {
+#pragma unroll
+        for (int f = 0; f < F; f += 2) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(g + f));
+            v[f] = t.x;
+            v[f + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int f = 0; f < F; ++f) v[f] = __ldg(g + f);
+    }
+}
+template <int F>
+__device__ __forceinline__ void load_feats(const __half* g, __half* v, bool /*vec_ok*/) {
+#pragma unroll
+    for (int f = 0; f < F; f += 2) {  // offsets are always even -> 4-byte aligned
+        const __half2 t = __ldg(reinterpret_cast<const __half2*>(g + f));
+        v[f] = __low2half(t);
+        v[f + 1] = __high2half(t);
+    }
+}
+
+// value of one lattice corner for the "n-linear" level types
+template <int D, int F, typename PT>
+__device__ __forceinline__ void corner_val(const Ctx<D>& c, const PT* __restrict__ g, const uint32_t* pos, PT* v, bool vec_ok) {
+    using C = Cvt<PT>;
+    switch (c.type) {
+    case NR3D_LOD_DENSE:
+        load_feats<F>(g + (uint64_t)idx_dense<D>(c.res, pos) * c.n_feat + c.gfo, v, vec_ok);
+        break;
+    case NR3D_LOD_HASH:
+        load_feats<F>(g + (uint64_t)idx_hash<D>(pos, c.size) * c.n_feat + c.gfo, v, vec_ok);
+        break;
+    case NR3D_LOD_VM:
+        if constexpr (D == 3) {
+            uint32_t pl[D], ln[D];
+            idx_vm<D>(c.res, pos, pl, ln);
+#pragma unroll
+            for (int f = 0; f < F; ++f) v[f] = C::zero();
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                PT a[F], b[F];
+                load_feats<F>(g + (uint64_t)pl[k] * c.n_feat + c.gfo, a, vec_ok);
+                load_feats<F>(g + (uint64_t)ln[k] * c.n_feat + c.gfo, b, vec_ok);
+#pragma unroll
+                for (int f = 0; f < F; ++f) v[f] = C::add(v[f], C::from_f(C::to_f(a[f]) * C::to_f(b[f])));
+            }
+        }
+        break;
+    case NR3D_LOD_VECZMATXOY:
+        if constexpr (D == 3) {
+            const uint32_t ln = pos[2];
+            const uint32_t pl = c.res[2] + pos[1] + pos[0] * c.res[0];
+            PT a[F], b[F];
+            load_feats<F>(g + (uint64_t)pl * c.n_feat + c.gfo, a, vec_ok);
+            load_feats<F>(g + (uint64_t)ln * c.n_feat + c.gfo, b, vec_ok);
+#pragma unroll
+            for (int f = 0; f < F; ++f) v[f] = C::from_f(C::to_f(a[f]) * C::to_f(b[f]));
+        }
+        break;
+    case NR3D_LOD_NPLANEMUL: {
+        float r[F];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            PT a[F];
+            load_feats<F>(g + (uint64_t)idx_nplane<D>(c.res, pos, j) * c.n_feat + c.gfo, a, vec_ok);
+#pragma unroll
+            for (int f = 0; f < F; ++f) r[f] = (j == 0) ? C::to_f(a[f]) : r[f] * C::to_f(a[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < F; ++f) v[f] = C::from_f(r[f]);
+    } break;
+    case NR3D_LOD_CP: {
+        float r[F];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            PT a[F];
+            load_feats<F>(g + (uint64_t)idx_cp_line<D>(c.res, pos[k], k) * c.n_feat + c.gfo, a, vec_ok);
+#pragma unroll
+            for (int f = 0; f < F; ++f) r[f] = (k == 0) ? C::to_f(a[f]) : r[f] * C::to_f(a[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < F; ++f) v[f] = C::from_f(r[f]);
+    } break;
+    default:
+#pragma unroll
+        for (int f = 0; f < F; ++f) v[f] = C::zero();
+        break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gradient scatter
+// ------------------------------------------------------------------------------------------------
+template <int F>
+__device__ __forceinline__ void scatter_add(float* addr, const float* v, bool vec_ok) {
+    if (vec_ok) {
+#pragma unroll
+        for (int f = 0; f < F; f += 2) red_add_v2_f32(addr + f, v[f], v[f + 1]);
+    } else {
+#pragma unroll
+        for (int f = 0; f < F; ++f) red_add_f32(addr + f, v[f]);
+    }
+}
+template <int F>
+__device__ __forceinline__ void scatter_add(__half* addr, const float* v, bool /*vec_ok*/) {
+#pragma unroll
+    for (int f = 0; f < F; f += 2) red_add_h2(addr + f, __halves2half2(__float2half_rn(v[f]), __float2half_rn(v[f + 1])));
+}
+
+// d(corner value)/d(params) * (grad * weight) for the n-linear types (reference: add_grid_gridient_*_impl)
+template <int D, int F, typename PT>
+__device__ __forceinline__ void corner_add_grad(const Ctx<D>& c, const PT* __restrict__ g, PT* __restrict__ gg,
+                                                const uint32_t* pos, const float* grad, float w, bool vec_ok) {
+    using C = Cvt<PT>;
+    float wg[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) wg[f] = grad[f] * w;
+    switch (c.type) {
+    case NR3D_LOD_DENSE:
+        scatter_add<F>(gg + (uint64_t)idx_dense<D>(c.res, pos) * c.n_feat + c.gfo, wg, vec_ok);
+        break;
+    case NR3D_LOD_HASH:
+        scatter_add<F>(gg + (uint64_t)idx_hash<D>(pos, c.size) * c.n_feat + c.gfo, wg, vec_ok);
+        break;
+    case NR3D_LOD_VM:
+        if constexpr (D == 3) {
+            uint32_t pl[D], ln[D];
+            idx_vm<D>(c.res, pos, pl, ln);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const uint64_t ip = (uint64_t)pl[k] * c.n_feat + c.gfo, il = (uint64_t)ln[k] * c.n_feat + c.gfo;
+                PT a[F], b[F];
+                load_feats<F>(g + ip, a, vec_ok);
+                load_feats<F>(g + il, b, vec_ok);
+                float ga[F], gb[F];
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+                    ga[f] = wg[f] * C::to_f(b[f]);
+                    gb[f] = wg[f] * C::to_f(a[f]);
+                }
+                scatter_add<F>(gg + ip, ga, vec_ok);
+                scatter_add<F>(gg + il, gb, vec_ok);
+            }
+        }
+        break;
+    case NR3D_LOD_VECZMATXOY:
+        if constexpr (D == 3) {
+            const uint64_t il = (uint64_t)pos[2] * c.n_feat + c.gfo;
+            const uint64_t ip = (uint64_t)(c.res[2] + pos[1] + pos[0] * c.res[0]) * c.n_feat + c.gfo;
+            PT a[F], b[F];
+            load_feats<F>(g + ip, a, vec_ok);
+            load_feats<F>(g + il, b, vec_ok);
+            float ga[F], gb[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                ga[f] = wg[f] * C::to_f(b[f]);
+                gb[f] = wg[f] * C::to_f(a[f]);
+            }
+            scatter_add<F>(gg + ip, ga, vec_ok);
+            scatter_add<F>(gg + il, gb, vec_ok);
+        }
+        break;
+    case NR3D_LOD_NPLANEMUL:
+    case NR3D_LOD_CP: {
+        uint64_t id[D];
+        PT a[D][F];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const uint32_t ii = (c.type == NR3D_LOD_CP) ? idx_cp_line<D>(c.res, pos[k], k) : idx_nplane<D>(c.res, pos, k);
+            id[k] = (uint64_t)ii * c.n_feat + c.gfo;
+            load_feats<F>(g + id[k], a[k], vec_ok);
+        }
+#pragma unroll
+        for (int gd = 0; gd < D; ++gd) {
+            float gp[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                float cur = wg[f];
+#pragma unroll
+                for (int k = 0; k < D; ++k)
+                    if (k != gd) cur *= C::to_f(a[k][f]);
+                gp[f] = cur;
+            }
+            scatter_add<F>(gg + id[gd], gp, vec_ok);
+        }
+    } break;
+    default:
+        break;
+    }
+}
+
+// corner position for corner id `idx` (bit d set -> cell+1) and its n-linear weight
+template <int D>
+__device__ __forceinline__ float corner_weight(const Ctx<D>& c, int idx, uint32_t* pos) {
+    float w = 1.0f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        if ((idx & (1 << d)) == 0) {
+            w *= 1.0f - c.p[d];
+            pos[d] = c.cell[d];
+        } else {
+            w *= c.p[d];
+            pos[d] = c.cell[d] + 1;
+        }
+    }
+    return w;
+}
+// weight for the (D-1)-face corner `idx` (bits over the dims != g), starting from w0; sets pos for dims != g
+template <int D>
+__device__ __forceinline__ float face_weight(const Ctx<D>& c, int g, int idx, float w0, uint32_t* pos, int* left_idx) {
+    float w = w0;
+    int li = 0;
+#pragma unroll
+    for (int ng = 0; ng < D - 1; ++ng) {
+        const int dim = ng >= g ? ng + 1 : ng;
+        if ((idx & (1 << ng)) == 0) {
+            w *= 1.0f - c.p[dim];
+            pos[dim] = c.cell[dim];
+        } else {
+            w *= c.p[dim];
+            pos[dim] = c.cell[dim] + 1;
+            li += 1 << dim;
+        }
+    }
+    *left_idx = li;
+    return w;
+}
+
+__device__ __forceinline__ bool is_nlinear(uint32_t type) { return type != NR3D_LOD_NPLANESUM && type != NR3D_LOD_CPFAST; }
+
+}  // namespace nr3d

@@ -1,0 +1,217 @@
+// march.cu -- occupancy-grid ray marching (single + batched) for sm_100a.
+//
+// Behavioural contract: csrc/occ_grid/src/ray_marching.cu:17-134 and batched_marching.cu:18-148 with
+// include/occ_grid/helpers_march.h:11-77 and helpers_contraction.h:10-125.  The float expressions below keep the
+// reference's operation order (and rely on the same nvcc a*b+c contraction) so that sample counts and
+// pack offsets are bit-exact.  Differences in structure, not in results:
+//   * one templated kernel serves both passes and both the single / batched variants;
+//   * the per-ray counts are turned into packed_info by an on-device scan (pack_ops.cu) -- no cumsum/stack
+//     tensor ops and a single host read of the total;
+//   * rays with batch_inds < 0 get count 0 (the reference leaves `num_steps` uninitialised for them).
+#include "common.cuh"
+
+namespace nr3d {
+
+template <typename TI, typename TO>
+int scan_counts(uint64_t n, const TI* counts, TO* pack_infos, int64_t* total, void* ws, uint64_t* ws_bytes, cudaStream_t stream);
+
+struct F3 { float x, y, z; };
+
+__device__ __forceinline__ float clampf(float f, float a, float b) { return fmaxf(a, fminf(f, b)); }
+__device__ __forceinline__ float calc_dt(float t, float dt_gamma, float dt_min, float dt_max) { return clampf(t * dt_gamma, dt_min, dt_max); }
+
+__device__ __forceinline__ F3 roi_to_unit(F3 p, F3 lo, F3 hi) {
+    return F3{(p.x - lo.x) / (hi.x - lo.x), (p.y - lo.y) / (hi.y - lo.y), (p.z - lo.z) / (hi.z - lo.z)};
+}
+
+__device__ __forceinline__ F3 apply_contraction(F3 p, F3 lo, F3 hi, int type) {
+    F3 u = roi_to_unit(p, lo, hi);
+    if (type == NR3D_CONTRACTION_TANH) {  // helpers_contraction.h:24-35
+        u = F3{u.x - 0.5f, u.y - 0.5f, u.z - 0.5f};
+        return F3{tanhf(u.x) * 0.5f + 0.5f, tanhf(u.y) * 0.5f + 0.5f, tanhf(u.z) * 0.5f + 0.5f};
+    }
+    if (type == NR3D_CONTRACTION_SPHERE) {  // helpers_contraction.h:58-76
+        u = F3{u.x * 2.0f - 1.0f, u.y * 2.0f - 1.0f, u.z * 2.0f - 1.0f};
+        const float norm_sq = u.x * u.x + u.y * u.y + u.z * u.z;
+        const float norm = sqrtf(norm_sq);
+        if (norm > 1.0f) {
+            const float s = 2.0f - 1.0f / norm;
+            u = F3{s * (u.x / norm), s * (u.y / norm), s * (u.z / norm)};
+        }
+        return F3{u.x * 0.25f + 0.5f, u.y * 0.25f + 0.5f, u.z * 0.25f + 0.5f};
+    }
+    return u;
+}
+
+__device__ __forceinline__ bool grid_occupied_at(F3 p, F3 lo, F3 hi, int type, int3 res, const uint8_t* __restrict__ grid, int* idx_out) {
+    if (type == NR3D_CONTRACTION_AABB &&
+        (p.x < lo.x || p.x > hi.x || p.y < lo.y || p.y > hi.y || p.z < lo.z || p.z > hi.z)) return false;
+    const F3 u = apply_contraction(p, lo, hi, type);
+    int ix = (int)(u.x * (float)res.x), iy = (int)(u.y * (float)res.y), iz = (int)(u.z * (float)res.z);
+    ix = max(0, min(ix, res.x - 1));
+    iy = max(0, min(iy, res.y - 1));
+    iz = max(0, min(iz, res.z - 1));
+    const int idx = ix * (res.y * res.z) + iy * res.z + iz;
+    *idx_out = idx;
+    return grid[idx] != 0;
+}
+
+__device__ __forceinline__ float distance_to_next_voxel(F3 p, F3 dir, F3 inv_dir, F3 lo, F3 hi, int3 res) {
+    const F3 r = F3{(float)res.x, (float)res.y, (float)res.z};
+    const F3 u = roi_to_unit(p, lo, hi);
+    const F3 q = F3{u.x * r.x, u.y * r.y, u.z * r.z};
+    const float tx = ((floorf(q.x + 0.5f + 0.5f * copysignf(1.0f, dir.x)) - q.x) * inv_dir.x) / r.x * (hi.x - lo.x);
+    const float ty = ((floorf(q.y + 0.5f + 0.5f * copysignf(1.0f, dir.y)) - q.y) * inv_dir.y) / r.y * (hi.y - lo.y);
+    const float tz = ((floorf(q.z + 0.5f + 0.5f * copysignf(1.0f, dir.z)) - q.z) * inv_dir.z) / r.z * (hi.z - lo.z);
+    return fmaxf(fminf(fminf(tx, ty), tz), 0.0f);
+}
+
+__device__ __forceinline__ float advance_to_next_voxel(float t, float dt_min, F3 p, F3 dir, F3 inv_dir, F3 lo, F3 hi, int3 res) {
+    const float t_target = t + distance_to_next_voxel(p, dir, inv_dir, lo, hi, res);
+    float t_ = t;
+    do { t_ += dt_min; } while (t_ < t_target);
+    return t_;
+}
+
+struct MarchArgs {
+    uint64_t n_rays;
+    const float *rays_o, *rays_d, *t_min, *t_max;
+    const int32_t* batch_inds;
+    uint32_t batch_data_size;
+    const float* roi;
+    const uint8_t* grid;
+    int3 res;
+    int type;
+    float step_size, max_step_size, dt_gamma;
+    uint32_t max_steps;
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+march_kernel(const MarchArgs a, const int32_t* __restrict__ packed_info, int32_t* __restrict__ num_steps, float* __restrict__ t_starts,
+             float* __restrict__ t_ends, int32_t* __restrict__ ridx_out, int32_t* __restrict__ bidx_out, int32_t* __restrict__ gidx_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_rays) return;
+    uint32_t batch_ind = 0;
+    if (a.batch_inds) {
+        const int32_t b = a.batch_inds[i];
+        if (b < 0) {
+            if (!FILL) num_steps[i] = 0;
+            return;
+        }
+        batch_ind = (uint32_t)b;
+    } else if (a.batch_data_size) {
+        batch_ind = (uint32_t)(i / a.batch_data_size);
+    }
+    const uint32_t cells = (uint32_t)(a.res.x * a.res.y * a.res.z);
+    const uint32_t grid_offset = batch_ind * cells;
+    const uint8_t* __restrict__ grid = a.grid + grid_offset;
+    const float* roi = a.roi + (uint64_t)batch_ind * 6;
+
+    uint32_t max_steps = a.max_steps;
+    uint64_t base = 0;
+    if (FILL) {
+        base = (uint32_t)packed_info[i * 2 + 0];
+        max_steps = (uint32_t)packed_info[i * 2 + 1];
+        if (max_steps == 0) return;
+    }
+    const F3 origin = F3{a.rays_o[i * 3 + 0], a.rays_o[i * 3 + 1], a.rays_o[i * 3 + 2]};
+    const F3 dir = F3{a.rays_d[i * 3 + 0], a.rays_d[i * 3 + 1], a.rays_d[i * 3 + 2]};
+    const F3 inv_dir = F3{1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z};
+    const float near = a.t_min[i], far = a.t_max[i];
+    const F3 lo = F3{roi[0], roi[1], roi[2]};
+    const F3 hi = F3{roi[3], roi[4], roi[5]};
+    const float dt_min = a.step_size, dt_max = a.max_step_size;
+
+    uint32_t j = 0;
+    float t0 = near;
+    float dt = calc_dt(t0, a.dt_gamma, dt_min, dt_max);
+    float t1 = t0 + dt;
+    float t_mid = (t0 + t1) * 0.5f;
+    while ((t_mid < far) && (j < max_steps)) {
+        const F3 p = F3{origin.x + t_mid * dir.x, origin.y + t_mid * dir.y, origin.z + t_mid * dir.z};
+        int grid_idx = -1;
+        if (grid_occupied_at(p, lo, hi, a.type, a.res, grid, &grid_idx)) {
+            if (FILL) {
+                t_starts[base + j] = t0;
+                t_ends[base + j] = t1;
+                ridx_out[base + j] = (int32_t)i;
+                if (bidx_out) bidx_out[base + j] = (int32_t)batch_ind;
+                if (gidx_out) gidx_out[base + j] = grid_idx + (int32_t)grid_offset;
+            }
+            ++j;
+            t0 = t1;
+            t1 = t0 + calc_dt(t0, a.dt_gamma, dt_min, dt_max);
+            t_mid = (t0 + t1) * 0.5f;
+        } else if (a.type == NR3D_CONTRACTION_AABB) {
+            t_mid = advance_to_next_voxel(t_mid, dt_min, p, dir, inv_dir, lo, hi, a.res);
+            dt = calc_dt(t_mid, a.dt_gamma, dt_min, dt_max);
+            t0 = t_mid - dt * 0.5f;
+            t1 = t_mid + dt * 0.5f;
+        } else {
+            t0 = t1;
+            t1 = t0 + calc_dt(t0, a.dt_gamma, dt_min, dt_max);
+            t_mid = (t0 + t1) * 0.5f;
+        }
+    }
+    if (!FILL) num_steps[i] = (int32_t)j;
+}
+
+static int fill_args(MarchArgs& a, uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                     const int32_t* batch_inds, uint32_t batch_data_size, int32_t n_batches, const float* roi, const uint8_t* grid,
+                     int32_t rx, int32_t ry, int32_t rz, int32_t contraction, float step_size, float max_step_size, float dt_gamma,
+                     uint32_t max_steps) {
+    NR3D_CHECK(rays_o && rays_d && t_min && t_max && roi && grid, "ray_marching: null argument");
+    NR3D_CHECK(rx > 0 && ry > 0 && rz > 0 && n_batches > 0, "ray_marching: invalid grid shape");
+    NR3D_CHECK(contraction >= 0 && contraction <= 2, "ray_marching: invalid contraction type %d", contraction);
+    NR3D_CHECK(batch_data_size == 0 || n_rays % batch_data_size == 0,
+               "batched_ray_marching: Expect nonzero `batch_data_size`=%u to be a divisor of `n_rays`=%llu", batch_data_size,
+               (unsigned long long)n_rays);
+    NR3D_CHECK(n_rays < (1ull << 31), "ray_marching: n_rays must be < 2^31");
+    a.n_rays = n_rays; a.rays_o = rays_o; a.rays_d = rays_d; a.t_min = t_min; a.t_max = t_max;
+    a.batch_inds = batch_inds; a.batch_data_size = batch_data_size; a.roi = roi; a.grid = grid;
+    a.res = make_int3(rx, ry, rz); a.type = contraction;
+    a.step_size = step_size; a.max_step_size = max_step_size; a.dt_gamma = dt_gamma; a.max_steps = max_steps;
+    return 0;
+}
+
+}  // namespace nr3d
+
+using namespace nr3d;
+
+extern "C" {
+
+int nr3d_march_count(uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                     const int32_t* batch_inds, uint32_t batch_data_size, int32_t n_batches, const float* roi, const uint8_t* grid,
+                     int32_t rx, int32_t ry, int32_t rz, int32_t contraction, float step_size, float max_step_size, float dt_gamma,
+                     uint32_t max_steps, int32_t* num_steps, void* stream) {
+    if (n_rays == 0) return 0;
+    MarchArgs a;
+    if (int rc = fill_args(a, n_rays, rays_o, rays_d, t_min, t_max, batch_inds, batch_data_size, n_batches, roi, grid, rx, ry, rz,
+                           contraction, step_size, max_step_size, dt_gamma, max_steps)) return rc;
+    NR3D_CHECK(num_steps != nullptr, "ray_marching: null num_steps");
+    march_kernel<false><<<(unsigned)div_up<uint64_t>(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(a, nullptr, num_steps, nullptr, nullptr, nullptr, nullptr, nullptr);
+    NR3D_LAUNCH_CHECK("ray_marching(count)");
+    return 0;
+}
+
+int nr3d_march_pack(uint64_t n_rays, const int32_t* num_steps, int32_t* packed_info, int64_t* total, void* ws, uint64_t* ws_bytes, void* stream) {
+    return scan_counts<int32_t, int32_t>(n_rays, num_steps, packed_info, total, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int nr3d_march_fill(uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                    const int32_t* batch_inds, uint32_t batch_data_size, int32_t n_batches, const float* roi, const uint8_t* grid,
+                    int32_t rx, int32_t ry, int32_t rz, int32_t contraction, float step_size, float max_step_size, float dt_gamma,
+                    uint32_t max_steps, const int32_t* packed_info, float* t_starts, float* t_ends, int32_t* ridx, int32_t* bidx,
+                    int32_t* gidx, void* stream) {
+    if (n_rays == 0) return 0;
+    MarchArgs a;
+    if (int rc = fill_args(a, n_rays, rays_o, rays_d, t_min, t_max, batch_inds, batch_data_size, n_batches, roi, grid, rx, ry, rz,
+                           contraction, step_size, max_step_size, dt_gamma, max_steps)) return rc;
+    NR3D_CHECK(packed_info && t_starts && t_ends && ridx, "ray_marching: null output");
+    march_kernel<true><<<(unsigned)div_up<uint64_t>(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(a, packed_info, nullptr, t_starts, t_ends, ridx, bidx, gidx);
+    NR3D_LAUNCH_CHECK("ray_marching(fill)");
+    return 0;
+}
+
+}  // extern "C"
