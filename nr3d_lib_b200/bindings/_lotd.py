@@ -1,0 +1,348 @@
+"""Drop-in replacement for ``nr3d_lib.bindings._lotd`` (reference: csrc/lotd/src/lotd.cpp:23-110).
+
+Same names, argument order, defaults, validation rules, returned shapes / dtypes / stride patterns as the
+reference's pybind module, implemented on top of the C-ABI library ``libnr3d_b200.so``.
+"""
+import ctypes
+import enum
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from .. import _lib
+
+__all__ = ["LoDType", "InterpolationType", "LoDMeta", "lod_fwd", "lod_bwd", "lod_bwd_bwd_input", "lod_get_grid_index"]
+
+
+class LoDType(enum.IntEnum):
+    # values of the C++ enum incl. the un-exported VecZMatXoY=2 (csrc/lotd/include/lotd/lotd_types.h:16-26)
+    Dense = 0
+    VectorMatrix = 1
+    CP = 3
+    CPfast = 4
+    NPlaneMul = 5
+    NPlaneSum = 6
+    Hash = 7
+
+
+class InterpolationType(enum.IntEnum):
+    Linear = 0
+    Smoothstep = 1
+
+
+# py::enum_::export_values() (lotd.cpp:68,73)
+Dense, VectorMatrix, CP, CPfast, NPlaneMul, NPlaneSum, Hash = (LoDType.Dense, LoDType.VectorMatrix, LoDType.CP,
+                                                              LoDType.CPfast, LoDType.NPlaneMul, LoDType.NPlaneSum, LoDType.Hash)
+Linear, Smoothstep = InterpolationType.Linear, InterpolationType.Smoothstep
+
+_TYPE_FROM_STR = {  # case-insensitive names + aliases (lotd_types.h:42-62)
+    "dense": 0, "hash": 7, "nplane": 6, "nplanesum": 6, "nplanemul": 5, "vectormatrix": 1, "vm": 1,
+    "veczmatxoy": 2, "cpfast": 4, "cp": 3,
+}
+
+
+def _string_to_lod_type(s: str) -> int:
+    try:
+        return _TYPE_FROM_STR[str(s).lower()]
+    except KeyError:
+        raise RuntimeError(f"LoTDEncoding: Invalid lod type: {s}")
+
+
+class LoDMeta:
+    """Host-side description of a LoTD encoding (reference: LoDMeta, lotd_torch_api.h:81-135; pybind lotd.cpp:75-109)."""
+
+    _READONLY = ("level_res", "level_res_multidim", "level_n_params", "level_n_feats", "level_types", "level_sizes",
+                 "level_types_str", "level_offsets", "map_levels", "map_cnt", "n_levels", "n_pseudo_levels",
+                 "n_feat_per_pseudo_lvl", "n_dims_to_encode", "n_encoded_dims", "n_params", "interpolation_type")
+
+    def __init__(self, n_input_dims: int, lod_res: Union[Sequence[int], Sequence[Sequence[int]]], lod_n_feats: Sequence[int],
+                 lod_types: Sequence[str], hashmap_size: Optional[int] = None, use_smooth_step: Optional[bool] = None,
+                 *, lod_res_multidim=None):
+        if lod_res_multidim is not None:
+            lod_res = lod_res_multidim
+        n_input_dims = int(n_input_dims)
+        lod_res = list(lod_res)
+        lod_n_feats = [int(v) for v in lod_n_feats]
+        lod_types = [str(t) for t in lod_types]
+        if not (len(lod_res) == len(lod_n_feats) == len(lod_types)):
+            raise RuntimeError("LoTDEncoding: Expect los_res, lod_n_feats, lod_str_types to have the same length")
+        if n_input_dims not in (2, 3, 4):
+            raise RuntimeError("LoTDEncoding: `n_input_dim` must be 2/3/4.")
+        res_md = []
+        for r in lod_res:
+            if isinstance(r, (list, tuple)) or (hasattr(r, "__len__") and not isinstance(r, str)):
+                r = [int(v) for v in r]
+                if len(r) != n_input_dims:
+                    raise RuntimeError("LoTDEncoding: each entry of `lod_res_multidim` must have `n_input_dims` items")
+            else:
+                r = [int(r)] * n_input_dims
+            res_md.append(r)
+        L = len(res_md)
+        types = [_string_to_lod_type(t) for t in lod_types]
+        flat_res = (ctypes.c_int32 * max(1, L * n_input_dims))(*[v for r in res_md for v in r])
+        nf = (ctypes.c_int32 * max(1, L))(*lod_n_feats)
+        tp = (ctypes.c_int32 * max(1, L))(*types)
+        st = _lib.LotdMetaStruct()
+        _lib.check(_lib.get_lib().nr3d_lotd_meta_create(
+            n_input_dims, L, ctypes.cast(flat_res, ctypes.c_void_p), ctypes.cast(nf, ctypes.c_void_p),
+            ctypes.cast(tp, ctypes.c_void_p), int(hashmap_size or 0), int(bool(use_smooth_step)), ctypes.byref(st)))
+        object.__setattr__(self, "_c", st)
+        D = n_input_dims
+        ro = dict(
+            level_res_multidim=[[int(st.level_res[l][d]) for d in range(D)] for l in range(L)],
+            level_n_feats=[int(st.level_n_feats[l]) for l in range(L)],
+            level_types=[int(st.level_types[l]) for l in range(L)],
+            level_types_str=list(lod_types),
+            level_n_params=[int(st.level_n_params[l]) for l in range(L)],
+            level_sizes=[int(st.level_sizes[l]) for l in range(L)],
+            level_offsets=[int(st.level_offsets[l]) for l in range(L + 1)],
+            map_levels=[int(st.map_levels[p]) for p in range(st.n_pseudo_levels)],
+            map_cnt=[int(st.map_cnt[p]) for p in range(st.n_pseudo_levels)],
+            n_levels=int(st.n_levels), n_pseudo_levels=int(st.n_pseudo_levels),
+            n_feat_per_pseudo_lvl=int(st.n_feat_per_pseudo_lvl), n_dims_to_encode=int(st.n_dims_to_encode),
+            n_encoded_dims=int(st.n_encoded_dims), n_params=int(st.n_params),
+            interpolation_type=InterpolationType(int(st.interpolation_type)),
+        )
+        ro["level_res"] = [r[0] if all(v == r[0] for v in r) else 0 for r in ro["level_res_multidim"]]
+        for k, v in ro.items():
+            object.__setattr__(self, k, v)
+        # read-write configuration flags (lotd.cpp:105-109, defaults lotd_torch_api.h:99-103)
+        object.__setattr__(self, "c_hash_only", bool(st.hash_only))
+        object.__setattr__(self, "c_profile", False)
+        object.__setattr__(self, "c_bmm_backend", True)
+        object.__setattr__(self, "c_prefetch", True)
+        object.__setattr__(self, "c_permute_dydx", True)
+        object.__setattr__(self, "_ctor", (n_input_dims, res_md, lod_n_feats, lod_types, hashmap_size, use_smooth_step))
+
+    def __setattr__(self, key, value):
+        if key in self._READONLY:
+            raise AttributeError(f"LoDMeta.{key} is read-only")
+        object.__setattr__(self, key, bool(value) if key.startswith("c_") else value)
+
+    def __reduce__(self):
+        n, res, nf, tp, hs, ss = self._ctor
+        return (LoDMeta, (n, res, nf, tp, hs, ss))
+
+    def __repr__(self):
+        return (f"LoDMeta(n_dims={self.n_dims_to_encode}, n_levels={self.n_levels}, n_encoded_dims={self.n_encoded_dims}, "
+                f"n_params={self.n_params}, types={self.level_types_str})")
+
+
+# --------------------------------------------------------------------------------------------------------------
+# argument validation shared by all ops (reference: lotd_torch_api.cu:244-292, 412-490, 592-681, 781-825)
+# --------------------------------------------------------------------------------------------------------------
+def _is_forest(meta):
+    return isinstance(meta, (tuple, list))
+
+
+def _forest_unsupported():
+    raise RuntimeError("nr3d_lib_b200: forest (multi-block) LoTD overloads are not part of the B200 hot path yet "
+                       "(SURVEY.md section 8f, row n4).")
+
+
+def _check_common(fn, meta: LoDMeta, input, params, batch_inds, batch_offsets, batch_data_size):
+    if not isinstance(meta, LoDMeta):
+        raise TypeError(f"{fn}: `lod_meta` must be a nr3d_lib_b200 LoDMeta, got {type(meta)}")
+    if input.dim() != 2:
+        raise RuntimeError(f"{fn}: Expected 2-dimensional tensor, but got {input.dim()}-dimensional tensor for argument 'x'")
+    if input.dtype not in (torch.float16, torch.float32):
+        raise RuntimeError(f"{fn}: Expected 'x' to have scalar type Half or Float, got {input.dtype}")
+    if not input.is_contiguous():
+        raise RuntimeError(f"{fn}: Expected contiguous tensor for argument 'x'")
+    N = input.shape[0]
+    if input.shape[1] != meta.n_dims_to_encode:
+        raise RuntimeError(f"{fn}: Expected tensor to have size {meta.n_dims_to_encode} at dimension 1, but got size "
+                           f"{input.shape[1]} for argument 'x'")
+    if params is not None:
+        if params.dim() != 1:
+            raise RuntimeError(f"{fn}: Expected 1-dimensional tensor, but got {params.dim()}-dimensional tensor for argument 'grid'")
+        if params.dtype not in (torch.float16, torch.float32):
+            raise RuntimeError(f"{fn}: Expected 'grid' to have scalar type Half or Float, got {params.dtype}")
+        if not params.is_contiguous():
+            raise RuntimeError(f"{fn}: Expected contiguous tensor for argument 'grid'")
+        if meta.n_params == 0 or params.shape[0] % meta.n_params != 0:
+            raise RuntimeError(f"LoTDEncoding::{fn}: Expect size of `params`={params.shape[0]} to be an integral multiple of "
+                               f"`n_param`={meta.n_params}")
+    if batch_inds is not None:
+        if batch_inds.dim() != 1 or batch_inds.dtype != torch.int64 or not batch_inds.is_contiguous() or batch_inds.shape[0] != N:
+            raise RuntimeError(f"{fn}: `batch_inds` must be a contiguous int64 tensor of shape [{N}]")
+    if batch_offsets is not None:
+        if batch_offsets.dim() != 1 or batch_offsets.dtype != torch.int64 or not batch_offsets.is_contiguous():
+            raise RuntimeError(f"{fn}: `batch_offsets` must be a contiguous 1-D int64 tensor")
+    bds = 0
+    if batch_data_size is not None:
+        bds = int(batch_data_size)
+        if not (bds == 0 or (N % bds) == 0):
+            raise RuntimeError(f"LoTDEncoding::{fn}: Expect nonzero `batch_data_size`={bds} to be a divisor of `batch_size`={N}")
+    dev = _lib.require_cuda(input, params, batch_inds, batch_offsets, who=fn)
+    return N, bds, dev
+
+
+def _dydx_view(dy_dx, N, meta):
+    """[N, n_enc, D] view of a dy_dx tensor in either reference layout; returns (tensor, stride_n, stride_j)."""
+    D, E = meta.n_dims_to_encode, meta.n_encoded_dims
+    v = dy_dx.view(N, E, D) if dy_dx.dim() != 3 else dy_dx
+    if tuple(v.shape) != (N, E, D):
+        raise RuntimeError(f"lod_bwd: `dy_dx` has shape {tuple(dy_dx.shape)}, expected [{N}, {E}, {D}] or [{N}, {E * D}]")
+    if v.stride(2) != 1:
+        v = v.contiguous()
+    return v, v.stride(0), v.stride(1)
+
+
+def lod_fwd(lod_meta, input: torch.Tensor, params: torch.Tensor, batch_inds: Optional[torch.Tensor] = None,
+            batch_offsets: Optional[torch.Tensor] = None, batch_data_size: Optional[int] = None,
+            max_level: Optional[int] = None, need_input_grad: Optional[bool] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """== lotd::torch::lod_fwd (csrc/lotd/src/lotd_torch_api.cu:232-395)."""
+    if _is_forest(lod_meta):
+        _forest_unsupported()
+    meta = lod_meta
+    N, bds, dev = _check_common("fwd", meta, input, params, batch_inds, batch_offsets, batch_data_size)
+    D, E = meta.n_dims_to_encode, meta.n_encoded_dims
+    max_level = meta.n_levels if max_level is None else int(max_level)
+    need_input_grad = input.requires_grad if need_input_grad is None else bool(need_input_grad)
+    if max_level <= -1:
+        return (torch.zeros([N, E], dtype=params.dtype, device=dev), torch.zeros([N, E * D], dtype=input.dtype, device=dev))
+    dy_dx = None
+    ds_n = ds_f = 0
+    with torch.cuda.device(dev):
+        if meta.c_hash_only:
+            # feature-major storage returned through a transposed view (lotd_torch_api.cu:303,317)
+            y_store = torch.empty([E, N], dtype=params.dtype, device=dev)
+            y, ys_n, ys_f = y_store.t(), 1, N
+            if need_input_grad:
+                if meta.c_permute_dydx:
+                    store = torch.empty([E, N, D], dtype=input.dtype, device=dev)
+                    dy_dx, ds_n, ds_f = store.permute(1, 0, 2), D, N * D
+                else:
+                    dy_dx = torch.empty([N, E * D], dtype=input.dtype, device=dev)
+                    ds_n, ds_f = E * D, D
+        else:
+            y = torch.empty([N, E], dtype=params.dtype, device=dev)
+            ys_n, ys_f = E, 1
+            if need_input_grad:
+                dy_dx = torch.empty([N, E * D], dtype=input.dtype, device=dev)
+                ds_n, ds_f = E * D, D
+        _lib.check(_lib.get_lib().nr3d_lotd_fwd(
+            ctypes.byref(meta._c), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, _lib.ptr(input), _lib.ptr(params),
+            _lib.ptr(batch_inds), _lib.ptr(batch_offsets), bds, max_level, y.data_ptr(), ys_n, ys_f,
+            _lib.ptr(dy_dx), ds_n, ds_f, _lib.stream_of(dev)))
+    return y, dy_dx
+
+
+def lod_bwd(lod_meta, dL_dy: torch.Tensor, input: torch.Tensor, params: torch.Tensor, dy_dx: Optional[torch.Tensor] = None,
+            batch_inds: Optional[torch.Tensor] = None, batch_offsets: Optional[torch.Tensor] = None,
+            batch_data_size: Optional[int] = None, max_level: Optional[int] = None, need_input_grad: Optional[bool] = None,
+            need_param_grad: Optional[bool] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """== lotd::torch::lod_bwd (csrc/lotd/src/lotd_torch_api.cu:397-573)."""
+    if _is_forest(lod_meta):
+        _forest_unsupported()
+    meta = lod_meta
+    N, bds, dev = _check_common("bwd", meta, input, params, batch_inds, batch_offsets, batch_data_size)
+    D, E = meta.n_dims_to_encode, meta.n_encoded_dims
+    if dL_dy.dim() != 2 or tuple(dL_dy.shape) != (N, E):
+        raise RuntimeError(f"bwd: Expected tensor of size [{N}, {E}] for argument 'dL_dy', got {tuple(dL_dy.shape)}")
+    if dL_dy.dtype != params.dtype:
+        raise RuntimeError(f"bwd: Expected 'dL_dy' ({dL_dy.dtype}) to have the same type as 'grid' ({params.dtype})")
+    _lib.require_cuda(dL_dy, input, dy_dx, who="bwd")
+    if dy_dx is not None and dy_dx.dtype != input.dtype:
+        raise RuntimeError(f"bwd: Expected 'dy_dx' ({dy_dx.dtype}) to have the same type as 'x' ({input.dtype})")
+    max_level = meta.n_levels if max_level is None else int(max_level)
+    need_input_grad = input.requires_grad if need_input_grad is None else bool(need_input_grad)
+    need_param_grad = params.requires_grad if need_param_grad is None else bool(need_param_grad)
+    dL_dx = dL_dparam = None
+    lib = _lib.get_lib()
+    with torch.cuda.device(dev):
+        if need_input_grad:
+            if dy_dx is None:
+                raise RuntimeError("LoTDEncoding::bwd: need `dy_dx` to comput `dL_dx`.")
+            dL_dx = torch.zeros([N, D], dtype=input.dtype, device=dev) if max_level <= -1 else torch.empty([N, D], dtype=input.dtype, device=dev)
+        if need_param_grad:
+            dL_dparam = torch.zeros([params.shape[0]], dtype=params.dtype, device=dev)
+        if max_level <= -1:
+            return dL_dx, dL_dparam
+        st = _lib.stream_of(dev)
+        if need_input_grad:
+            dv, ds_n, ds_f = _dydx_view(dy_dx, N, meta)
+            _lib.check(lib.nr3d_lotd_bwd_input(
+                ctypes.byref(meta._c), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, dL_dy.data_ptr(),
+                dL_dy.stride(0), dL_dy.stride(1), dv.data_ptr(), ds_n, ds_f, dL_dx.data_ptr(), st))
+        if need_param_grad:
+            _lib.check(lib.nr3d_lotd_bwd_param(
+                ctypes.byref(meta._c), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, dL_dy.data_ptr(),
+                dL_dy.stride(0), dL_dy.stride(1), input.data_ptr(), params.data_ptr(), _lib.ptr(batch_inds),
+                _lib.ptr(batch_offsets), bds, max_level, dL_dparam.data_ptr(), st))
+    return dL_dx, dL_dparam
+
+
+def lod_bwd_bwd_input(lod_meta, dL_ddLdx: torch.Tensor, dL_dy: torch.Tensor, input: torch.Tensor, params: torch.Tensor,
+                      dy_dx: Optional[torch.Tensor] = None, batch_inds: Optional[torch.Tensor] = None,
+                      batch_offsets: Optional[torch.Tensor] = None, batch_data_size: Optional[int] = None,
+                      max_level: Optional[int] = None, need_dLdinput_ddLdoutput: Optional[bool] = None,
+                      need_dLdinput_dparams: Optional[bool] = None, need_dLdinput_dinput: Optional[bool] = None):
+    """== lotd::torch::lod_bwd_bwd_input (csrc/lotd/src/lotd_torch_api.cu:575-769) -> (dL_ddLdy, dL_dparams, dL_dx)."""
+    if _is_forest(lod_meta):
+        _forest_unsupported()
+    meta = lod_meta
+    N, bds, dev = _check_common("bwd_bwd_input", meta, input, params, batch_inds, batch_offsets, batch_data_size)
+    D, E = meta.n_dims_to_encode, meta.n_encoded_dims
+    if dL_ddLdx.dim() != 2 or tuple(dL_ddLdx.shape) != (N, D) or not dL_ddLdx.is_contiguous():
+        raise RuntimeError(f"bwd_bwd_input: Expected contiguous tensor of size [{N}, {D}] for argument 'dL_ddLdx'")
+    if dL_ddLdx.dtype != input.dtype:
+        raise RuntimeError("bwd_bwd_input: Expected 'dL_ddLdx' to have the same type as 'x'")
+    if dL_dy.dim() != 2 or tuple(dL_dy.shape) != (N, E):
+        raise RuntimeError(f"bwd_bwd_input: Expected tensor of size [{N}, {E}] for argument 'dL_dy'")
+    if dL_dy.dtype != params.dtype:
+        raise RuntimeError("bwd_bwd_input: Expected 'dL_dy' to have the same type as 'grid'")
+    if input.dtype != torch.float32:
+        raise RuntimeError("LoTDEncoding: Input type combination not supported. Supported types are: "
+                           "<input,param> -> (half, half), (float, half), (float, float)")
+    _lib.require_cuda(dL_ddLdx, dL_dy, dy_dx, who="bwd_bwd_input")
+    max_level = meta.n_levels if max_level is None else int(max_level)
+    need_dLdy = dL_dy.requires_grad if need_dLdinput_ddLdoutput is None else bool(need_dLdinput_ddLdoutput)
+    need_input = input.requires_grad if need_dLdinput_dinput is None else bool(need_dLdinput_dinput)
+    need_param = params.requires_grad if need_dLdinput_dparams is None else bool(need_dLdinput_dparams)
+    dL_ddLdy = dL_dx = dL_dparams = None
+    with torch.cuda.device(dev):
+        if need_dLdy:
+            if dy_dx is None:
+                raise RuntimeError("LoTDEncoding::bwd_bwd_input: need `dy_dx` to compute `dL_d(dLdy)`.")
+            dL_ddLdy = torch.zeros([N, E], dtype=dL_dy.dtype, device=dev) if max_level <= -1 else torch.empty([N, E], dtype=dL_dy.dtype, device=dev)
+        if need_input:
+            dL_dx = torch.zeros([N, D], dtype=input.dtype, device=dev)
+        if need_param:
+            dL_dparams = torch.zeros([params.shape[0]], dtype=params.dtype, device=dev)
+        if max_level <= -1 or not (need_dLdy or need_input or need_param):
+            return dL_ddLdy, dL_dparams, dL_dx
+        dv, ds_n, ds_f = (None, 0, 0)
+        if need_dLdy:
+            dv, ds_n, ds_f = _dydx_view(dy_dx, N, meta)
+        _lib.check(_lib.get_lib().nr3d_lotd_bwd_bwd_input(
+            ctypes.byref(meta._c), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, dL_ddLdx.data_ptr(),
+            dL_dy.data_ptr(), dL_dy.stride(0), dL_dy.stride(1), input.data_ptr(), params.data_ptr(), _lib.ptr(dv), ds_n, ds_f,
+            _lib.ptr(batch_inds), _lib.ptr(batch_offsets), bds, max_level, _lib.ptr(dL_ddLdy), _lib.ptr(dL_dparams),
+            _lib.ptr(dL_dx), _lib.stream_of(dev)))
+    return dL_ddLdy, dL_dparams, dL_dx
+
+
+def lod_get_grid_index(lod_meta, input: torch.Tensor, batch_inds: Optional[torch.Tensor] = None,
+                       batch_offsets: Optional[torch.Tensor] = None, batch_data_size: Optional[int] = None,
+                       max_level: Optional[int] = None) -> torch.Tensor:
+    """== lotd::torch::lod_get_grid_index (csrc/lotd/src/lotd_torch_api.cu:771-855): int64 [N, n_enc, 2^D]."""
+    if _is_forest(lod_meta):
+        raise RuntimeError("LoTDEncoding::lod_get_grid_index: Not implemented for forest for now")
+    meta = lod_meta
+    if not input.is_contiguous():
+        input = input.contiguous()
+    N, bds, dev = _check_common("get_grid_index", meta, input, None, batch_inds, batch_offsets, batch_data_size)
+    for tp in meta.level_types:
+        if tp not in (int(LoDType.Dense), int(LoDType.Hash)):
+            raise RuntimeError("LoTDEncoding::get_grid_index: Only support Dense/Hash type.")
+    max_level = meta.n_levels if max_level is None else int(max_level)
+    with torch.cuda.device(dev):
+        out = torch.zeros([N, meta.n_encoded_dims, 1 << meta.n_dims_to_encode], dtype=torch.int64, device=dev)
+        if max_level <= -1:
+            return out
+        _lib.check(_lib.get_lib().nr3d_lotd_grid_index(
+            ctypes.byref(meta._c), _lib.dtype_code(input.dtype), N, input.data_ptr(), _lib.ptr(batch_inds),
+            _lib.ptr(batch_offsets), bds, max_level, out.data_ptr(), _lib.stream_of(dev)))
+    return out

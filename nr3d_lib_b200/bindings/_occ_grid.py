@@ -1,0 +1,111 @@
+"""Drop-in replacement for ``nr3d_lib.bindings._occ_grid`` (reference: csrc/occ_grid/src/occ_grid.cpp:22-33).
+
+``ray_marching`` / ``batched_ray_marching`` keep the reference's signature and return list
+(``[packed_info i32[R,2], t_starts f32[S,1], t_ends f32[S,1], ridx i32[S], (bidx i32[S],) gidx i32[S] | None]``).
+Both passes and the exclusive scan between them run on the device; the only host synchronisation is the single
+read of the total sample count that sizes the outputs (the reference also needs it, ray_marching.cu:209).
+"""
+import ctypes
+import enum
+from typing import List, Optional
+
+import torch
+
+from .. import _lib
+
+
+class ContractionType(enum.IntEnum):  # csrc/occ_grid/include/occ_grid/cpp_api.h:14-19
+    AABB = 0
+    UN_BOUNDED_TANH = 1
+    UN_BOUNDED_SPHERE = 2
+
+
+AABB, UN_BOUNDED_TANH, UN_BOUNDED_SPHERE = ContractionType.AABB, ContractionType.UN_BOUNDED_TANH, ContractionType.UN_BOUNDED_SPHERE
+
+
+def _check(name, t, dim, dtype=None):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if t.dim() != dim:
+        raise RuntimeError(f"Expected {name}.ndimension() == {dim}")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"expected scalar type {dtype} for {name} but found {t.dtype}")
+
+
+def _march(rays_o, rays_d, t_min, t_max, batch_inds, batch_data_size, n_batches, roi, grid, res, type_, step_size, max_step_size,
+           dt_gamma, max_steps, return_gidx, batched):
+    dev = _lib.require_cuda(rays_o, rays_d, t_min, t_max, batch_inds, roi, grid, who="ray_marching")
+    lib = _lib.get_lib()
+    R = rays_o.shape[0]
+    grid_u8 = grid.view(torch.uint8) if grid.dtype == torch.bool else grid
+    if grid_u8.dtype != torch.uint8:
+        raise RuntimeError("expected scalar type Bool for grid_binary")
+    common = (R, rays_o.data_ptr(), rays_d.data_ptr(), t_min.data_ptr(), t_max.data_ptr(), _lib.ptr(batch_inds), int(batch_data_size),
+              int(n_batches), roi.data_ptr(), grid_u8.data_ptr(), int(res[0]), int(res[1]), int(res[2]), int(type_), float(step_size),
+              float(max_step_size), float(dt_gamma), int(max_steps))
+    with torch.cuda.device(dev):
+        st = _lib.stream_of(dev)
+        num_steps = torch.empty([R], dtype=torch.int32, device=dev)
+        packed_info = torch.empty([R, 2], dtype=torch.int32, device=dev)
+        total = torch.zeros([1], dtype=torch.int64, device=dev)
+        if R > 0:
+            _lib.check(lib.nr3d_march_count(*common, num_steps.data_ptr(), st))
+        nbytes = ctypes.c_uint64(0)
+        _lib.check(lib.nr3d_march_pack(R, None, None, None, None, ctypes.byref(nbytes), None))
+        ws = torch.empty([max(8, nbytes.value)], dtype=torch.uint8, device=dev)
+        nbytes = ctypes.c_uint64(ws.numel())
+        _lib.check(lib.nr3d_march_pack(R, num_steps.data_ptr(), packed_info.data_ptr(), total.data_ptr(), ws.data_ptr(),
+                                       ctypes.byref(nbytes), st))
+        S = int(total.item())
+        t_starts = torch.empty([S, 1], dtype=torch.float32, device=dev)
+        t_ends = torch.empty([S, 1], dtype=torch.float32, device=dev)
+        ridx = torch.empty([S], dtype=torch.int32, device=dev)
+        bidx = torch.empty([S], dtype=torch.int32, device=dev) if batched else None
+        gidx = torch.empty([S], dtype=torch.int32, device=dev) if return_gidx else None
+        if R > 0 and S > 0:
+            _lib.check(lib.nr3d_march_fill(*common, packed_info.data_ptr(), t_starts.data_ptr(), t_ends.data_ptr(), ridx.data_ptr(),
+                                           _lib.ptr(bidx), _lib.ptr(gidx), st))
+    if batched:
+        return [packed_info, t_starts, t_ends, ridx, bidx, gidx]
+    return [packed_info, t_starts, t_ends, ridx, gidx]
+
+
+def ray_marching(rays_o: torch.Tensor, rays_d: torch.Tensor, t_min: torch.Tensor, t_max: torch.Tensor, roi: torch.Tensor,
+                 grid_binary: torch.Tensor, type: ContractionType, step_size: float, max_step_size: float, dt_gamma: float,
+                 max_steps: int, return_gidx: bool) -> List[Optional[torch.Tensor]]:
+    """== ray_marching (csrc/occ_grid/src/ray_marching.cu:136-243)."""
+    _check("rays_o", rays_o, 2, torch.float32); _check("rays_d", rays_d, 2, torch.float32)
+    _check("t_min", t_min, 1, torch.float32); _check("t_max", t_max, 1, torch.float32)
+    _check("roi", roi, 1, torch.float32); _check("grid_binary", grid_binary, 3)
+    if rays_o.shape[1] != 3 or rays_d.shape[1] != 3 or roi.shape[0] != 6:
+        raise RuntimeError("ray_marching: expected rays_o/rays_d of shape [n_rays, 3] and roi of shape [6]")
+    return _march(rays_o, rays_d, t_min, t_max, None, 0, 1, roi, grid_binary, grid_binary.shape, type, step_size, max_step_size,
+                  dt_gamma, max_steps, return_gidx, batched=False)
+
+
+def batched_ray_marching(rays_o: torch.Tensor, rays_d: torch.Tensor, t_min: torch.Tensor, t_max: torch.Tensor,
+                         batch_inds: Optional[torch.Tensor], batch_data_size: Optional[int], roi: torch.Tensor,
+                         grid_binary: torch.Tensor, type: ContractionType, step_size: float, max_step_size: float, dt_gamma: float,
+                         max_steps: int, return_gidx: bool) -> List[Optional[torch.Tensor]]:
+    """== batched_ray_marching (csrc/occ_grid/src/batched_marching.cu:154-287)."""
+    _check("rays_o", rays_o, 2, torch.float32); _check("rays_d", rays_d, 2, torch.float32)
+    _check("t_min", t_min, 1, torch.float32); _check("t_max", t_max, 1, torch.float32)
+    _check("roi", roi, 2, torch.float32); _check("grid_binary", grid_binary, 4)
+    if rays_o.shape[1] != 3 or rays_d.shape[1] != 3 or roi.shape[1] != 6 or grid_binary.shape[0] != roi.shape[0]:
+        raise RuntimeError("batched_ray_marching: expected rays [n_rays,3], roi [B,6], grid_binary [B,rx,ry,rz]")
+    R = rays_o.shape[0]
+    if batch_inds is not None:
+        _check("batch_inds", batch_inds, 1, torch.int32)
+        if batch_inds.shape[0] != R:
+            raise RuntimeError("batched_ray_marching: batch_inds must have one entry per ray")
+    bds = int(batch_data_size or 0)
+    if not (bds == 0 or R % bds == 0):
+        raise RuntimeError(f"batched_ray_marching: Expect nonzero `batch_data_size`={bds} to be a divisor of `n_rays`={R}")
+    return _march(rays_o, rays_d, t_min, t_max, batch_inds, bds, grid_binary.shape[0], roi, grid_binary, grid_binary.shape[1:], type,
+                  step_size, max_step_size, dt_gamma, max_steps, return_gidx, batched=True)
+
+
+def forest_ray_marching(*args, **kwargs):
+    raise RuntimeError("nr3d_lib_b200: forest_ray_marching is a 'next' row of the hot-path scope table (SURVEY.md 8f, n4).")

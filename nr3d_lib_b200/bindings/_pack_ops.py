@@ -1,0 +1,298 @@
+"""Drop-in replacement for ``nr3d_lib.bindings._pack_ops`` (reference: csrc/pack_ops/pack_ops.cpp:20-58).
+
+Implemented ops (hot path): interleave_arange, interleave_linstep,
+interleave_sample_step_wrt_depth_clamped, packed_{add,sub,mul,div,gt,geq,lt,leq,eq,neq}, packed_sum, packed_diff,
+packed_backward_diff, packed_cumsum, packed_cumprod, packed_alpha_to_vw_forward/backward, mark_pack_boundaries_cuda.
+The hierarchical-sampling ops (sort / searchsorted / merge / invert_cdf / in_packed_segments / matmul / octree) are the
+"next" rows of the scope table and raise RuntimeError here.
+"""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from .. import _lib
+
+# exclusive packed_cumprod: documented semantics by default; set True to reproduce the reference CUDA output
+# (all zeros).
+EXCLUSIVE_CUMPROD_BUG_COMPAT = False
+
+
+def _check_feats(fn, feats, pack_infos, check_size=False):
+    if feats.dim() not in (1, 2):
+        raise RuntimeError(f"{fn}: Expected 1 to 2 dimensions, but got {feats.dim()} for argument 'feats'")
+    _check_pack_infos(fn, pack_infos)
+    if not feats.is_contiguous():
+        raise RuntimeError(f"{fn}: Expected contiguous tensor for argument 'feats'")
+    dev = _lib.require_cuda(feats, pack_infos, who=fn)
+    C = 1 if feats.dim() == 1 else feats.shape[1]
+    return dev, pack_infos.shape[0], C
+
+
+def _check_pack_infos(fn, pack_infos):
+    if pack_infos.dim() != 2 or pack_infos.shape[1] != 2:
+        raise RuntimeError(f"{fn}: Expected `pack_infos` of shape [num_packs, 2], got {tuple(pack_infos.shape)}")
+    if pack_infos.dtype != torch.int64:
+        raise RuntimeError(f"{fn}: Expected `pack_infos` to have scalar type Long, got {pack_infos.dtype}")
+    if not pack_infos.is_contiguous():
+        raise RuntimeError(f"{fn}: Expected contiguous tensor for argument 'pack_infos'")
+
+
+def _opt_like(fn, name, t, feats, P, C):
+    if t is None:
+        return None
+    if t.dtype != feats.dtype or not t.is_contiguous() or t.device != feats.device:
+        raise RuntimeError(f"{fn}: `{name}` must be a contiguous tensor with the dtype/device of `feats`")
+    want = (P,) if feats.dim() == 1 else (P, C)
+    if tuple(t.shape) != want:
+        raise RuntimeError(f"{fn}: `{name}` has shape {tuple(t.shape)}, expected {want}")
+    return t
+
+
+def _total_from_device(total: torch.Tensor) -> int:
+    return int(total.item())  # the single host read needed to size the outputs
+
+
+def packed_sum(feats: torch.Tensor, pack_infos: torch.Tensor) -> torch.Tensor:
+    """== packed_sum (pack_ops_cuda.cu:826-861)."""
+    dev, P, C = _check_feats("packed_sum", feats, pack_infos)
+    with torch.cuda.device(dev):
+        out = torch.empty([P] if feats.dim() == 1 else [P, C], dtype=feats.dtype, device=dev)
+        _lib.check(_lib.get_lib().nr3d_pack_sum(_lib.dtype_code(feats.dtype), P, C, feats.data_ptr(), pack_infos.data_ptr(),
+                                                out.data_ptr(), _lib.stream_of(dev)))
+    return out
+
+
+def _scan(fn_name, cfun, feats, pack_infos, exclusive, reverse, extra=()):
+    dev, P, C = _check_feats(fn_name, feats, pack_infos)
+    with torch.cuda.device(dev):
+        out = torch.zeros_like(feats)
+        _lib.check(cfun(_lib.dtype_code(feats.dtype), P, C, feats.data_ptr(), pack_infos.data_ptr(), int(bool(exclusive)),
+                        int(bool(reverse)), *extra, out.data_ptr(), _lib.stream_of(dev)))
+    return out
+
+
+def packed_cumsum(feats: torch.Tensor, pack_infos: torch.Tensor, exclusive: bool, reverse: bool) -> torch.Tensor:
+    """== packed_cumsum (pack_ops_cuda.cu:1048-1095)."""
+    return _scan("packed_cumsum", _lib.get_lib().nr3d_pack_cumsum, feats, pack_infos, exclusive, reverse)
+
+
+def packed_cumprod(feats: torch.Tensor, pack_infos: torch.Tensor, exclusive: bool, reverse: bool) -> torch.Tensor:
+    """== packed_cumprod (pack_ops_cuda.cu:931-978); exclusive follows the documented semantics (see module flag)."""
+    return _scan("packed_cumprod", _lib.get_lib().nr3d_pack_cumprod, feats, pack_infos, exclusive, reverse,
+                 extra=(int(EXCLUSIVE_CUMPROD_BUG_COMPAT),))
+
+
+def _diff(fn_name, cfun, feats, pack_infos, edge, fill, edge_name, fill_name):
+    dev, P, C = _check_feats(fn_name, feats, pack_infos)
+    if edge is not None and fill is not None:
+        raise RuntimeError("You should only specify AT MOST one of [appends, prepends, last_fill, first_fill]")
+    edge = _opt_like(fn_name, edge_name, edge, feats, P, C)
+    fill = _opt_like(fn_name, fill_name, fill, feats, P, C)
+    with torch.cuda.device(dev):
+        out = torch.zeros_like(feats)
+        _lib.check(cfun(_lib.dtype_code(feats.dtype), P, C, feats.data_ptr(), pack_infos.data_ptr(), _lib.ptr(edge), _lib.ptr(fill),
+                        out.data_ptr(), _lib.stream_of(dev)))
+    return out
+
+
+def packed_diff(feats, pack_infos, pack_appends: Optional[torch.Tensor] = None, pack_last_fill: Optional[torch.Tensor] = None):
+    """== packed_diff (pack_ops_cuda.cu:1186-1259)."""
+    return _diff("packed_diff", _lib.get_lib().nr3d_pack_diff, feats, pack_infos, pack_appends, pack_last_fill,
+                 "pack_appends", "pack_last_fill")
+
+
+def packed_backward_diff(feats, pack_infos, pack_prepends: Optional[torch.Tensor] = None, pack_first_fill: Optional[torch.Tensor] = None):
+    """== packed_backward_diff (pack_ops_cuda.cu:1261-1334)."""
+    return _diff("packed_backward_diff", _lib.get_lib().nr3d_pack_backward_diff, feats, pack_infos, pack_prepends, pack_first_fill,
+                 "pack_prepends", "pack_first_fill")
+
+
+def _binary(op, name, feats, other, pack_infos):
+    dev, P, C = _check_feats(name, feats, pack_infos)
+    if other.dim() != feats.dim() or other.shape[0] != P or (feats.dim() == 2 and other.shape[1] != C):
+        raise RuntimeError(f"{name}: `other` has shape {tuple(other.shape)}, expected [{P}{', %d' % C if feats.dim() == 2 else ''}]")
+    if other.dtype != feats.dtype or not other.is_contiguous():
+        raise RuntimeError(f"{name}: `other` must be contiguous and share the dtype of `feats`")
+    _lib.require_cuda(feats, other, who=name)
+    with torch.cuda.device(dev):
+        out = torch.zeros(feats.shape, dtype=feats.dtype if op < 4 else torch.bool, device=dev)
+        _lib.check(_lib.get_lib().nr3d_pack_binary(op, _lib.dtype_code(feats.dtype), P, C, feats.data_ptr(), other.data_ptr(),
+                                                   pack_infos.data_ptr(), out.data_ptr(), _lib.stream_of(dev)))
+    return out
+
+
+def packed_add(feats, other, pack_infos): return _binary(0, "packed_add", feats, other, pack_infos)
+def packed_sub(feats, other, pack_infos): return _binary(1, "packed_sub", feats, other, pack_infos)
+def packed_mul(feats, other, pack_infos): return _binary(2, "packed_mul", feats, other, pack_infos)
+def packed_div(feats, other, pack_infos): return _binary(3, "packed_div", feats, other, pack_infos)
+def packed_gt(feats, other, pack_infos): return _binary(5, "packed_gt", feats, other, pack_infos)
+def packed_geq(feats, other, pack_infos): return _binary(6, "packed_geq", feats, other, pack_infos)
+def packed_lt(feats, other, pack_infos): return _binary(7, "packed_lt", feats, other, pack_infos)
+def packed_leq(feats, other, pack_infos): return _binary(8, "packed_leq", feats, other, pack_infos)
+def packed_eq(feats, other, pack_infos): return _binary(9, "packed_eq", feats, other, pack_infos)
+def packed_neq(feats, other, pack_infos): return _binary(10, "packed_neq", feats, other, pack_infos)
+
+
+def _pack_infos_from_counts(counts: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """counts int64 [P] -> (pack_infos int64 [P,2], total int64 [1]) entirely on device."""
+    dev = counts.device
+    P = counts.shape[0]
+    lib = _lib.get_lib()
+    pack_infos = torch.empty([P, 2], dtype=torch.int64, device=dev)
+    total = torch.zeros([1], dtype=torch.int64, device=dev)
+    nbytes = ctypes.c_uint64(0)
+    _lib.check(lib.nr3d_pack_infos_from_counts(P, None, None, None, None, ctypes.byref(nbytes), None))
+    ws = torch.empty([max(8, nbytes.value)], dtype=torch.uint8, device=dev)
+    nbytes = ctypes.c_uint64(ws.numel())
+    _lib.check(lib.nr3d_pack_infos_from_counts(P, counts.data_ptr(), pack_infos.data_ptr(), total.data_ptr(), ws.data_ptr(),
+                                               ctypes.byref(nbytes), _lib.stream_of(dev)))
+    return pack_infos, total
+
+
+def packed_alpha_to_vw_forward(alphas: torch.Tensor, pack_infos: torch.Tensor, early_stop_eps: float, alpha_thre: float,
+                               compression: bool):
+    """== packed_alpha_to_vw_forward (pack_ops_cuda.cu:1850-1911) -> (weights, compact_pack_info, compact_selector)."""
+    fn = "packed_alpha_to_vw_forward"
+    if alphas.dim() != 1:
+        raise RuntimeError(f"{fn}: Expected 1-dimensional tensor for argument 'alphas'")
+    if alphas.dtype not in (torch.float16, torch.float32, torch.float64):
+        raise RuntimeError(f"{fn}: Expected 'alphas' to have scalar type Half, Float or Double")
+    dev, P, _ = _check_feats(fn, alphas, pack_infos)
+    lib = _lib.get_lib()
+    weights = compact_pack_info = compact_selector = None
+    with torch.cuda.device(dev):
+        st = _lib.stream_of(dev)
+        if compression:
+            num_steps = torch.zeros([P], dtype=torch.int64, device=dev)
+            compact_selector = torch.zeros([alphas.shape[0]], dtype=torch.bool, device=dev)
+            _lib.check(lib.nr3d_pack_alpha_to_vw_fwd(_lib.dtype_code(alphas.dtype), P, alphas.data_ptr(), pack_infos.data_ptr(),
+                                                     float(early_stop_eps), float(alpha_thre), None, num_steps.data_ptr(),
+                                                     compact_selector.data_ptr(), st))
+            # the reference builds this with cumsum(at::kInt) + stack => an int32 [P,2] tensor (pack_ops_cuda.cu:1874-1875)
+            compact_pack_info = _pack_infos_from_counts(num_steps)[0].to(torch.int32)
+        else:
+            weights = torch.zeros_like(alphas)
+            _lib.check(lib.nr3d_pack_alpha_to_vw_fwd(_lib.dtype_code(alphas.dtype), P, alphas.data_ptr(), pack_infos.data_ptr(),
+                                                     float(early_stop_eps), float(alpha_thre), weights.data_ptr(), None, None, st))
+    return weights, compact_pack_info, compact_selector
+
+
+def packed_alpha_to_vw_backward(weights: torch.Tensor, grad_weights: torch.Tensor, alphas: torch.Tensor, pack_infos: torch.Tensor,
+                                early_stop_eps: float, alpha_thre: float) -> torch.Tensor:
+    """== packed_alpha_to_vw_backward (pack_ops_cuda.cu:1914-1958)."""
+    fn = "packed_alpha_to_vw_backward"
+    for name, t in (("weights", weights), ("grad_weights", grad_weights), ("alphas", alphas)):
+        if t.dim() != 1 or not t.is_contiguous():
+            raise RuntimeError(f"{fn}: Expected contiguous 1-dimensional tensor for argument '{name}'")
+    if not (weights.dtype == grad_weights.dtype == alphas.dtype) or weights.dtype not in (torch.float16, torch.float32, torch.float64):
+        raise RuntimeError(f"{fn}: weights / grad_weights / alphas must share a Half, Float or Double dtype")
+    if not (weights.shape == grad_weights.shape == alphas.shape):
+        raise RuntimeError(f"{fn}: weights / grad_weights / alphas must have the same size")
+    _check_pack_infos(fn, pack_infos)
+    dev = _lib.require_cuda(weights, grad_weights, alphas, pack_infos, who=fn)
+    P = pack_infos.shape[0]
+    with torch.cuda.device(dev):
+        grad_alphas = torch.zeros_like(alphas)
+        _lib.check(_lib.get_lib().nr3d_pack_alpha_to_vw_bwd(
+            _lib.dtype_code(weights.dtype), P, weights.data_ptr(), grad_weights.data_ptr(), alphas.data_ptr(), pack_infos.data_ptr(),
+            float(early_stop_eps), float(alpha_thre), grad_alphas.data_ptr(), _lib.stream_of(dev)))
+    return grad_alphas
+
+
+def interleave_arange(stop: torch.Tensor, return_idx: bool):
+    """== interleave_arange (pack_ops_cuda.cu:85-118): concatenated arange(stop[p]) (+ pack ids)."""
+    if stop.dim() != 1 or stop.dtype != torch.int64 or not stop.is_contiguous():
+        raise RuntimeError("interleave_arange: `stop` must be a contiguous 1-D int64 tensor")
+    dev = _lib.require_cuda(stop, who="interleave_arange")
+    with torch.cuda.device(dev):
+        pack_infos, total = _pack_infos_from_counts(stop)
+        num = _total_from_device(total)
+        out = torch.empty([num], dtype=torch.int64, device=dev)
+        nidx = torch.empty([num], dtype=torch.int64, device=dev) if return_idx else None
+        _lib.check(_lib.get_lib().nr3d_pack_interleave_linstep(_lib.I64, stop.shape[0], pack_infos.data_ptr(), None, None, 0.0, 1.0,
+                                                               out.data_ptr(), _lib.ptr(nidx), _lib.stream_of(dev)))
+    return out, nidx
+
+
+def interleave_linstep(start: torch.Tensor, num_steps: torch.Tensor, step_size, return_idx: bool):
+    """== interleave_linstep, three overloads (pack_ops_cuda.cu:120-218)."""
+    if start.dim() != 1 or num_steps.dim() != 1 or start.shape != num_steps.shape:
+        raise RuntimeError("interleave_linstep: `start` and `num_steps` must be 1-D tensors of the same size")
+    if num_steps.dtype != torch.int64:
+        raise RuntimeError("interleave_linstep: `num_steps` must have scalar type Long")
+    steps_t = None
+    step_s = 0.0
+    if isinstance(step_size, torch.Tensor):
+        if step_size.dim() != 1 or step_size.dtype != start.dtype or not step_size.is_contiguous():
+            raise RuntimeError("interleave_linstep: tensor `step_size` must be 1-D, contiguous and share the dtype of `start`")
+        steps_t = step_size
+    else:
+        step_s = float(step_size)
+    start, num_steps = start.contiguous(), num_steps.contiguous()
+    dev = _lib.require_cuda(start, num_steps, steps_t, who="interleave_linstep")
+    with torch.cuda.device(dev):
+        pack_infos, total = _pack_infos_from_counts(num_steps)
+        num = _total_from_device(total)
+        out = torch.empty([num], dtype=start.dtype, device=dev)
+        nidx = torch.empty([num], dtype=torch.int64, device=dev) if return_idx else None
+        _lib.check(_lib.get_lib().nr3d_pack_interleave_linstep(_lib.dtype_code(start.dtype), start.shape[0], pack_infos.data_ptr(),
+                                                               start.data_ptr(), _lib.ptr(steps_t), 0.0, step_s, out.data_ptr(),
+                                                               _lib.ptr(nidx), _lib.stream_of(dev)))
+    return out, nidx
+
+
+def interleave_sample_step_wrt_depth_clamped(near: torch.Tensor, far: torch.Tensor, max_steps: int, dt_gamma: float,
+                                             min_step_size: float, max_step_size: float):
+    """== interleave_sample_step_wrt_depth_clamped (pack_ops_cuda.cu:547-604) -> (t_samples, deltas, ridx, pack_infos)."""
+    fn = "interleave_sample_step_wrt_depth_clamped"
+    if near.dim() != 1 or far.dim() != 1 or near.shape != far.shape or near.dtype != far.dtype:
+        raise RuntimeError(f"{fn}: `near` / `far` must be 1-D tensors of the same size and dtype")
+    if not (near.is_contiguous() and far.is_contiguous()):
+        raise RuntimeError(f"{fn}: Expected contiguous tensors")
+    dev = _lib.require_cuda(near, far, who=fn)
+    lib = _lib.get_lib()
+    P = near.shape[0]
+    code = _lib.dtype_code(near.dtype)
+    with torch.cuda.device(dev):
+        st = _lib.stream_of(dev)
+        n_per_pack = torch.empty([P], dtype=torch.int64, device=dev)
+        _lib.check(lib.nr3d_pack_sample_step_count(code, P, near.data_ptr(), far.data_ptr(), int(max_steps), float(dt_gamma),
+                                                   float(min_step_size), float(max_step_size), n_per_pack.data_ptr(), st))
+        pack_infos, total = _pack_infos_from_counts(n_per_pack)
+        num = _total_from_device(total)
+        t_samples = torch.empty([num], dtype=near.dtype, device=dev)
+        deltas = torch.empty([num], dtype=near.dtype, device=dev)
+        nidx = torch.empty([num], dtype=torch.int64, device=dev)
+        _lib.check(lib.nr3d_pack_sample_step_fill(code, P, near.data_ptr(), pack_infos.data_ptr(), float(dt_gamma),
+                                                  float(min_step_size), float(max_step_size), t_samples.data_ptr(), deltas.data_ptr(),
+                                                  nidx.data_ptr(), st))
+    return t_samples, deltas, nidx, pack_infos
+
+
+def mark_pack_boundaries_cuda(pack_ids: torch.Tensor) -> torch.Tensor:
+    """== mark_pack_boundaries_cuda (pack_ops_cuda.cu:2784-2805): int32 [S]."""
+    if pack_ids.dim() != 1 or not pack_ids.is_contiguous():
+        raise RuntimeError("mark_pack_boundaries_cuda: Expected contiguous 1-dimensional tensor")
+    if pack_ids.dtype not in (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
+        raise RuntimeError("mark_pack_boundaries_cuda: Expected an integral scalar type (Byte, Char, Short, Int, Long)")
+    dev = _lib.require_cuda(pack_ids, who="mark_pack_boundaries_cuda")
+    with torch.cuda.device(dev):
+        out = torch.zeros([pack_ids.shape[0]], dtype=torch.int32, device=dev)
+        _lib.check(_lib.get_lib().nr3d_pack_mark_boundaries(_lib.dtype_code(pack_ids.dtype), pack_ids.shape[0], pack_ids.data_ptr(),
+                                                            out.data_ptr(), _lib.stream_of(dev)))
+    return out
+
+
+def _next_row(name):
+    def fn(*args, **kwargs):
+        raise RuntimeError(f"nr3d_lib_b200: `{name}` is a 'next' row of the hot-path scope table (SURVEY.md section 8f, n2) and "
+                           "is not implemented in the B200 build yet.")
+    fn.__name__ = name
+    return fn
+
+
+for _n in ("interleave_sample_step_wrt_depth_clamp_deprecated", "interleave_sample_step_wrt_depth_in_packed_segments",
+           "packed_matmul", "packed_sort_qsort", "packed_sort_thrust", "packed_searchsorted", "packed_searchsorted_packed_vals",
+           "try_merge_two_packs_sorted_aligned", "packed_invert_cdf", "octree_mark_consecutive_segments"):
+    globals()[_n] = _next_row(_n)

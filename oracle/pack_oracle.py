@@ -1,0 +1,212 @@
+"""CPU oracle for pack_ops -- TEST INFRASTRUCTURE ONLY (numpy; sequential per-pack loops).
+
+Each function restates one reference kernel of csrc/pack_ops/pack_ops_cuda.cu with the SAME sequential order of
+floating-point operations (numpy scalars of the tensor's dtype are IEEE-exact), so order-sensitive decisions -- the
+``T < eps`` early stop and ``alpha <= thre`` skip of the alpha composite -- are reproduced bit for bit.
+
+Pinned by: the literal known-answer vectors of the reference's own unit test
+(nr3d_lib/graphics/pack_ops/unit_test.py:547-563, exclusive cumsum / cumprod as produced by kaolin), the
+torch-equivalence identities of unit_test.py:188-241, and golden vectors from the reference CUDA build (tests/golden/).
+"""
+import numpy as np
+
+
+def _ranges(pack_infos):
+    pi = np.asarray(pack_infos, dtype=np.int64)
+    return [(int(b), int(max(n, 0))) for b, n in pi]
+
+
+def _as2d(a):
+    a = np.asarray(a)
+    return (a.reshape(a.shape[0], 1), True) if a.ndim == 1 else (a, False)
+
+
+def packed_sum(feats, pack_infos):
+    """pack_ops_cuda.cu:798-824 (empty packs give 0; the reference reads feats[begin] there)."""
+    f, squeeze = _as2d(feats)
+    out = np.zeros((len(pack_infos), f.shape[1]), dtype=f.dtype)
+    for p, (b, n) in enumerate(_ranges(pack_infos)):
+        for j in range(f.shape[1]):
+            if n == 0:
+                continue
+            r = f[b, j]
+            for i in range(b + 1, b + n):
+                r = f.dtype.type(r + f[i, j])
+            out[p, j] = r
+    return out[:, 0] if squeeze else out
+
+
+def _scan(feats, pack_infos, exclusive, reverse, op, ident):
+    f, squeeze = _as2d(feats)
+    out = np.zeros_like(f)
+    T = f.dtype.type
+    for (b, n) in _ranges(pack_infos):
+        if n == 0:
+            continue
+        order = range(b + n - 1, b - 1, -1) if reverse else range(b, b + n)
+        for j in range(f.shape[1]):
+            acc = T(ident)
+            for i in order:
+                if exclusive:
+                    out[i, j] = acc
+                    acc = T(op(acc, f[i, j]))
+                else:
+                    acc = T(op(acc, f[i, j]))
+                    out[i, j] = acc
+    return out[:, 0] if squeeze else out
+
+
+def packed_cumsum(feats, pack_infos, exclusive=False, reverse=False):
+    """pack_ops_cuda.cu:981-1046: inclusive, or right-shifted with a leading 0."""
+    return _scan(feats, pack_infos, exclusive, reverse, lambda a, b: a + b, 0)
+
+
+def packed_cumprod(feats, pack_infos, exclusive=False, reverse=False, bug_compat=False):
+    """pack_ops_cuda.cu:864-929.  ``exclusive`` follows the documented semantics (leading 1, pack_ops.py:149);
+    ``bug_compat`` reproduces the reference CUDA output for exclusive=True: all zeros."""
+    if exclusive and bug_compat:
+        return np.zeros_like(np.asarray(feats))
+    return _scan(feats, pack_infos, exclusive, reverse, lambda a, b: a * b, 1)
+
+
+def packed_diff(feats, pack_infos, appends=None, last_fill=None):
+    """pack_ops_cuda.cu:1098-1140."""
+    f, squeeze = _as2d(feats)
+    out = np.zeros_like(f)
+    ap = None if appends is None else _as2d(appends)[0]
+    lf = None if last_fill is None else _as2d(last_fill)[0]
+    for p, (b, n) in enumerate(_ranges(pack_infos)):
+        if n == 0:
+            continue
+        out[b:b + n - 1] = f[b + 1:b + n] - f[b:b + n - 1]
+        if ap is not None:
+            out[b + n - 1] = ap[p] - f[b + n - 1]
+        elif lf is not None:
+            out[b + n - 1] = lf[p]
+    return out[:, 0] if squeeze else out
+
+
+def packed_backward_diff(feats, pack_infos, prepends=None, first_fill=None):
+    """pack_ops_cuda.cu:1142-1184."""
+    f, squeeze = _as2d(feats)
+    out = np.zeros_like(f)
+    pp = None if prepends is None else _as2d(prepends)[0]
+    ff = None if first_fill is None else _as2d(first_fill)[0]
+    for p, (b, n) in enumerate(_ranges(pack_infos)):
+        if n == 0:
+            continue
+        out[b + 1:b + n] = f[b + 1:b + n] - f[b:b + n - 1]
+        if pp is not None:
+            out[b] = f[b] - pp[p]
+        elif ff is not None:
+            out[b] = ff[p]
+    return out[:, 0] if squeeze else out
+
+
+_OPS = {0: np.add, 1: np.subtract, 2: np.multiply, 3: np.divide, 5: np.greater, 6: np.greater_equal, 7: np.less,
+        8: np.less_equal, 9: np.equal, 10: np.not_equal}
+
+
+def packed_binary(op, feats, other, pack_infos):
+    """pack_ops_cuda.cu:1960-2249: broadcast one operand per pack."""
+    f, squeeze = _as2d(feats)
+    o = _as2d(other)[0]
+    out = np.zeros(f.shape, dtype=f.dtype if op < 4 else np.bool_)
+    for p, (b, n) in enumerate(_ranges(pack_infos)):
+        if n:
+            with np.errstate(all="ignore"):
+                out[b:b + n] = _OPS[op](f[b:b + n], o[p])
+    return out[:, 0] if squeeze else out
+
+
+def alpha_to_vw_forward(alphas, pack_infos, early_stop_eps, alpha_thre):
+    """pack_ops_cuda.cu:1735-1793 -> (weights, num_steps int64 [P], selector bool [S])."""
+    a = np.asarray(alphas)
+    T_ = a.dtype.type
+    w = np.zeros_like(a)
+    sel = np.zeros(a.shape, dtype=np.bool_)
+    cnt = np.zeros(len(pack_infos), dtype=np.int64)
+    eps, thre, one = T_(early_stop_eps), T_(alpha_thre), np.float32(1.0)
+    for p, (b, n) in enumerate(_ranges(pack_infos)):
+        T = T_(1.0)
+        for j in range(n):
+            if T < eps:
+                break
+            al = a[b + j]
+            if al <= thre:
+                continue
+            w[b + j] = T_(al * T)
+            T = T_(T * T_(one - al)) if a.dtype != np.float16 else T_(np.float32(T) * (one - np.float32(al)))
+            sel[b + j] = True
+            cnt[p] += 1
+    return w, cnt, sel
+
+
+def alpha_to_vw_backward(weights, grad_weights, alphas, pack_infos, early_stop_eps, alpha_thre):
+    """pack_ops_cuda.cu:1795-1848 (note ``alpha < thre`` here vs ``<=`` in the forward)."""
+    a, w, gw = np.asarray(alphas), np.asarray(weights), np.asarray(grad_weights)
+    T_ = a.dtype.type
+    ga = np.zeros_like(a)
+    eps, thre = T_(early_stop_eps), T_(alpha_thre)
+    for (b, n) in _ranges(pack_infos):
+        accum = T_(0)
+        for j in range(n):
+            accum = T_(accum + gw[b + j] * w[b + j])
+        T = T_(1.0)
+        for j in range(n):
+            if T < eps:
+                break
+            al = a[b + j]
+            if al < thre:
+                continue
+            denom = np.float32(max(np.float32(np.float32(1.0) - np.float32(al)) if a.dtype != np.float64 else np.float32(1.0 - al), np.float32(1e-10)))
+            ga[b + j] = T_((gw[b + j] * T - accum) / T_(denom))
+            accum = T_(accum - gw[b + j] * w[b + j])
+            T = T_(T * T_(np.float32(1.0) - al))
+    return ga
+
+
+def interleave_linstep(starts, num_steps, steps, dtype=None):
+    """pack_ops_cuda.cu:47-83 -> (out, nidx)."""
+    starts = np.asarray(starts)
+    T_ = starts.dtype.type
+    steps = np.broadcast_to(np.asarray(steps, dtype=starts.dtype), starts.shape)
+    out, nidx = [], []
+    for p, n in enumerate(np.asarray(num_steps, dtype=np.int64)):
+        for j in range(int(n)):
+            out.append(T_(starts[p] + T_(j) * steps[p]))
+            nidx.append(p)
+    return np.asarray(out, dtype=starts.dtype), np.asarray(nidx, dtype=np.int64)
+
+
+def sample_step_wrt_depth_clamped(near, far, max_steps, dt_gamma, min_step, max_step):
+    """pack_ops_cuda.cu:480-545 -> (t_samples, deltas, nidx, pack_infos)."""
+    near, far = np.asarray(near), np.asarray(far)
+    T_ = near.dtype.type
+    g, lo, hi = T_(dt_gamma), T_(min_step), T_(max_step)
+    clamp = lambda v: lo if v < lo else (hi if hi < v else v)
+    ts, ds, ni, counts = [], [], [], []
+    for p in range(near.shape[0]):
+        t, n = near[p], 0
+        while t <= far[p] and n < max_steps:
+            dt = clamp(T_(t * g))
+            ts.append(t); ds.append(dt); ni.append(p)
+            t = T_(t + dt)
+            n += 1
+        counts.append(n)
+    counts = np.asarray(counts, dtype=np.int64)
+    pack_infos = np.stack([np.cumsum(counts) - counts, counts], 1)
+    return (np.asarray(ts, dtype=near.dtype), np.asarray(ds, dtype=near.dtype), np.asarray(ni, dtype=np.int64), pack_infos)
+
+
+def mark_pack_boundaries(ids):
+    """pack_ops_cuda.cu:2765-2782."""
+    ids = np.asarray(ids)
+    out = np.ones(ids.shape[0], dtype=np.int32)
+    out[1:] = (ids[1:] != ids[:-1]).astype(np.int32)
+    return out
+
+
+def pack_infos_from_counts(counts):
+    c = np.asarray(counts, dtype=np.int64)
+    return np.stack([np.cumsum(c) - c, c], 1)

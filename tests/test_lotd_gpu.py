@@ -1,0 +1,206 @@
+"""GPU parity tests of the LoTD kernels (call through the C-ABI via nr3d_lib_b200.bindings._lotd).
+
+Three checkers, in decreasing authority:
+  1. golden vectors produced by the reference's own CUDA build (tests/golden/lotd_*.npz);
+  2. the reference's own CUDA build run live on the same inputs (oracle/_ref/_lotd.so), incl. larger sizes;
+  3. the float64 CPU oracle (oracle/lotd_oracle.py).
+Tolerances: fp32 params 1e-5 relative to the tensor's max magnitude (BASELINE.json north_star), fp16 params 2e-3
+(the reference accumulates in half); grid indices bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import LOTD_CONFIGS, golden, load_ref, lotd_inputs, meta_args, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.float16: 2e-3}
+TOL_ATOMIC = {torch.float32: 2e-5, torch.float16: 4e-3}
+
+
+def _mine():
+    from nr3d_lib_b200.bindings import _lotd
+    return _lotd
+
+
+def _run_all(backend, meta, inp, dev, pdtype, second_dx=True):
+    x = inp["x"].to(dev)
+    params = inp["params"].to(dev).to(pdtype)
+    dL_dy = inp["dL_dy"].to(dev).to(pdtype)
+    ddx = inp["dL_ddLdx"].to(dev)
+    bi = None if inp.get("batch_inds") is None else inp["batch_inds"].to(dev)
+    bds = inp.get("batch_data_size") or None
+    kw = dict(batch_inds=bi, batch_offsets=None, batch_data_size=bds, max_level=None)
+    N, E, D = x.shape[0], meta.n_encoded_dims, meta.n_dims_to_encode
+    y, dy_dx = backend.lod_fwd(meta, x, params, need_input_grad=True, **kw)
+    y0, none = backend.lod_fwd(meta, x, params, need_input_grad=False, **kw)
+    assert none is None
+    assert torch.equal(y, y0)
+    dL_dx, dL_dparam = backend.lod_bwd(meta, dL_dy, x, params, dy_dx, need_input_grad=True, need_param_grad=True, **kw)
+    g_dLdy, g_p2, g_x2 = backend.lod_bwd_bwd_input(meta, ddx, dL_dy, x, params, dy_dx, need_dLdinput_ddLdoutput=True,
+                                                   need_dLdinput_dparams=True, need_dLdinput_dinput=second_dx, **kw)
+    ymax, _ = backend.lod_fwd(meta, x, params, batch_inds=bi, batch_data_size=bds, max_level=1, need_input_grad=False)
+    out = dict(y=y, dy_dx=dy_dx.reshape(N, E, D) if dy_dx.dim() == 2 else dy_dx, dL_dx=dL_dx, dL_dparam=dL_dparam, dL_ddLdy=g_dLdy,
+               dL_dparam2=g_p2, dL_dx2=g_x2, y_maxlevel1=ymax)
+    if meta.c_hash_only:
+        out["grid_index"] = backend.lod_get_grid_index(meta, x, **kw)
+    return out
+
+
+def _compare(got, want, pdtype, what):
+    bad = []
+    for k, w in want.items():
+        if k not in got or got[k] is None or w is None:
+            continue
+        g = got[k]
+        w = torch.as_tensor(w)
+        assert tuple(g.shape) == tuple(w.shape), (what, k, g.shape, w.shape)
+        if k == "grid_index":
+            if not torch.equal(g.cpu(), w.cpu()):
+                bad.append((k, "indices differ", int((g.cpu() != w.cpu()).sum())))
+            continue
+        tol = TOL_ATOMIC[pdtype] if k in ("dL_dparam", "dL_dparam2", "dL_dx2") else TOL[pdtype]
+        e = rel_err(g.float().cpu(), w.float().cpu())
+        if not (e <= tol):
+            bad.append((k, e, tol))
+    assert not bad, f"{what}: {bad}"
+
+
+@pytest.mark.parametrize("name", list(LOTD_CONFIGS))
+def test_lotd_vs_golden(name, dev):
+    """B200 kernels vs vectors recorded from the reference CUDA build."""
+    mine = _mine()
+    cfg = LOTD_CONFIGS[name]
+    ran = False
+    for tag, pdtype in (("f32", torch.float32), ("f16", torch.float16)):
+        g = golden(f"lotd_{name}_{tag}")
+        if g is None:
+            continue
+        ran = True
+        meta = mine.LoDMeta(*meta_args(cfg))
+        inp = dict(x=torch.from_numpy(g["x"]), params=torch.from_numpy(g["params"]).float(), dL_dy=torch.from_numpy(g["dL_dy"]).float(),
+                   dL_ddLdx=torch.from_numpy(g["dL_ddLdx"]), batch_inds=torch.from_numpy(g["batch_inds"]) if "batch_inds" in g else None)
+        got = _run_all(mine, meta, inp, dev, pdtype)
+        want = {k: g[k] for k in ("y", "dy_dx", "dL_dx", "dL_dparam", "dL_ddLdy", "dL_dparam2", "dL_dx2", "y_maxlevel1", "grid_index") if k in g}
+        _compare(got, want, pdtype, f"golden:{name}:{tag}")
+    if not ran:
+        pytest.skip("golden fixture not generated yet")
+
+
+@pytest.mark.parametrize("name", list(LOTD_CONFIGS))
+@pytest.mark.parametrize("pdtype", [torch.float32, torch.float16])
+def test_lotd_vs_reference_build(name, pdtype, dev):
+    """B200 kernels vs the reference's own CUDA kernels, live, on 20k seeded points."""
+    ref = load_ref("_lotd")
+    if ref is None:
+        pytest.skip("oracle/_ref/_lotd.so not built")
+    mine = _mine()
+    cfg = LOTD_CONFIGS[name]
+    m_ref, m_mine = ref.LoDMeta(*meta_args(cfg)), mine.LoDMeta(*meta_args(cfg))
+    inp = lotd_inputs(cfg, m_mine.n_params, N=20000 if cfg["B"] == 1 else 19998, seed=11)
+    want = _run_all(ref, m_ref, inp, dev, pdtype)
+    got = _run_all(mine, m_mine, inp, dev, pdtype)
+    # stride contract of the fast path: feature-major storage behind transposed / permuted views
+    assert got["y"].stride() == want["y"].stride()
+    _compare(got, want, pdtype, f"ref:{name}:{pdtype}")
+
+
+@pytest.mark.parametrize("name", ["ngp8", "mixed", "mixed_smooth", "batched", "d2", "d4", "cuboid_vm"])
+def test_lotd_vs_oracle(name, dev):
+    """B200 kernels vs the float64 CPU oracle (first and second order)."""
+    from oracle import lotd_oracle as O
+    mine = _mine()
+    cfg = LOTD_CONFIGS[name]
+    meta = mine.LoDMeta(*meta_args(cfg))
+    om = O.OracleMeta(*meta_args(cfg))
+    inp = lotd_inputs(cfg, meta.n_params, N=600, seed=5)
+    got = _run_all(mine, meta, inp, dev, torch.float32)
+    kw = dict(batch_inds=inp["batch_inds"], batch_data_size=inp["batch_data_size"])
+    y, dydx = O.fwd_dydx(om, inp["x"], inp["params"], **kw)
+    gx, gp = O.bwd(om, inp["dL_dy"], inp["x"], inp["params"], **kw)
+    g_gy, g_p2, g_x2 = O.bwd_bwd_input(om, inp["dL_ddLdx"], inp["dL_dy"], inp["x"], inp["params"], **kw)
+    want = dict(y=y, dy_dx=dydx, dL_dx=gx, dL_dparam=gp, dL_ddLdy=g_gy, dL_dparam2=g_p2, dL_dx2=g_x2,
+                y_maxlevel1=O.encode(om, inp["x"], inp["params"], max_level=1, **kw))
+    if meta.c_hash_only:
+        want["grid_index"] = O.grid_index(om, inp["x"], **kw)
+    _compare(got, want, torch.float32, f"oracle:{name}")
+
+
+def test_lotd_batch_data_size_and_offsets(dev):
+    """batched-by-size and explicit batch_offsets (unaligned -> scalar access path) agree with batch_inds."""
+    mine = _mine()
+    cfg = LOTD_CONFIGS["batched"]
+    meta = mine.LoDMeta(*meta_args(cfg))
+    N, B = 600, cfg["B"]
+    inp = lotd_inputs(cfg, meta.n_params, N=N, seed=3, batch_mode="size")
+    x, params, dL_dy = inp["x"].to(dev), inp["params"].to(dev), inp["dL_dy"].to(dev)
+    bi = (torch.arange(N, device=dev) // (N // B)).long()
+    y_a, _ = mine.lod_fwd(meta, x, params, batch_data_size=N // B, need_input_grad=False)
+    y_b, _ = mine.lod_fwd(meta, x, params, batch_inds=bi, need_input_grad=False)
+    assert torch.equal(y_a, y_b)
+    # shifted copy of the parameters addressed through batch_offsets (odd offset => no vector access)
+    pad = 3
+    params2 = torch.cat([torch.zeros(pad, device=dev), params])
+    off = (torch.arange(B, device=dev) * meta.n_params + pad).long()
+    y_c, _ = mine.lod_fwd(meta, x, params2, batch_inds=bi, batch_offsets=off, need_input_grad=False)
+    assert torch.equal(y_a, y_c)
+    _, g_a = mine.lod_bwd(meta, dL_dy, x, params, None, batch_inds=bi, need_input_grad=False, need_param_grad=True)
+    _, g_c = mine.lod_bwd(meta, dL_dy, x, params2, None, batch_inds=bi, batch_offsets=off, need_input_grad=False, need_param_grad=True)
+    assert rel_err(g_c[pad:].cpu(), g_a.cpu()) < 1e-5 and g_c[:pad].abs().max() == 0
+
+
+def test_lotd_edge_cases(dev):
+    mine = _mine()
+    cfg = LOTD_CONFIGS["ngp8"]
+    meta = mine.LoDMeta(*meta_args(cfg))
+    params = torch.randn(meta.n_params, device=dev)
+    # empty input
+    y, dy = mine.lod_fwd(meta, torch.zeros(0, 3, device=dev), params, need_input_grad=True)
+    assert y.shape == (0, meta.n_encoded_dims) and dy.shape[0] == 0
+    # max_level = -1 -> zeros (lotd_torch_api.cu:294-297)
+    x = torch.rand(10, 3, device=dev)
+    y, dy = mine.lod_fwd(meta, x, params, max_level=-1, need_input_grad=True)
+    assert y.abs().max() == 0 and dy.shape == (10, meta.n_encoded_dims * 3)
+    # validation errors surface as RuntimeError like the reference's
+    with pytest.raises(RuntimeError):
+        mine.lod_fwd(meta, x, params[:-1])
+    with pytest.raises(RuntimeError):
+        mine.lod_fwd(meta, x[:, :2].contiguous(), params)
+    with pytest.raises(RuntimeError):
+        mine.lod_fwd(meta, x.cpu(), params.cpu())
+    with pytest.raises(RuntimeError):
+        mine.lod_bwd(meta, torch.zeros(10, meta.n_encoded_dims, device=dev), x, params, None, need_input_grad=True, need_param_grad=False)
+    # domain corners (the wrappers clamp to [1e-6, 1-1e-6])
+    xc = torch.tensor([[1e-6, 1e-6, 1e-6], [1 - 1e-6, 1 - 1e-6, 1 - 1e-6], [0.5, 1e-6, 1 - 1e-6]], device=dev)
+    y, _ = mine.lod_fwd(meta, xc, params, need_input_grad=False)
+    assert torch.isfinite(y).all()
+
+
+def test_lotd_autograd_wrappers(dev):
+    """The host-side mirror of LoTDFunction / FwdDydx / BwdDydx produces the oracle's gradients end to end."""
+    from nr3d_lib_b200.lotd import LoTD
+    from oracle import lotd_oracle as O
+    cfg = LOTD_CONFIGS["mixed"]
+    enc = LoTD(cfg["D"], cfg["res"], cfg["feats"], cfg["types"], hashmap_size=cfg["T"], use_smooth_step=cfg["smooth"], dtype=torch.float)
+    om = O.OracleMeta(*meta_args(cfg))
+    inp = lotd_inputs(cfg, enc.n_params, N=300, seed=9)
+    x = inp["x"].to(dev).requires_grad_(True)
+    p = inp["params"].to(dev).requires_grad_(True)
+    w = inp["dL_dy"].to(dev)
+    y = enc(x, p)
+    (y * w).sum().backward()
+    gx, gp = O.bwd(om, inp["dL_dy"], inp["x"], inp["params"])
+    assert rel_err(x.grad.cpu(), gx) < 1e-5 and rel_err(p.grad.cpu(), gp) < 2e-5
+    # nablas path with second order onto the parameters
+    x2 = inp["x"].to(dev).requires_grad_(True)
+    p2 = inp["params"].to(dev).requires_grad_(True)
+    h, dy_dx = enc.forward_dydx(x2, p2)
+    sdf = (h * w).sum(-1)
+    dL_dh = torch.autograd.grad(sdf.sum(), h, create_graph=True)[0]
+    nablas = enc.backward_dydx(dL_dh, dy_dx, x2, p2)
+    assert rel_err(nablas.detach().cpu(), gx) < 1e-5
+    v = inp["dL_ddLdx"].to(dev)
+    (nablas * v).sum().backward()
+    _, g_p2, _ = O.bwd_bwd_input(om, inp["dL_ddLdx"], inp["dL_dy"], inp["x"], inp["params"])
+    assert rel_err(p2.grad.cpu(), g_p2) < 2e-5

@@ -1,0 +1,145 @@
+"""Shared test helpers: seeded input generators, config zoo, loaders for the oracle and the reference CUDA build."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+# --------------------------------------------------------------------------------------------------------------
+# LoTD config zoo (name -> LoDMeta ctor args + batch info).  Small enough for committed golden fixtures.
+# --------------------------------------------------------------------------------------------------------------
+LOTD_CONFIGS = {
+    # hash-only fast path: NGP-style Dense -> Hash ladder (gen_ngp_cfg geometry, lotd_cfg.py:48-57, reduced T)
+    "ngp8": dict(D=3, res=[16, 22, 30, 42, 58, 80, 111, 154], feats=[2] * 8, types=["Dense"] * 3 + ["Hash"] * 5, T=2 ** 12, smooth=False, B=1),
+    "hash_f4": dict(D=3, res=[12, 20, 33, 70], feats=[4, 4, 8, 4], types=["Dense", "Hash", "Hash", "Hash"], T=2 ** 10, smooth=False, B=1),
+    "ngp_smooth": dict(D=3, res=[10, 17, 40], feats=[2, 2, 2], types=["Dense", "Hash", "Hash"], T=2 ** 9, smooth=True, B=1),
+    # generic path: every level type, mixed widths (exercises pseudo levels)
+    "mixed": dict(D=3, res=[8, 12, 16, 20, 24, 28], feats=[4, 4, 2, 2, 4, 2], types=["Dense", "VM", "CP", "CPfast", "NPlaneMul", "NPlaneSum"], T=None, smooth=False, B=1),
+    "mixed_smooth": dict(D=3, res=[9, 11, 13, 10, 12], feats=[2, 2, 2, 2, 2], types=["VM", "CP", "CPfast", "NPlaneSum", "Dense"], T=None, smooth=True, B=1),
+    "cuboid_vm": dict(D=3, res=[[8, 10, 12], [14, 9, 11]], feats=[2, 4], types=["VM", "Dense"], T=None, smooth=False, B=1),
+    # batched scenes with per-point batch indices (-1 = skip)
+    "batched": dict(D=3, res=[8, 16, 32], feats=[2, 2, 2], types=["Dense", "Hash", "VM"], T=2 ** 10, smooth=False, B=3),
+    "batched_hash": dict(D=3, res=[8, 16, 32], feats=[2, 2, 2], types=["Dense", "Dense", "Hash"], T=2 ** 10, smooth=False, B=3),
+    # other input dimensions
+    "d2": dict(D=2, res=[10, 40, 90], feats=[2, 4, 2], types=["Dense", "Hash", "CP"], T=2 ** 9, smooth=False, B=1),
+    "d2_hash": dict(D=2, res=[10, 40, 300], feats=[2, 2, 2], types=["Dense", "Dense", "Hash"], T=2 ** 9, smooth=False, B=1),
+    "d4": dict(D=4, res=[5, 7, 9], feats=[2, 2, 2], types=["Dense", "Hash", "CP"], T=2 ** 10, smooth=False, B=1),
+}
+
+
+def meta_args(cfg):
+    return (cfg["D"], cfg["res"], cfg["feats"], cfg["types"], cfg["T"], cfg["smooth"])
+
+
+def lotd_inputs(cfg, n_params, N=192, seed=0, batch_mode="inds"):
+    """Deterministic (numpy RandomState) inputs.  Returns dict of CPU torch tensors."""
+    rs = np.random.RandomState(seed)
+    D, B, E = cfg["D"], cfg["B"], sum(cfg["feats"])
+    x = np.clip(rs.rand(N, D).astype(np.float32), 1e-6, 1 - 1e-6)
+    # a few points close to cell borders / domain borders
+    x[:4] = np.clip(np.round(x[:4] * 8) / 8 + 1e-4, 1e-6, 1 - 1e-6)
+    params = (rs.randn(B * n_params) * 0.1).astype(np.float32)
+    dL_dy = rs.randn(N, E).astype(np.float32)
+    dL_ddLdx = rs.randn(N, D).astype(np.float32)
+    out = dict(x=torch.from_numpy(x), params=torch.from_numpy(params), dL_dy=torch.from_numpy(dL_dy), dL_ddLdx=torch.from_numpy(dL_ddLdx),
+               batch_inds=None, batch_data_size=0)
+    if B > 1:
+        if batch_mode == "inds":
+            bi = rs.randint(0, B, size=N).astype(np.int64)
+            bi[rs.rand(N) < 0.1] = -1
+            out["batch_inds"] = torch.from_numpy(bi)
+        else:
+            out["batch_data_size"] = N // B
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# pack / march inputs
+# --------------------------------------------------------------------------------------------------------------
+def pack_inputs(P=37, max_len=70, C=3, seed=0, min_len=1):
+    rs = np.random.RandomState(seed)
+    n = rs.randint(min_len, max_len + 1, size=P).astype(np.int64)
+    pack_infos = np.stack([np.cumsum(n) - n, n], 1)
+    S = int(n.sum())
+    d = dict(pack_infos=pack_infos, S=S, n=n,
+             feats1=rs.randn(S).astype(np.float32), featsC=rs.randn(S, C).astype(np.float32),
+             other1=(rs.randn(P) + 3.0).astype(np.float32), otherC=(rs.randn(P, C) + 3.0).astype(np.float32),
+             prod1=(1.0 + 0.2 * rs.randn(S)).astype(np.float32),
+             alphas=np.clip(rs.rand(S) ** 2 * 0.6, 0, 0.999).astype(np.float32), grad_w=rs.randn(S).astype(np.float32),
+             near=(rs.rand(P) * 0.5 + 0.1).astype(np.float32), ids=np.repeat(rs.randint(0, 5, size=P), n).astype(np.int64))
+    d["far"] = (d["near"] + rs.rand(P).astype(np.float32) * 2.0).astype(np.float32)
+    d["alphas"][rs.rand(S) < 0.15] = 0.0   # exactly-zero alphas exercise the `<= thre` / `< thre` asymmetry
+    return d
+
+
+def march_inputs(R=512, res=32, seed=0, B=1, occupancy=0.5, shell=False):
+    """Rays looking at the [-1,1]^3 box (the reference's smoke-test style, occgrid_raymarch.py:274-295, randomised)."""
+    rs = np.random.RandomState(seed)
+    if shell:
+        g = np.stack(np.meshgrid(*[np.linspace(-1, 1, res)] * 3, indexing="ij"), -1)
+        grid = (np.abs(np.linalg.norm(g, axis=-1) - 0.6) < 0.08)
+        grid = np.broadcast_to(grid, (B, res, res, res)).copy()
+    else:
+        grid = rs.rand(B, res, res, res) > (1.0 - occupancy)
+    o = rs.randn(R, 3)
+    o = (4.0 * o / np.linalg.norm(o, axis=1, keepdims=True)).astype(np.float32)
+    tgt = (rs.rand(R, 3) - 0.5).astype(np.float32)
+    d = tgt - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    # ray / box [-1,1]^3 intersection (slab method) for near / far
+    with np.errstate(divide="ignore"):
+        t1 = (-1.0 - o) / d
+        t2 = (1.0 - o) / d
+    near = np.maximum(np.minimum(t1, t2).max(1), 0.0).astype(np.float32)
+    far = np.maximum(t1, t2).min(1).astype(np.float32)
+    miss = far <= near
+    far[miss] = near[miss]
+    roi = np.tile(np.array([-1, -1, -1, 1, 1, 1], dtype=np.float32), (B, 1))
+    bi = rs.randint(0, B, size=R).astype(np.int32) if B > 1 else None
+    return dict(rays_o=o, rays_d=d, near=near, far=far, roi=roi if B > 1 else roi[0], grid=grid if B > 1 else grid[0], batch_inds=bi)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# loaders
+# --------------------------------------------------------------------------------------------------------------
+_ref_cache = {}
+
+
+def load_ref(name):
+    """Load one of the reference's own CUDA extensions built by oracle/build_ref.py (None if absent)."""
+    if name in _ref_cache:
+        return _ref_cache[name]
+    path = os.path.join(REF_DIR, name + ".so")
+    mod = None
+    if os.path.exists(path):
+        try:
+            spec = importlib.util.spec_from_file_location(name, path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+        except Exception as e:  # pragma: no cover
+            print(f"[tests] could not load reference build {path}: {e}")
+            mod = None
+    _ref_cache[name] = mod
+    return mod
+
+
+def golden(name):
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    if not os.path.exists(path):
+        return None
+    return dict(np.load(path, allow_pickle=False))
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|_inf, tiny): error relative to the magnitude of the reference tensor."""
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    denom = max(b.abs().max().item(), 1e-30)
+    return ((a - b).abs().max().item() / denom) if a.numel() else 0.0
