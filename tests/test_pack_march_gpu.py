@@ -162,7 +162,7 @@ def _march(be, d, dev, ct, step, mx, gamma, ms, bds=None):
 
 def _march_equal(got, want, what, exact_float=True):
     for k in ("packed_info", "ridx", "bidx", "gidx"):
-        if k in want and want[k] is not None:
+        if k in want and want[k] is not None and k in got:
             w = torch.as_tensor(want[k]).cpu().long().flatten()
             g = got[k].cpu().long().flatten()
             assert g.shape == w.shape and torch.equal(g, w), f"{what}: {k} differs"
