@@ -104,6 +104,11 @@ REF = "/root/reference/nr3d_lib"
 def shell(name, path=None):
     m = types.ModuleType(name); m.__path__ = [path] if path else []; sys.modules[name] = m; return m
 shell("nr3d_lib", REF)
+# parent packages as shells (their __init__ pull in the whole model zoo and its third-party deps, all out of scope)
+shell("nr3d_lib.models", REF + "/models")
+shell("nr3d_lib.models.grid_encodings", REF + "/models/grid_encodings")
+shell("nr3d_lib.models.grid_encodings.lotd", REF + "/models/grid_encodings/lotd")
+shell("nr3d_lib.graphics", REF + "/graphics")
 install()
 import nr3d_lib.bindings._lotd as b
 from nr3d_lib.models.grid_encodings.lotd import lotd as ref_lotd      # unmodified reference file
@@ -112,6 +117,8 @@ assert enc.n_params == b.LoDMeta(3, [8, 16, 32], [2, 2, 2], ["Dense", "Hash", "V
 assert [t.name for t in enc.level_types] == ["Dense", "Hash", "VectorMatrix"]
 from nr3d_lib.graphics.pack_ops import pack_ops as ref_pack              # unmodified reference file
 assert ref_pack._backend is sys.modules["nr3d_lib.bindings._pack_ops"]
+from nr3d_lib.graphics.raymarch import occgrid_raymarch as ref_march   # unmodified reference file
+assert ref_march._backend is sys.modules["nr3d_lib.bindings._occ_grid"] and ref_march.ContractionType.AABB.value == 0
 print("DROPIN_OK")
 """ % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
