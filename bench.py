@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native LoTD hot path.
+
+Metric (BASELINE.json): "LoTD-Hash 16L fwd+bwd Msamples/s" on configs[1]: 16-level NGP LoTD (gen_ngp_cfg defaults,
+T=2^19, F=2, fp32 params; nr3d_lib/models/grid_encodings/lotd/lotd_cfg.py:48-57), 4 Mi uniform random 3-D points per GPU.
+
+One step  = lod_fwd(need_input_grad=False) + lod_bwd(need_param_grad=True) through the reference-facing operator
+            surface (nr3d_lib_b200.bindings._lotd == nr3d_lib.bindings._lotd) [+ one NCCL all-reduce of dL/dparams if N > 1].
+`value`   = whole-job samples/s with x and dL_dy already resident in HBM (device-timed, max over ranks).
+`e2e`     = the same step driven from HOST buffers: x comes from pinned host memory every step (H2D inside the timed
+            region), dL_dy is derived on the device from the step's own output y (stand-in for the decoder's backward),
+            and the step's result dL/dparams is read back to the host (D2H inside the timed region).
+`--impl reference` times the CPU port of the reference's algorithm (oracle/lotd_oracle.py, fp32, all host threads) on a
+            bounded sample of the same workload -- the reference has no CPU implementation of this path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "LoTD-Hash 16L fwd+bwd Msamples/s"
+UNIT = "Msamples/s"
+N_POINTS = 4 * 1024 * 1024          # per GPU (weak scaling)
+# algorithmic bytes per sample, SURVEY.md section 8d (fp32 params, L=16, F=2, D=3):
+#   fwd 12 (x) + 1024 (corner reads) + 128 (y write); bwd 12 (x) + 128 (dL_dy read) + 1024 (gradient scatter); + 23 (table zero-init/read)
+BYTES_FWD, BYTES_BWD, BYTES_TABLE = 12 + 1024 + 128, 12 + 128 + 1024, 23
+BYTES_PER_SAMPLE = BYTES_FWD + BYTES_BWD + BYTES_TABLE   # 2351
+
+
+def ngp_cfg(min_res=16, n_levels=16, scale=1.382, log2_T=19, F=2):
+    res = (min_res * scale ** np.arange(n_levels)).astype(int).tolist()
+    types = ["Dense" if r ** 3 <= 2 ** log2_T else "Hash" for r in res]
+    return (3, res, [F] * n_levels, types, 2 ** log2_T, False)
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self._stop_evt, self.sm_max = index, [], set(), threading.Event(), None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().splitlines()[0].split(",")
+                self.samples.append(float(out[0]))
+                self.sm_max = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=10)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm restated for the host (kind "port"), all threads, bounded sample
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_fwd_bwd(sample_points, steps, warmup, seed=42):
+    from oracle import lotd_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    meta = O.OracleMeta(*ngp_cfg())
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(sample_points, 3, generator=g).clamp(1e-6, 1 - 1e-6)
+    params = ((torch.rand(meta.n_params, generator=g) * 2 - 1) * 1e-4).requires_grad_(True)
+    dL_dy = torch.randn(sample_points, meta.n_encoded_dims, generator=g) * 1e-4
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        y = O.encode(meta, x, params, dtype=torch.float32)
+        y.backward(dL_dy)
+        params.grad = None
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    return dict(value=sample_points / sec / 1e6, unit=UNIT, cores=cores, kind="port",
+                sample=f"{sample_points} of the {N_POINTS} points per step, {steps} steps, fp32, torch CPU ops via oracle/lotd_oracle.py"), sec
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample = 262144
+    base, sec = cpu_fwd_bwd(sample, args.steps, min(args.warmup, 2))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus) | {"sample_points_per_step": sample},
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[1]: 16-level Hash LoTD (NGP gen_ngp_cfg: res 16..2049, 6 Dense + 10 Hash levels, T=2^19, F=2), "
+                        "4Mi uniform points per GPU, lod_fwd + lod_bwd(dL/dparam)",
+            "points_per_gpu": N_POINTS, "n_params": 12131648, "param_dtype": "f32", "parallelism": f"dp{n_gpus} (points sharded, params replicated, "
+                                                                                                 "1 NCCL all-reduce of dL/dparams per step)",
+            "l2_policy": "inputs larger than L2 (x 48 MB + dL_dy 512 MB + y 512 MB per step >> 126 MB); the 48.5 MB parameter table is "
+                         "L2-resident by nature of the workload"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    from nr3d_lib_b200 import _lib, dist as ndist
+    from nr3d_lib_b200.bindings import _lotd
+
+    rank, world, local = ndist.init_from_env("nccl")
+    if world != args.gpus and rank == 0 and world > 1:
+        print(f"[bench] note: WORLD_SIZE={world} differs from --gpus {args.gpus}; using WORLD_SIZE", file=sys.stderr)
+    n_gpus = max(world, 1)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    meta = _lotd.LoDMeta(*ngp_cfg())
+    torch.manual_seed(42 + rank)
+    N = N_POINTS
+    x = torch.rand(N, 3, device=dev).clamp(1e-6, 1 - 1e-6)
+    gen = torch.Generator(device=dev).manual_seed(42)                      # parameters are replicated: same seed on every rank
+    params = (torch.rand(meta.n_params, device=dev, generator=gen) * 2 - 1) * 1e-4
+    dL_dy = torch.randn(N, meta.n_encoded_dims, device=dev) * 1e-4
+    x_host = x.cpu().pin_memory()
+    grad_host = torch.empty(meta.n_params, dtype=torch.float32).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def step_resident():
+        y, _ = _lotd.lod_fwd(meta, x, params, need_input_grad=False)
+        _, g = _lotd.lod_bwd(meta, dL_dy, x, params, None, need_input_grad=False, need_param_grad=True)
+        ndist.allreduce_param_grads(g, n_gpus)
+        return y, g
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        y, _ = _lotd.lod_fwd(meta, xd, params, need_input_grad=False)
+        gy = y * 1.0e-4                                                   # stand-in for the decoder's backward (device-side)
+        _, g = _lotd.lod_bwd(meta, gy, xd, params, None, need_input_grad=False, need_param_grad=True)
+        ndist.allreduce_param_grads(g, n_gpus)
+        grad_host.copy_(g, non_blocking=True)
+        return g
+
+    def timed(fn, steps, sampler=None):
+        ndist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ndist.barrier()
+        return ndist.max_over_ranks(e0.elapsed_time(e1), dev)              # ms, slowest rank
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = n_gpus * N / (ms_step * 1e-3) / 1e6
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = n_gpus * N / (ms_e2e * 1e-3) / 1e6
+
+    # per-kernel durations for the roofline block: CUDA events on the launch stream around each call, inside this run
+    def kernel_ms(fn, iters):
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); fn(); b.record(stream)
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+    it = max(3, min(args.steps, 10))
+    ms_fwd = kernel_ms(lambda: _lotd.lod_fwd(meta, x, params, need_input_grad=False), it)
+    ms_bwd = kernel_ms(lambda: _lotd.lod_bwd(meta, dL_dy, x, params, None, need_input_grad=False, need_param_grad=True), it)
+    peak, peak_src = measured_peak_gbs()
+    dom = "lod_bwd (dL/dparam scatter)" if ms_bwd >= ms_fwd else "lod_fwd (corner gather)"
+    dom_ms, dom_bytes = (ms_bwd, BYTES_BWD + BYTES_TABLE) if ms_bwd >= ms_fwd else (ms_fwd, BYTES_FWD)
+    achieved = N * dom_bytes / (dom_ms * 1e-3) / 1e9
+    whole = value * 1e6 / n_gpus * BYTES_PER_SAMPLE / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_sample": {"fwd": BYTES_FWD, "bwd": BYTES_BWD, "table": BYTES_TABLE},
+                "ms": {"lod_fwd": ms_fwd, "lod_bwd": ms_bwd},
+                "whole_step": {"achieved": whole, "frac": whole / peak, "bytes_per_sample": BYTES_PER_SAMPLE}}
+
+    if rank != 0:
+        return 0
+    cpu_base = None
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        cpu_base, _ = cpu_fwd_bwd(262144, steps=8, warmup=1)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(n_gpus), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(x_host.numel() * 4),
+                    "d2h_bytes_per_step": int(grad_host.numel() * 4),
+                    "note": "x from pinned host memory each step, dL_dy derived on device from the step's y, dL/dparams read back to host"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

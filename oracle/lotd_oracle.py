@@ -120,11 +120,12 @@ class OracleMeta:
 # helpers
 # ------------------------------------------------------------------------------------------------------------------
 def _pos(x32: torch.Tensor, xd: torch.Tensor, R: List[int], smooth: bool):
-    """cell (int64 [N,D]) and (p, dp/dv) as float64; value path identical to the fp32 kernels, grad path exact."""
+    """cell (int64 [N,D]) and (p, dp/dv) in xd's dtype; value path identical to the fp32 kernels, grad path exact."""
     scale = torch.tensor([r - 2 for r in R], dtype=torch.float64)
     v32 = (x32.double() * scale + 0.5).float()          # == fmaf(x, scale, 0.5f): the double product/sum is exact before rounding
     cell = torch.floor(v32)
-    f32 = (v32 - cell).double()                          # exact in float32
+    f32 = (v32 - cell).to(xd.dtype)                      # exact in float32
+    scale = scale.to(xd.dtype)
     lin = xd * scale
     f = f32 + (lin - lin.detach())                       # value from the fp32 path, derivative d f / d x = scale
     cell = cell.long()
@@ -244,9 +245,9 @@ def _level_value(tp, R, size, cell, p, G: _Gather):
     D = len(R)
     N = cell.shape[0]
     if tp in (DENSE, HASH, VM, VECZMATXOY, NPLANEMUL, CP):
-        out = torch.zeros(N, G.F, dtype=torch.float64)
+        out = torch.zeros(N, G.F, dtype=p.dtype)
         for bits in _corner_bits(D):
-            w = torch.ones(N, dtype=torch.float64)
+            w = torch.ones(N, dtype=p.dtype)
             pos = cell.clone()
             for d in range(D):
                 if bits[d]:
@@ -257,11 +258,11 @@ def _level_value(tp, R, size, cell, p, G: _Gather):
             out = out + w.unsqueeze(-1) * _corner_value(tp, R, size, pos, G)
         return out
     if tp == NPLANESUM:
-        out = torch.zeros(N, G.F, dtype=torch.float64)
+        out = torch.zeros(N, G.F, dtype=p.dtype)
         for j in range(D):
             dims3 = [d for d in range(D) if d != j]
             for bits in _corner_bits(D - 1):
-                w = torch.ones(N, dtype=torch.float64)
+                w = torch.ones(N, dtype=p.dtype)
                 pp = cell[:, dims3].clone()
                 for d2, d3 in enumerate(dims3):
                     if bits[d2]:
@@ -272,7 +273,7 @@ def _level_value(tp, R, size, cell, p, G: _Gather):
                 out = out + w.unsqueeze(-1) * G(_idx_nplane_sub(R, pp, j))
         return out
     if tp == CPFAST:
-        out = torch.ones(N, G.F, dtype=torch.float64)
+        out = torch.ones(N, G.F, dtype=p.dtype)
         for k in range(D):
             L_ = G(_idx_cp_line(R, cell[:, k], k))
             R_ = G(_idx_cp_line(R, cell[:, k] + 1, k))
@@ -296,14 +297,14 @@ def _point_batches(N, batch_inds, batch_data_size):
 
 
 def encode_levels(meta, x: torch.Tensor, params: torch.Tensor, batch_inds=None, batch_offsets=None, batch_data_size=0,
-                  max_level=None):
+                  max_level=None, dtype=torch.float64):
     """Returns a list with one [N, F_pl] float64 tensor per pseudo level (differentiable w.r.t. x / params if they
     are float64 leaves requiring grad; otherwise they are promoted)."""
     D = meta.n_dims_to_encode
     N = x.shape[0]
     x32 = x.detach().float()
-    xd = x if x.dtype == torch.float64 else x.double()
-    pd = params if params.dtype == torch.float64 else params.double()
+    xd = x if x.dtype == dtype else x.to(dtype)
+    pd = params if params.dtype == dtype else params.to(dtype)
     max_level = meta.n_levels if max_level is None else int(max_level)
     b, valid = _point_batches(N, batch_inds, batch_data_size)
     boff = batch_offsets.long()[b] if batch_offsets is not None else b * meta.n_params
@@ -314,7 +315,7 @@ def encode_levels(meta, x: torch.Tensor, params: torch.Tensor, batch_inds=None, 
     for pl in range(meta.n_pseudo_levels):
         lvl = meta.map_levels[pl]
         if lvl > max_level or max_level <= -1:
-            outs.append(torch.zeros(N, F, dtype=torch.float64))
+            outs.append(torch.zeros(N, F, dtype=dtype))
             continue
         R = list(meta.level_res_multidim[lvl])
         if lvl not in cache:
