@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sort", action="store_true", help="use the generic (unsorted, feature-major) kernels instead of lotd_fast.cu")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -162,6 +163,7 @@ def main():
     torch.cuda.set_device(dev)
 
     meta = _lotd.LoDMeta(*ngp_cfg())
+    meta.c_sort_points = not args.no_sort      # B200 fast path (lotd_fast.cu); the point sort is redone EVERY step (cache cleared)
     torch.manual_seed(42 + rank)
     N = N_POINTS
     x = torch.rand(N, 3, device=dev).clamp(1e-6, 1 - 1e-6)
@@ -173,6 +175,7 @@ def main():
     stream = torch.cuda.current_stream(dev)
 
     def step_resident():
+        _lotd.clear_sort_cache()               # a training step sees new points: never reuse the previous step's sort
         y, _ = _lotd.lod_fwd(meta, x, params, need_input_grad=False)
         _, g = _lotd.lod_bwd(meta, dL_dy, x, params, None, need_input_grad=False, need_param_grad=True)
         ndist.allreduce_param_grads(g, n_gpus)
@@ -227,7 +230,10 @@ def main():
             ts.append(a.elapsed_time(b))
         return float(np.mean(ts))
     it = max(3, min(args.steps, 10))
-    ms_fwd = kernel_ms(lambda: _lotd.lod_fwd(meta, x, params, need_input_grad=False), it)
+    def fwd_with_sort():
+        _lotd.clear_sort_cache()
+        _lotd.lod_fwd(meta, x, params, need_input_grad=False)
+    ms_fwd = kernel_ms(fwd_with_sort, it)      # includes the per-step point sort of the fast path
     ms_bwd = kernel_ms(lambda: _lotd.lod_bwd(meta, dL_dy, x, params, None, need_input_grad=False, need_param_grad=True), it)
     peak, peak_src = measured_peak_gbs()
     dom = "lod_bwd (dL/dparam scatter)" if ms_bwd >= ms_fwd else "lod_fwd (corner gather)"

