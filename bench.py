@@ -90,34 +90,47 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm restated for the host (kind "port"), all threads, bounded sample
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_fwd_bwd(sample_points, steps, warmup, seed=42):
+def cpu_fwd_bwd(steps, warmup, seed=42, budget_s=20.0):
+    """fp32 torch-CPU port of the reference algorithm on a bounded sample.  The sample size is chosen from a short probe
+    so that warmup + steps fit in `budget_s` seconds (torch's index ops scale poorly beyond ~32 threads, so the thread
+    count is capped there; `cores` reports the threads actually used)."""
     from oracle import lotd_oracle as O
-    cores = os.cpu_count() or 1
+    cores = max(1, min(os.cpu_count() or 1, 32))
     torch.set_num_threads(cores)
     meta = O.OracleMeta(*ngp_cfg())
     g = torch.Generator().manual_seed(seed)
-    x = torch.rand(sample_points, 3, generator=g).clamp(1e-6, 1 - 1e-6)
     params = ((torch.rand(meta.n_params, generator=g) * 2 - 1) * 1e-4).requires_grad_(True)
-    dL_dy = torch.randn(sample_points, meta.n_encoded_dims, generator=g) * 1e-4
-    times = []
-    for it in range(warmup + steps):
+
+    def one(n):
+        x = torch.rand(n, 3, generator=g).clamp(1e-6, 1 - 1e-6)
+        dL_dy = torch.randn(n, meta.n_encoded_dims, generator=g) * 1e-4
         t0 = time.perf_counter()
         y = O.encode(meta, x, params, dtype=torch.float32)
         y.backward(dL_dy)
         params.grad = None
+        return time.perf_counter() - t0
+
+    one(4096)                                  # page in / thread-pool start
+    probe = one(16384)
+    per_point = probe / 16384
+    sample = int(min(262144, max(8192, budget_s / max(1, warmup + steps) / per_point)))
+    sample = 1 << (sample.bit_length() - 1)     # power of two <= estimate
+    times = []
+    for it in range(warmup + steps):
+        dt = one(sample)
         if it >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(dt)
     sec = float(np.mean(times))
-    return dict(value=sample_points / sec / 1e6, unit=UNIT, cores=cores, kind="port",
-                sample=f"{sample_points} of the {N_POINTS} points per step, {steps} steps, fp32, torch CPU ops via oracle/lotd_oracle.py"), sec
+    return dict(value=sample / sec / 1e6, unit=UNIT, cores=cores, kind="port",
+                sample=f"{sample} of the {N_POINTS} points per step, {steps} steps after {warmup} warm-up, fp32, torch CPU ops "
+                       f"(oracle/lotd_oracle.py), {cores} threads"), sec, sample
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample = 262144
-    base, sec = cpu_fwd_bwd(sample, args.steps, min(args.warmup, 2))
+    base, sec, sample = cpu_fwd_bwd(args.steps, min(args.warmup, 2), budget_s=60.0)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus) | {"sample_points_per_step": sample},
@@ -249,7 +262,7 @@ def main():
         return 0
     cpu_base = None
     if n_gpus == 1 and not args.no_cpu_baseline:
-        cpu_base, _ = cpu_fwd_bwd(262144, steps=8, warmup=1)
+        cpu_base, _, _ = cpu_fwd_bwd(steps=5, warmup=1, budget_s=15.0)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(n_gpus), "clocks": clocks,
