@@ -113,16 +113,15 @@ int nr3d_lotd_grid_index(const nr3d_lotd_meta* meta, int32_t input_dtype, uint64
 
 /* B200 fast path for Dense/Hash-only metas (D = 3, 2 features per pseudo level, fp32 params, single scene).  No
  * reference counterpart: the shim uses it for lod_fwd / lod_bwd when LoDMeta.c_sort_points is set.
- *   sort_points : counting sort of the points by a 128^3 cell key (x fastest); perm[sorted position] = original
- *                 index (uint32 [N]), xs = sorted copy of x (float [N,3]).  Query the workspace size with ws == NULL.
+ *   sort_points : counting sort of the points by a 128^3 cell key (x fastest) into `xs`, float4 [N] records
+ *                 (x, y, z, original index as raw uint32 bits).  Query the workspace size with ws == NULL.
  *   fwd_sorted  : same values as nr3d_lotd_fwd; y element (n, j) at y + n*y_stride_n + j*y_stride_f (row-major is fastest).
  *   bwd_param_sorted : same values as nr3d_lotd_bwd_param (up to fp32 summation order); dL_dparam zero-filled by caller. */
-int nr3d_lotd_sort_points(uint64_t N, const float* x, uint32_t* perm, float* xs, void* ws, uint64_t* ws_bytes, void* stream);
-int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const float* xs, const uint32_t* perm,
-                         const void* params, int32_t max_level, void* y, int64_t y_stride_n, int64_t y_stride_f, void* stream);
-int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const float* xs, const uint32_t* perm,
-                               const void* dL_dy, int64_t dLdy_stride_n, int64_t dLdy_stride_f, int32_t max_level, void* dL_dparam,
-                               void* stream);
+int nr3d_lotd_sort_points(uint64_t N, const float* x, void* xs, void* ws, uint64_t* ws_bytes, void* stream);
+int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* params,
+                         int32_t max_level, void* y, int64_t y_stride_n, int64_t y_stride_f, void* stream);
+int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* dL_dy,
+                               int64_t dLdy_stride_n, int64_t dLdy_stride_f, int32_t max_level, void* dL_dparam, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * occupancy-grid ray marching (replaces nr3d_lib.bindings._occ_grid, csrc/occ_grid/src/occ_grid.cpp:22-33)

@@ -204,20 +204,18 @@ def _sorted_points(x: torch.Tensor):
     dev = x.device
     ent = _sort_cache.get(dev)
     if ent is not None:
-        x_ref, ver, perm, xs = ent
+        x_ref, ver, xs = ent
         if x_ref.data_ptr() == x.data_ptr() and x_ref.shape == x.shape and x._version == ver and x_ref._version == ver:
-            return perm, xs
+            return xs
     lib = _lib.get_lib()
     N = x.shape[0]
-    perm = torch.empty([N], dtype=torch.int32, device=dev)
-    xs = torch.empty_like(x)
+    xs = torch.empty([N, 4], dtype=torch.float32, device=dev)      # (x, y, z, original index bits) per sorted point
     nbytes = ctypes.c_uint64(0)
-    _lib.check(lib.nr3d_lotd_sort_points(N, None, None, None, None, ctypes.byref(nbytes), None))
+    _lib.check(lib.nr3d_lotd_sort_points(N, None, None, None, ctypes.byref(nbytes), None))
     ws = torch.empty([nbytes.value], dtype=torch.uint8, device=dev)
-    _lib.check(lib.nr3d_lotd_sort_points(N, x.data_ptr(), perm.data_ptr(), xs.data_ptr(), ws.data_ptr(), ctypes.byref(nbytes),
-                                         _lib.stream_of(dev)))
-    _sort_cache[dev] = (x, x._version, perm, xs)
-    return perm, xs
+    _lib.check(lib.nr3d_lotd_sort_points(N, x.data_ptr(), xs.data_ptr(), ws.data_ptr(), ctypes.byref(nbytes), _lib.stream_of(dev)))
+    _sort_cache[dev] = (x, x._version, xs)
+    return xs
 
 
 def _dydx_view(dy_dx, N, meta):
@@ -248,10 +246,10 @@ def lod_fwd(lod_meta, input: torch.Tensor, params: torch.Tensor, batch_inds: Opt
     ds_n = ds_f = 0
     with torch.cuda.device(dev):
         if not need_input_grad and _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
-            perm, xs = _sorted_points(input)
+            xs = _sorted_points(input)
             y = torch.empty([N, E], dtype=params.dtype, device=dev)
             _lib.check(_lib.get_lib().nr3d_lotd_fwd_sorted(
-                ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), perm.data_ptr(), params.data_ptr(), max_level,
+                ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), params.data_ptr(), max_level,
                 y.data_ptr(), E, 1, _lib.stream_of(dev)))
             return y, None
         if meta.c_hash_only:
@@ -316,9 +314,9 @@ def lod_bwd(lod_meta, dL_dy: torch.Tensor, input: torch.Tensor, params: torch.Te
                 ctypes.byref(meta._c), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, dL_dy.data_ptr(),
                 dL_dy.stride(0), dL_dy.stride(1), dv.data_ptr(), ds_n, ds_f, dL_dx.data_ptr(), st))
         if need_param_grad and _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
-            perm, xs = _sorted_points(input)
+            xs = _sorted_points(input)
             _lib.check(lib.nr3d_lotd_bwd_param_sorted(
-                ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), perm.data_ptr(), dL_dy.data_ptr(),
+                ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), dL_dy.data_ptr(),
                 dL_dy.stride(0), dL_dy.stride(1), max_level, dL_dparam.data_ptr(), st))
         elif need_param_grad:
             _lib.check(lib.nr3d_lotd_bwd_param(

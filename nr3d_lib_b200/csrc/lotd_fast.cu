@@ -36,12 +36,13 @@ __device__ __forceinline__ uint32_t bin_key(float x, float y, float z) {
     return (bz * kBinRes + by) * kBinRes + bx;
 }
 
-__global__ void __launch_bounds__(256) sort_hist_kernel(uint64_t N, const float* __restrict__ x, uint32_t* __restrict__ hist, uint32_t* __restrict__ keys) {
+// pass 1: bin key and rank of the point inside its bin (the rank makes the scatter pass atomic-free)
+__global__ void __launch_bounds__(256) sort_hist_kernel(uint64_t N, const float* __restrict__ x, uint32_t* __restrict__ hist, uint2* __restrict__ keyrank) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const uint32_t k = bin_key(x[i * 3], x[i * 3 + 1], x[i * 3 + 2]);
-    keys[i] = k;
-    atomicAdd(hist + k, 1u);
+    const uint32_t r = atomicAdd(hist + k, 1u);
+    keyrank[i] = make_uint2(k, r);
 }
 
 // exclusive scan of `hist` in place (three launches, like pack_ops.cu's scan but for uint32)
@@ -108,15 +109,14 @@ __global__ void __launch_bounds__(kScanBlockF) scanu_apply(uint32_t n, uint32_t*
     if (i < n) v[i] = off + s - x;
 }
 
-__global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t N, const float* __restrict__ x, const uint32_t* __restrict__ keys,
-                                                           uint32_t* __restrict__ offsets, uint32_t* __restrict__ perm, float* __restrict__ xs) {
+// pass 2: sorted record = (x, y, z, original index) written with ONE 16-byte store per point
+__global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t N, const float* __restrict__ x, const uint2* __restrict__ keyrank,
+                                                           const uint32_t* __restrict__ offsets, float4* __restrict__ xs) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const uint32_t pos = atomicAdd(offsets + keys[i], 1u);
-    perm[pos] = (uint32_t)i;
-    xs[(uint64_t)pos * 3 + 0] = x[i * 3 + 0];
-    xs[(uint64_t)pos * 3 + 1] = x[i * 3 + 1];
-    xs[(uint64_t)pos * 3 + 2] = x[i * 3 + 2];
+    const uint2 kr = keyrank[i];
+    const uint32_t pos = __ldg(offsets + kr.x) + kr.y;
+    xs[pos] = make_float4(x[i * 3 + 0], x[i * 3 + 1], x[i * 3 + 2], __uint_as_float((uint32_t)i));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -124,12 +124,13 @@ __global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t N, const flo
 // ------------------------------------------------------------------------------------------------------------
 struct FastIn {
     uint64_t N;
-    const float* xs;         // sorted copy of the points [N,3]
-    const uint32_t* perm;    // sorted position -> original index
+    const float4* xs;        // sorted records (x, y, z, original index as bits) [N]
     const float* params;
     int32_t max_level;
     uint32_t base_aligned16;  // params pointer is 16-byte aligned
 };
+
+constexpr int kRowStride = 33;  // floats per staged row (32 features + 1 pad: conflict-free for row and column access)
 
 // The 8 corners are handled as 4 pairs (a, b) of memory neighbours:
 //   Dense: pair q = (dx | dy << 1), a = (dx, dy, z), b = (dx, dy, z + 1);   Hash: pair q = (dy | dz << 1), a = (x, dy, dz), b = (x + 1, dy, dz)
@@ -190,18 +191,25 @@ __device__ __forceinline__ void fast_geo(const LevelDesc& L, uint32_t gfo, bool 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// forward: thread = one (sorted) point, loop over pseudo levels; y row-major (or any strides)
+// forward: thread = one (sorted) point, loop over pseudo levels.
+// Row-major y: the warp stages its 32 rows (up to 32 features at a time) in shared memory and writes each point's row
+// with one fully coalesced 128-byte store -- 32 line-writes per warp instead of 8 x 32 partial-line stores.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFastThreads)
 lotd_fast_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, float* __restrict__ y, int64_t ys_n, int64_t ys_f) {
+    __shared__ float rows[kFastThreads / 32][32 * kRowStride];
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= in.N) return;
-    const float x = in.xs[p * 3], yv = in.xs[p * 3 + 1], z = in.xs[p * 3 + 2];
-    const uint64_t i = in.perm[p];
-    float* yrow = y + (int64_t)i * ys_n;
+    const bool active = p < in.N;
+    const int lane = threadIdx.x & 31;
+    float* myrows = rows[threadIdx.x >> 5];
+    float4 rec = make_float4(0.5f, 0.5f, 0.5f, 0.f);
+    if (active) rec = __ldcs(in.xs + p);
+    const float x = rec.x, yv = rec.y, z = rec.z;
+    const uint64_t i = __float_as_uint(rec.w);
     const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
-    const bool row4 = (ys_f == 1) && ((ys_n & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
-    float hold0 = 0.f, hold1 = 0.f;
+    const bool staged = (ys_f == 1);
+    uint32_t chunk_base = 0;  // first feature of the chunk currently staged
+#pragma unroll 2
     for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
         const uint32_t level = tab.map_level[pl];
         float r0 = 0.f, r1 = 0.f;
@@ -230,15 +238,24 @@ lotd_fast_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, flo
                 r0 += g.wb[q] * v[q].z; r1 += g.wb[q] * v[q].w;
             }
         }
-        if (row4) {
-            if (pl & 1) {
-                __stcs(reinterpret_cast<float4*>(yrow + (pl - 1) * 2), make_float4(hold0, hold1, r0, r1));
-            } else if (pl + 1 == tab.n_pseudo) {
-                __stcs(reinterpret_cast<float2*>(yrow + pl * 2), make_float2(r0, r1));
-            } else {
-                hold0 = r0; hold1 = r1;
+        if (staged) {
+            const uint32_t c = pl * 2u - chunk_base;
+            myrows[lane * kRowStride + c] = r0;
+            myrows[lane * kRowStride + c + 1] = r1;
+            const bool last = (pl + 1 == tab.n_pseudo);
+            if (c + 2 == 32 || last) {  // flush the chunk: one coalesced row store per point of the warp
+                const uint32_t width = c + 2;
+                __syncwarp();
+                for (int r = 0; r < 32; ++r) {
+                    const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, r);
+                    const bool ok = __shfl_sync(0xffffffffu, (int)active, r);
+                    if (ok && (uint32_t)lane < width) __stcs(y + (int64_t)ir * ys_n + chunk_base + lane, myrows[r * kRowStride + lane]);
+                }
+                __syncwarp();
+                chunk_base += 32;
             }
-        } else {
+        } else if (active) {
+            float* yrow = y + (int64_t)i * ys_n;
             __stcs(yrow + (int64_t)(pl * 2) * ys_f, r0);
             __stcs(yrow + (int64_t)(pl * 2 + 1) * ys_f, r1);
         }
@@ -260,39 +277,47 @@ __device__ __forceinline__ void scatter_pair(float* tbl, const Geo& g, int q, fl
     }
 }
 
-__global__ void __launch_bounds__(kFastThreads)
+constexpr int kBwdThreads = 128;
+
+__global__ void __launch_bounds__(kBwdThreads)
 lotd_fast_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, const float* __restrict__ dLdy, int64_t gs_n, int64_t gs_f,
                      float* __restrict__ grad) {
-    __shared__ __align__(16) float tile[kFastThreads / 32][32 * kTileStride];
+    __shared__ __align__(16) float tile[kBwdThreads / 32][32 * kTileStride];
+    __shared__ float rows[kBwdThreads / 32][32 * kRowStride];
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = p < in.N;
     const int lane = threadIdx.x & 31;
     float* mytile = tile[threadIdx.x >> 5];
-    float x = 0.5f, yv = 0.5f, z = 0.5f;
-    uint64_t i = 0;
-    if (active) {
-        x = in.xs[p * 3]; yv = in.xs[p * 3 + 1]; z = in.xs[p * 3 + 2];
-        i = in.perm[p];
-    }
+    float* myrows = rows[threadIdx.x >> 5];
+    float4 rec = make_float4(0.5f, 0.5f, 0.5f, 0.f);
+    if (active) rec = __ldcs(in.xs + p);
+    const float x = rec.x, yv = rec.y, z = rec.z;
+    const uint64_t i = __float_as_uint(rec.w);
     const float* grow = dLdy + (int64_t)i * gs_n;
     const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
-    const bool row4 = (gs_f == 1) && ((gs_n & 3) == 0) && ((reinterpret_cast<uintptr_t>(dLdy) & 15u) == 0);
+    const bool staged = (gs_f == 1);
     const bool grad_aligned = (reinterpret_cast<uintptr_t>(grad) & 15u) == 0;
-    float4 gbuf = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t chunk_base = 0;
     for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
         const uint32_t level = tab.map_level[pl];
         float g0 = 0.f, g1 = 0.f;
-        if (active) {
-            if (row4) {
-                if ((pl & 1) == 0) {
-                    if (pl + 1 < tab.n_pseudo) gbuf = __ldcs(reinterpret_cast<const float4*>(grow + pl * 2));
-                    else { const float2 t = __ldcs(reinterpret_cast<const float2*>(grow + pl * 2)); gbuf.x = t.x; gbuf.y = t.y; }
-                    g0 = gbuf.x; g1 = gbuf.y;
-                } else { g0 = gbuf.z; g1 = gbuf.w; }
-            } else {
-                g0 = grow[(int64_t)(pl * 2) * gs_f];
-                g1 = grow[(int64_t)(pl * 2 + 1) * gs_f];
+        if (staged) {
+            if (pl * 2u == chunk_base + 32u) chunk_base += 32u;
+            if (pl * 2u == chunk_base) {  // stage the next (up to) 32 features of the warp's 32 rows: one coalesced 128-byte read per point
+                const uint32_t width = min(32u, tab.n_enc - chunk_base);
+                __syncwarp();
+                for (int r = 0; r < 32; ++r) {
+                    const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, r);
+                    const bool ok = __shfl_sync(0xffffffffu, (int)active, r);
+                    if (ok && (uint32_t)lane < width) myrows[r * kRowStride + lane] = __ldcs(dLdy + (int64_t)ir * gs_n + chunk_base + lane);
+                }
+                __syncwarp();
             }
+            g0 = myrows[lane * kRowStride + pl * 2u - chunk_base];
+            g1 = myrows[lane * kRowStride + pl * 2u - chunk_base + 1];
+        } else if (active) {
+            g0 = grow[(int64_t)(pl * 2) * gs_f];
+            g1 = grow[(int64_t)(pl * 2 + 1) * gs_f];
         }
         if ((int32_t)level > in.max_level) continue;  // uniform
         const LevelDesc& L = tab.lv[level];
@@ -370,9 +395,9 @@ using namespace nr3d;
 
 extern "C" {
 
-int nr3d_lotd_sort_points(uint64_t N, const float* x, uint32_t* perm, float* xs, void* ws, uint64_t* ws_bytes, void* stream) {
+int nr3d_lotd_sort_points(uint64_t N, const float* x, void* xs /* float4 [N] */, void* ws, uint64_t* ws_bytes, void* stream) {
     const uint32_t nb = div_up<uint32_t>(kBins, kScanBlockF);
-    const uint64_t need = (uint64_t)kBins * 4 + (uint64_t)nb * 4 + N * 4;
+    const uint64_t need = (uint64_t)kBins * 4 + (uint64_t)nb * 4 + 64 + N * 8;
     if (ws == nullptr) {
         NR3D_CHECK(ws_bytes != nullptr, "sort_points: null ws_bytes");
         *ws_bytes = need;
@@ -381,14 +406,15 @@ int nr3d_lotd_sort_points(uint64_t N, const float* x, uint32_t* perm, float* xs,
     NR3D_CHECK(ws_bytes && *ws_bytes >= need, "sort_points: workspace too small");
     NR3D_CHECK(N < (1ull << 32), "sort_points: N must be < 2^32");
     if (N == 0) return 0;
-    NR3D_CHECK(x && perm && xs, "sort_points: null argument");
+    NR3D_CHECK(x && xs, "sort_points: null argument");
+    NR3D_CHECK((reinterpret_cast<uintptr_t>(xs) & 15u) == 0 && (reinterpret_cast<uintptr_t>(ws) & 15u) == 0, "sort_points: xs / ws must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* hist = reinterpret_cast<uint32_t*>(ws);
     uint32_t* bs = hist + kBins;
-    uint32_t* keys = bs + nb;
+    uint2* keyrank = reinterpret_cast<uint2*>(reinterpret_cast<char*>(ws) + (((uint64_t)kBins * 4 + (uint64_t)nb * 4 + 63) / 64) * 64);
     cudaMemsetAsync(hist, 0, (size_t)kBins * 4, st);
     const unsigned grid = (unsigned)div_up<uint64_t>(N, 256);
-    sort_hist_kernel<<<grid, 256, 0, st>>>(N, x, hist, keys);
+    sort_hist_kernel<<<grid, 256, 0, st>>>(N, x, hist, keyrank);
     NR3D_LAUNCH_CHECK("sort_hist");
     scanu_block_sums<<<nb, kScanBlockF, 0, st>>>(kBins, hist, bs);
     NR3D_LAUNCH_CHECK("sort_scan1");
@@ -396,34 +422,33 @@ int nr3d_lotd_sort_points(uint64_t N, const float* x, uint32_t* perm, float* xs,
     NR3D_LAUNCH_CHECK("sort_scan2");
     scanu_apply<<<nb, kScanBlockF, 0, st>>>(kBins, hist, bs);
     NR3D_LAUNCH_CHECK("sort_scan3");
-    sort_scatter_kernel<<<grid, 256, 0, st>>>(N, x, keys, hist, perm, xs);
+    sort_scatter_kernel<<<grid, 256, 0, st>>>(N, x, keyrank, hist, reinterpret_cast<float4*>(xs));
     NR3D_LAUNCH_CHECK("sort_scatter");
     return 0;
 }
 
-int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const float* xs, const uint32_t* perm,
-                         const void* params, int32_t max_level, void* y, int64_t y_stride_n, int64_t y_stride_f, void* stream) {
+int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* params,
+                         int32_t max_level, void* y, int64_t y_stride_n, int64_t y_stride_f, void* stream) {
     if (int rc = check_fast(meta, param_dtype, N)) return rc;
     if (N == 0) return 0;
-    NR3D_CHECK(xs && perm && params && y, "LoTDEncoding::fwd_sorted: null argument");
+    NR3D_CHECK(xs && params && y, "LoTDEncoding::fwd_sorted: null argument");
     LotdTable tab;
     make_table(meta, tab);
-    FastIn in{N, xs, perm, (const float*)params, max_level, (uint32_t)((reinterpret_cast<uintptr_t>(params) & 15u) == 0)};
+    FastIn in{N, reinterpret_cast<const float4*>(xs), (const float*)params, max_level, (uint32_t)((reinterpret_cast<uintptr_t>(params) & 15u) == 0)};
     lotd_fast_fwd_kernel<<<(unsigned)div_up<uint64_t>(N, kFastThreads), kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (float*)y, y_stride_n, y_stride_f);
     NR3D_LAUNCH_CHECK("lotd_fast_fwd");
     return 0;
 }
 
-int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const float* xs, const uint32_t* perm,
-                               const void* dL_dy, int64_t dLdy_stride_n, int64_t dLdy_stride_f, int32_t max_level, void* dL_dparam,
-                               void* stream) {
+int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* dL_dy,
+                               int64_t dLdy_stride_n, int64_t dLdy_stride_f, int32_t max_level, void* dL_dparam, void* stream) {
     if (int rc = check_fast(meta, param_dtype, N)) return rc;
     if (N == 0) return 0;
-    NR3D_CHECK(xs && perm && dL_dy && dL_dparam, "LoTDEncoding::bwd_sorted: null argument");
+    NR3D_CHECK(xs && dL_dy && dL_dparam, "LoTDEncoding::bwd_sorted: null argument");
     LotdTable tab;
     make_table(meta, tab);
-    FastIn in{N, xs, perm, nullptr, max_level, 1u};
-    lotd_fast_bwd_kernel<<<(unsigned)div_up<uint64_t>(N, kFastThreads), kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, (float*)dL_dparam);
+    FastIn in{N, reinterpret_cast<const float4*>(xs), nullptr, max_level, 1u};
+    lotd_fast_bwd_kernel<<<(unsigned)div_up<uint64_t>(N, kBwdThreads), kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, (float*)dL_dparam);
     NR3D_LAUNCH_CHECK("lotd_fast_bwd");
     return 0;
 }

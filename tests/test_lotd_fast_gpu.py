@@ -45,7 +45,7 @@ def test_sorted_path_matches_generic_and_oracle(name, N, dev):
     assert rel_err(y2.cpu(), O.encode(om, x.cpu(), inp["params"])) < 1e-5
     # dy_dx requests fall back to the reference layout
     y3, dy = _lotd.lod_fwd(meta_s, x, p, need_input_grad=True)
-    assert dy is not None and not y3.is_contiguous()
+    assert dy is not None and (N == 1 or not y3.is_contiguous())
 
 
 def test_sorted_path_clustered_points(dev):
