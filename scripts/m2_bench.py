@@ -1,0 +1,96 @@
+"""M2 of BASELINE.json (configs[2] / configs[4]): occupancy march (128^3 grid) + 16-level NGP LoTD + packed alpha-composite,
+forward + backward to the LoTD parameters, 1024^2 rays per GPU in chunks; reports rays/s and samples/ray.
+
+    python scripts/m2_bench.py [--rays 1048576] [--chunk 262144] [--grid random|shell] [--steps 3]
+    python -m torch.distributed.run --nproc-per-node N ... scripts/m2_bench.py        # rays sharded, one all-reduce per step
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import ngp_cfg  # noqa: E402
+from nr3d_lib_b200 import dist as ndist  # noqa: E402
+from nr3d_lib_b200.lotd import LoTD  # noqa: E402
+from nr3d_lib_b200.pipeline import march_encode_composite  # noqa: E402
+
+
+def make_rays(n, dev, seed):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    o = torch.randn(n, 3, device=dev, generator=g)
+    o = 4.0 * o / o.norm(dim=-1, keepdim=True)
+    tgt = torch.rand(n, 3, device=dev, generator=g) - 0.5
+    d = tgt - o
+    d = d / d.norm(dim=-1, keepdim=True)
+    t1, t2 = (-1.0 - o) / d, (1.0 - o) / d
+    near = torch.minimum(t1, t2).amax(-1).clamp_min(0.0)
+    far = torch.maximum(t1, t2).amin(-1)
+    far = torch.where(far <= near, near, far)
+    return o.contiguous(), d.contiguous(), near.contiguous(), far.contiguous()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rays", type=int, default=1024 * 1024)
+    ap.add_argument("--chunk", type=int, default=262144)
+    ap.add_argument("--grid", default="random", choices=["random", "shell"])
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--no-sort", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = ndist.init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    _, res, feats, types, T, _ = ngp_cfg()
+    enc = LoTD(3, res, feats, types, hashmap_size=T, dtype=torch.float)
+    enc.meta.c_sort_points = not args.no_sort
+    g = torch.Generator(device=dev).manual_seed(42)
+    params = ((torch.rand(enc.n_params, device=dev, generator=g) * 2 - 1) * 1e-2).requires_grad_(True)
+    R = 128
+    if args.grid == "random":
+        grid = torch.rand(R, R, R, device=dev, generator=g) > 0.5
+    else:
+        ax = torch.linspace(-1, 1, R, device=dev)
+        pts = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1)
+        grid = (pts.norm(dim=-1) - 0.6).abs() < 0.05
+    rays = make_rays(args.rays, dev, 1000 + rank)
+    n_samples = 0
+
+    def step():
+        nonlocal n_samples
+        params.grad = None
+        n_samples = 0
+        for b in range(0, args.rays, args.chunk):
+            o, d, near, far = (r[b:b + args.chunk] for r in rays)
+            out = march_encode_composite(enc, params, grid, o, d, near, far, step_size=0.01, max_steps=512, gain=2.0)
+            if out.depth is None:
+                continue
+            n_samples += out.weights.numel()
+            ((out.depth ** 2).sum() + out.acc.sum()).backward()
+        if params.grad is not None:
+            ndist.allreduce_param_grads(params.grad, world)
+
+    for _ in range(args.warmup):
+        step()
+    ndist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = ndist.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    if rank == 0:
+        print(json.dumps({"metric": "full march+encode+composite fwd+bwd Mrays/s", "value": world * args.rays / ms / 1e3, "unit": "Mrays/s",
+                          "n_gpus": world, "ms_per_step": ms, "rays_per_gpu": args.rays, "samples_per_ray": n_samples / args.rays,
+                          "Msamples_per_s": world * n_samples / ms / 1e3, "grid": args.grid, "chunk": args.chunk,
+                          "sort_points": not args.no_sort, "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+"""End-to-end parity of march -> encode -> composite (BASELINE.json configs[2] shape, reduced size): the B200 path
+against a pipeline assembled from the three CPU oracles, forward values and dL/dparams."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import march_inputs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngp(levels=10, T=2 ** 14):
+    res = (16 * 1.382 ** np.arange(levels)).astype(int).tolist()
+    return dict(in_features=3, lod_res=res, lod_n_feats=[2] * levels, lod_types=["Dense" if r ** 3 <= T else "Hash" for r in res], hashmap_size=T)
+
+
+@pytest.mark.parametrize("sort_points", [False, True])
+def test_march_encode_composite_matches_oracles(sort_points, dev):
+    from nr3d_lib_b200.lotd import LoTD
+    from nr3d_lib_b200.pipeline import march_encode_composite
+    from oracle import lotd_oracle as O, march_oracle as MO, pack_oracle as PO
+    cfg = _ngp()
+    enc = LoTD(dtype=torch.float, **cfg)
+    enc.meta.c_sort_points = sort_points
+    d = march_inputs(R=3000, res=32, seed=12, occupancy=0.25)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    rs = np.random.RandomState(1)
+    p_host = torch.from_numpy((rs.randn(enc.n_params) * 0.05).astype(np.float32))
+    params = p_host.to(dev).requires_grad_(True)
+    out = march_encode_composite(enc, params, t(d["grid"]), t(d["rays_o"]), t(d["rays_d"]), t(d["near"]), t(d["far"]), step_size=0.02, max_steps=256)
+    assert out.march.num_hit_rays > 100
+    loss = (out.depth ** 2).sum() + out.acc.sum()
+    loss.backward()
+
+    # ---- oracle pipeline (float64 everywhere after the bit-exact march)
+    m = MO.ray_marching(d["rays_o"], d["rays_d"], d["near"], d["far"], d["roi"], d["grid"], 0, 0.02, 1e10, 0.0, 256)
+    assert np.array_equal(out.march.pack_infos.cpu().numpy()[:, 1], m["packed_info"][m["packed_info"][:, 1] > 0, 1])
+    t0, t1, ridx = torch.from_numpy(m["t_starts"]), torch.from_numpy(m["t_ends"]), torch.from_numpy(m["ridx"]).long()
+    samples = torch.addcmul(torch.from_numpy(d["rays_o"])[ridx], torch.from_numpy(d["rays_d"])[ridx], t0.unsqueeze(-1))   # fp32 like the wrapper
+    assert torch.equal(samples, out.march.samples.cpu())
+    x01 = (samples * 0.5 + 0.5).clamp(1e-6, 1 - 1e-6)
+    om = O.OracleMeta(3, cfg["lod_res"], cfg["lod_n_feats"], cfg["lod_types"], cfg["hashmap_size"])
+    pd = p_host.double().requires_grad_(True)
+    h = O.encode(om, x01, pd)
+    sigma = F.softplus(h.sum(-1) * 20.0)
+    alpha = 1.0 - torch.exp(-sigma * (t1 - t0).double())
+    pi = m["packed_info"][m["packed_info"][:, 1] > 0].astype(np.int64)
+    w = torch.zeros_like(alpha)
+    for b, n in pi:   # differentiable front-to-back compositing (early stop never triggers at eps=1e-4 for this scene's opacities)
+        a = alpha[b:b + n]
+        T = torch.cumprod(torch.cat([torch.ones(1, dtype=torch.float64), 1.0 - a[:-1]]), 0)
+        w[b:b + n] = torch.where(T >= 1e-4, a * T, torch.zeros_like(a))
+    w_np, _, _ = PO.alpha_to_vw_forward(alpha.detach().float().numpy(), pi, 1e-4, 0.0)
+    assert rel_err(out.weights.detach().cpu(), w_np) < 1e-5 and rel_err(w.detach(), w_np) < 1e-5
+    depth = torch.stack([(w[b:b + n] * t0[b:b + n].double()).sum() for b, n in pi])
+    acc = torch.stack([w[b:b + n].sum() for b, n in pi])
+    assert rel_err(out.depth.detach().cpu(), depth.detach()) < 1e-5 and rel_err(out.acc.detach().cpu(), acc.detach()) < 1e-5
+    ((depth ** 2).sum() + acc.sum()).backward()
+    assert rel_err(params.grad.cpu(), pd.grad) < 5e-5
