@@ -258,6 +258,8 @@ def main():
                 "ms": {"lod_fwd": ms_fwd, "lod_bwd": ms_bwd},
                 "whole_step": {"achieved": whole, "frac": whole / peak, "bytes_per_sample": BYTES_PER_SAMPLE}}
 
+    ndist.barrier()
+    ndist.shutdown()
     if rank != 0:
         return 0
     cpu_base = None

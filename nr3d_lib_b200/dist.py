@@ -61,6 +61,12 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+def shutdown():
+    """Tear the default process group down (silences NCCL's leak warning at interpreter exit)."""
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def barrier():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()

@@ -85,6 +85,8 @@ def main():
     e1.record()
     torch.cuda.synchronize(dev)
     ms = ndist.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    ndist.barrier()
+    ndist.shutdown()
     if rank == 0:
         print(json.dumps({"metric": "full march+encode+composite fwd+bwd Mrays/s", "value": world * args.rays / ms / 1e3, "unit": "Mrays/s",
                           "n_gpus": world, "ms_per_step": ms, "rays_per_gpu": args.rays, "samples_per_ray": n_samples / args.rays,
