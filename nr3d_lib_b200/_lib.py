@@ -10,7 +10,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnr3d_b200.so")
+LIB_PATH = os.environ.get("NR3D_B200_LIB") or os.path.join(_HERE, "lib", "libnr3d_b200.so")   # env override: A/B builds only
 
 NR3D_MAX_LEVELS = 32
 NR3D_MAX_DIMS = 4

@@ -52,6 +52,26 @@ def _compile(src, verbose):
     return obj, time.time() - t0, p.stdout
 
 
+def build_variant(name, defines):
+    """A/B build of the library with extra -D flags into lib/variants/<name>.so (used by scripts/ab_bench.py)."""
+    out_dir = os.path.join(LIB_DIR, "variants")
+    obj_dir = os.path.join(OBJ_DIR, "variant_" + name)
+    os.makedirs(out_dir, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
+    objs = []
+    for s in SOURCES:
+        src = os.path.join(HERE, s)
+        if s == "lotd_fast.cu":
+            obj = os.path.join(obj_dir, s + ".o")
+            subprocess.check_call([NVCC] + FLAGS + ["-D" + d for d in defines] + ["-c", src, "-o", obj])
+        else:
+            obj = os.path.join(OBJ_DIR, s + ".o")
+        objs.append(obj)
+    lib = os.path.join(out_dir, name + ".so")
+    subprocess.check_call([NVCC, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs)
+    return lib
+
+
 def build(verbose=False, force=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)

@@ -24,16 +24,35 @@
 
 namespace nr3d {
 
-constexpr uint32_t kBinRes = 128;                       // bins per axis of the point sort
+// tunables (overridable with -D for A/B runs, see scripts/build_variants.py)
+#ifndef NR3D_BIN_RES
+#define NR3D_BIN_RES 128
+#endif
+#ifndef NR3D_BIN_ORDER      // 0: x fastest, 1: z fastest
+#define NR3D_BIN_ORDER 0
+#endif
+#ifndef NR3D_MERGE_MAX_HEADS
+#define NR3D_MERGE_MAX_HEADS 20
+#endif
+#ifndef NR3D_FWD_UNROLL
+#define NR3D_FWD_UNROLL 2
+#endif
+#ifndef NR3D_FWD_THREADS
+#define NR3D_FWD_THREADS 256
+#endif
+#ifndef NR3D_BWD_THREADS
+#define NR3D_BWD_THREADS 128
+#endif
+constexpr uint32_t kBinRes = NR3D_BIN_RES;               // bins per axis of the point sort
 constexpr uint32_t kBins = kBinRes * kBinRes * kBinRes;  // 2 Mi bins (8 MB of counters)
-constexpr int kFastThreads = 256;
+constexpr int kFastThreads = NR3D_FWD_THREADS;
 constexpr int kScanBlockF = 1024;
 
 __device__ __forceinline__ uint32_t bin_key(float x, float y, float z) {
     const uint32_t bx = min(kBinRes - 1, (uint32_t)fmaxf(x * (float)kBinRes, 0.f));
     const uint32_t by = min(kBinRes - 1, (uint32_t)fmaxf(y * (float)kBinRes, 0.f));
     const uint32_t bz = min(kBinRes - 1, (uint32_t)fmaxf(z * (float)kBinRes, 0.f));
-    return (bz * kBinRes + by) * kBinRes + bx;
+    return NR3D_BIN_ORDER == 0 ? (bz * kBinRes + by) * kBinRes + bx : (bx * kBinRes + by) * kBinRes + bz;
 }
 
 // pass 1: bin key and rank of the point inside its bin (the rank makes the scatter pass atomic-free)
@@ -209,7 +228,8 @@ lotd_fast_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, flo
     const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
     const bool staged = (ys_f == 1);
     uint32_t chunk_base = 0;  // first feature of the chunk currently staged
-#pragma unroll 2
+    constexpr int kFwdUnroll = NR3D_FWD_UNROLL;
+#pragma unroll kFwdUnroll
     for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
         const uint32_t level = tab.map_level[pl];
         float r0 = 0.f, r1 = 0.f;
@@ -277,7 +297,7 @@ __device__ __forceinline__ void scatter_pair(float* tbl, const Geo& g, int q, fl
     }
 }
 
-constexpr int kBwdThreads = 128;
+constexpr int kBwdThreads = NR3D_BWD_THREADS;
 
 __global__ void __launch_bounds__(kBwdThreads)
 lotd_fast_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, const float* __restrict__ dLdy, int64_t gs_n, int64_t gs_f,
@@ -333,7 +353,7 @@ lotd_fast_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
             const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
             heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
         }
-        if (__popc(heads) > 20) {  // (almost) nothing to merge: scatter directly
+        if (__popc(heads) > NR3D_MERGE_MAX_HEADS) {  // (almost) nothing to merge: scatter directly
             if (active) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
