@@ -197,6 +197,27 @@ int nr3d_pack_sample_step_fill(int32_t dtype, uint64_t P, const void* nears, con
 /* == mark_pack_boundaries_cuda, pack_ops_cuda.cu:2765-2805. ids dtype in {U8,I8,I16,I32,I64}; out int32 [S]. */
 int nr3d_pack_mark_boundaries(int32_t dtype, uint64_t S, const void* pack_ids, int32_t* boundaries, void* stream);
 
+/* ---- hierarchical-sampling ops ("next" row n2 of SURVEY.md 8f) ---- */
+/* == packed_searchsorted / packed_searchsorted_packed_vals, pack_ops_cuda.cu:1374-1503.  val_pack_infos == NULL: vals is
+ * [P, num_to_search]; otherwise vals is packed by val_pack_infos.  pidx (int64, same shape as vals) fully written for every
+ * listed query: begin + min(lower_bound, len-1). */
+int nr3d_pack_searchsorted(int32_t dtype, uint64_t P, const void* bins, const int64_t* pack_infos, const void* vals,
+                           uint32_t num_to_search, const int64_t* val_pack_infos, int64_t* pidx, void* stream);
+/* == packed_invert_cdf, pack_ops_cuda.cu:1633-1733.  u_vals / samples / bin_idx: [P, num_to_sample]. */
+int nr3d_pack_invert_cdf(int32_t dtype, uint64_t P, const void* bins, const void* cdfs, const int64_t* pack_infos, const void* u_vals,
+                         uint32_t num_to_sample, void* samples, int64_t* bin_idx, void* stream);
+/* == try_merge_two_packs_sorted_aligned, pack_ops_cuda.cu:1505-1631.  pack_infos_merged = pack infos of n_a + n_b;
+ * pidx_a [S_a] must be zero-filled; pidx_b [S_b]. */
+int nr3d_pack_merge_sorted_aligned(int32_t dtype, uint64_t P, const void* vals_a, const int64_t* pack_infos_a, const void* vals_b,
+                                   const int64_t* pack_infos_b, const int64_t* pack_infos_merged, int64_t* pidx_a, int64_t* pidx_b,
+                                   void* stream);
+/* == packed_sort_qsort / packed_sort_thrust, pack_ops_cuda.cu:2556-2763: ascending in-place sort of every pack; idx (nullable,
+ * int64 [S], pre-filled with arange) receives the same permutation. */
+int nr3d_pack_sort(int32_t dtype, uint64_t P, void* vals, const int64_t* pack_infos, int64_t* idx, void* stream);
+/* == packed_matmul, pack_ops_cuda.cu:2060-2085: out[i, o] = sum_k feats[i, k] * other[p(i), o, k]; feats [S, C], other [P, C_out, C]. */
+int nr3d_pack_matmul(int32_t dtype, uint64_t P, uint32_t C, uint32_t C_out, const void* feats, const void* other, const int64_t* pack_infos,
+                     void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,8 +3,10 @@
 Implemented ops (hot path): interleave_arange, interleave_linstep,
 interleave_sample_step_wrt_depth_clamped, packed_{add,sub,mul,div,gt,geq,lt,leq,eq,neq}, packed_sum, packed_diff,
 packed_backward_diff, packed_cumsum, packed_cumprod, packed_alpha_to_vw_forward/backward, mark_pack_boundaries_cuda.
-The hierarchical-sampling ops (sort / searchsorted / merge / invert_cdf / in_packed_segments / matmul / octree) are the
-"next" rows of the scope table and raise RuntimeError here.
+Hierarchical-sampling ops: packed_searchsorted, packed_searchsorted_packed_vals,
+packed_invert_cdf, try_merge_two_packs_sorted_aligned, packed_sort_qsort / packed_sort_thrust, packed_matmul.
+Still raising RuntimeError: the deprecated depth sampler, interleave_sample_step_wrt_depth_in_packed_segments and
+octree_mark_consecutive_segments.
 """
 import ctypes
 from typing import Optional, Tuple
@@ -284,6 +286,122 @@ def mark_pack_boundaries_cuda(pack_ids: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# hierarchical-sampling ops
+# ------------------------------------------------------------------------------------------------------------------
+def _check_1d_same(fn, *named):
+    ref = named[0][1]
+    for name, t in named:
+        if t.dim() != 1 or not t.is_contiguous():
+            raise RuntimeError(f"{fn}: Expected contiguous 1-dimensional tensor for argument '{name}'")
+        if t.dtype != ref.dtype:
+            raise RuntimeError(f"{fn}: '{name}' must have the dtype of '{named[0][0]}'")
+
+
+def packed_searchsorted(bins: torch.Tensor, vals: torch.Tensor, pack_infos: torch.Tensor) -> torch.Tensor:
+    """== packed_searchsorted (pack_ops_cuda.cu:1409-1455): vals [num_packs, num_to_search] searched in the sorted packs of `bins`."""
+    fn = "packed_searchsorted"
+    _check_1d_same(fn, ("bins", bins))
+    _check_pack_infos(fn, pack_infos)
+    if vals.dim() != 2 or not vals.is_contiguous() or vals.dtype != bins.dtype or vals.shape[0] != pack_infos.shape[0]:
+        raise RuntimeError(f"{fn}: `vals` must be a contiguous [num_packs, num_to_search] tensor with the dtype of `bins`")
+    dev = _lib.require_cuda(bins, vals, pack_infos, who=fn)
+    with torch.cuda.device(dev):
+        pidx = torch.full(vals.shape, -1, dtype=torch.int64, device=dev)
+        _lib.check(_lib.get_lib().nr3d_pack_searchsorted(_lib.dtype_code(bins.dtype), pack_infos.shape[0], bins.data_ptr(), pack_infos.data_ptr(),
+                                                         vals.data_ptr(), vals.shape[1], None, pidx.data_ptr(), _lib.stream_of(dev)))
+    return pidx
+
+
+def packed_searchsorted_packed_vals(bins: torch.Tensor, pack_infos: torch.Tensor, vals: torch.Tensor, val_pack_infos: torch.Tensor) -> torch.Tensor:
+    """== packed_searchsorted_packed_vals (pack_ops_cuda.cu:1457-1503): packed queries, one query pack per bin pack."""
+    fn = "packed_searchsorted_packed_vals"
+    _check_1d_same(fn, ("bins", bins), ("vals", vals))
+    _check_pack_infos(fn, pack_infos)
+    _check_pack_infos(fn, val_pack_infos)
+    if val_pack_infos.shape[0] != pack_infos.shape[0]:
+        raise RuntimeError(f"{fn}: `val_pack_infos` must have one row per pack")
+    dev = _lib.require_cuda(bins, vals, pack_infos, val_pack_infos, who=fn)
+    with torch.cuda.device(dev):
+        pidx = torch.full(vals.shape, -1, dtype=torch.int64, device=dev)
+        _lib.check(_lib.get_lib().nr3d_pack_searchsorted(_lib.dtype_code(bins.dtype), pack_infos.shape[0], bins.data_ptr(), pack_infos.data_ptr(),
+                                                         vals.data_ptr(), 0, val_pack_infos.data_ptr(), pidx.data_ptr(), _lib.stream_of(dev)))
+    return pidx
+
+
+def packed_invert_cdf(bins: torch.Tensor, cdfs: torch.Tensor, u_vals: torch.Tensor, pack_infos: torch.Tensor):
+    """== packed_invert_cdf (pack_ops_cuda.cu:1683-1733) -> (samples, bin_idx), both [num_packs, num_to_sample]."""
+    fn = "packed_invert_cdf"
+    _check_1d_same(fn, ("bins", bins), ("cdfs", cdfs))
+    _check_pack_infos(fn, pack_infos)
+    if bins.shape != cdfs.shape:
+        raise RuntimeError(f"{fn}: `bins` and `cdfs` must have the same size")
+    if u_vals.dim() != 2 or not u_vals.is_contiguous() or u_vals.dtype != bins.dtype or u_vals.shape[0] != pack_infos.shape[0]:
+        raise RuntimeError(f"{fn}: `u_vals` must be a contiguous [num_packs, num_to_sample] tensor with the dtype of `bins`")
+    dev = _lib.require_cuda(bins, cdfs, u_vals, pack_infos, who=fn)
+    with torch.cuda.device(dev):
+        bin_idx = torch.full(u_vals.shape, -1, dtype=torch.int64, device=dev)
+        samples = torch.zeros_like(u_vals)
+        _lib.check(_lib.get_lib().nr3d_pack_invert_cdf(_lib.dtype_code(bins.dtype), pack_infos.shape[0], bins.data_ptr(), cdfs.data_ptr(),
+                                                       pack_infos.data_ptr(), u_vals.data_ptr(), u_vals.shape[1], samples.data_ptr(),
+                                                       bin_idx.data_ptr(), _lib.stream_of(dev)))
+    return samples, bin_idx
+
+
+def try_merge_two_packs_sorted_aligned(vals_a: torch.Tensor, pack_infos_a: torch.Tensor, vals_b: torch.Tensor, pack_infos_b: torch.Tensor,
+                                       b_sorted: bool):
+    """== try_merge_two_packs_sorted_aligned (pack_ops_cuda.cu:1573-1631) -> (pidx_a, pidx_b, merged pack_infos)."""
+    fn = "try_merge_two_packs_sorted_aligned"
+    _check_1d_same(fn, ("vals_a", vals_a), ("vals_b", vals_b))
+    _check_pack_infos(fn, pack_infos_a)
+    _check_pack_infos(fn, pack_infos_b)
+    if pack_infos_a.shape[0] != pack_infos_b.shape[0]:
+        raise RuntimeError(f"{fn}: the two packs must be aligned (same number of packs)")
+    dev = _lib.require_cuda(vals_a, vals_b, pack_infos_a, pack_infos_b, who=fn)
+    with torch.cuda.device(dev):
+        n = (pack_infos_a[:, 1] + pack_infos_b[:, 1]).contiguous()
+        pack_infos, _ = _pack_infos_from_counts(n)
+        pidx_a = torch.zeros([vals_a.shape[0]], dtype=torch.int64, device=dev)
+        pidx_b = torch.zeros([vals_b.shape[0]], dtype=torch.int64, device=dev)
+        _lib.check(_lib.get_lib().nr3d_pack_merge_sorted_aligned(
+            _lib.dtype_code(vals_a.dtype), pack_infos_a.shape[0], vals_a.data_ptr(), pack_infos_a.data_ptr(), vals_b.data_ptr(),
+            pack_infos_b.data_ptr(), pack_infos.data_ptr(), pidx_a.data_ptr(), pidx_b.data_ptr(), _lib.stream_of(dev)))
+    return pidx_a, pidx_b, pack_infos
+
+
+def packed_sort_qsort(vals: torch.Tensor, pack_infos: torch.Tensor, return_idx: bool):
+    """== packed_sort_qsort (pack_ops_cuda.cu:2709-2763): ascending sort of every pack IN PLACE; returns the permuted global
+    indices when `return_idx` (equal keys may come out in a different order than the reference's quicksort)."""
+    fn = "packed_sort_qsort"
+    _check_1d_same(fn, ("vals", vals))
+    _check_pack_infos(fn, pack_infos)
+    dev = _lib.require_cuda(vals, pack_infos, who=fn)
+    with torch.cuda.device(dev):
+        idx = torch.arange(vals.shape[0], dtype=torch.int64, device=dev) if return_idx else None
+        _lib.check(_lib.get_lib().nr3d_pack_sort(_lib.dtype_code(vals.dtype), pack_infos.shape[0], vals.data_ptr(), pack_infos.data_ptr(),
+                                                 _lib.ptr(idx), _lib.stream_of(dev)))
+    return idx
+
+
+packed_sort_thrust = packed_sort_qsort   # same contract (pack_ops_cuda.cu:2556-2621)
+
+
+def packed_matmul(feats: torch.Tensor, other: torch.Tensor, pack_infos: torch.Tensor) -> torch.Tensor:
+    """== packed_matmul (pack_ops_cuda.cu:2251-2540, Matmul branch): out = other[pack] @ feat, feats [S, C], other [P, C_out, C]."""
+    fn = "packed_matmul"
+    _check_pack_infos(fn, pack_infos)
+    if feats.dim() != 2 or other.dim() != 3 or other.shape[2] != feats.shape[1] or other.shape[0] != pack_infos.shape[0]:
+        raise RuntimeError(f"{fn}: expected feats [num_feats, C] and other [num_packs, C_out, C]")
+    if not (feats.is_contiguous() and other.is_contiguous()) or feats.dtype != other.dtype:
+        raise RuntimeError(f"{fn}: feats / other must be contiguous and share a dtype")
+    dev = _lib.require_cuda(feats, other, pack_infos, who=fn)
+    with torch.cuda.device(dev):
+        out = torch.zeros([feats.shape[0], other.shape[1]], dtype=feats.dtype, device=dev)
+        _lib.check(_lib.get_lib().nr3d_pack_matmul(_lib.dtype_code(feats.dtype), pack_infos.shape[0], feats.shape[1], other.shape[1],
+                                                   feats.data_ptr(), other.data_ptr(), pack_infos.data_ptr(), out.data_ptr(), _lib.stream_of(dev)))
+    return out
+
+
 def _next_row(name):
     def fn(*args, **kwargs):
         raise RuntimeError(f"nr3d_lib_b200: `{name}` is a 'next' row of the hot-path scope table (SURVEY.md section 8f, n2) and "
@@ -293,6 +411,5 @@ def _next_row(name):
 
 
 for _n in ("interleave_sample_step_wrt_depth_clamp_deprecated", "interleave_sample_step_wrt_depth_in_packed_segments",
-           "packed_matmul", "packed_sort_qsort", "packed_sort_thrust", "packed_searchsorted", "packed_searchsorted_packed_vals",
-           "try_merge_two_packs_sorted_aligned", "packed_invert_cdf", "octree_mark_consecutive_segments"):
+           "octree_mark_consecutive_segments"):   # forest / octree segment ops and the deprecated sampler
     globals()[_n] = _next_row(_n)

@@ -1,0 +1,296 @@
+// pack_next.cu -- the hierarchical-sampling pack ops ("next" row n2 of SURVEY.md section 8f): searchsorted, invert_cdf,
+// merge of two sorted packs, per-pack sort, per-pack matmul.  They sit between the march and the composite in the
+// reference's NeuS / StreetSurf samplers (nr3d_lib/graphics/neus/neus_ray_query.py, graphics/raysample.py).
+//
+// The reference gives every pack to ONE thread (csrc/pack_ops/pack_ops_cuda.cu:1374-1407, 1505-1571, 1633-1681, 2634-2763,
+// 2060-2085).  Every query of searchsorted / invert_cdf is independent, so here a warp owns a pack and its lanes take
+// the queries; the merge is three warp-parallel phases (lower bounds, counts + scan, ranks); the sort is a block-wide
+// direction-free bitonic network in shared memory (global memory for packs that do not fit).
+#include "common.cuh"
+
+namespace nr3d {
+
+constexpr int kNextThreads = 256;
+constexpr int kNextWarps = kNextThreads / 32;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+template <typename T> struct Num { static __device__ __forceinline__ float f(T v) { return (float)v; } };
+
+// first index with data[idx] >= val  (== binary_search_unsafe, pack_ops_cuda.cu:1336-1362)
+template <typename T>
+__device__ __forceinline__ uint32_t lower_bound_dev(T val, const T* __restrict__ data, uint32_t length) {
+    uint32_t first = 0, count = length;
+    while (count > 0) {
+        const uint32_t step = count >> 1;
+        const uint32_t it = first + step;
+        if (data[it] < val) { first = it + 1; count -= step + 1; }
+        else count = step;
+    }
+    return first;
+}
+
+struct PR { uint64_t begin; uint32_t len; };
+__device__ __forceinline__ PR pack_of(const int64_t* __restrict__ pi, uint64_t p) {
+    PR r;
+    r.begin = (uint64_t)pi[2 * p];
+    const int64_t n = pi[2 * p + 1];
+    r.len = n > 0 ? (uint32_t)n : 0u;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kNextThreads)
+searchsorted_kernel(uint64_t P, const T* __restrict__ bins, const int64_t* __restrict__ pack_infos, const T* __restrict__ vals,
+                    uint32_t num_to_search, const int64_t* __restrict__ val_pack_infos, int64_t* __restrict__ pidx) {
+    const uint64_t p = (uint64_t)blockIdx.x * kNextWarps + (threadIdx.x >> 5);
+    if (p >= P) return;
+    const int lane = threadIdx.x & 31;
+    const PR b = pack_of(pack_infos, p);
+    uint64_t out_begin = p * num_to_search;
+    uint32_t nq = num_to_search;
+    if (val_pack_infos) { const PR q = pack_of(val_pack_infos, p); out_begin = q.begin; nq = q.len; }
+    for (uint32_t i = lane; i < nq; i += 32) {
+        uint32_t pos = 0;
+        if (b.len) pos = min(lower_bound_dev<T>(vals[out_begin + i], bins + b.begin, b.len), b.len - 1);
+        pidx[out_begin + i] = (int64_t)(b.begin + pos);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kNextThreads)
+invert_cdf_kernel(uint64_t P, const T* __restrict__ bins, const T* __restrict__ cdfs, const int64_t* __restrict__ pack_infos,
+                  const T* __restrict__ u_vals, uint32_t num_to_sample, T* __restrict__ samples, int64_t* __restrict__ bin_idx) {
+    const uint64_t p = (uint64_t)blockIdx.x * kNextWarps + (threadIdx.x >> 5);
+    if (p >= P) return;
+    const int lane = threadIdx.x & 31;
+    const PR b = pack_of(pack_infos, p);
+    const T eps = (T)1.0e-5f;
+    const T* bn = bins + b.begin;
+    const T* cd = cdfs + b.begin;
+    for (uint32_t i = lane; i < num_to_sample; i += 32) {
+        const uint64_t o = p * num_to_sample + i;
+        const T u = u_vals[o];
+        uint32_t pos = 0;
+        if (b.len) pos = min(lower_bound_dev<T>(u, cd, b.len), b.len - 1);
+        bin_idx[o] = (int64_t)(pos + b.begin);
+        if (pos == 0) {
+            samples[o] = bn[0];
+        } else {
+            const T pmf = cd[pos] - cd[pos - 1];
+            samples[o] = pmf < eps ? bn[pos - 1] : (bn[pos - 1] + ((u - cd[pos - 1]) / pmf) * (bn[pos] - bn[pos - 1]));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// try_merge_two_packs_sorted_aligned (pack_ops_cuda.cu:1505-1571): positions of a's and b's elements in the merged
+// sorted pack.  pidx_a must be zero-filled.  Semantics kept: a[i] goes after every b whose lower bound in a is <= i;
+// b's with equal lower bound keep their order when they are consecutive.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kNextThreads)
+merge_sorted_kernel(uint64_t P, const T* __restrict__ vals_a, const int64_t* __restrict__ pi_a, const T* __restrict__ vals_b,
+                    const int64_t* __restrict__ pi_b, const int64_t* __restrict__ pi_m, int64_t* __restrict__ pidx_a,
+                    int64_t* __restrict__ pidx_b) {
+    const uint64_t p = (uint64_t)blockIdx.x * kNextWarps + (threadIdx.x >> 5);
+    if (p >= P) return;
+    const int lane = threadIdx.x & 31;
+    const PR a = pack_of(pi_a, p), b = pack_of(pi_b, p);
+    const int64_t out_begin = pi_m[2 * p];
+    const T* va = vals_a + a.begin;
+    const T* vb = vals_b + b.begin;
+    int64_t* pa = pidx_a + a.begin;
+    int64_t* pb = pidx_b + b.begin;
+    // phase 1: lower bound of every b in a; count per a-slot
+    for (uint32_t j = lane; j < b.len; j += 32) {
+        const uint32_t i = lower_bound_dev<T>(vb[j], va, a.len);
+        pb[j] = (int64_t)i;
+        if (i < a.len) atomicAdd(reinterpret_cast<unsigned long long*>(pa + i), 1ull);
+    }
+    __syncwarp();
+    __threadfence_block();
+    // phase 2: pidx_a[i] = out_begin + i + inclusive_cumsum(count)[i]
+    int64_t carry = 0;
+    for (uint32_t base = 0; base < a.len; base += 32) {
+        const uint32_t i = base + lane;
+        const int64_t c = i < a.len ? __ldcg(reinterpret_cast<const long long*>(pa + i)) : 0;
+        int64_t s = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int64_t t = __shfl_up_sync(kFullMask, s, d); if (lane >= d) s += t; }
+        if (i < a.len) pa[i] = out_begin + (int64_t)i + carry + s;
+        carry += __shfl_sync(kFullMask, s, 31);
+    }
+    __syncwarp();
+    __threadfence_block();
+    // phase 3: rank of b inside its run of equal lower bounds + slot after a[i-1]
+    int64_t prev_last = -1;          // lower bound of the last b of the previous chunk
+    int64_t run_start_carry = 0;     // index j where the run that reaches into this chunk started
+    for (uint32_t base = 0; base < b.len; base += 32) {
+        const uint32_t j = base + lane;
+        const bool ok = j < b.len;
+        const int64_t i = ok ? pb[j] : -2;
+        int64_t prev = __shfl_up_sync(kFullMask, i, 1);
+        if (lane == 0) prev = prev_last;
+        const bool start = ok && (i != prev);
+        int64_t st = start ? (int64_t)j : -1;   // max-scan of run starts
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int64_t t = __shfl_up_sync(kFullMask, st, d); if (lane >= d) st = max(st, t); }
+        if (st < 0) st = run_start_carry;
+        if (ok) {
+            const int64_t acc = (int64_t)j - st;
+            pb[j] = acc + ((i == 0) ? out_begin : ((int64_t)__ldcg(reinterpret_cast<const long long*>(pa + i - 1)) + 1));
+        }
+        const int last_lane = (int)min(31u, b.len - 1 - base);
+        prev_last = __shfl_sync(kFullMask, i, last_lane);
+        run_start_carry = __shfl_sync(kFullMask, st, last_lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-pack sort (packed_sort_qsort / packed_sort_thrust, pack_ops_cuda.cu:2556-2763): ascending, in place, optional
+// permutation of the GLOBAL indices.  Direction-free bitonic network: every compare-exchange puts the smaller key at
+// the lower index, so virtual +inf padding beyond the pack needs no storage.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void bitonic_network(T* keys, int64_t* ids, uint32_t n) {
+    uint32_t Pw = 1;
+    while (Pw < n) Pw <<= 1;
+    for (uint32_t k = 2; k <= Pw; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            const bool first = (j == (k >> 1));
+            for (uint32_t i = threadIdx.x; i < Pw; i += blockDim.x) {
+                const uint32_t l = first ? (i ^ (k - 1)) : (i ^ j);
+                if (l > i && l < n) {
+                    const T a = keys[i], b = keys[l];
+                    if (b < a) {
+                        keys[i] = b; keys[l] = a;
+                        if (ids) { const int64_t t = ids[i]; ids[i] = ids[l]; ids[l] = t; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+constexpr uint32_t kSortSmemElems = 2048;
+
+template <typename T>
+__global__ void __launch_bounds__(kNextThreads)
+pack_sort_kernel(uint64_t P, T* __restrict__ vals, const int64_t* __restrict__ pack_infos, int64_t* __restrict__ idx) {
+    __shared__ T skeys[kSortSmemElems];
+    __shared__ int64_t sids[kSortSmemElems];
+    for (uint64_t p = blockIdx.x; p < P; p += gridDim.x) {
+        const PR r = pack_of(pack_infos, p);
+        if (r.len < 2) continue;   // uniform per block
+        T* v = vals + r.begin;
+        int64_t* id = idx ? idx + r.begin : nullptr;
+        if (r.len <= kSortSmemElems) {
+            for (uint32_t i = threadIdx.x; i < r.len; i += blockDim.x) { skeys[i] = v[i]; if (id) sids[i] = id[i]; }
+            __syncthreads();
+            bitonic_network<T>(skeys, id ? sids : nullptr, r.len);
+            for (uint32_t i = threadIdx.x; i < r.len; i += blockDim.x) { v[i] = skeys[i]; if (id) id[i] = sids[i]; }
+            __syncthreads();
+        } else {
+            __syncthreads();
+            bitonic_network<T>(v, id, r.len);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// packed_matmul (pack_ops_cuda.cu:2060-2085): out[i, o] = sum_k feats[i, k] * other[p, o, k]
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kNextThreads)
+pack_matmul_kernel(uint64_t P, uint32_t C, uint32_t Co, const T* __restrict__ feats, const T* __restrict__ other,
+                   const int64_t* __restrict__ pack_infos, T* __restrict__ out) {
+    const uint64_t p = (uint64_t)blockIdx.x * kNextWarps + (threadIdx.x >> 5);
+    if (p >= P) return;
+    const int lane = threadIdx.x & 31;
+    const PR r = pack_of(pack_infos, p);
+    const T* w = other + p * (uint64_t)Co * C;
+    const uint64_t n = (uint64_t)r.len * Co;
+    for (uint64_t t = lane; t < n; t += 32) {
+        const uint64_t i = r.begin + t / Co;
+        const uint32_t o = (uint32_t)(t % Co);
+        T acc = (T)0;
+        for (uint32_t k = 0; k < C; ++k) acc += feats[i * C + k] * w[(uint64_t)o * C + k];
+        out[i * Co + o] = acc;
+    }
+}
+
+static inline unsigned wgrid(uint64_t warps) { return (unsigned)div_up<uint64_t>(warps, kNextWarps); }
+
+#define NR3D_NEXT_DISPATCH(dtype, NAME, ...)                                                         \
+    switch (dtype) {                                                                                 \
+    case NR3D_F32: { using T = float; __VA_ARGS__; } break;                                          \
+    case NR3D_F64: { using T = double; __VA_ARGS__; } break;                                         \
+    case NR3D_I32: { using T = int32_t; __VA_ARGS__; } break;                                        \
+    case NR3D_I64: { using T = int64_t; __VA_ARGS__; } break;                                        \
+    default: return fail(NAME ": unsupported dtype code %d (supported: f32, f64, i32, i64)", (int)dtype); }
+#define NR3D_NEXT_DISPATCH_FLOAT(dtype, NAME, ...)                                                   \
+    switch (dtype) {                                                                                 \
+    case NR3D_F32: { using T = float; __VA_ARGS__; } break;                                          \
+    case NR3D_F64: { using T = double; __VA_ARGS__; } break;                                         \
+    default: return fail(NAME ": expected f32 / f64, got dtype code %d", (int)dtype); }
+
+}  // namespace nr3d
+
+using namespace nr3d;
+
+extern "C" {
+
+int nr3d_pack_searchsorted(int32_t dtype, uint64_t P, const void* bins, const int64_t* pack_infos, const void* vals,
+                           uint32_t num_to_search, const int64_t* val_pack_infos, int64_t* pidx, void* stream) {
+    if (P == 0) return 0;
+    NR3D_CHECK(bins && pack_infos && vals && pidx, "packed_searchsorted: null argument");
+    NR3D_NEXT_DISPATCH(dtype, "packed_searchsorted",
+        (searchsorted_kernel<T><<<wgrid(P), kNextThreads, 0, (cudaStream_t)stream>>>(P, (const T*)bins, pack_infos, (const T*)vals, num_to_search, val_pack_infos, pidx)));
+    NR3D_LAUNCH_CHECK("packed_searchsorted");
+    return 0;
+}
+
+int nr3d_pack_invert_cdf(int32_t dtype, uint64_t P, const void* bins, const void* cdfs, const int64_t* pack_infos, const void* u_vals,
+                         uint32_t num_to_sample, void* samples, int64_t* bin_idx, void* stream) {
+    if (P == 0 || num_to_sample == 0) return 0;
+    NR3D_CHECK(bins && cdfs && pack_infos && u_vals && samples && bin_idx, "packed_invert_cdf: null argument");
+    NR3D_NEXT_DISPATCH_FLOAT(dtype, "packed_invert_cdf",
+        (invert_cdf_kernel<T><<<wgrid(P), kNextThreads, 0, (cudaStream_t)stream>>>(P, (const T*)bins, (const T*)cdfs, pack_infos, (const T*)u_vals, num_to_sample, (T*)samples, bin_idx)));
+    NR3D_LAUNCH_CHECK("packed_invert_cdf");
+    return 0;
+}
+
+int nr3d_pack_merge_sorted_aligned(int32_t dtype, uint64_t P, const void* vals_a, const int64_t* pack_infos_a, const void* vals_b,
+                                   const int64_t* pack_infos_b, const int64_t* pack_infos_merged, int64_t* pidx_a, int64_t* pidx_b,
+                                   void* stream) {
+    if (P == 0) return 0;
+    NR3D_CHECK(vals_a && pack_infos_a && vals_b && pack_infos_b && pack_infos_merged && pidx_a && pidx_b, "try_merge_two_packs_sorted_aligned: null argument");
+    NR3D_NEXT_DISPATCH(dtype, "try_merge_two_packs_sorted_aligned",
+        (merge_sorted_kernel<T><<<wgrid(P), kNextThreads, 0, (cudaStream_t)stream>>>(P, (const T*)vals_a, pack_infos_a, (const T*)vals_b, pack_infos_b, pack_infos_merged, pidx_a, pidx_b)));
+    NR3D_LAUNCH_CHECK("try_merge_two_packs_sorted_aligned");
+    return 0;
+}
+
+int nr3d_pack_sort(int32_t dtype, uint64_t P, void* vals, const int64_t* pack_infos, int64_t* idx, void* stream) {
+    if (P == 0) return 0;
+    NR3D_CHECK(vals && pack_infos, "packed_sort: null argument");
+    const unsigned grid = (unsigned)(P < 148ull * 32 ? P : 148ull * 32);
+    NR3D_NEXT_DISPATCH(dtype, "packed_sort",
+        (pack_sort_kernel<T><<<grid, kNextThreads, 0, (cudaStream_t)stream>>>(P, (T*)vals, pack_infos, idx)));
+    NR3D_LAUNCH_CHECK("packed_sort");
+    return 0;
+}
+
+int nr3d_pack_matmul(int32_t dtype, uint64_t P, uint32_t C, uint32_t C_out, const void* feats, const void* other, const int64_t* pack_infos,
+                     void* out, void* stream) {
+    if (P == 0) return 0;
+    NR3D_CHECK(feats && other && pack_infos && out && C > 0 && C_out > 0, "packed_matmul: null argument");
+    NR3D_NEXT_DISPATCH_FLOAT(dtype, "packed_matmul",
+        (pack_matmul_kernel<T><<<wgrid(P), kNextThreads, 0, (cudaStream_t)stream>>>(P, C, C_out, (const T*)feats, (const T*)other, pack_infos, (T*)out)));
+    NR3D_LAUNCH_CHECK("packed_matmul");
+    return 0;
+}
+
+}  // extern "C"

@@ -11,7 +11,8 @@ from torch.autograd.function import once_differentiable
 
 from .bindings import _pack_ops as _backend
 
-__all__ = ['packed_sum', 'packed_mean', 'packed_cumprod', 'packed_cumsum', 'packed_diff', 'packed_backward_diff',
+__all__ = ['packed_sort_inplace', 'packed_sort', 'packed_searchsorted', 'packed_searchsorted_packed_vals', 'packed_invert_cdf',
+           'packed_matmul', 'merge_two_packs_sorted_aligned', 'packed_sum', 'packed_mean', 'packed_cumprod', 'packed_cumsum', 'packed_diff', 'packed_backward_diff',
            'packed_alpha_to_vw', 'packed_volume_render_compression', 'packed_add', 'packed_sub', 'packed_mul', 'packed_div',
            'packed_gt', 'packed_geq', 'packed_lt', 'packed_leq', 'packed_eq', 'packed_neq', 'interleave_arange_simple',
            'interleave_arange', 'interleave_linstep', 'interleave_linspace', 'interleave_sample_step_wrt_depth_clamped',
@@ -299,6 +300,51 @@ def packed_lt(feats, other, pack_infos): return _backend.packed_lt(feats.contigu
 def packed_leq(feats, other, pack_infos): return _backend.packed_leq(feats.contiguous(), other.contiguous(), pack_infos.contiguous())
 def packed_eq(feats, other, pack_infos): return _backend.packed_eq(feats.contiguous(), other.contiguous(), pack_infos.contiguous())
 def packed_neq(feats, other, pack_infos): return _backend.packed_neq(feats.contiguous(), other.contiguous(), pack_infos.contiguous())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sort / search / inverse-CDF sampling / merge (reference pack_ops.py:74-95, 398-407, 550-570)
+# ---------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def packed_sort_inplace(vals: torch.Tensor, pack_infos: torch.LongTensor, return_idx=True) -> torch.Tensor:
+    return _backend.packed_sort_qsort(vals.contiguous(), pack_infos, return_idx)
+
+
+def packed_sort(vals: torch.Tensor, pack_infos: torch.LongTensor):
+    indices = packed_sort_inplace(vals.data.clone(), pack_infos, return_idx=True)
+    return vals[indices], indices
+
+
+@torch.no_grad()
+def packed_searchsorted(bins: torch.Tensor, vals: torch.Tensor, pack_infos: torch.LongTensor) -> torch.Tensor:
+    """Search a batch (vals [num_packs, n]) in a sorted pack (bins)."""
+    return _backend.packed_searchsorted(bins.contiguous(), vals.contiguous(), pack_infos)
+
+
+@torch.no_grad()
+def packed_searchsorted_packed_vals(bins, pack_infos, vals, u_pack_infos) -> torch.Tensor:
+    """Search a pack (vals, u_pack_infos) in a sorted pack (bins, pack_infos)."""
+    return _backend.packed_searchsorted_packed_vals(bins.contiguous(), pack_infos.contiguous(), vals.contiguous(), u_pack_infos)
+
+
+@torch.no_grad()
+def packed_invert_cdf(bins, cdfs, u_vals, pack_infos) -> Tuple[torch.Tensor, torch.Tensor]:
+    return _backend.packed_invert_cdf(bins.contiguous(), cdfs.contiguous(), u_vals.contiguous(), pack_infos)
+
+
+def packed_matmul(feats: torch.Tensor, other: torch.Tensor, pack_infos: torch.LongTensor) -> torch.Tensor:
+    """Pack-wise left multiplication ``other[pack] @ feat``; differentiable torch formulation as in the reference (pack_ops.py:407)."""
+    return (feats.unsqueeze(-2) * torch.repeat_interleave(other, pack_infos[:, 1], dim=0)).sum(-1)
+
+
+def merge_two_packs_sorted_aligned(vals_a, pack_infos_a, vals_b, pack_infos_b, b_sorted=True, return_val=False):
+    """Merge two aligned sorted packs (vals_b may be unsorted): positions of a / b in the merged pack (reference pack_ops.py:550-570)."""
+    pidx_a, pidx_b, pack_infos = _backend.try_merge_two_packs_sorted_aligned(vals_a.contiguous(), pack_infos_a, vals_b.contiguous(), pack_infos_b, b_sorted)
+    if return_val:
+        val = vals_a.new_empty([vals_a.numel() + vals_b.numel()])
+        val[pidx_a], val[pidx_b] = vals_a, vals_b
+        return val, pack_infos
+    return pidx_a, pidx_b, pack_infos
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -211,6 +211,110 @@ def mark_pack_boundaries(ids):
     return out
 
 
+def _lower_bound(val, data):
+    """binary_search_unsafe (pack_ops_cuda.cu:1336-1362): first index with data[idx] >= val."""
+    first, count = 0, len(data)
+    while count > 0:
+        step = count // 2
+        it = first + step
+        if data[it] < val:
+            first, count = it + 1, count - step - 1
+        else:
+            count = step
+    return first
+
+
+def packed_searchsorted(bins, vals, pack_infos, val_pack_infos=None):
+    """pack_ops_cuda.cu:1374-1407: begin + min(lower_bound, len-1); vals [P, n] or packed by val_pack_infos."""
+    bins, vals = np.asarray(bins), np.asarray(vals)
+    out = np.full(vals.shape, -1, dtype=np.int64)
+    for p, (b, n) in enumerate(_ranges(pack_infos)):
+        if val_pack_infos is None:
+            qs = [(p, i) for i in range(vals.shape[1])]
+        else:
+            qb, qn = _ranges(val_pack_infos)[p]
+            qs = [(qb + i,) for i in range(qn)]
+        for q in qs:
+            pos = min(_lower_bound(vals[q], bins[b:b + n]), n - 1) if n else 0
+            out[q] = b + pos
+    return out
+
+
+def packed_invert_cdf(bins, cdfs, u_vals, pack_infos):
+    """pack_ops_cuda.cu:1633-1681 -> (samples, bin_idx); `a + b*c` evaluated with one rounding (nvcc FMA contraction)."""
+    bins, cdfs, u = np.asarray(bins), np.asarray(cdfs), np.asarray(u_vals)
+    T_ = bins.dtype.type
+    samples = np.zeros_like(u)
+    idx = np.full(u.shape, -1, dtype=np.int64)
+    eps = T_(1.0e-5)
+    for p, (b, n) in enumerate(_ranges(pack_infos)):
+        bn, cd = bins[b:b + n], cdfs[b:b + n]
+        for i in range(u.shape[1]):
+            pos = min(_lower_bound(u[p, i], cd), n - 1) if n else 0
+            idx[p, i] = pos + b
+            if pos == 0:
+                samples[p, i] = bn[0]
+            else:
+                pmf = T_(cd[pos] - cd[pos - 1])
+                if pmf < eps:
+                    samples[p, i] = bn[pos - 1]
+                else:
+                    r = T_(T_(u[p, i] - cd[pos - 1]) / pmf)
+                    d = T_(bn[pos] - bn[pos - 1])
+                    samples[p, i] = T_(np.float64(bn[pos - 1]) + np.float64(r) * np.float64(d)) if bins.dtype == np.float32 else T_(bn[pos - 1] + r * d)
+    return samples, idx
+
+
+def try_merge_two_packs_sorted_aligned(vals_a, pack_infos_a, vals_b, pack_infos_b):
+    """pack_ops_cuda.cu:1505-1571 -> (pidx_a, pidx_b, merged pack_infos)."""
+    va, vb = np.asarray(vals_a), np.asarray(vals_b)
+    n = np.asarray(pack_infos_a)[:, 1] + np.asarray(pack_infos_b)[:, 1]
+    pm = pack_infos_from_counts(n)
+    pa = np.zeros(va.shape[0], dtype=np.int64)
+    pb = np.zeros(vb.shape[0], dtype=np.int64)
+    for p, ((ab, an), (bb, bn)) in enumerate(zip(_ranges(pack_infos_a), _ranges(pack_infos_b))):
+        out_begin = int(pm[p, 0])
+        lb = [_lower_bound(vb[bb + j], va[ab:ab + an]) for j in range(bn)]
+        cnt = np.zeros(an, dtype=np.int64)
+        for i in lb:
+            if i < an:
+                cnt[i] += 1
+        if an:
+            pa[ab:ab + an] = out_begin + np.arange(an) + np.cumsum(cnt)
+        acc, last = 1, -1
+        for j, i in enumerate(lb):
+            acc = acc + 1 if i == last else 0
+            pb[bb + j] = acc + (out_begin if i == 0 else pa[ab + i - 1] + 1)
+            last = i
+    return pa, pb, pm
+
+
+def packed_sort(vals, pack_infos):
+    """ascending per-pack sort -> (sorted vals, permuted global indices); equal keys: any order is acceptable."""
+    v = np.asarray(vals).copy()
+    idx = np.arange(v.shape[0], dtype=np.int64)
+    for (b, n) in _ranges(pack_infos):
+        o = np.argsort(v[b:b + n], kind="stable")
+        v[b:b + n] = v[b:b + n][o]
+        idx[b:b + n] = idx[b:b + n][o]
+    return v, idx
+
+
+def packed_matmul(feats, other, pack_infos):
+    """pack_ops_cuda.cu:2060-2085: sequential dot products in the tensor's dtype."""
+    f, o = np.asarray(feats), np.asarray(other)
+    out = np.zeros((f.shape[0], o.shape[1]), dtype=f.dtype)
+    T_ = f.dtype.type
+    for p, (b, n) in enumerate(_ranges(pack_infos)):
+        for i in range(b, b + n):
+            for j in range(o.shape[1]):
+                acc = T_(0)
+                for k in range(f.shape[1]):
+                    acc = T_(np.float64(acc) + np.float64(f[i, k]) * np.float64(o[p, j, k])) if f.dtype == np.float32 else T_(acc + f[i, k] * o[p, j, k])
+                out[i, j] = acc
+    return out
+
+
 def pack_infos_from_counts(counts):
     c = np.asarray(counts, dtype=np.int64)
     return np.stack([np.cumsum(c) - c, c], 1)

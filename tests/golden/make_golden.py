@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from tests.util import LOTD_CONFIGS, lotd_inputs, load_ref, march_inputs, meta_args, pack_inputs  # noqa: E402
+from tests.util import LOTD_CONFIGS, lotd_inputs, load_ref, march_inputs, meta_args, pack_inputs, pack_next_inputs  # noqa: E402
 
 dev = torch.device("cuda:0")
 
@@ -100,6 +100,27 @@ def make_pack(out_dir):
     save(out_dir, "pack_ops", **out)
 
 
+def make_pack_next(out_dir):
+    ref = load_ref("_pack_ops")
+    d = pack_next_inputs()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    pi, pib = t(d["pack_infos"]), t(d["pack_infos_b"])
+    out = dict(d)
+    out["ss"] = npy(ref.packed_searchsorted(t(d["bins"]), t(d["vals_q"]), pi))
+    out["ss_packed"] = npy(ref.packed_searchsorted_packed_vals(t(d["bins"]), pi, t(d["vals_b"]), pib))
+    smp, bidx = ref.packed_invert_cdf(t(d["bins"]), t(d["cdfs"]), t(d["u"]), pi)
+    out["icdf_samples"], out["icdf_idx"] = npy(smp), npy(bidx)
+    pa, pb, pm = ref.try_merge_two_packs_sorted_aligned(t(d["bins"]), pi, t(d["vals_b"]), pib, True)
+    out["merge_a"], out["merge_b"], out["merge_pi"] = npy(pa), npy(pb), npy(pm)
+    pa2, pb2, _ = ref.try_merge_two_packs_sorted_aligned(t(d["bins"]), pi, t(d["vals_b"]), pib, False)
+    out["merge_a_unsorted_flag"], out["merge_b_unsorted_flag"] = npy(pa2), npy(pb2)
+    v = t(d["unsorted"]).clone()
+    idx = ref.packed_sort_qsort(v, pi, True)
+    out["sorted"], out["sort_idx"] = npy(v), npy(idx)
+    out["matmul"] = npy(ref.packed_matmul(t(d["feats"]), t(d["mats"]), pi))
+    save(out_dir, "pack_next", **out)
+
+
 def make_march(out_dir):
     ref = load_ref("_occ_grid")
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -135,10 +156,14 @@ def make_march(out_dir):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    ap.add_argument("--only", default="", help="comma separated subset of make_lotd,make_pack,make_pack_next,make_march")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     assert torch.cuda.is_available(), "golden vectors are produced by the reference CUDA build: a GPU is required"
-    for fn in (make_lotd, make_pack, make_march):
+    only = set(args.only.split(',')) if args.only else None
+    for fn in (make_lotd, make_pack, make_pack_next, make_march):
+        if only and fn.__name__ not in only:
+            continue
         try:
             fn(args.out)
         except Exception as e:  # keep going so one failing family does not lose the others

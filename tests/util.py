@@ -143,3 +143,26 @@ def rel_err(a, b):
     b = torch.as_tensor(b).double()
     denom = max(b.abs().max().item(), 1e-30)
     return ((a - b).abs().max().item() / denom) if a.numel() else 0.0
+
+
+def pack_next_inputs(P=29, max_len=60, nq=7, seed=0, min_len=2):
+    """Sorted packs, CDFs and queries for the hierarchical-sampling ops (searchsorted / invert_cdf / merge / sort / matmul)."""
+    rs = np.random.RandomState(seed)
+    n = rs.randint(min_len, max_len + 1, size=P).astype(np.int64)
+    nb = rs.randint(1, max_len // 2 + 1, size=P).astype(np.int64)
+    pi = np.stack([np.cumsum(n) - n, n], 1)
+    pib = np.stack([np.cumsum(nb) - nb, nb], 1)
+    bins = np.concatenate([np.sort(rs.rand(k)).astype(np.float32) + i for i, k in enumerate(n)])          # strictly increasing per pack
+    w = np.concatenate([rs.rand(k).astype(np.float32) + 0.01 for k in n])
+    cdfs = np.concatenate([(np.cumsum(w[b:b + k]) / w[b:b + k].sum()).astype(np.float32) for b, k in pi])
+    vals_q = (rs.rand(P, nq).astype(np.float32) * 1.2 - 0.1 + np.arange(P, dtype=np.float32)[:, None])   # some out of range on both sides
+    u = rs.rand(P, nq).astype(np.float32)
+    vals_b = np.concatenate([np.sort(rs.rand(k)).astype(np.float32) * 1.1 - 0.05 + i for i, k in enumerate(nb)])
+    # duplicates: copy a few bins values into b so that ties (b == a[i]) are exercised
+    for p in range(0, P, 3):
+        vals_b[pib[p, 0]] = bins[pi[p, 0] + n[p] // 2]
+        vals_b[pib[p, 0]:pib[p, 0] + nb[p]] = np.sort(vals_b[pib[p, 0]:pib[p, 0] + nb[p]])
+    unsorted = rs.randn(int(n.sum())).astype(np.float32)
+    feats = rs.randn(int(n.sum()), 3).astype(np.float32)
+    mats = rs.randn(P, 4, 3).astype(np.float32)
+    return dict(pack_infos=pi, pack_infos_b=pib, bins=bins, cdfs=cdfs, vals_q=vals_q, u=u, vals_b=vals_b, unsorted=unsorted, feats=feats, mats=mats)
