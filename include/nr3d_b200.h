@@ -218,6 +218,20 @@ int nr3d_pack_sort(int32_t dtype, uint64_t P, void* vals, const int64_t* pack_in
 int nr3d_pack_matmul(int32_t dtype, uint64_t P, uint32_t C, uint32_t C_out, const void* feats, const void* other, const int64_t* pack_infos,
                      void* out, void* stream);
 
+/* == interleave_sample_step_wrt_depth_in_packed_segments, pack_ops_cuda.cu:606-795 (two passes: per-ray step counts, then
+ *    t_samples / deltas / ray index / segment index written at the offsets of `pack_infos`). */
+int nr3d_pack_seg_sample_count(int32_t dtype, uint64_t P, const void* nears, const void* fars, const void* entries, const void* exits,
+                               const int64_t* seg_pack_infos, uint32_t max_steps, double dt_gamma, double min_step, double max_step,
+                               int64_t* n_per_pack, void* stream);
+int nr3d_pack_seg_sample_fill(int32_t dtype, uint64_t P, const void* nears, const void* fars, const void* entries, const void* exits,
+                              const int64_t* seg_pack_infos, const int64_t* pack_infos, double dt_gamma, double min_step, double max_step,
+                              void* t_samples, void* deltas, int64_t* nidx, int64_t* sidx, void* stream);
+/* == octree_mark_consecutive_segments, pack_ops_cuda.cu:2807-2885.  point_hierarchies: int16 [n_points, 3]; marks: bool (1 byte),
+ *    zero-initialised by the caller.  offset_fix = 0 reproduces the reference's un-offset `point_indices` walk. */
+int nr3d_pack_mark_consecutive_segments(uint64_t P, const int64_t* pack_infos, const int32_t* pidx, const int16_t* point_hierarchies,
+                                        int32_t offset_fix, uint8_t* mark_start, uint8_t* mark_end, void* stream);
+
+
 #ifdef __cplusplus
 }
 #endif

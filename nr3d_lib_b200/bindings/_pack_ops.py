@@ -5,8 +5,8 @@ interleave_sample_step_wrt_depth_clamped, packed_{add,sub,mul,div,gt,geq,lt,leq,
 packed_backward_diff, packed_cumsum, packed_cumprod, packed_alpha_to_vw_forward/backward, mark_pack_boundaries_cuda.
 Hierarchical-sampling ops: packed_searchsorted, packed_searchsorted_packed_vals,
 packed_invert_cdf, try_merge_two_packs_sorted_aligned, packed_sort_qsort / packed_sort_thrust, packed_matmul.
-Still raising RuntimeError: the deprecated depth sampler, interleave_sample_step_wrt_depth_in_packed_segments and
-octree_mark_consecutive_segments.
+Also: interleave_sample_step_wrt_depth_in_packed_segments, interleave_sample_step_wrt_depth_clamp_deprecated and
+octree_mark_consecutive_segments -- every name the reference module exports is implemented.
 """
 import ctypes
 from typing import Optional, Tuple
@@ -402,14 +402,71 @@ def packed_matmul(feats: torch.Tensor, other: torch.Tensor, pack_infos: torch.Te
     return out
 
 
-def _next_row(name):
-    def fn(*args, **kwargs):
-        raise RuntimeError(f"nr3d_lib_b200: `{name}` is a 'next' row of the hot-path scope table (SURVEY.md section 8f, n2) and "
-                           "is not implemented in the B200 build yet.")
-    fn.__name__ = name
-    return fn
+def interleave_sample_step_wrt_depth_clamp_deprecated(near: torch.Tensor, far: torch.Tensor, max_steps: int, dt_gamma: float,
+                                                      min_step_size: float, max_step_size: float):
+    """== interleave_sample_step_wrt_depth_clamp_deprecated (pack_ops_cuda.cu:226-396): the buffered two-storage variant of the
+    depth sampler; its compacted outputs equal `interleave_sample_step_wrt_depth_clamped`'s, so both share one implementation."""
+    return interleave_sample_step_wrt_depth_clamped(near, far, max_steps, dt_gamma, min_step_size, max_step_size)
 
 
-for _n in ("interleave_sample_step_wrt_depth_clamp_deprecated", "interleave_sample_step_wrt_depth_in_packed_segments",
-           "octree_mark_consecutive_segments"):   # forest / octree segment ops and the deprecated sampler
-    globals()[_n] = _next_row(_n)
+def interleave_sample_step_wrt_depth_in_packed_segments(near: torch.Tensor, far: torch.Tensor, entry: torch.Tensor, exit: torch.Tensor,
+                                                        seg_pack_infos: torch.Tensor, max_steps: int, dt_gamma: float, min_step_size: float,
+                                                        max_step_size: float):
+    """== interleave_sample_step_wrt_depth_in_packed_segments (pack_ops_cuda.cu:723-795)
+    -> (t_samples, deltas, sidx, nidx, pack_infos)."""
+    fn = "interleave_sample_step_wrt_depth_in_packed_segments"
+    for name, t_ in (("near", near), ("far", far), ("entry", entry), ("exit", exit)):
+        if t_.dim() != 1:
+            raise RuntimeError(f"{fn}: Expected 1-dimensional tensor for argument '{name}'")
+        if not t_.is_contiguous():
+            raise RuntimeError(f"{fn}: Expected contiguous tensor for argument '{name}'")
+        if t_.dtype != near.dtype:
+            raise RuntimeError(f"{fn}: Expected `{name}` to have the same scalar type as `near` ({near.dtype}), got {t_.dtype}")
+    if near.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError(f"{fn}: supported scalar types are Float and Double (Half: not built), got {near.dtype}")
+    _check_pack_infos(fn, seg_pack_infos)
+    if near.shape != far.shape or entry.shape != exit.shape or seg_pack_infos.shape[0] != near.shape[0]:
+        raise RuntimeError(f"{fn}: size mismatch between near/far [{near.shape[0]}], entry/exit [{entry.shape[0]}] and seg_pack_infos")
+    dev = _lib.require_cuda(near, far, entry, exit, seg_pack_infos, who=fn)
+    lib = _lib.get_lib()
+    P = near.shape[0]
+    code = _lib.dtype_code(near.dtype)
+    with torch.cuda.device(dev):
+        st = _lib.stream_of(dev)
+        n_per_pack = torch.empty([P], dtype=torch.int64, device=dev)
+        _lib.check(lib.nr3d_pack_seg_sample_count(code, P, near.data_ptr(), far.data_ptr(), _lib.ptr(entry), _lib.ptr(exit),
+                                                  seg_pack_infos.data_ptr(), int(max_steps), float(dt_gamma), float(min_step_size),
+                                                  float(max_step_size), n_per_pack.data_ptr(), st))
+        pack_infos, total = _pack_infos_from_counts(n_per_pack)
+        num = _total_from_device(total)
+        t_samples = torch.empty([num], dtype=near.dtype, device=dev)
+        deltas = torch.empty([num], dtype=near.dtype, device=dev)
+        nidx = torch.empty([num], dtype=torch.int64, device=dev)
+        sidx = torch.empty([num], dtype=torch.int64, device=dev)
+        _lib.check(lib.nr3d_pack_seg_sample_fill(code, P, near.data_ptr(), far.data_ptr(), _lib.ptr(entry), _lib.ptr(exit),
+                                                 seg_pack_infos.data_ptr(), pack_infos.data_ptr(), float(dt_gamma), float(min_step_size),
+                                                 float(max_step_size), _lib.ptr(t_samples), _lib.ptr(deltas), _lib.ptr(nidx), _lib.ptr(sidx), st))
+    return t_samples, deltas, sidx, nidx, pack_infos
+
+
+# octree_mark_consecutive_segments: the reference walks `point_indices` from element 0 for every pack (pack_ops_cuda.cu:2832-2833),
+# which is only right for the first pack.  Default reproduces it; set True to walk each pack's own nuggets.
+OCTREE_SEGMENTS_OFFSET_FIX = False
+
+
+def octree_mark_consecutive_segments(pidx: torch.Tensor, pack_infos: torch.Tensor, point_hierarchies: torch.Tensor):
+    """== octree_mark_consecutive_segments (pack_ops_cuda.cu:2843-2885) -> (mark_start, mark_end), bool [num_nuggets]."""
+    fn = "octree_mark_consecutive_segments"
+    if pidx.dim() != 1 or pidx.dtype != torch.int32 or not pidx.is_contiguous():
+        raise RuntimeError(f"{fn}: Expected contiguous 1-dimensional Int tensor for argument 'pidx'")
+    _check_pack_infos(fn, pack_infos)
+    if point_hierarchies.dtype != torch.int16 or not point_hierarchies.is_contiguous():
+        raise RuntimeError(f"{fn}: Expected contiguous Short tensor for argument 'point_hierarchies'")
+    dev = _lib.require_cuda(pidx, pack_infos, point_hierarchies, who=fn)
+    with torch.cuda.device(dev):
+        mark_start = torch.zeros([pidx.shape[0]], dtype=torch.bool, device=dev)
+        mark_end = torch.zeros([pidx.shape[0]], dtype=torch.bool, device=dev)
+        _lib.check(_lib.get_lib().nr3d_pack_mark_consecutive_segments(pack_infos.shape[0], pack_infos.data_ptr(), _lib.ptr(pidx),
+                                                                      _lib.ptr(point_hierarchies), int(OCTREE_SEGMENTS_OFFSET_FIX),
+                                                                      _lib.ptr(mark_start), _lib.ptr(mark_end), _lib.stream_of(dev)))
+    return mark_start, mark_end

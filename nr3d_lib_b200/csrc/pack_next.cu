@@ -221,6 +221,69 @@ pack_matmul_kernel(uint64_t P, uint32_t C, uint32_t Co, const T* __restrict__ fe
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// interleave_sample_step_wrt_depth_in_packed_segments (pack_ops_cuda.cu:606-795): depth-proportional stepping restricted to
+// the [entry, exit] segments of every ray.  Stepping is a serial recurrence per ray -> one thread per ray, two passes.
+// Quirks kept: the walk to a segment entry advances by min_step at least once per segment; max_steps bounds the ray total.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T clamp_next(T v, T lo, T hi) { return v < lo ? lo : (hi < v ? hi : v); }
+
+template <typename T, bool FILL>
+__global__ void __launch_bounds__(kNextThreads)
+seg_sample_kernel(uint64_t P, uint32_t max_steps, T dt_gamma, T min_step, T max_step, const T* __restrict__ nears, const T* __restrict__ fars,
+                  const T* __restrict__ entries, const T* __restrict__ exits, const int64_t* __restrict__ seg_pack_infos,
+                  const int64_t* __restrict__ pack_infos, int64_t* __restrict__ n_per_pack, T* __restrict__ t_samples, T* __restrict__ deltas,
+                  int64_t* __restrict__ nidx, int64_t* __restrict__ sidx) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const T near = nears[p], far = fars[p];
+    const uint64_t seg_begin = (uint64_t)seg_pack_infos[2 * p], seg_end = seg_begin + (uint64_t)seg_pack_infos[2 * p + 1];
+    uint64_t begin = 0;
+    uint32_t limit = max_steps;
+    if (FILL) { begin = (uint64_t)pack_infos[2 * p]; limit = (uint32_t)pack_infos[2 * p + 1]; }
+    T t = near;
+    uint32_t step = 0;
+    for (uint64_t i = seg_begin; i < seg_end; ++i) {
+        const T entry = entries[i], exit_ = exits[i];
+        if (entry >= far || exit_ <= near) break;
+        do { t += min_step; } while (t < entry);
+        while (t <= exit_ && t <= far && step < limit) {
+            const T dt = clamp_next<T>(t * dt_gamma, min_step, max_step);
+            if (FILL) {
+                t_samples[begin + step] = t;
+                deltas[begin + step] = dt;
+                nidx[begin + step] = (int64_t)p;
+                sidx[begin + step] = (int64_t)i;
+            }
+            t += dt;
+            step++;
+        }
+    }
+    if (!FILL) n_per_pack[p] = step;
+}
+
+// octree_mark_consecutive_segments (pack_ops_cuda.cu:2807-2841).  `offset_fix == 0` reproduces the reference, which indexes
+// `point_indices` from 0 for every pack (only the first pack sees its own nuggets); `offset_fix != 0` indexes from the pack's begin.
+__global__ void __launch_bounds__(kNextThreads)
+mark_consecutive_kernel(uint64_t P, const int64_t* __restrict__ pack_infos, const int32_t* __restrict__ pidx, const int16_t* __restrict__ points,
+                        int32_t offset_fix, uint8_t* __restrict__ mark_start, uint8_t* __restrict__ mark_end) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const uint64_t begin = (uint64_t)pack_infos[2 * p], len = (uint64_t)pack_infos[2 * p + 1];
+    if (len == 0) return;
+    const int32_t* pi = offset_fix ? pidx + begin : pidx;
+    mark_start[begin] = 1;
+    int32_t q = pi[0];
+    int px = points[3 * q], py = points[3 * q + 1], pz = points[3 * q + 2];
+    for (uint64_t j = 1; j < len; ++j) {
+        q = pi[j];
+        const int nx = points[3 * q], ny = points[3 * q + 1], nz = points[3 * q + 2];
+        if (abs(nx - px) + abs(ny - py) + abs(nz - pz) > 1) { mark_end[begin + j - 1] = 1; mark_start[begin + j] = 1; }
+        px = nx; py = ny; pz = nz;
+    }
+    mark_end[begin + len - 1] = 1;
+}
+
 static inline unsigned wgrid(uint64_t warps) { return (unsigned)div_up<uint64_t>(warps, kNextWarps); }
 
 #define NR3D_NEXT_DISPATCH(dtype, NAME, ...)                                                         \
@@ -290,6 +353,42 @@ int nr3d_pack_matmul(int32_t dtype, uint64_t P, uint32_t C, uint32_t C_out, cons
     NR3D_NEXT_DISPATCH_FLOAT(dtype, "packed_matmul",
         (pack_matmul_kernel<T><<<wgrid(P), kNextThreads, 0, (cudaStream_t)stream>>>(P, C, C_out, (const T*)feats, (const T*)other, pack_infos, (T*)out)));
     NR3D_LAUNCH_CHECK("packed_matmul");
+    return 0;
+}
+
+int nr3d_pack_seg_sample_count(int32_t dtype, uint64_t P, const void* nears, const void* fars, const void* entries, const void* exits,
+                               const int64_t* seg_pack_infos, uint32_t max_steps, double dt_gamma, double min_step, double max_step,
+                               int64_t* n_per_pack, void* stream) {
+    if (P == 0) return 0;
+    NR3D_CHECK(nears && fars && seg_pack_infos && n_per_pack, "interleave_sample_step_wrt_depth_in_packed_segments: null argument");
+    const unsigned grid = (unsigned)div_up<uint64_t>(P, kNextThreads);
+    NR3D_NEXT_DISPATCH_FLOAT(dtype, "interleave_sample_step_wrt_depth_in_packed_segments",
+        (seg_sample_kernel<T, false><<<grid, kNextThreads, 0, (cudaStream_t)stream>>>(P, max_steps, (T)dt_gamma, (T)min_step, (T)max_step, (const T*)nears,
+            (const T*)fars, (const T*)entries, (const T*)exits, seg_pack_infos, nullptr, n_per_pack, nullptr, nullptr, nullptr, nullptr)));
+    NR3D_LAUNCH_CHECK("seg_sample_count");
+    return 0;
+}
+
+int nr3d_pack_seg_sample_fill(int32_t dtype, uint64_t P, const void* nears, const void* fars, const void* entries, const void* exits,
+                              const int64_t* seg_pack_infos, const int64_t* pack_infos, double dt_gamma, double min_step, double max_step,
+                              void* t_samples, void* deltas, int64_t* nidx, int64_t* sidx, void* stream) {
+    if (P == 0) return 0;
+    NR3D_CHECK(nears && fars && seg_pack_infos && pack_infos, "interleave_sample_step_wrt_depth_in_packed_segments: null argument");
+    const unsigned grid = (unsigned)div_up<uint64_t>(P, kNextThreads);
+    NR3D_NEXT_DISPATCH_FLOAT(dtype, "interleave_sample_step_wrt_depth_in_packed_segments",
+        (seg_sample_kernel<T, true><<<grid, kNextThreads, 0, (cudaStream_t)stream>>>(P, 0u, (T)dt_gamma, (T)min_step, (T)max_step, (const T*)nears,
+            (const T*)fars, (const T*)entries, (const T*)exits, seg_pack_infos, pack_infos, nullptr, (T*)t_samples, (T*)deltas, nidx, sidx)));
+    NR3D_LAUNCH_CHECK("seg_sample_fill");
+    return 0;
+}
+
+int nr3d_pack_mark_consecutive_segments(uint64_t P, const int64_t* pack_infos, const int32_t* pidx, const int16_t* point_hierarchies,
+                                        int32_t offset_fix, uint8_t* mark_start, uint8_t* mark_end, void* stream) {
+    if (P == 0) return 0;
+    NR3D_CHECK(pack_infos && pidx && point_hierarchies && mark_start && mark_end, "octree_mark_consecutive_segments: null argument");
+    mark_consecutive_kernel<<<(unsigned)div_up<uint64_t>(P, kNextThreads), kNextThreads, 0, (cudaStream_t)stream>>>(P, pack_infos, pidx,
+        point_hierarchies, offset_fix, mark_start, mark_end);
+    NR3D_LAUNCH_CHECK("octree_mark_consecutive_segments");
     return 0;
 }
 

@@ -16,7 +16,7 @@ __all__ = ['packed_sort_inplace', 'packed_sort', 'packed_searchsorted', 'packed_
            'packed_alpha_to_vw', 'packed_volume_render_compression', 'packed_add', 'packed_sub', 'packed_mul', 'packed_div',
            'packed_gt', 'packed_geq', 'packed_lt', 'packed_leq', 'packed_eq', 'packed_neq', 'interleave_arange_simple',
            'interleave_arange', 'interleave_linstep', 'interleave_linspace', 'interleave_sample_step_wrt_depth_clamped',
-           'get_pack_infos_from_boundary', 'get_pack_infos_from_first', 'get_pack_infos_from_n', 'get_pack_infos_from_batch',
+           'interleave_sample_step_wrt_depth_in_packed_segments', 'get_pack_infos_from_boundary', 'get_pack_infos_from_first', 'get_pack_infos_from_n', 'get_pack_infos_from_batch',
            'mark_pack_boundaries', 'expand_pack_boundary']
 
 
@@ -390,6 +390,26 @@ def interleave_sample_step_wrt_depth_clamped(near, far, max_steps: int = 512, dt
         last = pack_infos[..., 0] + pack_infos[..., 1] - 1
         deltas = t_samples.diff(append=t_samples.new_empty([1])).index_put_((last,), deltas[last])
     return t_samples, deltas, ridx, pack_infos
+
+
+@torch.no_grad()
+def interleave_sample_step_wrt_depth_in_packed_segments(near, far, entry: torch.Tensor, exit: torch.Tensor, seg_pack_infos: torch.Tensor,
+                                                        max_steps: int = 512, dt_gamma: float = 0.01, min_step_size: float = 0.01,
+                                                        max_step_size: float = 1e10, step_size_factor: float = 1.0, perturb=False):
+    """reference pack_ops.py:476-499 -> (t_samples, deltas, ridx, ray_pack_infos, sidx, out_seg_pack_infos)"""
+    num_rays = seg_pack_infos.shape[0]
+    near = entry.new_full([num_rays], near) if not isinstance(near, torch.Tensor) else near
+    far = entry.new_full([num_rays], far) if not isinstance(far, torch.Tensor) else far
+    t_samples, deltas, sidx, ridx, ray_pack_infos = _backend.interleave_sample_step_wrt_depth_in_packed_segments(
+        near.contiguous(), far.contiguous(), entry.contiguous(), exit.contiguous(), seg_pack_infos.contiguous(), max_steps,
+        dt_gamma * step_size_factor, min_step_size * step_size_factor, max_step_size * step_size_factor)
+    out_seg_pack_infos = get_pack_infos_from_boundary(mark_pack_boundaries(sidx))
+    if perturb:
+        noise = torch.rand_like(deltas)
+        t_samples = torch.addcmul(t_samples, noise, deltas)
+        last = ray_pack_infos[..., 0] + ray_pack_infos[..., 1] - 1
+        deltas = t_samples.diff(append=t_samples.new_empty([1])).index_put_((last,), deltas[last])
+    return t_samples, deltas, ridx, ray_pack_infos, sidx, out_seg_pack_infos
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -315,6 +315,52 @@ def packed_matmul(feats, other, pack_infos):
     return out
 
 
+def sample_step_in_packed_segments(near, far, entry, exit_, seg_pack_infos, max_steps, dt_gamma, min_step, max_step):
+    """pack_ops_cuda.cu:606-721 -> (t_samples, deltas, sidx, nidx, pack_infos)."""
+    near, far, entry, exit_ = (np.asarray(a) for a in (near, far, entry, exit_))
+    T_ = near.dtype.type
+    g, lo, hi = T_(dt_gamma), T_(min_step), T_(max_step)
+    clamp = lambda v: lo if v < lo else (hi if hi < v else v)
+    ts, ds, si, ni, counts = [], [], [], [], []
+    for p, (sb, sn) in enumerate(_ranges(seg_pack_infos)):
+        t, n = near[p], 0
+        for i in range(sb, sb + sn):
+            if entry[i] >= far[p] or exit_[i] <= near[p]:
+                break
+            while True:                       # do { t += min_step } while (t < entry)
+                t = T_(t + lo)
+                if not (t < entry[i]):
+                    break
+            while t <= exit_[i] and t <= far[p] and n < max_steps:
+                dt = clamp(T_(t * g))
+                ts.append(t); ds.append(dt); si.append(i); ni.append(p)
+                t = T_(t + dt)
+                n += 1
+        counts.append(n)
+    counts = np.asarray(counts, dtype=np.int64)
+    pack_infos = np.stack([np.cumsum(counts) - counts, counts], 1)
+    return (np.asarray(ts, dtype=near.dtype), np.asarray(ds, dtype=near.dtype), np.asarray(si, dtype=np.int64),
+            np.asarray(ni, dtype=np.int64), pack_infos)
+
+
+def octree_mark_consecutive_segments(pidx, pack_infos, points, offset_fix=False):
+    """pack_ops_cuda.cu:2807-2841; offset_fix=False keeps the reference's un-offset walk over `point_indices`."""
+    pidx, points = np.asarray(pidx), np.asarray(points).astype(np.int64)
+    ms = np.zeros(pidx.shape[0], dtype=bool)
+    me = np.zeros(pidx.shape[0], dtype=bool)
+    for (b, n) in _ranges(pack_infos):
+        if n == 0:
+            continue
+        pi = pidx[b:] if offset_fix else pidx
+        ms[b] = True
+        for j in range(1, n):
+            if np.abs(points[pi[j]] - points[pi[j - 1]]).sum() > 1:
+                me[b + j - 1] = True
+                ms[b + j] = True
+        me[b + n - 1] = True
+    return ms, me
+
+
 def pack_infos_from_counts(counts):
     c = np.asarray(counts, dtype=np.int64)
     return np.stack([np.cumsum(c) - c, c], 1)

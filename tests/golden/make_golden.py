@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from tests.util import LOTD_CONFIGS, lotd_inputs, load_ref, march_inputs, meta_args, pack_inputs, pack_next_inputs  # noqa: E402
+from tests.util import LOTD_CONFIGS, lotd_inputs, load_ref, march_inputs, meta_args, pack_inputs, pack_next_inputs, seg_inputs  # noqa: E402
 
 dev = torch.device("cuda:0")
 
@@ -121,6 +121,22 @@ def make_pack_next(out_dir):
     save(out_dir, "pack_next", **out)
 
 
+def make_pack_seg(out_dir):
+    ref = load_ref("_pack_ops")
+    d = seg_inputs()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = dict(d)
+    cfg = (48, 0.05, 0.02, 0.3)
+    ts, ds, sidx, nidx, pi = ref.interleave_sample_step_wrt_depth_in_packed_segments(t(d["near"]), t(d["far"]), t(d["entry"]), t(d["exit"]),
+                                                                                      t(d["seg_pack_infos"]), *cfg)
+    out.update(cfg=np.array(cfg, dtype=np.float64), seg_t=npy(ts), seg_d=npy(ds), seg_sidx=npy(sidx), seg_nidx=npy(nidx), seg_pi=npy(pi))
+    ts, ds, nidx, pi = ref.interleave_sample_step_wrt_depth_clamp_deprecated(t(d["near"]), t(d["far"]), *cfg)
+    out.update(dep_t=npy(ts), dep_d=npy(ds), dep_nidx=npy(nidx), dep_pi=npy(pi))
+    ms, me = ref.octree_mark_consecutive_segments(t(d["pidx"]), t(d["oct_pack_infos"]), t(d["points"]))
+    out.update(mark_start=npy(ms), mark_end=npy(me))
+    save(out_dir, "pack_seg", **out)
+
+
 def make_march(out_dir):
     ref = load_ref("_occ_grid")
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -161,7 +177,7 @@ if __name__ == "__main__":
     os.makedirs(args.out, exist_ok=True)
     assert torch.cuda.is_available(), "golden vectors are produced by the reference CUDA build: a GPU is required"
     only = set(args.only.split(',')) if args.only else None
-    for fn in (make_lotd, make_pack, make_pack_next, make_march):
+    for fn in (make_lotd, make_pack, make_pack_next, make_pack_seg, make_march):
         if only and fn.__name__ not in only:
             continue
         try:

@@ -114,3 +114,97 @@ def test_gpu_host_mirror_and_edges(dev):
     assert np.array_equal(vi.cpu().numpy(), PO.packed_sort(ints, d["pack_infos"])[0])
     s64, i64 = P.packed_invert_cdf(t(d["bins"].astype(np.float64)), t(d["cdfs"].astype(np.float64)), t(d["u"].astype(np.float64)), pi)
     assert np.array_equal(i64.cpu().numpy(), PO.packed_invert_cdf(d["bins"].astype(np.float64), d["cdfs"].astype(np.float64), d["u"].astype(np.float64), d["pack_infos"])[1])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# segment-restricted depth sampler, deprecated depth sampler, octree consecutive-segment marker
+# ------------------------------------------------------------------------------------------------------------------
+from tests.util import seg_inputs  # noqa: E402
+
+SEG_CFG = (48, 0.05, 0.02, 0.3)
+
+
+def _seg_oracle(d, cfg=SEG_CFG):
+    o = {}
+    o["seg_t"], o["seg_d"], o["seg_sidx"], o["seg_nidx"], o["seg_pi"] = PO.sample_step_in_packed_segments(
+        d["near"], d["far"], d["entry"], d["exit"], d["seg_pack_infos"], *cfg)
+    o["dep_t"], o["dep_d"], o["dep_nidx"], o["dep_pi"] = PO.sample_step_wrt_depth_clamped(d["near"], d["far"], *cfg)
+    o["mark_start"], o["mark_end"] = PO.octree_mark_consecutive_segments(d["pidx"], d["oct_pack_infos"], d["points"])
+    return o
+
+
+def _seg_gpu(be, d, dev, cfg=SEG_CFG):
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    o = {}
+    o["seg_t"], o["seg_d"], o["seg_sidx"], o["seg_nidx"], o["seg_pi"] = be.interleave_sample_step_wrt_depth_in_packed_segments(
+        t(d["near"]), t(d["far"]), t(d["entry"]), t(d["exit"]), t(d["seg_pack_infos"]), *cfg)
+    o["dep_t"], o["dep_d"], o["dep_nidx"], o["dep_pi"] = be.interleave_sample_step_wrt_depth_clamp_deprecated(t(d["near"]), t(d["far"]), *cfg)
+    o["mark_start"], o["mark_end"] = be.octree_mark_consecutive_segments(t(d["pidx"]), t(d["oct_pack_infos"]), t(d["points"]))
+    return {k: v.cpu().numpy() for k, v in o.items()}
+
+
+def _seg_check(got, want):
+    for k in ("seg_t", "seg_d", "seg_sidx", "seg_nidx", "seg_pi", "dep_t", "dep_d", "dep_nidx", "dep_pi", "mark_start", "mark_end"):
+        assert np.array_equal(got[k], want[k]), k            # bit-exact: no fused operation on this path
+
+
+def test_seg_oracle_vs_golden():
+    g = golden("pack_seg")
+    if g is None:
+        pytest.skip("golden fixture missing")
+    _seg_check(_seg_oracle(g), g)
+    assert g["seg_t"].shape[0] > 100 and g["mark_end"].sum() > 41
+
+
+def test_seg_oracle_properties():
+    d = seg_inputs(seed=7)
+    o = _seg_oracle(d)
+    near, far = d["near"][o["seg_nidx"]], d["far"][o["seg_nidx"]]
+    assert np.all(o["seg_t"] <= far) and np.all(o["seg_t"] > near)
+    assert np.all(o["seg_t"] <= d["exit"][o["seg_sidx"]]) and np.all(o["seg_t"] >= d["entry"][o["seg_sidx"]])
+    assert np.all(o["seg_pi"][:, 1] <= SEG_CFG[0])
+    fixed = PO.octree_mark_consecutive_segments(d["pidx"], d["oct_pack_infos"], d["points"], offset_fix=True)
+    assert fixed[0].sum() == fixed[1].sum() >= d["oct_pack_infos"].shape[0]
+
+
+@pytest.mark.gpu
+def test_seg_gpu_vs_golden(dev):
+    from nr3d_lib_b200.bindings import _pack_ops
+    g = golden("pack_seg")
+    if g is None:
+        pytest.skip("golden fixture missing")
+    _seg_check(_seg_gpu(_pack_ops, g, dev), g)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,max_segs,seed", [(100, 4, 1), (5000, 9, 2)])
+def test_seg_gpu_vs_oracle_and_reference(P, max_segs, seed, dev):
+    from nr3d_lib_b200.bindings import _pack_ops
+    d = seg_inputs(P=P, max_segs=max_segs, seed=seed, n_points=500)
+    got = _seg_gpu(_pack_ops, d, dev)
+    if P <= 1000:
+        _seg_check(got, _seg_oracle(d))
+    ref = load_ref("_pack_ops")
+    if ref is not None:
+        _seg_check(got, _seg_gpu(ref, d, dev))
+    _pack_ops.OCTREE_SEGMENTS_OFFSET_FIX = True
+    try:
+        ms, me = _pack_ops.octree_mark_consecutive_segments(*(torch.from_numpy(d[k]).to(dev) for k in ("pidx", "oct_pack_infos", "points")))
+    finally:
+        _pack_ops.OCTREE_SEGMENTS_OFFSET_FIX = False
+    want = PO.octree_mark_consecutive_segments(d["pidx"], d["oct_pack_infos"], d["points"], offset_fix=True)
+    assert np.array_equal(ms.cpu().numpy(), want[0]) and np.array_equal(me.cpu().numpy(), want[1])
+
+
+@pytest.mark.gpu
+def test_seg_host_mirror(dev):
+    from nr3d_lib_b200 import pack_ops as P
+    d = seg_inputs(seed=9)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    ts, ds, ridx, rpi, sidx, spi = P.interleave_sample_step_wrt_depth_in_packed_segments(
+        t(d["near"]), t(d["far"]), t(d["entry"]), t(d["exit"]), t(d["seg_pack_infos"]), max_steps=48, dt_gamma=0.05, min_step_size=0.02, max_step_size=0.3)
+    o = _seg_oracle(d)
+    assert np.array_equal(ts.cpu().numpy(), o["seg_t"]) and np.array_equal(rpi.cpu().numpy(), o["seg_pi"])
+    assert int(spi[:, 1].sum()) == ts.shape[0]
+    ts2 = P.interleave_sample_step_wrt_depth_in_packed_segments(0.1, 5.0, t(d["entry"]), t(d["exit"]), t(d["seg_pack_infos"]), perturb=True)[0]
+    assert torch.isfinite(ts2).all()

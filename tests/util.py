@@ -166,3 +166,31 @@ def pack_next_inputs(P=29, max_len=60, nq=7, seed=0, min_len=2):
     feats = rs.randn(int(n.sum()), 3).astype(np.float32)
     mats = rs.randn(P, 4, 3).astype(np.float32)
     return dict(pack_infos=pi, pack_infos_b=pib, bins=bins, cdfs=cdfs, vals_q=vals_q, u=u, vals_b=vals_b, unsorted=unsorted, feats=feats, mats=mats)
+
+
+def seg_inputs(P=41, max_segs=6, seed=0, n_points=64):
+    """Rays with sorted, disjoint [entry, exit] segments (some before near / after far, some rays without segments) for the
+    in-packed-segments sampler, plus octree nuggets (point indices into an int16 xyz table) for the consecutive-segment marker."""
+    rs = np.random.RandomState(seed)
+    n = rs.randint(0, max_segs + 1, size=P).astype(np.int64)
+    n[0] = max(n[0], 1)
+    n[-1] = max(n[-1], 1)            # the reference reads seg_pack_infos[-1] to size-check `entry`
+    spi = np.stack([np.cumsum(n) - n, n], 1)
+    entry, exit_ = [], []
+    for k in n:
+        cuts = np.sort(rs.rand(2 * k).astype(np.float32) * 6.0 + 0.05)
+        entry.append(cuts[0::2]); exit_.append(cuts[1::2])
+    entry = np.concatenate(entry).astype(np.float32) if n.sum() else np.zeros(0, np.float32)
+    exit_ = np.concatenate(exit_).astype(np.float32) if n.sum() else np.zeros(0, np.float32)
+    near = (rs.rand(P) * 1.5).astype(np.float32)
+    far = (near + rs.rand(P).astype(np.float32) * 5.0 + 0.2).astype(np.float32)
+    # octree nuggets: walks on the integer lattice with occasional jumps
+    points = rs.randint(0, 16, size=(n_points, 3)).astype(np.int16)
+    for i in range(1, n_points):
+        if rs.rand() < 0.7:
+            step = np.zeros(3, np.int16); step[rs.randint(3)] = rs.choice([-1, 1])
+            points[i] = points[i - 1] + step
+    ln = rs.randint(1, 9, size=P).astype(np.int64)
+    opi = np.stack([np.cumsum(ln) - ln, ln], 1)
+    pidx = np.concatenate([np.sort(rs.randint(0, n_points, size=k)) for k in ln]).astype(np.int32)
+    return dict(seg_pack_infos=spi, entry=entry, exit=exit_, near=near, far=far, points=points, oct_pack_infos=opi, pidx=pidx)
