@@ -150,6 +150,32 @@ int nr3d_march_fill(uint64_t n_rays, const float* rays_o, const float* rays_d, c
                     int32_t* gidx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * occupancy value-grid maintenance.  Replaces the torch + torch_scatter compositions of
+ * nr3d_lib/models/accelerations/occgrid/utils.py:18-133 and ema_single.py:186-218.  Grids are [B, rx, ry, rz] (z fastest).
+ * ---------------------------------------------------------------------------------------------- */
+/* Pass 1 of update_[batched_]occ_val_grid[_idx]_ (utils.py:93-133): scratch[cell(i)] = max(scratch, ordered_bits(vals[i])).
+ * Exactly one of pts ([N,3] f32 in [-1,1], cell = ((p/2+0.5)*res).long().clamp(0,res-1)) / gidx ([N,3] i64).
+ * bidx: [N] i64 or NULL; with NULL and batch_data_size > 0 the batch of point i is i / batch_data_size.
+ * scratch: u32 [B*rx*ry*rz], all zero on entry (nr3d_occ_apply leaves it all zero again). */
+int nr3d_occ_scatter_max(uint64_t N, const float* pts, const int64_t* gidx, const int64_t* bidx, uint64_t batch_data_size,
+                         const float* vals, uint32_t B, const int32_t* res, uint32_t* scratch, void* stream);
+/* Pass 2: for every touched cell grid = max(ema_decay * grid, scattered max) (utils.py:101-102), scratch reset to zero;
+ * write_occ != 0 also writes occ = grid > occ_thre (binarize, utils.py:84-87); sum != NULL accumulates the sum of the updated
+ * grid (f64, must be zero on entry) for the mean-relative threshold. */
+int nr3d_occ_apply(uint64_t n_cells, float* grid, uint32_t* scratch, float ema_decay, int32_t write_occ, float occ_thre,
+                   uint8_t* occ, double* sum, void* stream);
+/* == binarize (utils.py:84-87): occ = grid > (consider_mean ? min(sum/n - eps, occ_thre) : occ_thre). */
+int nr3d_occ_binarize(uint64_t n_cells, const float* grid, float occ_thre, int32_t consider_mean, float eps, const double* sum,
+                      uint8_t* occ, void* stream);
+/* == arithmetic of sample_pts_in_voxels (utils.py:18-39): pts[i] = ((gidx[v] + offsets[i]) / res) * 2 - 1 with v = vidx[i]
+ *    (random voxel per point) or i / n_per_vox (vidx == NULL); the random offsets / voxel picks stay the caller's RNG. */
+int nr3d_occ_sample_in_voxels(uint64_t n_pts, const int64_t* gidx, const int64_t* vidx, uint64_t n_per_vox, const float* offsets,
+                              const int32_t* res, float* pts, int64_t* vidx_out, void* stream);
+/* == query (ema_single.py:214-218, ema_batched.py): out[i] = occ[b(i), cell(pts[i])]; out-of-range batch -> 0. */
+int nr3d_occ_query(uint64_t N, const float* pts, const int64_t* bidx, uint64_t batch_data_size, uint32_t B, const int32_t* res,
+                   const uint8_t* occ, uint8_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * pack_ops (replaces nr3d_lib.bindings._pack_ops, csrc/pack_ops/pack_ops.cpp:20-58)
  * pack_infos: int64 [P, 2] = (first index, length).  feats: [S, C] contiguous (C = 1 for 1-D tensors).
  * ---------------------------------------------------------------------------------------------- */

@@ -84,6 +84,11 @@ SIGNATURES = {
     "nr3d_pack_merge_sorted_aligned": [_i32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "nr3d_pack_sort": [_i32, _u64, _vp, _vp, _vp, _vp],
     "nr3d_pack_matmul": [_i32, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp],
+    "nr3d_occ_scatter_max": [_u64, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp, _vp],
+    "nr3d_occ_apply": [_u64, _vp, _vp, _f32, _i32, _f32, _vp, _vp, _vp],
+    "nr3d_occ_binarize": [_u64, _vp, _f32, _i32, _f32, _vp, _vp, _vp],
+    "nr3d_occ_sample_in_voxels": [_u64, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp],
+    "nr3d_occ_query": [_u64, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp],
     "nr3d_pack_seg_sample_count": [_i32, _u64, _vp, _vp, _vp, _vp, _vp, _u32, _f64, _f64, _f64, _vp, _vp],
     "nr3d_pack_seg_sample_fill": [_i32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _vp, _vp, _vp, _vp, _vp],
     "nr3d_pack_mark_consecutive_segments": [_u64, _vp, _vp, _vp, _i32, _vp, _vp, _vp],

@@ -168,6 +168,28 @@ def pack_next_inputs(P=29, max_len=60, nq=7, seed=0, min_len=2):
     return dict(pack_infos=pi, pack_infos_b=pib, bins=bins, cdfs=cdfs, vals_q=vals_q, u=u, vals_b=vals_b, unsorted=unsorted, feats=feats, mats=mats)
 
 
+def occ_inputs(res=(16, 12, 20), N=3000, B=3, seed=0):
+    """Value grids + update samples for the occupancy-grid maintenance ops (single + batched, points and voxel indices)."""
+    rs = np.random.RandomState(seed)
+    r = np.array(res)
+    grid = rs.rand(*res).astype(np.float32)
+    bgrid = rs.rand(B, *res).astype(np.float32)
+    pts = (rs.rand(N, 3) * 2.1 - 1.05).astype(np.float32)        # a few outside [-1,1]: exercises the clamp
+    pts[:8] = np.array([-1.0, 1.0, 0.0])[rs.randint(0, 3, size=(8, 3))]   # exactly on cell / domain borders
+    vals = (rs.rand(N) * 1.2 - 0.1).astype(np.float32)
+    vals[rs.rand(N) < 0.2] *= -1.0                                 # negative values (raw sdf occupancy can be negative)
+    gidx = np.stack([rs.randint(0, k, size=N) for k in res], 1).astype(np.int64)
+    gidx[N // 2:] = gidx[: N - N // 2]                             # many duplicates -> the max matters
+    bidx = rs.randint(0, B, size=N).astype(np.int64)
+    n = N // B
+    bpts = (rs.rand(B, n, 3) * 2 - 1).astype(np.float32)
+    bgidx = np.stack([rs.randint(0, k, size=(B, n)) for k in res], -1).astype(np.int64)
+    bvals = rs.rand(B, n).astype(np.float32)
+    vox = np.stack(np.nonzero(rs.rand(*res) > 0.8), 1).astype(np.int64)
+    return dict(grid=grid, bgrid=bgrid, pts=pts, vals=vals, gidx=gidx, bidx=bidx, bpts=bpts, bgidx=bgidx, bvals=bvals, vox=vox,
+                ema=np.float32(0.9), thre=np.float32(0.55))
+
+
 def seg_inputs(P=41, max_segs=6, seed=0, n_points=64):
     """Rays with sorted, disjoint [entry, exit] segments (some before near / after far, some rays without segments) for the
     in-packed-segments sampler, plus octree nuggets (point indices into an int16 xyz table) for the consecutive-segment marker."""
