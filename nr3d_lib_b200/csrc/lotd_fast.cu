@@ -43,9 +43,13 @@ namespace nr3d {
 #ifndef NR3D_BWD_THREADS
 #define NR3D_BWD_THREADS 128
 #endif
+#ifndef NR3D_FAST_PAIR      // 1: two lanes per point (default), 0: one thread per point (kept for A/B runs)
+#define NR3D_FAST_PAIR 1
+#endif
 constexpr uint32_t kBinRes = NR3D_BIN_RES;               // bins per axis of the point sort
 constexpr uint32_t kBins = kBinRes * kBinRes * kBinRes;  // 2 Mi bins (8 MB of counters)
 constexpr int kFastThreads = NR3D_FWD_THREADS;
+constexpr int kBwdThreads = NR3D_BWD_THREADS;
 constexpr int kScanBlockF = 1024;
 
 __device__ __forceinline__ uint32_t bin_key(float x, float y, float z) {
@@ -149,6 +153,7 @@ struct FastIn {
     uint32_t base_aligned16;  // params pointer is 16-byte aligned
 };
 
+#if !NR3D_FAST_PAIR  // ---- one thread per point (round-1 v3 kernels), compiled only for A/B runs ----
 constexpr int kRowStride = 33;  // floats per staged row (32 features + 1 pad: conflict-free for row and column access)
 
 // The 8 corners are handled as 4 pairs (a, b) of memory neighbours:
@@ -297,8 +302,6 @@ __device__ __forceinline__ void scatter_pair(float* tbl, const Geo& g, int q, fl
     }
 }
 
-constexpr int kBwdThreads = NR3D_BWD_THREADS;
-
 __global__ void __launch_bounds__(kBwdThreads)
 lotd_fast_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, const float* __restrict__ dLdy, int64_t gs_n, int64_t gs_f,
                      float* __restrict__ grad) {
@@ -388,6 +391,213 @@ lotd_fast_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
     }
 }
 
+#endif  // !NR3D_FAST_PAIR
+
+// ------------------------------------------------------------------------------------------------------------
+// "pair" layout (default).  Measured on B200 (scripts/ubench_pair.cu -> profiles/r1_ubench_pair.txt): a warp-wide gather
+// costs one LSU slot per DISTINCT 128-BYTE LINE (two lanes in one line, even in different sectors: 572 G lanes/s vs 287),
+// a warp-wide red.global costs one L2 slot per DISTINCT 32-BYTE SECTOR (two lanes in one sector: 460 G lanes/s vs 231).
+// The two corners of a Hash level that differ in x sit at (x ^ h) and ((x+1) ^ h): the same 128-byte line 15/16 of the time
+// and the same sector 3/4 of the time, for odd x as well -- which the one-thread-per-point layout above can only exploit
+// for even x (16-byte accesses).  So here TWO ADJACENT LANES share one point: lane side s handles the four corners with
+// x + s (Hash) or z + s (Dense, z fastest), the pair's partial sums meet with one shuffle, and the hardware coalesces the
+// pair's accesses.  Hash-level cost drops from 6 to ~4.25 lines (gather) and from 6 to 5 sectors (reduction) per point.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kPairRowStride = 34;   // floats per staged row: row k starts at bank 2k -> conflict-free pair writes and row reads
+constexpr int kPairTileStride = 12;  // floats per lane in the run-merge tile (8 used): conflict-free 16-byte stores
+
+struct Geo2 {
+    uint32_t key;   // cell key (10 bits per axis) for run detection
+    float w[4];     // n-linear weights of this lane's four corners
+    uint32_t e[4];  // element offsets (floats, from the start of the parameter array) of their feature pairs
+};
+
+__device__ __forceinline__ void pair_geo(const LevelDesc& L, uint32_t gfo, bool smooth, float x, float y, float z, uint32_t side, Geo2& g) {
+    const uint32_t Ry = L.res[1], Rz = L.res[2];
+    float p[3];
+    uint32_t c[3];
+    const float xv[3] = {x, y, z};
+    const uint32_t R[3] = {L.res[0], Ry, Rz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float sc = (float)(R[d] - 2u);
+        float v = xv[d] * sc + 0.5f;
+        const float fl = floorf(v);
+        c[d] = (uint32_t)fl;
+        v -= (float)c[d];
+        p[d] = smooth ? v * v * (3.0f - 2.0f * v) : v;
+    }
+    g.key = c[0] | (c[1] << 10) | (c[2] << 20);
+    const float wx[2] = {1.0f - p[0], p[0]}, wy[2] = {1.0f - p[1], p[1]}, wz[2] = {1.0f - p[2], p[2]};
+    const uint32_t nf = L.n_feat;
+    const uint32_t base = L.offset + gfo;
+    if (L.type == NR3D_LOD_DENSE) {
+        const float wzs = side ? wz[1] : wz[0];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t dx = q & 1, dy = q >> 1;
+            const uint32_t cell = ((c[0] + dx) * Ry + (c[1] + dy)) * Rz + c[2] + side;  // uint32 arithmetic as in the reference
+            g.e[q] = base + cell * nf;
+            g.w[q] = (wx[dx] * wy[dy]) * wzs;
+        }
+    } else {  // Hash
+        const uint32_t size = L.size;
+        const bool pow2 = (size & (size - 1u)) == 0;
+        const uint32_t hx = c[0] + side;
+        const float wxs = side ? wx[1] : wx[0];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t dy = q & 1, dz = q >> 1;
+            const uint32_t hyz = ((c[1] + dy) * 2654435761u) ^ ((c[2] + dz) * 805459861u);
+            const uint32_t h = pow2 ? ((hx ^ hyz) & (size - 1u)) : ((hx ^ hyz) % size);
+            g.e[q] = base + h * nf;
+            g.w[q] = (wxs * wy[dy]) * wz[dz];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFastThreads)
+lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, float* __restrict__ y, int64_t ys_n, int64_t ys_f) {
+    __shared__ float rows[kFastThreads / 32][16 * kPairRowStride];
+    const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const bool active = p < in.N;
+    const int lane = threadIdx.x & 31;
+    const uint32_t side = lane & 1;
+    const int k = lane >> 1;  // point slot inside the warp
+    float* myrows = rows[threadIdx.x >> 5];
+    float4 rec = make_float4(0.5f, 0.5f, 0.5f, 0.f);
+    if (active) rec = __ldcs(in.xs + p);
+    const float x = rec.x, yv = rec.y, z = rec.z;
+    const uint64_t i = __float_as_uint(rec.w);
+    const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
+    const bool staged = (ys_f == 1);
+    uint32_t chunk_base = 0;
+    constexpr int kFwdUnroll = NR3D_FWD_UNROLL;
+#pragma unroll kFwdUnroll
+    for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
+        const uint32_t level = tab.map_level[pl];
+        float r0 = 0.f, r1 = 0.f;
+        if ((int32_t)level <= in.max_level) {
+            Geo2 g;
+            pair_geo(tab.lv[level], (uint32_t)tab.map_cnt[pl] * 2u, smooth, x, yv, z, side, g);
+            float2 v[4];  // all four loads are issued before the first use
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float2*>(in.params + g.e[q]));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { r0 += g.w[q] * v[q].x; r1 += g.w[q] * v[q].y; }
+            r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
+            r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+        }
+        const float mine = side ? r1 : r0;  // lane `side` owns feature 2 * pl + side of its point
+        if (staged) {
+            const uint32_t c = pl * 2u - chunk_base;
+            myrows[k * kPairRowStride + c + side] = mine;
+            const bool last = (pl + 1 == tab.n_pseudo);
+            if (c + 2 == 32 || last) {  // flush the chunk: one coalesced row store per point of the warp
+                const uint32_t width = c + 2;
+                __syncwarp();
+#pragma unroll 4
+                for (int r = 0; r < 16; ++r) {
+                    const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * r);
+                    const bool ok = __shfl_sync(0xffffffffu, (int)active, 2 * r);
+                    if (ok && (uint32_t)lane < width) __stcs(y + (int64_t)ir * ys_n + chunk_base + lane, myrows[r * kPairRowStride + lane]);
+                }
+                __syncwarp();
+                chunk_base += 32;
+            }
+        } else if (active) {
+            __stcs(y + (int64_t)i * ys_n + (int64_t)(pl * 2 + side) * ys_f, mine);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBwdThreads)
+lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, const float* __restrict__ dLdy, int64_t gs_n, int64_t gs_f,
+                     float* __restrict__ grad) {
+    __shared__ __align__(16) float tile[kBwdThreads / 32][32 * kPairTileStride];
+    __shared__ float rows[kBwdThreads / 32][16 * kPairRowStride];
+    const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const bool active = p < in.N;
+    const int lane = threadIdx.x & 31;
+    const uint32_t side = lane & 1;
+    const int k = lane >> 1;
+    float* mytile = tile[threadIdx.x >> 5];
+    float* myrows = rows[threadIdx.x >> 5];
+    float4 rec = make_float4(0.5f, 0.5f, 0.5f, 0.f);
+    if (active) rec = __ldcs(in.xs + p);
+    const float x = rec.x, yv = rec.y, z = rec.z;
+    const uint64_t i = __float_as_uint(rec.w);
+    const float* grow = dLdy + (int64_t)i * gs_n;
+    const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
+    const bool staged = (gs_f == 1);
+    uint32_t chunk_base = 0;
+    for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
+        const uint32_t level = tab.map_level[pl];
+        float g0 = 0.f, g1 = 0.f;
+        if (staged) {
+            if (pl * 2u == chunk_base + 32u) chunk_base += 32u;
+            if (pl * 2u == chunk_base) {  // stage the next (up to) 32 features of the warp's 16 rows: one coalesced 128-byte read per point
+                const uint32_t width = min(32u, tab.n_enc - chunk_base);
+                __syncwarp();
+#pragma unroll 4
+                for (int r = 0; r < 16; ++r) {
+                    const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * r);
+                    const bool ok = __shfl_sync(0xffffffffu, (int)active, 2 * r);
+                    if (ok && (uint32_t)lane < width) myrows[r * kPairRowStride + lane] = __ldcs(dLdy + (int64_t)ir * gs_n + chunk_base + lane);
+                }
+                __syncwarp();
+            }
+            g0 = myrows[k * kPairRowStride + pl * 2u - chunk_base];
+            g1 = myrows[k * kPairRowStride + pl * 2u - chunk_base + 1];
+        } else if (active) {
+            g0 = grow[(int64_t)(pl * 2) * gs_f];
+            g1 = grow[(int64_t)(pl * 2 + 1) * gs_f];
+        }
+        if ((int32_t)level > in.max_level) continue;  // uniform
+        const LevelDesc& L = tab.lv[level];
+        Geo2 g;
+        pair_geo(L, (uint32_t)tab.map_cnt[pl] * 2u, smooth, x, yv, z, side, g);
+        // points of one run (consecutive points in the same cell) merge their contributions before touching L2
+        const bool can_key = L.res[0] <= 1024u && L.res[1] <= 1024u && L.res[2] <= 1024u;
+        uint32_t hmask = 0x55555555u;  // bit 2k set: point k starts a run
+        if (can_key) {
+            const uint32_t key = active ? g.key : (0xffffffffu - (uint32_t)k);
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 2);
+            hmask = __ballot_sync(0xffffffffu, k == 0 || key != prev) & 0x55555555u;
+        }
+        if (__popc(hmask) > NR3D_MERGE_MAX_HEADS / 2) {  // (almost) nothing to merge: scatter directly
+            if (active) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) red_add_v2_f32(grad + g.e[q], g.w[q] * g0, g.w[q] * g1);
+            }
+        } else {
+            *reinterpret_cast<float4*>(mytile + lane * kPairTileStride) = make_float4(g.w[0] * g0, g.w[0] * g1, g.w[1] * g0, g.w[1] * g1);
+            *reinterpret_cast<float4*>(mytile + lane * kPairTileStride + 4) = make_float4(g.w[2] * g0, g.w[2] * g1, g.w[3] * g0, g.w[3] * g1);
+            __syncwarp();
+            const uint32_t le = hmask & (0xffffffffu >> (31 - 2 * k));  // run starts at or below my point
+            const int s0 = (31 - __clz(le)) >> 1;
+            const uint32_t above = hmask & (0xffffffffu << (2 * k + 1));
+            const int e0 = above ? ((__ffs(above) - 1) >> 1) : 16;
+            const int r = e0 - s0, j = k - s0;
+            if (active) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // position j of a run of length r owns corners j, j + r, j + 2r, ... of its side
+                    const int d = q - j;
+                    if (d == 0 || (d > 0 && (d == r || d == 2 * r || d == 3 * r))) {
+                        float2 acc = make_float2(0.f, 0.f);
+                        for (int m = s0; m < e0; ++m) {
+                            const float2 t = *reinterpret_cast<const float2*>(mytile + (2 * m + side) * kPairTileStride + q * 2);
+                            acc.x += t.x; acc.y += t.y;
+                        }
+                        red_add_v2_f32(grad + g.e[q], acc.x, acc.y);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 static int make_table(const nr3d_lotd_meta* m, LotdTable& tab) {
     memset(&tab, 0, sizeof(tab));
     for (uint32_t l = 0; l < m->n_levels; ++l) {
@@ -455,7 +665,11 @@ int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64
     LotdTable tab;
     make_table(meta, tab);
     FastIn in{N, reinterpret_cast<const float4*>(xs), (const float*)params, max_level, (uint32_t)((reinterpret_cast<uintptr_t>(params) & 15u) == 0)};
+#if NR3D_FAST_PAIR
+    lotd_pair_fwd_kernel<<<(unsigned)div_up<uint64_t>(2 * N, kFastThreads), kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (float*)y, y_stride_n, y_stride_f);
+#else
     lotd_fast_fwd_kernel<<<(unsigned)div_up<uint64_t>(N, kFastThreads), kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (float*)y, y_stride_n, y_stride_f);
+#endif
     NR3D_LAUNCH_CHECK("lotd_fast_fwd");
     return 0;
 }
@@ -468,7 +682,11 @@ int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, 
     LotdTable tab;
     make_table(meta, tab);
     FastIn in{N, reinterpret_cast<const float4*>(xs), nullptr, max_level, 1u};
+#if NR3D_FAST_PAIR
+    lotd_pair_bwd_kernel<<<(unsigned)div_up<uint64_t>(2 * N, kBwdThreads), kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, (float*)dL_dparam);
+#else
     lotd_fast_bwd_kernel<<<(unsigned)div_up<uint64_t>(N, kBwdThreads), kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, (float*)dL_dparam);
+#endif
     NR3D_LAUNCH_CHECK("lotd_fast_bwd");
     return 0;
 }

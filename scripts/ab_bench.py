@@ -4,10 +4,8 @@
 import json, os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 VARIANTS = {
-    "base": [],
-    "bin64": ["NR3D_BIN_RES=64"],
-    "bin256": ["NR3D_BIN_RES=256"],
-    "zfast": ["NR3D_BIN_ORDER=1"],
+    "base": [],                                   # pair layout (two lanes per point)
+    "nopair": ["NR3D_FAST_PAIR=0"],               # one thread per point (round-1 v3 kernels)
     "heads12": ["NR3D_MERGE_MAX_HEADS=12"],
     "heads28": ["NR3D_MERGE_MAX_HEADS=28"],
     "unroll1": ["NR3D_FWD_UNROLL=1"],
