@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-serial", action="store_true", help="e2e leg without copy/compute overlap (single stream)")
     ap.add_argument("--no-sort", action="store_true", help="use the generic (unsorted, feature-major) kernels instead of lotd_fast.cu")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -194,14 +195,26 @@ def main():
         ndist.allreduce_param_grads(g, n_gpus)
         return y, g
 
-    def step_e2e():
-        xd = x_host.to(dev, non_blocking=True)
-        y, _ = _lotd.lod_fwd(meta, xd, params, need_input_grad=False)
-        gy = y * 1.0e-4                                                   # stand-in for the decoder's backward (device-side)
-        _, g = _lotd.lod_bwd(meta, gy, xd, params, None, need_input_grad=False, need_param_grad=True)
-        ndist.allreduce_param_grads(g, n_gpus)
-        grad_host.copy_(g, non_blocking=True)
-        return g
+    # e2e: the same step fed from / drained to HOST buffers through the public host-fed driver (pipeline.HostFedLoTDStep):
+    # every step copies its 48 MB of points host->device and its 48.5 MB of gradients device->host; the copies of neighbouring
+    # steps overlap the kernels (3 streams, double buffers).  `--e2e-serial` issues everything on one stream instead.
+    from nr3d_lib_b200.pipeline import HostFedLoTDStep
+    grad_host2 = [grad_host, torch.empty(meta.n_params, dtype=torch.float32).pin_memory()]
+    pipe = HostFedLoTDStep(meta, params, N, dev, grad_of_y=lambda y: y * 1.0e-4, world=n_gpus)   # y * 1e-4: stand-in for the decoder's backward
+
+    def run_e2e(steps):
+        if args.e2e_serial:
+            for k in range(steps):
+                xd = x_host.to(dev, non_blocking=True)
+                y, _ = _lotd.lod_fwd(meta, xd, params, need_input_grad=False)
+                _, g = _lotd.lod_bwd(meta, y * 1.0e-4, xd, params, None, need_input_grad=False, need_param_grad=True)
+                ndist.allreduce_param_grads(g, n_gpus)
+                grad_host2[k % 2].copy_(g, non_blocking=True)
+            return
+        pipe.prefetch(x_host)
+        for k in range(steps):
+            pipe.step(x_host if k + 1 < steps else None, grad_host2[k % 2])
+        pipe.drain()
 
     def timed(fn, steps, sampler=None):
         ndist.barrier()
@@ -227,9 +240,8 @@ def main():
     ms_step = ms_total / args.steps
     value = n_gpus * N / (ms_step * 1e-3) / 1e6
 
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    run_e2e(2)
+    ms_e2e = timed(lambda: run_e2e(args.steps), 1) / args.steps
     e2e_value = n_gpus * N / (ms_e2e * 1e-3) / 1e6
 
     # per-kernel durations for the roofline block: CUDA events on the launch stream around each call, inside this run
@@ -270,7 +282,8 @@ def main():
             "config": workload_config(n_gpus), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(x_host.numel() * 4),
                     "d2h_bytes_per_step": int(grad_host.numel() * 4),
-                    "note": "x from pinned host memory each step, dL_dy derived on device from the step's y, dL/dparams read back to host"},
+                    "note": "x from pinned host memory each step, dL_dy derived on device from the step's y, dL/dparams read back to host; "
+                            + ("single stream" if args.e2e_serial else "copies of neighbouring steps overlap the kernels (pipeline.HostFedLoTDStep)")},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base}
     print(json.dumps(line), flush=True)
     return 0

@@ -46,3 +46,74 @@ def march_encode_composite(encoder: LoTD, params: torch.Tensor, occ_grid: torch.
     depth = packed_sum(w * ret.depth_samples, ret.pack_infos)
     acc = packed_sum(w, ret.pack_infos)
     return RenderOut(ret, depth, acc, w)
+
+
+class HostFedLoTDStep:
+    """LoTD fwd + bwd(dL/dparam) steps whose inputs and results live in HOST memory.
+
+    Every step copies its points host->device and its parameter gradients device->host, like a trainer whose sampler and
+    optimizer sit on the host.  Three CUDA streams and double buffers keep both copy engines and the SMs busy at once: while
+    the kernels of step i run, the points of step i+1 are already crossing PCIe and the gradients of step i-1 are on their way
+    back.  No copy is skipped or shortened -- they are only taken off the critical path.
+
+        pipe = HostFedLoTDStep(meta, params, n_points, device, grad_of_y=lambda y: y * 1e-4)
+        pipe.prefetch(x_host[0])
+        for i in range(steps):
+            pipe.step(x_host[i + 1] if i + 1 < steps else None, grad_host[i % 2])
+        pipe.drain()                    # the compute stream waits for the last device->host copy
+
+    `x_host` / `grad_host` must be pinned.  `grad_of_y` stands for whatever turns the step's features into dL/dy on the
+    device (decoder + loss); with world > 1 the gradients are all-reduced (one NCCL call) before they leave the device.
+    """
+
+    def __init__(self, meta, params: torch.Tensor, n_points: int, device, grad_of_y, world: int = 1):
+        from .bindings import _lotd
+        self._lotd, self.meta, self.params, self.world, self.grad_of_y = _lotd, meta, params, world, grad_of_y
+        self.dev = torch.device(device)
+        self.compute = torch.cuda.current_stream(self.dev)
+        self.h2d, self.d2h = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        self.xbuf = [torch.empty(n_points, 3, dtype=torch.float32, device=self.dev) for _ in range(2)]
+        self.x_ready = [torch.cuda.Event(), torch.cuda.Event()]     # H2D of buffer b finished
+        self.x_free = [torch.cuda.Event(), torch.cuda.Event()]      # kernels reading buffer b finished
+        self.inflight = []                                          # (event, grad tensor) of pending device->host copies
+        self.slot = 0
+        for e in self.x_free:
+            e.record(self.compute)
+
+    def prefetch(self, x_host: torch.Tensor):
+        b = self.slot
+        self.h2d.wait_event(self.x_free[b])
+        with torch.cuda.stream(self.h2d):
+            self.xbuf[b].copy_(x_host, non_blocking=True)
+            self.x_ready[b].record(self.h2d)
+
+    def step(self, next_x_host: Optional[torch.Tensor], grad_host: torch.Tensor):
+        from . import dist as ndist
+        b = self.slot
+        self.slot ^= 1
+        if next_x_host is not None:
+            self.prefetch(next_x_host)                              # goes into the other buffer, overlaps the kernels below
+        self.compute.wait_event(self.x_ready[b])
+        x = self.xbuf[b]
+        self._lotd.clear_sort_cache()
+        y, _ = self._lotd.lod_fwd(self.meta, x, self.params, need_input_grad=False)
+        gy = self.grad_of_y(y)
+        _, g = self._lotd.lod_bwd(self.meta, gy, x, self.params, None, need_input_grad=False, need_param_grad=True)
+        self.x_free[b].record(self.compute)
+        if self.world > 1:
+            ndist.allreduce_param_grads(g, self.world)
+        done = torch.cuda.Event()
+        done.record(self.compute)
+        self.d2h.wait_event(done)
+        with torch.cuda.stream(self.d2h):
+            grad_host.copy_(g, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self.d2h)
+        g.record_stream(self.d2h)
+        self.inflight = [(e, t) for (e, t) in self.inflight if not e.query()] + [(copied, g)]
+        return g
+
+    def drain(self):
+        for e, _ in self.inflight:
+            self.compute.wait_event(e)
+        self.inflight = []
