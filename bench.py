@@ -38,6 +38,7 @@ N_POINTS = 4 * 1024 * 1024          # per GPU (weak scaling)
 #   fwd 12 (x) + 1024 (corner reads) + 128 (y write); bwd 12 (x) + 128 (dL_dy read) + 1024 (gradient scatter); + 23 (table zero-init/read)
 BYTES_FWD, BYTES_BWD, BYTES_TABLE = 12 + 1024 + 128, 12 + 128 + 1024, 23
 BYTES_PER_SAMPLE = BYTES_FWD + BYTES_BWD + BYTES_TABLE   # 2351
+BYTES_PER_SAMPLE_F16 = (12 + 512 + 64) + (12 + 64 + 512) + 12   # 1188 (SURVEY.md 8d, fp16 parameter tables)
 
 
 def ngp_cfg(min_res=16, n_levels=16, scale=1.382, log2_T=19, F=2):
@@ -270,6 +271,21 @@ def main():
                 "ms": {"lod_fwd": ms_fwd, "lod_bwd": ms_bwd},
                 "whole_step": {"achieved": whole, "frac": whole / peak, "bytes_per_sample": BYTES_PER_SAMPLE}}
 
+    # secondary number of metric M1: the same step with fp16 parameter tables (y, dL_dy and dL/dparams in half)
+    params_h, dL_dy_h = params.half(), dL_dy.half()
+    def step_half():
+        _lotd.clear_sort_cache()
+        _lotd.lod_fwd(meta, x, params_h, need_input_grad=False)
+        _, g = _lotd.lod_bwd(meta, dL_dy_h, x, params_h, None, need_input_grad=False, need_param_grad=True)
+        ndist.allreduce_param_grads(g, n_gpus)
+    for _ in range(3):
+        step_half()
+    ms_half = timed(step_half, args.steps) / args.steps
+    half_value = n_gpus * N / (ms_half * 1e-3) / 1e6
+    whole_h = half_value * 1e6 / n_gpus * BYTES_PER_SAMPLE_F16 / 1e9
+    fp16_block = {"value": half_value, "unit": UNIT, "ms_per_step": ms_half, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE_F16,
+                  "roofline_frac_whole_step": whole_h / peak}
+
     ndist.barrier()
     ndist.shutdown()
     if rank != 0:
@@ -284,7 +300,7 @@ def main():
                     "d2h_bytes_per_step": int(grad_host.numel() * 4),
                     "note": "x from pinned host memory each step, dL_dy derived on device from the step's y, dL/dparams read back to host; "
                             + ("single stream" if args.e2e_serial else "copies of neighbouring steps overlap the kernels (pipeline.HostFedLoTDStep)")},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base}
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "fp16_params": fp16_block}
     print(json.dumps(line), flush=True)
     return 0
 

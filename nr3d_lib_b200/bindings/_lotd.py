@@ -195,7 +195,7 @@ def clear_sort_cache():
 
 def _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
     return (getattr(meta, "c_sort_points", False) and meta.c_hash_only and meta.n_dims_to_encode == 3
-            and meta.n_feat_per_pseudo_lvl == 2 and params is not None and params.dtype == torch.float32
+            and meta.n_feat_per_pseudo_lvl == 2 and params is not None and params.dtype in (torch.float32, torch.float16)
             and input.dtype == torch.float32 and batch_inds is None and batch_offsets is None and not bds
             and (params.shape[0] == meta.n_params) and input.shape[0] > 0)
 

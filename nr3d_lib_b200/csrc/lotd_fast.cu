@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t N, const flo
 struct FastIn {
     uint64_t N;
     const float4* xs;        // sorted records (x, y, z, original index as bits) [N]
-    const float* params;
+    const void* params;      // fp32 or fp16 table
     int32_t max_level;
     uint32_t base_aligned16;  // params pointer is 16-byte aligned
 };
@@ -243,7 +243,7 @@ lotd_fast_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, flo
             const bool lvl_aligned = in.base_aligned16 && ((L.offset & 3u) == 0);
             Geo g;
             fast_geo(L, (uint32_t)tab.map_cnt[pl] * 2u, smooth, lvl_aligned, x, yv, z, g);
-            const float* tbl = in.params + L.offset;
+            const float* tbl = reinterpret_cast<const float*>(in.params) + L.offset;
             float4 v[4];  // (a.f0, a.f1, b.f0, b.f1) per pair; all loads are issued before the first use
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -456,8 +456,25 @@ __device__ __forceinline__ void pair_geo(const LevelDesc& L, uint32_t gfo, bool 
     }
 }
 
+// parameter-type specifics: fp32 tables accumulate in fp32; fp16 tables accumulate every term in half like the reference
+// (linear_interpolate.cuh:118) and scatter with packed-half reductions.
+template <typename PT> struct PairIO;
+template <> struct PairIO<float> {
+    static __device__ __forceinline__ float2 load2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+    static __device__ __forceinline__ float ldcs(const float* p) { return __ldcs(p); }
+    static __device__ __forceinline__ void red2(float* p, float a, float b) { red_add_v2_f32(p, a, b); }
+};
+template <> struct PairIO<__half> {
+    static __device__ __forceinline__ float2 load2(const __half* p) { return __half22float2(__ldg(reinterpret_cast<const __half2*>(p))); }
+    static __device__ __forceinline__ float ldcs(const __half* p) { return __half2float(__ldcs(p)); }
+    static __device__ __forceinline__ void red2(__half* p, float a, float b) { red_add_h2(p, __floats2half2_rn(a, b)); }
+};
+
+template <typename PT>
 __global__ void __launch_bounds__(kFastThreads)
-lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, float* __restrict__ y, int64_t ys_n, int64_t ys_f) {
+lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT* __restrict__ y, int64_t ys_n, int64_t ys_f) {
+    using C = Cvt<PT>;
+    const PT* params = reinterpret_cast<const PT*>(in.params);
     __shared__ float rows[kFastThreads / 32][16 * kPairRowStride];
     const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     const bool active = p < in.N;
@@ -476,17 +493,20 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, flo
 #pragma unroll kFwdUnroll
     for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
         const uint32_t level = tab.map_level[pl];
-        float r0 = 0.f, r1 = 0.f;
+        float r0 = 0.f, r1 = 0.f;  // (for fp16 tables these always hold half-representable values)
         if ((int32_t)level <= in.max_level) {
             Geo2 g;
             pair_geo(tab.lv[level], (uint32_t)tab.map_cnt[pl] * 2u, smooth, x, yv, z, side, g);
             float2 v[4];  // all four loads are issued before the first use
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float2*>(in.params + g.e[q]));
+            for (int q = 0; q < 4; ++q) v[q] = PairIO<PT>::load2(params + g.e[q]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { r0 += g.w[q] * v[q].x; r1 += g.w[q] * v[q].y; }
-            r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
-            r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+            for (int q = 0; q < 4; ++q) {
+                r0 = C::to_f(C::add(C::from_f(r0), C::from_f(g.w[q] * v[q].x)));
+                r1 = C::to_f(C::add(C::from_f(r1), C::from_f(g.w[q] * v[q].y)));
+            }
+            r0 = C::to_f(C::add(C::from_f(r0), C::from_f(__shfl_xor_sync(0xffffffffu, r0, 1))));
+            r1 = C::to_f(C::add(C::from_f(r1), C::from_f(__shfl_xor_sync(0xffffffffu, r1, 1))));
         }
         const float mine = side ? r1 : r0;  // lane `side` owns feature 2 * pl + side of its point
         if (staged) {
@@ -500,20 +520,22 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, flo
                 for (int r = 0; r < 16; ++r) {
                     const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * r);
                     const bool ok = __shfl_sync(0xffffffffu, (int)active, 2 * r);
-                    if (ok && (uint32_t)lane < width) __stcs(y + (int64_t)ir * ys_n + chunk_base + lane, myrows[r * kPairRowStride + lane]);
+                    if (ok && (uint32_t)lane < width) st_cs(y + (int64_t)ir * ys_n + chunk_base + lane, C::from_f(myrows[r * kPairRowStride + lane]));
                 }
                 __syncwarp();
                 chunk_base += 32;
             }
         } else if (active) {
-            __stcs(y + (int64_t)i * ys_n + (int64_t)(pl * 2 + side) * ys_f, mine);
+            st_cs(y + (int64_t)i * ys_n + (int64_t)(pl * 2 + side) * ys_f, C::from_f(mine));
         }
     }
 }
 
+template <typename PT>
 __global__ void __launch_bounds__(kBwdThreads)
-lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, const float* __restrict__ dLdy, int64_t gs_n, int64_t gs_f,
-                     float* __restrict__ grad) {
+lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, const PT* __restrict__ dLdy, int64_t gs_n, int64_t gs_f,
+                     PT* __restrict__ grad) {
+    using C = Cvt<PT>;
     __shared__ __align__(16) float tile[kBwdThreads / 32][32 * kPairTileStride];
     __shared__ float rows[kBwdThreads / 32][16 * kPairRowStride];
     const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
@@ -527,7 +549,7 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
     if (active) rec = __ldcs(in.xs + p);
     const float x = rec.x, yv = rec.y, z = rec.z;
     const uint64_t i = __float_as_uint(rec.w);
-    const float* grow = dLdy + (int64_t)i * gs_n;
+    const PT* grow = dLdy + (int64_t)i * gs_n;
     const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
     const bool staged = (gs_f == 1);
     uint32_t chunk_base = 0;
@@ -536,22 +558,22 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
         float g0 = 0.f, g1 = 0.f;
         if (staged) {
             if (pl * 2u == chunk_base + 32u) chunk_base += 32u;
-            if (pl * 2u == chunk_base) {  // stage the next (up to) 32 features of the warp's 16 rows: one coalesced 128-byte read per point
+            if (pl * 2u == chunk_base) {  // stage the next (up to) 32 features of the warp's 16 rows: one coalesced row read per point
                 const uint32_t width = min(32u, tab.n_enc - chunk_base);
                 __syncwarp();
 #pragma unroll 4
                 for (int r = 0; r < 16; ++r) {
                     const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * r);
                     const bool ok = __shfl_sync(0xffffffffu, (int)active, 2 * r);
-                    if (ok && (uint32_t)lane < width) myrows[r * kPairRowStride + lane] = __ldcs(dLdy + (int64_t)ir * gs_n + chunk_base + lane);
+                    if (ok && (uint32_t)lane < width) myrows[r * kPairRowStride + lane] = PairIO<PT>::ldcs(dLdy + (int64_t)ir * gs_n + chunk_base + lane);
                 }
                 __syncwarp();
             }
             g0 = myrows[k * kPairRowStride + pl * 2u - chunk_base];
             g1 = myrows[k * kPairRowStride + pl * 2u - chunk_base + 1];
         } else if (active) {
-            g0 = grow[(int64_t)(pl * 2) * gs_f];
-            g1 = grow[(int64_t)(pl * 2 + 1) * gs_f];
+            g0 = C::to_f(grow[(int64_t)(pl * 2) * gs_f]);
+            g1 = C::to_f(grow[(int64_t)(pl * 2 + 1) * gs_f]);
         }
         if ((int32_t)level > in.max_level) continue;  // uniform
         const LevelDesc& L = tab.lv[level];
@@ -568,7 +590,7 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
         if (__popc(hmask) > NR3D_MERGE_MAX_HEADS / 2) {  // (almost) nothing to merge: scatter directly
             if (active) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) red_add_v2_f32(grad + g.e[q], g.w[q] * g0, g.w[q] * g1);
+                for (int q = 0; q < 4; ++q) PairIO<PT>::red2(grad + g.e[q], g.w[q] * g0, g.w[q] * g1);
             }
         } else {
             *reinterpret_cast<float4*>(mytile + lane * kPairTileStride) = make_float4(g.w[0] * g0, g.w[0] * g1, g.w[1] * g0, g.w[1] * g1);
@@ -589,7 +611,7 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
                             const float2 t = *reinterpret_cast<const float2*>(mytile + (2 * m + side) * kPairTileStride + q * 2);
                             acc.x += t.x; acc.y += t.y;
                         }
-                        red_add_v2_f32(grad + g.e[q], acc.x, acc.y);
+                        PairIO<PT>::red2(grad + g.e[q], acc.x, acc.y);
                     }
                 }
             }
@@ -613,8 +635,13 @@ static int make_table(const nr3d_lotd_meta* m, LotdTable& tab) {
 
 static int check_fast(const nr3d_lotd_meta* m, int32_t param_dtype, uint64_t N) {
     NR3D_CHECK(m != nullptr, "LoTDEncoding: null meta");
-    NR3D_CHECK(m->hash_only && m->n_dims_to_encode == 3 && m->n_feat_per_pseudo_lvl == 2 && param_dtype == NR3D_F32,
-               "LoTDEncoding: the sorted fast path needs a Dense/Hash-only meta with D=3, 2 features per pseudo level and fp32 params");
+#if NR3D_FAST_PAIR
+    const bool dtype_ok = param_dtype == NR3D_F32 || param_dtype == NR3D_F16;
+#else
+    const bool dtype_ok = param_dtype == NR3D_F32;
+#endif
+    NR3D_CHECK(m->hash_only && m->n_dims_to_encode == 3 && m->n_feat_per_pseudo_lvl == 2 && dtype_ok,
+               "LoTDEncoding: the sorted fast path needs a Dense/Hash-only meta with D=3, 2 features per pseudo level and fp32 / fp16 params");
     NR3D_CHECK(N < (1ull << 32), "LoTDEncoding: batch_size must be < 2^32");
     return 0;
 }
@@ -664,9 +691,11 @@ int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64
     NR3D_CHECK(xs && params && y, "LoTDEncoding::fwd_sorted: null argument");
     LotdTable tab;
     make_table(meta, tab);
-    FastIn in{N, reinterpret_cast<const float4*>(xs), (const float*)params, max_level, (uint32_t)((reinterpret_cast<uintptr_t>(params) & 15u) == 0)};
+    FastIn in{N, reinterpret_cast<const float4*>(xs), params, max_level, (uint32_t)((reinterpret_cast<uintptr_t>(params) & 15u) == 0)};
 #if NR3D_FAST_PAIR
-    lotd_pair_fwd_kernel<<<(unsigned)div_up<uint64_t>(2 * N, kFastThreads), kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (float*)y, y_stride_n, y_stride_f);
+    const unsigned grid = (unsigned)div_up<uint64_t>(2 * N, kFastThreads);
+    if (param_dtype == NR3D_F16) lotd_pair_fwd_kernel<__half><<<grid, kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (__half*)y, y_stride_n, y_stride_f);
+    else lotd_pair_fwd_kernel<float><<<grid, kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (float*)y, y_stride_n, y_stride_f);
 #else
     lotd_fast_fwd_kernel<<<(unsigned)div_up<uint64_t>(N, kFastThreads), kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (float*)y, y_stride_n, y_stride_f);
 #endif
@@ -683,7 +712,9 @@ int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, 
     make_table(meta, tab);
     FastIn in{N, reinterpret_cast<const float4*>(xs), nullptr, max_level, 1u};
 #if NR3D_FAST_PAIR
-    lotd_pair_bwd_kernel<<<(unsigned)div_up<uint64_t>(2 * N, kBwdThreads), kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, (float*)dL_dparam);
+    const unsigned grid = (unsigned)div_up<uint64_t>(2 * N, kBwdThreads);
+    if (param_dtype == NR3D_F16) lotd_pair_bwd_kernel<__half><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const __half*)dL_dy, dLdy_stride_n, dLdy_stride_f, (__half*)dL_dparam);
+    else lotd_pair_bwd_kernel<float><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, (float*)dL_dparam);
 #else
     lotd_fast_bwd_kernel<<<(unsigned)div_up<uint64_t>(N, kBwdThreads), kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, (float*)dL_dparam);
 #endif

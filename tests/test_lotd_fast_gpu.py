@@ -103,3 +103,34 @@ def test_full_size_headline_config(dev):
         assert rel_err(y_s, y_r) < 1e-5
         _, g_r = ref.lod_bwd(m_r, gy, x, p, None, need_input_grad=False, need_param_grad=True)
         assert rel_err(g_s.double(), g_r.double()) < 1e-4
+
+
+@pytest.mark.parametrize("name,N", [("ngp8", 37), ("ngp8", 6000), ("ngp_smooth", 3000)])
+def test_sorted_path_fp16_params(name, N, dev):
+    """fp16 tables on the fast path: y in half (every term rounded to half like the reference, linear_interpolate.cuh:118),
+    dL/dparam scattered with packed-half reductions.  Checked against the generic kernels, the float64 oracle and, when
+    built, the reference CUDA extension -- at fp16 tolerances (the reference's own fp16 atomics are order dependent)."""
+    from nr3d_lib_b200.bindings import _lotd
+    from oracle import lotd_oracle as O
+    cfg = dict(LOTD_CONFIGS[name], B=1)
+    meta_s, meta_g = _lotd.LoDMeta(*meta_args(cfg)), _lotd.LoDMeta(*meta_args(cfg))
+    meta_s.c_sort_points = True
+    inp = lotd_inputs(cfg, meta_g.n_params, N=N, seed=11)
+    x, p, gy = inp["x"].to(dev), inp["params"].to(dev).half(), inp["dL_dy"].to(dev).half()
+    _lotd.clear_sort_cache()
+    y_s, _ = _lotd.lod_fwd(meta_s, x, p, need_input_grad=False)
+    y_g, _ = _lotd.lod_fwd(meta_g, x, p, need_input_grad=False)
+    assert y_s.dtype == torch.float16 and y_s.is_contiguous()
+    om = O.OracleMeta(*meta_args(cfg))
+    y_o = O.encode(om, inp["x"], p.float().cpu())
+    assert rel_err(y_s.float().cpu(), y_o) < 4e-3 and rel_err(y_g.float().cpu(), y_o) < 4e-3     # 8 half roundings per feature
+    _, g_s = _lotd.lod_bwd(meta_s, gy, x, p, None, need_input_grad=False, need_param_grad=True)
+    _, g_g = _lotd.lod_bwd(meta_g, gy, x, p, None, need_input_grad=False, need_param_grad=True)
+    assert g_s.dtype == torch.float16
+    g_o = O.bwd(om, gy.float().cpu(), inp["x"], p.float().cpu())[1]
+    assert rel_err(g_s.float().cpu(), g_o) < 2e-2 and rel_err(g_g.float().cpu(), g_o) < 3e-2
+    ref = load_ref("_lotd")
+    if ref is not None:
+        rmeta = ref.LoDMeta(*meta_args(cfg))
+        y_r, _ = ref.lod_fwd(rmeta, x, p, None, None, None, None, False)
+        assert rel_err(y_s.float().cpu(), y_r.float().cpu()) < 4e-3
