@@ -424,7 +424,7 @@ __device__ __forceinline__ void pair_geo(const LevelDesc& L, uint32_t gfo, bool 
         float v = xv[d] * sc + 0.5f;
         const float fl = floorf(v);
         c[d] = (uint32_t)fl;
-        v -= (float)c[d];
+        v -= fl;  // == (float)c[d] for the valid range x >= 0
         p[d] = smooth ? v * v * (3.0f - 2.0f * v) : v;
     }
     g.key = c[0] | (c[1] << 10) | (c[2] << 20);
@@ -587,7 +587,14 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
             const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 2);
             hmask = __ballot_sync(0xffffffffu, k == 0 || key != prev) & 0x55555555u;
         }
-        if (__popc(hmask) > NR3D_MERGE_MAX_HEADS / 2) {  // (almost) nothing to merge: scatter directly
+        // run of my point: points [s0, e0), length r, my position j
+        const uint32_t le = hmask & (0xffffffffu >> (31 - 2 * k));
+        const int s0 = (31 - __clz(le)) >> 1;
+        const uint32_t above = hmask & (0xffffffffu << (2 * k + 1));
+        const int e0 = above ? ((__ffs(above) - 1) >> 1) : 16;
+        const int r = e0 - s0, j = k - s0;
+        const bool longrun = active && r >= 4;  // shorter runs are not worth the detour through shared memory
+        if (!__any_sync(0xffffffffu, longrun)) {
             if (active) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) PairIO<PT>::red2(grad + g.e[q], g.w[q] * g0, g.w[q] * g1);
@@ -596,24 +603,28 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
             *reinterpret_cast<float4*>(mytile + lane * kPairTileStride) = make_float4(g.w[0] * g0, g.w[0] * g1, g.w[1] * g0, g.w[1] * g1);
             *reinterpret_cast<float4*>(mytile + lane * kPairTileStride + 4) = make_float4(g.w[2] * g0, g.w[2] * g1, g.w[3] * g0, g.w[3] * g1);
             __syncwarp();
-            const uint32_t le = hmask & (0xffffffffu >> (31 - 2 * k));  // run starts at or below my point
-            const int s0 = (31 - __clz(le)) >> 1;
-            const uint32_t above = hmask & (0xffffffffu << (2 * k + 1));
-            const int e0 = above ? ((__ffs(above) - 1) >> 1) : 16;
-            const int r = e0 - s0, j = k - s0;
-            if (active) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {  // position j of a run of length r owns corners j, j + r, j + 2r, ... of its side
-                    const int d = q - j;
-                    if (d == 0 || (d > 0 && (d == r || d == 2 * r || d == 3 * r))) {
-                        float2 acc = make_float2(0.f, 0.f);
-                        for (int m = s0; m < e0; ++m) {
-                            const float2 t = *reinterpret_cast<const float2*>(mytile + (2 * m + side) * kPairTileStride + q * 2);
-                            acc.x += t.x; acc.y += t.y;
-                        }
-                        PairIO<PT>::red2(grad + g.e[q], acc.x, acc.y);
-                    }
+            // A long run is reduced by its first 4 * nch positions: position j sums corner q = j & 3 over the points
+            // s0 + c, s0 + c + nch, ... (c = j >> 2), the nch partial sums of a corner then meet through two shuffles and
+            // positions 0..3 issue ONE reduction per corner for the whole run.
+            const int nch = r >> 2;  // 1..4 groups of four positions
+            const int q = j & 3, c = j >> 2;
+            float2 acc = make_float2(0.f, 0.f);
+            if (longrun && c < nch) {
+                for (int m = s0 + c; m < e0; m += nch) {
+                    const float2 t = *reinterpret_cast<const float2*>(mytile + (2 * m + side) * kPairTileStride + q * 2);
+                    acc.x += t.x; acc.y += t.y;
                 }
+            }
+            const int lim = nch << 2;
+            float tx = __shfl_down_sync(0xffffffffu, acc.x, 16), ty = __shfl_down_sync(0xffffffffu, acc.y, 16);
+            if (longrun && j + 8 < lim) { acc.x += tx; acc.y += ty; }   // positions j + 8 (and, through them, j + 12)
+            tx = __shfl_down_sync(0xffffffffu, acc.x, 8); ty = __shfl_down_sync(0xffffffffu, acc.y, 8);
+            if (longrun && j < 4 && j + 4 < lim) { acc.x += tx; acc.y += ty; }
+            if (longrun) {
+                if (j < 4) PairIO<PT>::red2(grad + (q == 0 ? g.e[0] : (q == 1 ? g.e[1] : (q == 2 ? g.e[2] : g.e[3]))), acc.x, acc.y);
+            } else if (active) {
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) PairIO<PT>::red2(grad + g.e[qq], g.w[qq] * g0, g.w[qq] * g1);
             }
             __syncwarp();
         }
