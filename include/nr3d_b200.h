@@ -123,6 +123,18 @@ int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64
 int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* dL_dy,
                                int64_t dLdy_stride_n, int64_t dLdy_stride_f, int32_t max_level, void* dL_dparam, void* stream);
 
+/* Fused LoTD encode + density decoder, forward only.  Replaces the composition
+ * LoTDNeRF.query_density (nr3d_lib/models/fields/nerf/lotd_nerf.py:169-178): encoding(x) -> Linear(32,64) -> ReLU ->
+ * Linear(64, <=16) -> activation(out[...,0]), without writing the [N,32] features to HBM.  tcgen05 (bf16 operands, f32
+ * accumulation).  xs: sorted records from nr3d_lotd_sort_points; params: fp32 table; w1_packed / w2_packed: bf16 weights
+ * in K-major core-matrix order ([K/8][rows/8][8][8], rows = 64 resp. 16); b1 [64] / b2 [16] f32 or NULL;
+ * activation: 0 identity, 1 exp, 2 softplus, 3 relu.  sigma [N] f32 and out16 ([N,16] f32, nullable) are written at the
+ * points' original indices. */
+int nr3d_lotd_fused_density_fwd(const nr3d_lotd_meta* meta, uint64_t N, const void* xs, const void* params, int32_t max_level,
+                                const void* w1_packed, const float* b1, const void* w2_packed, const float* b2, int32_t activation,
+                                float* sigma, float* out16, void* stream);
+
+
 /* ------------------------------------------------------------------------------------------------
  * occupancy-grid ray marching (replaces nr3d_lib.bindings._occ_grid, csrc/occ_grid/src/occ_grid.cpp:22-33)
  * ---------------------------------------------------------------------------------------------- */

@@ -84,6 +84,7 @@ SIGNATURES = {
     "nr3d_pack_merge_sorted_aligned": [_i32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "nr3d_pack_sort": [_i32, _u64, _vp, _vp, _vp, _vp],
     "nr3d_pack_matmul": [_i32, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp],
+    "nr3d_lotd_fused_density_fwd": [_vp, _u64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "nr3d_occ_scatter_max": [_u64, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp, _vp],
     "nr3d_occ_apply": [_u64, _vp, _vp, _f32, _i32, _f32, _vp, _vp, _vp],
     "nr3d_occ_binarize": [_u64, _vp, _f32, _i32, _f32, _vp, _vp, _vp],

@@ -19,7 +19,7 @@
 //   4. y and dL_dy are accessed as [N, n_enc] rows (one 128-byte line per point), so the permutation costs no
 //      partial-sector traffic.
 // Results are identical to the generic kernels up to fp32 summation order (same index functions, same weights).
-#include "lotd_device.cuh"
+#include "lotd_pair.cuh"
 #include <string.h>
 
 namespace nr3d {
@@ -145,13 +145,6 @@ __global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t N, const flo
 // ------------------------------------------------------------------------------------------------------------
 // per-(point, level) geometry shared by forward and backward
 // ------------------------------------------------------------------------------------------------------------
-struct FastIn {
-    uint64_t N;
-    const float4* xs;        // sorted records (x, y, z, original index as bits) [N]
-    const void* params;      // fp32 or fp16 table
-    int32_t max_level;
-    uint32_t base_aligned16;  // params pointer is 16-byte aligned
-};
 
 #if !NR3D_FAST_PAIR  // ---- one thread per point (round-1 v3 kernels), compiled only for A/B runs ----
 constexpr int kRowStride = 33;  // floats per staged row (32 features + 1 pad: conflict-free for row and column access)
@@ -406,55 +399,6 @@ lotd_fast_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
 constexpr int kPairRowStride = 34;   // floats per staged row: row k starts at bank 2k -> conflict-free pair writes and row reads
 constexpr int kPairTileStride = 12;  // floats per lane in the run-merge tile (8 used): conflict-free 16-byte stores
 
-struct Geo2 {
-    uint32_t key;   // cell key (10 bits per axis) for run detection
-    float w[4];     // n-linear weights of this lane's four corners
-    uint32_t e[4];  // element offsets (floats, from the start of the parameter array) of their feature pairs
-};
-
-__device__ __forceinline__ void pair_geo(const LevelDesc& L, uint32_t gfo, bool smooth, float x, float y, float z, uint32_t side, Geo2& g) {
-    const uint32_t Ry = L.res[1], Rz = L.res[2];
-    float p[3];
-    uint32_t c[3];
-    const float xv[3] = {x, y, z};
-    const uint32_t R[3] = {L.res[0], Ry, Rz};
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        const float sc = (float)(R[d] - 2u);
-        float v = xv[d] * sc + 0.5f;
-        const float fl = floorf(v);
-        c[d] = (uint32_t)fl;
-        v -= fl;  // == (float)c[d] for the valid range x >= 0
-        p[d] = smooth ? v * v * (3.0f - 2.0f * v) : v;
-    }
-    g.key = c[0] | (c[1] << 10) | (c[2] << 20);
-    const float wx[2] = {1.0f - p[0], p[0]}, wy[2] = {1.0f - p[1], p[1]}, wz[2] = {1.0f - p[2], p[2]};
-    const uint32_t nf = L.n_feat;
-    const uint32_t base = L.offset + gfo;
-    if (L.type == NR3D_LOD_DENSE) {
-        const float wzs = side ? wz[1] : wz[0];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t dx = q & 1, dy = q >> 1;
-            const uint32_t cell = ((c[0] + dx) * Ry + (c[1] + dy)) * Rz + c[2] + side;  // uint32 arithmetic as in the reference
-            g.e[q] = base + cell * nf;
-            g.w[q] = (wx[dx] * wy[dy]) * wzs;
-        }
-    } else {  // Hash
-        const uint32_t size = L.size;
-        const bool pow2 = (size & (size - 1u)) == 0;
-        const uint32_t hx = c[0] + side;
-        const float wxs = side ? wx[1] : wx[0];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t dy = q & 1, dz = q >> 1;
-            const uint32_t hyz = ((c[1] + dy) * 2654435761u) ^ ((c[2] + dz) * 805459861u);
-            const uint32_t h = pow2 ? ((hx ^ hyz) & (size - 1u)) : ((hx ^ hyz) % size);
-            g.e[q] = base + h * nf;
-            g.w[q] = (wxs * wy[dy]) * wz[dz];
-        }
-    }
-}
 
 // parameter-type specifics: fp32 tables accumulate in fp32; fp16 tables accumulate every term in half like the reference
 // (linear_interpolate.cuh:118) and scatter with packed-half reductions.
@@ -643,6 +587,7 @@ static int make_table(const nr3d_lotd_meta* m, LotdTable& tab) {
     tab.interp = m->interpolation_type; tab.fpl = m->n_feat_per_pseudo_lvl;
     return 0;
 }
+int make_table_public(const nr3d_lotd_meta* m, LotdTable& tab) { return make_table(m, tab); }  // for lotd_fused.cu
 
 static int check_fast(const nr3d_lotd_meta* m, int32_t param_dtype, uint64_t N) {
     NR3D_CHECK(m != nullptr, "LoTDEncoding: null meta");

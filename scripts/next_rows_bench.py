@@ -116,7 +116,51 @@ def bench_n1():
     row("query (2^20 pts)", t_o, t_r, N * 13)
 
 
+def bench_n3():
+    from nr3d_lib_b200.bindings import _lotd
+    from nr3d_lib_b200.fused import FusedDensityDecoder
+    res = (16 * 1.382 ** np.arange(16)).astype(int).tolist()
+    meta = _lotd.LoDMeta(3, res, [2] * 16, ["Dense" if r ** 3 <= 2 ** 19 else "Hash" for r in res], 2 ** 19)
+    meta.c_sort_points = True
+    N = 4 * 2 ** 20
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    x = torch.rand(N, 3, device=dev, generator=g).clamp(1e-6, 1 - 1e-6)
+    params = (torch.rand(meta.n_params, device=dev, generator=g) * 2 - 1) * 1e-1
+    w1, b1 = torch.randn(64, 32, device=dev, generator=g) * 0.3, torch.randn(64, device=dev, generator=g) * 0.1
+    w2, b2 = torch.randn(16, 64, device=dev, generator=g) * 0.2, torch.randn(16, device=dev, generator=g) * 0.1
+    dec = FusedDensityDecoder(meta, w1, b1, w2, b2, activation="exp")
+    w1h, w2h = w1.half(), w2.half()
+
+    def unfused_fp32():      # the reference's composition: features to HBM, two GEMM launches, activation
+        _lotd.clear_sort_cache()
+        h, _ = _lotd.lod_fwd(meta, x, params, need_input_grad=False)
+        return (torch.relu(h @ w1.t() + b1) @ w2.t() + b2)[:, 0].exp()
+
+    def unfused_fp16_mlp():  # same with a half-precision MLP (what a tcnn-style decoder does)
+        _lotd.clear_sort_cache()
+        h, _ = _lotd.lod_fwd(meta, x, params, need_input_grad=False)
+        return (torch.relu(h.half() @ w1h.t() + b1.half()) @ w2h.t() + b2.half())[:, 0].float().exp()
+
+    def fused():
+        _lotd.clear_sort_cache()
+        return dec.query_density(x, params)[0]
+
+    def encode_only():
+        _lotd.clear_sort_cache()
+        return _lotd.lod_fwd(meta, x, params, need_input_grad=False)[0]
+    err = ((fused() - unfused_fp32()).abs().max() / unfused_fp32().abs().max()).item()
+    print(f"# n3: query_density on {N} points, 16-level NGP LoTD + MLP 32-64-16, exp; fused vs fp32 composition max rel err {err:.2e}")
+    t_f = timeit(fused)
+    row("fused encode + decoder (tcgen05)", t_f, timeit(unfused_fp32), N * (12 + 1024 + 4))
+    row("  vs unfused with fp16 MLP", t_f, timeit(unfused_fp16_mlp))
+    row("  (encode alone, features to HBM)", timeit(encode_only), None, N * (12 + 1024 + 128))
+
+
 if __name__ == "__main__":
     print(f"# {torch.cuda.get_device_name(0)}")
+    if len(sys.argv) > 1 and sys.argv[1] == "n3":
+        bench_n3()
+        sys.exit(0)
     bench_n1()
     bench_n2()
+    bench_n3()
