@@ -1,23 +1,24 @@
 // lotd_fast.cu -- B200 fast path of the LoTD encoder for the Dense/Hash ("hash-only") configuration, D = 3, F_pl = 2,
-// fp32 parameters, single scene: the workload of BASELINE.json's headline metric.
+// fp32 or fp16 parameters, single scene: the workload of BASELINE.json's headline metric.
 //
-// What bounds this workload on B200 (measured, scripts/ubench_mem.cu -> profiles/r1_ubench_mem.txt):
-//   * the 48.5 MB parameter table is L2 resident, so DRAM only sees x, y, dL_dy (about 1.1 GB per fwd+bwd step);
-//   * random 8-byte gathers run at ~291 G/s chip-wide = one distinct 128-byte line per clock per SM (LSU wavefront
-//     rate, 148 SMs x 1.965 GHz), independent of access width up to 16 bytes;
-//   * random red.global.add runs at ~228 G ops/s, also independent of width (f32, v2.f32 and v4.f32 cost the same),
-//     and same-address atomics from different SMs serialise in the L2 slice (coarse levels: up to 4.5x slower).
-// So the levers are (1) fewer, wider memory instructions, (2) lanes of a warp touching the same lines, (3) merging
-// same-address contributions before they reach L2.  This file implements them:
+// What bounds this workload on B200 (measured, scripts/ubench_mem.cu, scripts/ubench_pair.cu -> profiles/r1_ubench_*.txt):
+//   * the 48.5 MB parameter table is L2 resident, so DRAM only sees x, y, dL_dy (about 1.3 GB per fwd+bwd step);
+//   * a warp-wide gather costs one LSU slot per DISTINCT 128-BYTE LINE it touches (287 G lanes/s when every lane has its
+//     own line = 148 SMs x 1.965 GHz; 572 G lanes/s when lane pairs share a line), independent of the access width;
+//   * a warp-wide red.global.add costs one L2 slot per distinct 32-byte sector / 16-byte chunk (231 G lanes/s random,
+//     460 G lanes/s when lane pairs share a chunk), f32 / v2.f32 / v4.f32 cost the same, and same-address reductions
+//     from different SMs serialise in the L2 slice (coarse levels: up to 4.5x slower).
+// So the levers are (1) lanes of one instruction sharing lines / sectors, (2) merging same-address contributions before they
+// reach L2, (3) fewer instructions (both kernels end up ~85 % issue-bound).  This file implements them:
 //   1. points are binned once per step by a 128^3 cell key (x fastest) with a counting sort; forward and backward walk
-//      the points in that order (thread = point, loop over levels), so coarse and middle levels hit few lines per warp;
-//   2. the two corners that differ only in the fastest-varying coordinate are fetched / scattered with ONE 16-byte
-//      access when they are adjacent in memory: z-neighbours of Dense levels (cell index even), x-neighbours of Hash
-//      levels (x ^ c and (x+1) ^ c differ in bit 0 when x is even -- independent of the hash of y and z);
-//   3. in the backward pass, lanes that fall into the same cell (runs of equal cell key in the sorted order) sum their
-//      sixteen corner contributions through a shared-memory tile and issue one set of reductions per run;
-//   4. y and dL_dy are accessed as [N, n_enc] rows (one 128-byte line per point), so the permutation costs no
-//      partial-sector traffic.
+//      the points in that order, so coarse and middle levels hit few lines per warp;
+//   2. TWO ADJACENT LANES share one point (see "pair layout" below): the x-neighbour corners of a Hash level (z-neighbours
+//      of a Dense level) are fetched / scattered by the two lanes of a pair in the same instruction and coalesce in hardware;
+//   3. in the backward pass, runs of points in the same cell sum their corner contributions through a shared-memory tile
+//      and issue one reduction per corner per run;
+//   4. y and dL_dy are accessed as [N, n_enc] rows staged through shared memory (one coalesced 128-byte access per point),
+//      so the sort permutation costs no partial-sector traffic.
+// The thread-per-point kernels of the first iteration are kept behind NR3D_FAST_PAIR=0 for A/B runs (scripts/ab_bench.py).
 // Results are identical to the generic kernels up to fp32 summation order (same index functions, same weights).
 #include "lotd_pair.cuh"
 #include <string.h>
