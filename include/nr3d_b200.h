@@ -161,6 +161,42 @@ int nr3d_march_fill(uint64_t n_rays, const float* rays_o, const float* rays_d, c
                     const int32_t* packed_info, float* t_starts, float* t_ends, int32_t* ridx, int32_t* bidx,
                     int32_t* gidx, void* stream);
 
+/* Forest (multi-block) marcher, SURVEY.md section 8f row n4: == forest_ray_marching (csrc/occ_grid/src/forest_marching.cu:27-303,
+ * bound as nr3d_lib.bindings._occ_grid.forest_ray_marching, occ_grid.cpp:32).  Every ray owns a pack of block segments
+ * (seg_pack_infos int32 [R,2] -> seg_block_inds int32 / seg_entries f32 / seg_exits f32 [n_segments]) from the octree ray
+ * trace; block b occupies [world_origin + block_ks[b] * world_block_size, + world_block_size] (block_ks int16 [n_trees,3];
+ * world_origin / world_block_size: 3 HOST floats each = ForestMeta.world_origin / world_block_size, forest_cpp_api.h:27-28)
+ * and owns grid[b] (bool/uint8 [n_trees, rx, ry, rz]).  Count / pack (nr3d_march_pack) / fill like the single-grid marcher;
+ * fill additionally writes blidx int32 [S]; gidx (nullable) = voxel index + b * rx*ry*rz. */
+int nr3d_forest_march_count(uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                            const int32_t* seg_block_inds, const float* seg_entries, const float* seg_exits,
+                            const int32_t* seg_pack_infos, const int16_t* block_ks, const float* world_origin,
+                            const float* world_block_size, const uint8_t* grid, int32_t rx, int32_t ry, int32_t rz,
+                            float step_size, float max_step_size, float dt_gamma, uint32_t max_steps, int32_t* num_steps, void* stream);
+int nr3d_forest_march_fill(uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                           const int32_t* seg_block_inds, const float* seg_entries, const float* seg_exits,
+                           const int32_t* seg_pack_infos, const int16_t* block_ks, const float* world_origin,
+                           const float* world_block_size, const uint8_t* grid, int32_t rx, int32_t ry, int32_t rz,
+                           float step_size, float max_step_size, float dt_gamma, uint32_t max_steps, const int32_t* packed_info,
+                           float* t_starts, float* t_ends, int32_t* ridx, int32_t* blidx, int32_t* gidx, void* stream);
+
+/* Post-processing of the marcher's output in one pass (replaces index_select x2 + addcmul + sub of
+ * nr3d_lib/graphics/raymarch/occgrid_raymarch.py:96-107): samples[i] = rays_o[ridx[i]] + rays_d[ridx[i]] * t_starts[i]
+ * (product rounded, then sum rounded -- bit-identical to torch.addcmul), deltas[i] = t_ends[i] - t_starts[i] (deltas / t_ends nullable).
+ * ridx: int32 or int64 [S] (ridx_dtype = NR3D_I32 / NR3D_I64). */
+int nr3d_march_samples(uint64_t S, const float* rays_o, const float* rays_d, const float* t_starts, const float* t_ends,
+                       const void* ridx, int32_t ridx_dtype, float* samples, float* deltas, void* stream);
+
+/* Density head + opacity in one pass each way (M2 workload): sigma = softplus(gain * sum_c h[i,c]),
+ * alpha = 1 - exp(-sigma * deltas[i]) (nr3d_lib/graphics/nerf/nerf_ray_query.py:182).  The reference composes these from torch
+ * element-wise / reduce kernels; there is no reference entry point -- these two serve nr3d_lib_b200.pipeline only.
+ * h: f32 [S, C] with row stride h_stride (elements) and unit column stride.  Backward: d_h [S, C] contiguous =
+ * (d_alpha * deltas * (1 - alpha) + d_sigma_extra) * gain * sigmoid(gain * sum) broadcast over C (d_sigma_extra nullable). */
+int nr3d_density_alpha_fwd(uint64_t S, uint32_t C, const float* h, int64_t h_stride, const float* deltas, float gain, float* sigma,
+                           float* alpha, void* stream);
+int nr3d_density_alpha_bwd(uint64_t S, uint32_t C, const float* d_alpha, const float* d_sigma_extra, const float* sigma,
+                           const float* alpha, const float* deltas, float gain, float* d_h, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * occupancy value-grid maintenance.  Replaces the torch + torch_scatter compositions of
  * nr3d_lib/models/accelerations/occgrid/utils.py:18-133 and ema_single.py:186-218.  Grids are [B, rx, ry, rz] (z fastest).

@@ -48,6 +48,7 @@ _vp, _i32, _u32, _i64, _u64, _f32, _f64 = (ctypes.c_void_p, ctypes.c_int32, ctyp
                                            ctypes.c_uint64, ctypes.c_float, ctypes.c_double)
 _meta_p = ctypes.POINTER(LotdMetaStruct)
 _u64_p = ctypes.POINTER(ctypes.c_uint64)
+_f32_3 = ctypes.POINTER(ctypes.c_float)    # 3 host floats
 
 # name -> argtypes, exactly the declarations of include/nr3d_b200.h
 SIGNATURES = {
@@ -66,6 +67,13 @@ SIGNATURES = {
     "nr3d_march_pack": [_u64, _vp, _vp, _vp, _vp, _u64_p, _vp],
     "nr3d_march_fill": [_u64, _vp, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _u32,
                         _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "nr3d_forest_march_count": [_u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32_3, _f32_3, _vp, _i32, _i32, _i32, _f32, _f32, _f32,
+                                _u32, _vp, _vp],
+    "nr3d_forest_march_fill": [_u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32_3, _f32_3, _vp, _i32, _i32, _i32, _f32, _f32, _f32,
+                               _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "nr3d_march_samples": [_u64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
+    "nr3d_density_alpha_fwd": [_u64, _u32, _vp, _i64, _vp, _f32, _vp, _vp, _vp],
+    "nr3d_density_alpha_bwd": [_u64, _u32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp],
     "nr3d_pack_sum": [_i32, _u64, _u32, _vp, _vp, _vp, _vp],
     "nr3d_pack_cumsum": [_i32, _u64, _u32, _vp, _vp, _i32, _i32, _vp, _vp],
     "nr3d_pack_cumprod": [_i32, _u64, _u32, _vp, _vp, _i32, _i32, _i32, _vp, _vp],

@@ -175,6 +175,118 @@ static int fill_args(MarchArgs& a, uint64_t n_rays, const float* rays_o, const f
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// forest (multi-block) marcher: SURVEY.md 8f row n4, csrc/occ_grid/src/forest_marching.cu:27-150.
+// Each ray carries a pack of block segments (block index, entry depth, exit depth) produced by the octree ray trace; the
+// march walks them front to back with ONE running step counter / depth, using block `b`'s occupancy grid inside
+// [world_origin + k_b * world_block_size, + world_block_size].  Unlike the single-grid marcher there is no AABB test
+// (the segment bounds play that role) and the voxel index is clamped.  Same float op order as the reference.
+// ------------------------------------------------------------------------------------------------------------
+struct ForestMarchArgs {
+    uint64_t n_rays;
+    const float *rays_o, *rays_d, *t_min, *t_max;
+    const int32_t* seg_block_inds;
+    const float *seg_entries, *seg_exits;
+    const int32_t* seg_pack_infos;
+    const int16_t* block_ks;  // [n_trees, 3]
+    F3 world_origin, world_block_size;
+    const uint8_t* grid;      // [n_trees, rx, ry, rz]
+    int3 res;
+    float step_size, max_step_size, dt_gamma;
+    uint32_t max_steps;
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+forest_march_kernel(const ForestMarchArgs a, const int32_t* __restrict__ packed_info, int32_t* __restrict__ num_steps,
+                    float* __restrict__ t_starts, float* __restrict__ t_ends, int32_t* __restrict__ ridx_out,
+                    int32_t* __restrict__ blidx_out, int32_t* __restrict__ gidx_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_rays) return;
+    const uint32_t seg_begin = (uint32_t)a.seg_pack_infos[i * 2], seg_length = (uint32_t)a.seg_pack_infos[i * 2 + 1];
+    const uint32_t cells = (uint32_t)(a.res.x * a.res.y * a.res.z);
+    uint32_t max_steps = a.max_steps;
+    uint64_t base = 0;
+    if (FILL) {
+        base = (uint32_t)packed_info[i * 2 + 0];
+        max_steps = (uint32_t)packed_info[i * 2 + 1];
+        if (max_steps == 0) return;
+    }
+    const F3 origin = F3{a.rays_o[i * 3 + 0], a.rays_o[i * 3 + 1], a.rays_o[i * 3 + 2]};
+    const F3 dir = F3{a.rays_d[i * 3 + 0], a.rays_d[i * 3 + 1], a.rays_d[i * 3 + 2]};
+    const F3 inv_dir = F3{1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z};
+    const float near = a.t_min[i], far = a.t_max[i];
+    const float dt_min = a.step_size, dt_max = a.max_step_size;
+
+    uint32_t j = 0;
+    float t0 = near;
+    float dt = calc_dt(t0, a.dt_gamma, dt_min, dt_max);
+    float t1 = t0 + dt;
+    float t_mid = (t0 + t1) * 0.5f;
+    for (uint32_t s = 0; s < seg_length; ++s) {
+        const float cur_entry = a.seg_entries[seg_begin + s], cur_exit = a.seg_exits[seg_begin + s];
+        const uint32_t block_ind = (uint32_t)a.seg_block_inds[seg_begin + s];
+        const int16_t* k = a.block_ks + (uint64_t)block_ind * 3;
+        const F3 lo = F3{a.world_origin.x + (float)k[0] * a.world_block_size.x, a.world_origin.y + (float)k[1] * a.world_block_size.y,
+                         a.world_origin.z + (float)k[2] * a.world_block_size.z};
+        const F3 hi = F3{lo.x + a.world_block_size.x, lo.y + a.world_block_size.y, lo.z + a.world_block_size.z};
+        const uint32_t grid_offset = block_ind * cells;
+        const uint8_t* __restrict__ grid = a.grid + grid_offset;
+        if (cur_entry >= far || cur_exit <= near) break;
+        do { t_mid += a.step_size; } while (t_mid < cur_entry);   // march to the entry of this block segment
+        dt = calc_dt(t_mid, a.dt_gamma, dt_min, dt_max);
+        t0 = t_mid - dt * 0.5f;
+        t1 = t_mid + dt * 0.5f;
+        while ((t_mid <= cur_exit) && (t_mid <= far) && (j < max_steps)) {
+            const F3 p = F3{origin.x + t_mid * dir.x, origin.y + t_mid * dir.y, origin.z + t_mid * dir.z};
+            const F3 u = roi_to_unit(p, lo, hi);
+            int ix = (int)(u.x * (float)a.res.x), iy = (int)(u.y * (float)a.res.y), iz = (int)(u.z * (float)a.res.z);
+            ix = max(0, min(ix, a.res.x - 1));
+            iy = max(0, min(iy, a.res.y - 1));
+            iz = max(0, min(iz, a.res.z - 1));
+            const int grid_idx = ix * (a.res.y * a.res.z) + iy * a.res.z + iz;
+            if (grid[grid_idx] != 0) {
+                if (FILL) {
+                    t_starts[base + j] = t0;
+                    t_ends[base + j] = t1;
+                    ridx_out[base + j] = (int32_t)i;
+                    blidx_out[base + j] = (int32_t)block_ind;
+                    if (gidx_out) gidx_out[base + j] = grid_idx + (int32_t)grid_offset;
+                }
+                ++j;
+                t0 = t1;
+                t1 = t0 + calc_dt(t0, a.dt_gamma, dt_min, dt_max);
+                t_mid = (t0 + t1) * 0.5f;
+            } else {
+                t_mid = advance_to_next_voxel(t_mid, dt_min, p, dir, inv_dir, lo, hi, a.res);
+                dt = calc_dt(t_mid, a.dt_gamma, dt_min, dt_max);
+                t0 = t_mid - dt * 0.5f;
+                t1 = t_mid + dt * 0.5f;
+            }
+        }
+    }
+    if (!FILL) num_steps[i] = (int32_t)j;
+}
+
+static int fill_forest_args(ForestMarchArgs& a, uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                            const int32_t* seg_block_inds, const float* seg_entries, const float* seg_exits, const int32_t* seg_pack_infos,
+                            const int16_t* block_ks, const float* world_origin, const float* world_block_size, const uint8_t* grid,
+                            int32_t rx, int32_t ry, int32_t rz, float step_size, float max_step_size, float dt_gamma, uint32_t max_steps) {
+    NR3D_CHECK(rays_o && rays_d && t_min && t_max && seg_pack_infos && block_ks && world_origin && world_block_size && grid,
+               "forest_ray_marching: null argument");
+    NR3D_CHECK(rx > 0 && ry > 0 && rz > 0, "forest_ray_marching: invalid grid shape");
+    NR3D_CHECK(n_rays < (1ull << 31), "forest_ray_marching: n_rays must be < 2^31");
+    a.n_rays = n_rays; a.rays_o = rays_o; a.rays_d = rays_d; a.t_min = t_min; a.t_max = t_max;
+    a.seg_block_inds = seg_block_inds; a.seg_entries = seg_entries; a.seg_exits = seg_exits; a.seg_pack_infos = seg_pack_infos;
+    a.block_ks = block_ks;
+    a.world_origin = F3{world_origin[0], world_origin[1], world_origin[2]};
+    a.world_block_size = F3{world_block_size[0], world_block_size[1], world_block_size[2]};
+    a.grid = grid; a.res = make_int3(rx, ry, rz);
+    a.step_size = step_size; a.max_step_size = max_step_size; a.dt_gamma = dt_gamma; a.max_steps = max_steps;
+    return 0;
+}
+
 }  // namespace nr3d
 
 using namespace nr3d;
@@ -211,6 +323,37 @@ int nr3d_march_fill(uint64_t n_rays, const float* rays_o, const float* rays_d, c
     NR3D_CHECK(packed_info && t_starts && t_ends && ridx, "ray_marching: null output");
     march_kernel<true><<<(unsigned)div_up<uint64_t>(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(a, packed_info, nullptr, t_starts, t_ends, ridx, bidx, gidx);
     NR3D_LAUNCH_CHECK("ray_marching(fill)");
+    return 0;
+}
+
+int nr3d_forest_march_count(uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                            const int32_t* seg_block_inds, const float* seg_entries, const float* seg_exits, const int32_t* seg_pack_infos,
+                            const int16_t* block_ks, const float* world_origin, const float* world_block_size, const uint8_t* grid,
+                            int32_t rx, int32_t ry, int32_t rz, float step_size, float max_step_size, float dt_gamma, uint32_t max_steps,
+                            int32_t* num_steps, void* stream) {
+    if (n_rays == 0) return 0;
+    ForestMarchArgs a;
+    if (int rc = fill_forest_args(a, n_rays, rays_o, rays_d, t_min, t_max, seg_block_inds, seg_entries, seg_exits, seg_pack_infos, block_ks,
+                                  world_origin, world_block_size, grid, rx, ry, rz, step_size, max_step_size, dt_gamma, max_steps)) return rc;
+    NR3D_CHECK(num_steps != nullptr, "forest_ray_marching: null num_steps");
+    forest_march_kernel<false><<<(unsigned)div_up<uint64_t>(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(a, nullptr, num_steps, nullptr, nullptr, nullptr, nullptr, nullptr);
+    NR3D_LAUNCH_CHECK("forest_ray_marching(count)");
+    return 0;
+}
+
+int nr3d_forest_march_fill(uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                           const int32_t* seg_block_inds, const float* seg_entries, const float* seg_exits, const int32_t* seg_pack_infos,
+                           const int16_t* block_ks, const float* world_origin, const float* world_block_size, const uint8_t* grid,
+                           int32_t rx, int32_t ry, int32_t rz, float step_size, float max_step_size, float dt_gamma, uint32_t max_steps,
+                           const int32_t* packed_info, float* t_starts, float* t_ends, int32_t* ridx, int32_t* blidx, int32_t* gidx,
+                           void* stream) {
+    if (n_rays == 0) return 0;
+    ForestMarchArgs a;
+    if (int rc = fill_forest_args(a, n_rays, rays_o, rays_d, t_min, t_max, seg_block_inds, seg_entries, seg_exits, seg_pack_infos, block_ks,
+                                  world_origin, world_block_size, grid, rx, ry, rz, step_size, max_step_size, dt_gamma, max_steps)) return rc;
+    NR3D_CHECK(packed_info && t_starts && t_ends && ridx && blidx, "forest_ray_marching: null output");
+    forest_march_kernel<true><<<(unsigned)div_up<uint64_t>(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(a, packed_info, nullptr, t_starts, t_ends, ridx, blidx, gidx);
+    NR3D_LAUNCH_CHECK("forest_ray_marching(fill)");
     return 0;
 }
 

@@ -27,8 +27,54 @@ class RenderOut:
 
 
 def density_proxy(features: torch.Tensor, gain: float = 20.0) -> torch.Tensor:
-    """Stand-in for the density head of the decoder: softplus of the (scaled) feature sum."""
+    """Stand-in for the density head of the decoder: softplus of the (scaled) feature sum (torch composition; the
+    pipeline itself uses the one-pass `density_alpha` below, this one is what the tests compare it with)."""
     return F.softplus(features.sum(-1) * gain)
+
+
+class _DensityAlpha(torch.autograd.Function):
+    """sigma = softplus(gain * sum_c h), alpha = 1 - exp(-sigma * deltas) in ONE pass over the [S, C] features each way
+    (csrc/pipeline_ops.cu) instead of sum / mul / softplus / mul / exp / rsub and their six backward kernels."""
+
+    @staticmethod
+    def forward(ctx, h, deltas, gain):
+        from . import _lib
+        dev = _lib.require_cuda(h, deltas, who="density_alpha")
+        if h.dtype != torch.float32 or h.dim() != 2:
+            raise RuntimeError("density_alpha: features must be float32 [S, C]")
+        if h.stride(1) != 1:
+            h = h.contiguous()
+        deltas = deltas.contiguous()
+        S, C = h.shape
+        with torch.cuda.device(dev):
+            sigma = torch.empty(S, dtype=torch.float32, device=dev)
+            alpha = torch.empty(S, dtype=torch.float32, device=dev)
+            _lib.check(_lib.get_lib().nr3d_density_alpha_fwd(S, C, h.data_ptr(), h.stride(0), deltas.data_ptr(), float(gain), sigma.data_ptr(),
+                                                             alpha.data_ptr(), _lib.stream_of(dev)))
+        ctx.save_for_backward(sigma, alpha, deltas)
+        ctx.gain, ctx.C = float(gain), C
+        ctx.mark_non_differentiable(sigma)
+        return alpha, sigma
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_alpha, _d_sigma):
+        from . import _lib
+        sigma, alpha, deltas = ctx.saved_tensors
+        if d_alpha is None:
+            return None, None, None
+        d_alpha = d_alpha.contiguous()
+        S, dev = sigma.shape[0], sigma.device
+        with torch.cuda.device(dev):
+            d_h = torch.empty(S, ctx.C, dtype=torch.float32, device=dev)
+            _lib.check(_lib.get_lib().nr3d_density_alpha_bwd(S, ctx.C, d_alpha.data_ptr(), None, sigma.data_ptr(), alpha.data_ptr(),
+                                                             deltas.data_ptr(), ctx.gain, d_h.data_ptr(), _lib.stream_of(dev)))
+        return d_h, None, None
+
+
+def density_alpha(features: torch.Tensor, deltas: torch.Tensor, gain: float = 20.0):
+    """(alpha, sigma) of the stand-in density head; differentiable w.r.t. `features` through alpha."""
+    return _DensityAlpha.apply(features, deltas, gain)
 
 
 def march_encode_composite(encoder: LoTD, params: torch.Tensor, occ_grid: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor,
@@ -40,8 +86,7 @@ def march_encode_composite(encoder: LoTD, params: torch.Tensor, occ_grid: torch.
         return RenderOut(ret, None, None, None)
     x01 = ret.samples * 0.5 + 0.5                      # [-1,1] -> [0,1]  (LoTDEncoding.forward, lotd_encoding.py:162)
     h = encoder(x01, params)                           # [S, n_enc]
-    sigma = density_proxy(h.float(), gain)
-    alpha = 1.0 - torch.exp(-sigma * ret.deltas)       # nerf_ray_query.py:182
+    alpha, _sigma = density_alpha(h.float(), ret.deltas, gain)   # softplus head + (1 - exp(-sigma * delta)), nerf_ray_query.py:182
     w = packed_alpha_to_vw(alpha, ret.pack_infos, early_stop_eps, alpha_thre)
     depth = packed_sum(w * ret.depth_samples, ret.pack_infos)
     acc = packed_sum(w, ret.pack_infos)

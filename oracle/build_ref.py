@@ -98,6 +98,11 @@ def ext_specs(scratch):
                      ("ray_marching.cu", "batched_marching.cu", "forest_marching.cu", "occ_grid.cpp")],
             includes=[os.path.join(CSRC, "occ_grid", "include"), os.path.join(CSRC, "forest")],
             nvcc=other_nv, cxx=["-std=c++17", "-O3", "-fPIC", "-w"]),
+        # our own 20-line pybind registration of the reference's ForestMeta struct (the reference's forest.cpp needs kaolin)
+        "_forest": dict(
+            sources=[os.path.join(HERE, "ref_forest_meta.cpp")],
+            includes=[os.path.join(CSRC, "forest")],
+            nvcc=other_nv, cxx=["-std=c++17", "-O3", "-fPIC", "-w"]),
     }
 
 
@@ -112,7 +117,7 @@ def run(cmd, log):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--jobs", type=int, default=min(8, os.cpu_count() or 4))
-    ap.add_argument("--only", default="lotd,pack_ops,occ_grid")
+    ap.add_argument("--only", default="lotd,pack_ops,occ_grid,forest")
     args = ap.parse_args()
     if not os.path.isdir(CSRC):
         print(f"[build_ref] {CSRC} not present - nothing to build (GPU box uses the prebuilt oracle/_ref/*.so)")

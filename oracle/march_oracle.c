@@ -148,3 +148,93 @@ void march_oracle_fill(uint64_t n_rays, const float* rays_o, const float* rays_d
         for (uint32_t j = 0; j < n; ++j) { ridx[base + j] = (int32_t)i; if (bidx) bidx[base + j] = (int32_t)b; }
     }
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * forest (multi-block) marcher: csrc/occ_grid/src/forest_marching.cu:27-150.  One running (j, t0, t1, t_mid) per ray
+ * across its block segments; block b spans [world_origin + k_b * world_block_size, + world_block_size] (the product is
+ * contracted into an FMA by nvcc, hence fmaf) and is looked up WITHOUT the AABB test, with a clamped voxel index
+ * (forest_marching.cu:16-25).  If t_starts == NULL only counts.
+ * ------------------------------------------------------------------------------------------------------------- */
+static uint32_t forest_march_one(const float* o, const float* d, float near, float far, uint32_t seg_length, const int32_t* seg_block_inds,
+                                 const float* seg_entries, const float* seg_exits, const int16_t* block_ks, const float* world_origin,
+                                 const float* world_block_size, const int res[3], const uint8_t* grid_all, float step_size,
+                                 float max_step_size, float dt_gamma, uint32_t max_steps, float* t_starts, float* t_ends, int32_t* blidx,
+                                 int32_t* gidx) {
+    f3 origin = {o[0], o[1], o[2]}, dir = {d[0], d[1], d[2]};
+    f3 inv_dir = {1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z};
+    const uint32_t cells = (uint32_t)(res[0] * res[1] * res[2]);
+    float dt_min = step_size, dt_max = max_step_size;
+    uint32_t j = 0;
+    float t0 = near;
+    float dt = calc_dt(t0, dt_gamma, dt_min, dt_max);
+    float t1 = t0 + dt;
+    float t_mid = (t0 + t1) * 0.5f;
+    for (uint32_t s = 0; s < seg_length; ++s) {
+        const float cur_entry = seg_entries[s], cur_exit = seg_exits[s];
+        const uint32_t b = (uint32_t)seg_block_inds[s];
+        const int16_t* k = block_ks + 3 * (size_t)b;
+        f3 lo = {fmaf((float)k[0], world_block_size[0], world_origin[0]), fmaf((float)k[1], world_block_size[1], world_origin[1]),
+                 fmaf((float)k[2], world_block_size[2], world_origin[2])};
+        f3 hi = {lo.x + world_block_size[0], lo.y + world_block_size[1], lo.z + world_block_size[2]};
+        const uint32_t grid_offset = b * cells;
+        const uint8_t* grid = grid_all + grid_offset;
+        if (cur_entry >= far || cur_exit <= near) break;
+        do { t_mid += step_size; } while (t_mid < cur_entry);
+        dt = calc_dt(t_mid, dt_gamma, dt_min, dt_max);
+        t0 = t_mid - dt * 0.5f;
+        t1 = t_mid + dt * 0.5f;
+        while ((t_mid <= cur_exit) && (t_mid <= far) && (j < max_steps)) {
+            f3 p = {fmaf(t_mid, dir.x, origin.x), fmaf(t_mid, dir.y, origin.y), fmaf(t_mid, dir.z, origin.z)};
+            f3 u = roi_to_unit(p, lo, hi);
+            int ix = (int)(u.x * (float)res[0]), iy = (int)(u.y * (float)res[1]), iz = (int)(u.z * (float)res[2]);
+            ix = imax(0, imin(ix, res[0] - 1));
+            iy = imax(0, imin(iy, res[1] - 1));
+            iz = imax(0, imin(iz, res[2] - 1));
+            const int gi = ix * (res[1] * res[2]) + iy * res[2] + iz;
+            if (grid[gi] != 0) {
+                if (t_starts) { t_starts[j] = t0; t_ends[j] = t1; blidx[j] = (int32_t)b; if (gidx) gidx[j] = gi + (int32_t)grid_offset; }
+                ++j;
+                t0 = t1;
+                t1 = t0 + calc_dt(t0, dt_gamma, dt_min, dt_max);
+                t_mid = (t0 + t1) * 0.5f;
+            } else {
+                t_mid = advance_to_next_voxel(t_mid, dt_min, p, dir, inv_dir, lo, hi, res);
+                dt = calc_dt(t_mid, dt_gamma, dt_min, dt_max);
+                t0 = t_mid - dt * 0.5f;
+                t1 = t_mid + dt * 0.5f;
+            }
+        }
+    }
+    return j;
+}
+
+void forest_march_oracle_count(uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                               const int32_t* seg_block_inds, const float* seg_entries, const float* seg_exits, const int32_t* seg_pack_infos,
+                               const int16_t* block_ks, const float* world_origin, const float* world_block_size, const uint8_t* grid,
+                               int rx, int ry, int rz, float step_size, float max_step_size, float dt_gamma, uint32_t max_steps,
+                               int32_t* num_steps) {
+    const int res[3] = {rx, ry, rz};
+    for (uint64_t i = 0; i < n_rays; ++i) {
+        const int32_t sb = seg_pack_infos[2 * i], sl = seg_pack_infos[2 * i + 1];
+        num_steps[i] = (int32_t)forest_march_one(rays_o + 3 * i, rays_d + 3 * i, t_min[i], t_max[i], (uint32_t)sl, seg_block_inds + sb,
+                                                 seg_entries + sb, seg_exits + sb, block_ks, world_origin, world_block_size, res, grid,
+                                                 step_size, max_step_size, dt_gamma, max_steps, NULL, NULL, NULL, NULL);
+    }
+}
+
+void forest_march_oracle_fill(uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                              const int32_t* seg_block_inds, const float* seg_entries, const float* seg_exits, const int32_t* seg_pack_infos,
+                              const int16_t* block_ks, const float* world_origin, const float* world_block_size, const uint8_t* grid,
+                              int rx, int ry, int rz, float step_size, float max_step_size, float dt_gamma, const int32_t* packed_info,
+                              float* t_starts, float* t_ends, int32_t* ridx, int32_t* blidx, int32_t* gidx) {
+    const int res[3] = {rx, ry, rz};
+    for (uint64_t i = 0; i < n_rays; ++i) {
+        const int32_t sb = seg_pack_infos[2 * i], sl = seg_pack_infos[2 * i + 1];
+        const int32_t base = packed_info[2 * i], cnt = packed_info[2 * i + 1];
+        if (cnt <= 0) continue;
+        uint32_t n = forest_march_one(rays_o + 3 * i, rays_d + 3 * i, t_min[i], t_max[i], (uint32_t)sl, seg_block_inds + sb, seg_entries + sb,
+                                      seg_exits + sb, block_ks, world_origin, world_block_size, res, grid, step_size, max_step_size, dt_gamma,
+                                      (uint32_t)cnt, t_starts + base, t_ends + base, blidx + base, gidx ? gidx + base : NULL);
+        for (uint32_t j = 0; j < n; ++j) ridx[base + j] = (int32_t)i;
+    }
+}

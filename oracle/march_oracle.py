@@ -62,3 +62,31 @@ def ray_marching(rays_o, rays_d, t_min, t_max, roi, grid, contraction=0, step_si
     packed_info = np.ascontiguousarray(packed_info)
     lib.march_oracle_fill(*common, _p(packed_info), _p(t_starts), _p(t_ends), _p(ridx), _p(bidx), _p(gidx))
     return dict(packed_info=packed_info, t_starts=t_starts, t_ends=t_ends, ridx=ridx, bidx=bidx, gidx=gidx)
+
+
+def forest_ray_marching(rays_o, rays_d, t_min, t_max, seg_block_inds, seg_entries, seg_exits, seg_pack_infos, block_ks, world_origin,
+                        world_block_size, grid, step_size=1e-3, max_step_size=1e10, dt_gamma=0.0, max_steps=512):
+    """Forest (multi-block) marcher, csrc/occ_grid/src/forest_marching.cu.  ``grid`` bool/uint8 [n_trees,rx,ry,rz], ``block_ks`` int16
+    [n_trees,3].  Returns dict(packed_info int32 [R,2], t_starts, t_ends float32 [S], ridx, blidx, gidx int32 [S])."""
+    lib = _get()
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    rays_o, rays_d, t_min, t_max, seg_entries, seg_exits = map(f32, (rays_o, rays_d, t_min, t_max, seg_entries, seg_exits))
+    world_origin, world_block_size = f32(world_origin), f32(world_block_size)
+    seg_block_inds = np.ascontiguousarray(seg_block_inds, dtype=np.int32)
+    seg_pack_infos = np.ascontiguousarray(seg_pack_infos, dtype=np.int32)
+    block_ks = np.ascontiguousarray(block_ks, dtype=np.int16)
+    grid = np.ascontiguousarray(grid).astype(np.uint8)
+    res = grid.shape[-3:]
+    R = rays_o.shape[0]
+    num_steps = np.zeros(R, dtype=np.int32)
+    common = [ctypes.c_uint64(R), _p(rays_o), _p(rays_d), _p(t_min), _p(t_max), _p(seg_block_inds), _p(seg_entries), _p(seg_exits),
+              _p(seg_pack_infos), _p(block_ks), _p(world_origin), _p(world_block_size), _p(grid), ctypes.c_int(res[0]), ctypes.c_int(res[1]),
+              ctypes.c_int(res[2]), ctypes.c_float(step_size), ctypes.c_float(max_step_size), ctypes.c_float(dt_gamma)]
+    lib.forest_march_oracle_count(*common, ctypes.c_uint32(int(max_steps)), _p(num_steps))
+    cum = np.cumsum(num_steps.astype(np.int64))
+    packed_info = np.ascontiguousarray(np.stack([cum - num_steps, num_steps], 1).astype(np.int32))
+    S = int(cum[-1]) if R else 0
+    t_starts, t_ends = np.zeros(S, dtype=np.float32), np.zeros(S, dtype=np.float32)
+    ridx, blidx, gidx = (np.zeros(S, dtype=np.int32) for _ in range(3))
+    lib.forest_march_oracle_fill(*common, _p(packed_info), _p(t_starts), _p(t_ends), _p(ridx), _p(blidx), _p(gidx))
+    return dict(packed_info=packed_info, t_starts=t_starts, t_ends=t_ends, ridx=ridx, blidx=blidx, gidx=gidx)

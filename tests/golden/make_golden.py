@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from tests.util import LOTD_CONFIGS, lotd_inputs, load_ref, march_inputs, meta_args, pack_inputs, pack_next_inputs, seg_inputs  # noqa: E402
+from tests.util import FOREST_MARCH_CASES, LOTD_CONFIGS, forest_inputs, lotd_inputs, load_ref, march_inputs, meta_args, pack_inputs, pack_next_inputs, seg_inputs  # noqa: E402
 
 dev = torch.device("cuda:0")
 
@@ -169,6 +169,27 @@ def make_march(out_dir):
              packed_info=npy(pi), t_starts=npy(t0), t_ends=npy(t1), ridx=npy(ridx), bidx=npy(bidx), gidx=npy(gidx))
 
 
+def make_forest_march(out_dir):
+    """forest_ray_marching of the reference build (oracle/_ref/_occ_grid.so); ForestMeta comes from oracle/_ref/_forest.so, our
+    20-line pybind registration of the reference's struct (oracle/ref_forest_meta.cpp)."""
+    fm = load_ref("_forest")
+    ref = load_ref("_occ_grid")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    for name, c in FOREST_MARCH_CASES.items():
+        d = forest_inputs(**c["inp"])
+        meta = fm.ForestMeta()
+        meta.octree, meta.exsum, meta.block_ks = t(d["octree"]), t(d["exsum"]), t(d["block_ks"])
+        meta.world_origin, meta.world_block_size = [float(v) for v in d["world_origin"]], [float(v) for v in d["world_block_size"]]
+        meta.n_trees, meta.level, meta.level_poffset = int(d["block_ks"].shape[0]), int(d["level"]), int(d["level_poffset"])
+        meta.resolution = [1 << int(d["level"])] * 3     # ForestMetaRef reads resolution[0..2] unconditionally (forest.h:77)
+        res = ref.forest_ray_marching(meta, t(d["rays_o"]), t(d["rays_d"]), t(d["near"]), t(d["far"]), t(d["seg_block_inds"]), t(d["seg_entries"]),
+                                      t(d["seg_exits"]), t(d["seg_pack_infos"]), t(d["grid"]), c["step"], c["mx"], c["gamma"], c["ms"], True)
+        pi, t0, t1, ridx, blidx, gidx = res
+        save(out_dir, "forest_march_" + name, cfg=np.array([c["step"], c["mx"], c["gamma"], c["ms"]], dtype=np.float64),
+             packed_info=npy(pi), t_starts=npy(t0), t_ends=npy(t1), ridx=npy(ridx), blidx=npy(blidx), gidx=npy(gidx),
+             **{k: np.asarray(v) for k, v in d.items()})
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.abspath(__file__))))
@@ -177,7 +198,7 @@ if __name__ == "__main__":
     os.makedirs(args.out, exist_ok=True)
     assert torch.cuda.is_available(), "golden vectors are produced by the reference CUDA build: a GPU is required"
     only = set(args.only.split(',')) if args.only else None
-    for fn in (make_lotd, make_pack, make_pack_next, make_pack_seg, make_march):
+    for fn in (make_lotd, make_pack, make_pack_next, make_pack_seg, make_march, make_forest_march):
         if only and fn.__name__ not in only:
             continue
         try:

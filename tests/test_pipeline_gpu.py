@@ -84,3 +84,47 @@ def test_host_fed_steps_match_direct_calls(dev):
         _, want = _lotd.lod_bwd(meta, y * 0.5, xd, params, None, need_input_grad=False, need_param_grad=True)
         assert rel_err(outs[k], want.cpu()) < 1e-5, k         # atomics: summation order differs between runs
         assert outs[k].abs().max() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C", [32, 6, 5])
+def test_density_alpha_matches_torch_composition(C, dev):
+    """One-pass density head + opacity (csrc/pipeline_ops.cu) == softplus(sum * gain) -> 1 - exp(-sigma * delta), values and gradient."""
+    from nr3d_lib_b200.pipeline import density_alpha, density_proxy
+    g = torch.Generator().manual_seed(5)
+    S = 10007
+    h = (torch.randn(S, C, generator=g) * 0.3).to(dev)
+    h[:4] = 3.0                                               # gain * sum > 20: softplus' linear branch
+    deltas = (torch.rand(S, generator=g) * 0.05).to(dev)
+    w = torch.randn(S, generator=g).to(dev)
+    for hh in (h, h.t().contiguous().t()):                    # row-major and feature-major (the generic kernels' y layout)
+        a = hh.clone().requires_grad_(True)
+        alpha, sigma = density_alpha(a, deltas, 20.0)
+        (alpha * w).sum().backward()
+        b = hh.double().clone().requires_grad_(True)
+        sig_ref = density_proxy(b, 20.0)
+        alpha_ref = 1.0 - torch.exp(-sig_ref * deltas.double())
+        (alpha_ref * w.double()).sum().backward()
+        assert rel_err(sigma, sig_ref.detach()) < 1e-5 and rel_err(alpha.detach(), alpha_ref.detach()) < 1e-5
+        assert rel_err(a.grad, b.grad) < 1e-5
+    with pytest.raises(RuntimeError):
+        density_alpha(h.cpu(), deltas.cpu(), 20.0)
+
+
+@pytest.mark.gpu
+def test_march_samples_bit_identical_to_torch(dev):
+    from nr3d_lib_b200.bindings import _occ_grid
+    g = torch.Generator().manual_seed(6)
+    R, S = 513, 40001
+    o, d = torch.randn(R, 3, generator=g).to(dev), torch.randn(R, 3, generator=g).to(dev)
+    ridx = torch.randint(0, R, (S,), generator=g).sort().values.to(dev)
+    t0 = (torch.rand(S, generator=g) * 5).to(dev)
+    t1 = t0 + 0.01
+    want = torch.addcmul(o.index_select(0, ridx), d.index_select(0, ridx), t0.unsqueeze(-1))
+    for r in (ridx, ridx.int()):
+        s, dl = _occ_grid.march_samples(o, d, t0.unsqueeze(-1), t1.unsqueeze(-1), r)
+        assert torch.equal(s, want) and torch.equal(dl, t1 - t0)
+    s, dl = _occ_grid.march_samples(o, d, t0, None, ridx)
+    assert dl is None and torch.equal(s, want)
+    e, _ = _occ_grid.march_samples(o, d, t0[:0], None, ridx[:0])
+    assert e.shape == (0, 3)

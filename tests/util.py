@@ -216,3 +216,95 @@ def seg_inputs(P=41, max_segs=6, seed=0, n_points=64):
     opi = np.stack([np.cumsum(ln) - ln, ln], 1)
     pidx = np.concatenate([np.sort(rs.randint(0, n_points, size=k)) for k in ln]).astype(np.int32)
     return dict(seg_pack_infos=spi, entry=entry, exit=exit_, near=near, far=far, points=points, oct_pack_infos=opi, pidx=pidx)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# forest (multi-block) inputs: blocks of an octree level, SPC octree bytes, rays and their block segments
+# --------------------------------------------------------------------------------------------------------------
+def build_octree(block_ks, level):
+    """kaolin-SPC style octree of the occupied integer blocks at `level` (what kaolin.ops.spc.unbatched_points_to_octree +
+    Spc.exsum give the reference, lotd/tests/math_test_forest.py:36-57): BFS node bytes (bit `x<<2|y<<1|z` = child occupied),
+    exsum = exclusive prefix sum of the child counts (int32 [n_nodes+1], exsum[0] = 0 ... the reference's `identify` walks
+    `ord = exsum[ord] + inclusive_popc`, csrc/forest/forest.h:25-57), the level's blocks in Morton order and the number of
+    nodes above `level` (ForestMeta.level_poffset)."""
+    ks = sorted({tuple(int(v) for v in k) for k in block_ks})
+    def morton(k, lv):
+        m = 0
+        for d in range(lv):
+            m |= (((k[0] >> d) & 1) << 2 | ((k[1] >> d) & 1) << 1 | ((k[2] >> d) & 1)) << (3 * d)
+        return m
+    levels = [None] * (level + 1)
+    levels[level] = sorted(ks, key=lambda k: morton(k, level))
+    for lv in range(level - 1, -1, -1):
+        parents = {(k[0] >> 1, k[1] >> 1, k[2] >> 1) for k in levels[lv + 1]}
+        levels[lv] = sorted(parents, key=lambda k: morton(k, lv))
+    octree = []
+    for lv in range(level):
+        children = set(levels[lv + 1])
+        for k in levels[lv]:
+            byte = 0
+            for c in range(8):
+                ck = (2 * k[0] + ((c >> 2) & 1), 2 * k[1] + ((c >> 1) & 1), 2 * k[2] + (c & 1))
+                if ck in children:
+                    byte |= 1 << c
+            octree.append(byte)
+    octree = np.array(octree, dtype=np.uint8)
+    pop = np.array([bin(int(b)).count("1") for b in octree], dtype=np.int32)
+    exsum = np.concatenate([[0], np.cumsum(pop)]).astype(np.int32)
+    poffset = sum(len(levels[lv]) for lv in range(level))
+    return octree, exsum, np.array(levels[level], dtype=np.int16), int(poffset)
+
+
+def forest_inputs(R=400, res=16, seed=0, level=2, occupancy=0.5, n_blocks=6, block_size=0.5, origin=(-1.0, -1.0, -1.0)):
+    """A few blocks of a 2^level grid, one occupancy grid per block, rays through the forest and -- per ray -- the blocks
+    it crosses front to back with entry / exit depths (slab test per block; the reference gets these from kaolin's SPC ray trace)."""
+    rs = np.random.RandomState(seed)
+    n = 1 << level
+    all_k = np.stack(np.meshgrid(*[np.arange(n)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    pick = all_k[rs.permutation(len(all_k))[:n_blocks]]
+    octree, exsum, block_ks, poffset = build_octree(pick, level)
+    B = block_ks.shape[0]
+    grid = rs.rand(B, res, res, res) > (1.0 - occupancy)
+    origin = np.asarray(origin, dtype=np.float32)
+    bs = np.full(3, block_size, dtype=np.float32)
+    ext_lo, ext_hi = origin, origin + bs * n
+    ctr, half = (ext_lo + ext_hi) / 2, (ext_hi - ext_lo) / 2
+    o = rs.randn(R, 3)
+    o = (ctr + 2.5 * half.max() * o / np.linalg.norm(o, axis=1, keepdims=True)).astype(np.float32)
+    tgt = (ctr + (rs.rand(R, 3) - 0.5) * 2 * half * 0.9).astype(np.float32)
+    d = tgt - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    lo = origin + block_ks.astype(np.float32) * bs          # [B,3]
+    hi = lo + bs
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t1 = (lo[None] - o[:, None]) / d[:, None]            # [R,B,3]
+        t2 = (hi[None] - o[:, None]) / d[:, None]
+    ent = np.minimum(t1, t2).max(-1)
+    ext = np.maximum(t1, t2).min(-1)
+    hit = ext > np.maximum(ent, 0.0)
+    seg_b, seg_in, seg_out, spi = [], [], [], []
+    for r in range(R):
+        idx = np.nonzero(hit[r])[0]
+        idx = idx[np.argsort(ent[r, idx], kind="stable")]
+        spi.append((len(seg_b), len(idx)))
+        seg_b += idx.tolist()
+        seg_in += np.maximum(ent[r, idx], 0.0).tolist()
+        seg_out += ext[r, idx].tolist()
+    spi = np.array(spi, dtype=np.int32)
+    seg_in, seg_out = np.array(seg_in, dtype=np.float32), np.array(seg_out, dtype=np.float32)
+    near = np.zeros(R, dtype=np.float32)
+    far = np.full(R, 1e4, dtype=np.float32)
+    has = spi[:, 1] > 0
+    near[has] = seg_in[spi[has, 0]]
+    far[has] = seg_out[spi[has, 0] + spi[has, 1] - 1]
+    return dict(rays_o=o, rays_d=d, near=near, far=far, seg_block_inds=np.array(seg_b, dtype=np.int32), seg_entries=seg_in, seg_exits=seg_out,
+                seg_pack_infos=spi, grid=grid, block_ks=block_ks, octree=octree, exsum=exsum, level=level, level_poffset=poffset,
+                world_origin=origin, world_block_size=bs)
+
+
+FOREST_MARCH_CASES = {
+    "basic": dict(inp=dict(R=600, res=16, seed=31, level=2, n_blocks=24, occupancy=0.4), step=0.01, mx=1e10, gamma=0.0, ms=512),
+    "gamma": dict(inp=dict(R=400, res=12, seed=32, level=2, n_blocks=40, occupancy=0.6), step=0.004, mx=0.05, gamma=0.01, ms=256),
+    "maxsteps": dict(inp=dict(R=300, res=8, seed=33, level=1, n_blocks=7, occupancy=0.9, block_size=1.0), step=0.01, mx=1e10, gamma=0.0, ms=23),
+    "sparse": dict(inp=dict(R=500, res=20, seed=34, level=3, n_blocks=60, occupancy=0.15, block_size=0.25), step=0.003, mx=1e10, gamma=0.0, ms=1024),
+}
