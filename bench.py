@@ -39,6 +39,9 @@ N_POINTS = 4 * 1024 * 1024          # per GPU (weak scaling)
 BYTES_FWD, BYTES_BWD, BYTES_TABLE = 12 + 1024 + 128, 12 + 128 + 1024, 23
 BYTES_PER_SAMPLE = BYTES_FWD + BYTES_BWD + BYTES_TABLE   # 2351
 BYTES_PER_SAMPLE_F16 = (12 + 512 + 64) + (12 + 64 + 512) + 12   # 1188 (SURVEY.md 8d, fp16 parameter tables)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the two dominant kernels at this workload, from the committed
+# `ncu --set full` capture profiles/r1_s2_pair_ncu_summary.txt (4 Mi points): the table is L2 resident, DRAM only sees x / y / dL_dy
+NCU_DRAM_BYTES = {"lod_bwd (dL/dparam scatter)": 672.2e6 + 36.2e6, "lod_fwd (corner gather)": 151.2e6 + 500.4e6}
 
 
 def ngp_cfg(min_res=16, n_levels=16, scale=1.382, log2_T=19, F=2):
@@ -162,6 +165,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e leg without copy/compute overlap (single stream)")
     ap.add_argument("--no-sort", action="store_true", help="use the generic (unsorted, feature-major) kernels instead of lotd_fast.cu")
+    ap.add_argument("--no-m2", action="store_true", help="skip the secondary M2 block (march + encode + composite rays/s)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -266,7 +270,8 @@ def main():
     dom_ms, dom_bytes = (ms_bwd, BYTES_BWD + BYTES_TABLE) if ms_bwd >= ms_fwd else (ms_fwd, BYTES_FWD)
     achieved = N * dom_bytes / (dom_ms * 1e-3) / 1e9
     whole = value * 1e6 / n_gpus * BYTES_PER_SAMPLE / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES[dom],
+                "traffic_source": "ncu --set full capture of this kernel at this workload, profiles/r1_s2_pair_ncu_summary.txt (bytes per launch)",
                 "peak_source": peak_src, "algorithmic_bytes_per_sample": {"fwd": BYTES_FWD, "bwd": BYTES_BWD, "table": BYTES_TABLE},
                 "ms": {"lod_fwd": ms_fwd, "lod_bwd": ms_bwd},
                 "whole_step": {"achieved": whole, "frac": whole / peak, "bytes_per_sample": BYTES_PER_SAMPLE}}
@@ -286,6 +291,15 @@ def main():
     fp16_block = {"value": half_value, "unit": UNIT, "ms_per_step": ms_half, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE_F16,
                   "roofline_frac_whole_step": whole_h / peak}
 
+    # second half of BASELINE.json's metric ("full march+composite rays/s @1/2/4/8 GPU"): 1024^2 rays per GPU through
+    # march -> LoTD -> density head -> alpha-composite, forward + backward, one all-reduce per step (scripts/m2_bench.py)
+    m2_block = None
+    if not args.no_m2:
+        del params_h, dL_dy_h, dL_dy, x
+        torch.cuda.empty_cache()
+        from scripts.m2_bench import run_m2
+        m2_block = run_m2(dev, rank, n_gpus, steps=3, warmup=1)
+
     ndist.barrier()
     ndist.shutdown()
     if rank != 0:
@@ -300,7 +314,7 @@ def main():
                     "d2h_bytes_per_step": int(grad_host.numel() * 4),
                     "note": "x from pinned host memory each step, dL_dy derived on device from the step's y, dL/dparams read back to host; "
                             + ("single stream" if args.e2e_serial else "copies of neighbouring steps overlap the kernels (pipeline.HostFedLoTDStep)")},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "fp16_params": fp16_block}
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "fp16_params": fp16_block, "m2": m2_block}
     print(json.dumps(line), flush=True)
     return 0
 

@@ -61,6 +61,15 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+def sum_over_ranks(value: float, device=None) -> float:
+    """sum of a python float over all ranks (e.g. the number of samples every rank marched this step)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
 def shutdown():
     """Tear the default process group down (silences NCCL's leak warning at interpreter exit)."""
     if dist.is_available() and dist.is_initialized():

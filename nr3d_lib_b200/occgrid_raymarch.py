@@ -8,9 +8,10 @@ from typing import Literal, Optional, Union
 import torch
 
 from .bindings import _occ_grid as _backend
-from .pack_ops import packed_diff
+from .pack_ops import get_pack_infos_from_boundary, mark_pack_boundaries, packed_diff
 
-__all__ = ['ContractionType', 'RaymarchRetSingle', 'RaymarchRetBatched', 'occgrid_raymarch', 'occgrid_raymarch_batched']
+__all__ = ['ContractionType', 'RaymarchRetSingle', 'RaymarchRetBatched', 'RaymarchRetForest', 'occgrid_raymarch', 'occgrid_raymarch_batched',
+           'occgrid_raymarch_forest']
 
 
 class ContractionType(Enum):
@@ -45,6 +46,14 @@ class RaymarchRetSingle(_RetBase):
 @dataclass
 class RaymarchRetBatched(_RetBase):
     bidx: Optional[torch.Tensor]            # [num_samples] batch index of each sample
+    gidx: Optional[torch.Tensor]
+    gidx_pack_infos: Optional[torch.Tensor]
+
+
+@dataclass
+class RaymarchRetForest(_RetBase):
+    blidx: Optional[torch.Tensor]            # [num_samples] block index of each sample
+    blidx_pack_infos: Optional[torch.Tensor]  # [num_block_packs, 2] one pack per run of samples in the same block
     gidx: Optional[torch.Tensor]
     gidx_pack_infos: Optional[torch.Tensor]
 
@@ -141,3 +150,27 @@ def occgrid_raymarch_batched(occ_grid: torch.Tensor, rays_o: torch.Tensor, rays_
         return RaymarchRetBatched(0, None, None, None, None, None, None, None, None, None)
     ridx_hit, pack_infos, deltas, t_samples, samples = fin
     return RaymarchRetBatched(ridx_hit.numel(), ridx_hit, samples, t_samples, deltas, ridx, pack_infos, bidx, gidx, None)
+
+
+def occgrid_raymarch_forest(forest_meta, occ_grid: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor, near: Union[torch.Tensor, float],
+                            far: Union[torch.Tensor, float], seg_block_inds: torch.Tensor, seg_entries: torch.Tensor, seg_exits: torch.Tensor,
+                            seg_pack_infos: torch.Tensor, *, perturb=False, perturb_before_march=False, step_size: float = 1e-3,
+                            max_step_size: float = 1e10, dt_gamma: float = 0.0, max_steps: int = 512, step_size_factor=1.0) -> RaymarchRetForest:
+    """March rays through a forest of occupancy grids [n_blocks, rx, ry, rz] along their block segments
+    (reference occgrid_raymarch.py:223-272)."""
+    step_size *= step_size_factor
+    dt_gamma *= step_size_factor
+    near = rays_o.new_full(rays_o.shape[:-1], near) if not isinstance(near, torch.Tensor) else near
+    far = rays_o.new_full(rays_o.shape[:-1], far) if not isinstance(far, torch.Tensor) else far
+    if perturb and perturb_before_march:
+        near = near + step_size * torch.rand_like(near)
+    pack_infos, t_starts, t_ends, ridx, blidx, _ = _backend.forest_ray_marching(
+        forest_meta, rays_o, rays_d, near, far, seg_block_inds.int().contiguous(), seg_entries.contiguous(), seg_exits.contiguous(),
+        seg_pack_infos.int().contiguous(), occ_grid, step_size, max_step_size, dt_gamma, max_steps, False)
+    ridx, blidx = ridx.long(), blidx.long()
+    fin = _finish(rays_o, rays_d, pack_infos, t_starts, t_ends, ridx, perturb, perturb_before_march)
+    if fin is None:
+        return RaymarchRetForest(0, None, None, None, None, None, None, None, None, None, None)
+    ridx_hit, pack_infos, deltas, t_samples, samples = fin
+    blidx_pack_infos = get_pack_infos_from_boundary(mark_pack_boundaries(blidx))
+    return RaymarchRetForest(ridx_hit.numel(), ridx_hit, samples, t_samples, deltas, ridx, pack_infos, blidx, blidx_pack_infos, None, None)

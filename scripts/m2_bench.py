@@ -33,6 +33,59 @@ def make_rays(n, dev, seed):
     return o.contiguous(), d.contiguous(), near.contiguous(), far.contiguous()
 
 
+def run_m2(dev, rank, world, rays=1024 * 1024, chunk=262144, grid_kind="random", steps=3, warmup=1, sort_points=True):
+    """Times `steps` M2 steps (after `warmup`) on this rank's ray shard; returns the result dict (max over ranks inside)."""
+    _, res, feats, types, T, _ = ngp_cfg()
+    enc = LoTD(3, res, feats, types, hashmap_size=T, dtype=torch.float)
+    enc.meta.c_sort_points = sort_points
+    g = torch.Generator(device=dev).manual_seed(42)
+    params = ((torch.rand(enc.n_params, device=dev, generator=g) * 2 - 1) * 1e-2).requires_grad_(True)
+    R = 128
+    if grid_kind == "random":
+        grid = torch.rand(R, R, R, device=dev, generator=g) > 0.5
+    else:
+        ax = torch.linspace(-1, 1, R, device=dev)
+        pts = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1)
+        grid = (pts.norm(dim=-1) - 0.6).abs() < 0.05
+    ray_set = make_rays(rays, dev, 1000 + rank)
+    n_samples = 0
+
+    def step():
+        nonlocal n_samples
+        params.grad = None
+        n_samples = 0
+        for b in range(0, rays, chunk):
+            o, d, near, far = (r[b:b + chunk] for r in ray_set)
+            out = march_encode_composite(enc, params, grid, o, d, near, far, step_size=0.01, max_steps=512, gain=2.0)
+            if out.depth is None:
+                continue
+            n_samples += out.weights.numel()
+            ((out.depth ** 2).sum() + out.acc.sum()).backward()
+        if params.grad is not None:
+            ndist.allreduce_param_grads(params.grad, world)
+
+    for _ in range(warmup):
+        step()
+    ndist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = ndist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    ndist.barrier()
+    total_samples = ndist.sum_over_ranks(float(n_samples), dev)
+    return {"metric": "full march+encode+composite fwd+bwd Mrays/s", "value": world * rays / ms / 1e3, "unit": "Mrays/s",
+            "n_gpus": world, "ms_per_step": ms, "rays_per_gpu": rays, "samples_per_ray": total_samples / (world * rays),
+            "Msamples_per_s": total_samples / ms / 1e3, "grid": grid_kind, "chunk": chunk, "steps": steps, "warmup": warmup,
+            "sort_points": sort_points, "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+            "workload": "configs[2]/[4]: occ_grid 128^3 march (step 0.01, <=512 steps) + 16L NGP LoTD + softplus density head + "
+                        "packed alpha-composite + per-ray sums, forward + backward to the LoTD parameters, rays sharded over the GPUs, "
+                        "one NCCL all-reduce of dL/dparams per step"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=1024 * 1024)
@@ -45,53 +98,10 @@ def main():
     rank, world, local = ndist.init_from_env("nccl")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    _, res, feats, types, T, _ = ngp_cfg()
-    enc = LoTD(3, res, feats, types, hashmap_size=T, dtype=torch.float)
-    enc.meta.c_sort_points = not args.no_sort
-    g = torch.Generator(device=dev).manual_seed(42)
-    params = ((torch.rand(enc.n_params, device=dev, generator=g) * 2 - 1) * 1e-2).requires_grad_(True)
-    R = 128
-    if args.grid == "random":
-        grid = torch.rand(R, R, R, device=dev, generator=g) > 0.5
-    else:
-        ax = torch.linspace(-1, 1, R, device=dev)
-        pts = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1)
-        grid = (pts.norm(dim=-1) - 0.6).abs() < 0.05
-    rays = make_rays(args.rays, dev, 1000 + rank)
-    n_samples = 0
-
-    def step():
-        nonlocal n_samples
-        params.grad = None
-        n_samples = 0
-        for b in range(0, args.rays, args.chunk):
-            o, d, near, far = (r[b:b + args.chunk] for r in rays)
-            out = march_encode_composite(enc, params, grid, o, d, near, far, step_size=0.01, max_steps=512, gain=2.0)
-            if out.depth is None:
-                continue
-            n_samples += out.weights.numel()
-            ((out.depth ** 2).sum() + out.acc.sum()).backward()
-        if params.grad is not None:
-            ndist.allreduce_param_grads(params.grad, world)
-
-    for _ in range(args.warmup):
-        step()
-    ndist.barrier()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = ndist.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
-    ndist.barrier()
+    out = run_m2(dev, rank, world, args.rays, args.chunk, args.grid, args.steps, args.warmup, not args.no_sort)
     ndist.shutdown()
     if rank == 0:
-        print(json.dumps({"metric": "full march+encode+composite fwd+bwd Mrays/s", "value": world * args.rays / ms / 1e3, "unit": "Mrays/s",
-                          "n_gpus": world, "ms_per_step": ms, "rays_per_gpu": args.rays, "samples_per_ray": n_samples / args.rays,
-                          "Msamples_per_s": world * n_samples / ms / 1e3, "grid": args.grid, "chunk": args.chunk,
-                          "sort_points": not args.no_sort, "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}))
+        print(json.dumps(out))
 
 
 if __name__ == "__main__":

@@ -132,3 +132,29 @@ def test_forest_march_edges(dev):
         c = lambda a: torch.from_numpy(np.ascontiguousarray(a))
         og.forest_ray_marching(_forest_meta(og.ForestMeta, d, c), c(d["rays_o"]), c(d["rays_d"]), c(d["near"]), c(d["far"]), c(d["seg_block_inds"]),
                                c(d["seg_entries"]), c(d["seg_exits"]), c(d["seg_pack_infos"]), c(d["grid"]), 0.01, 1e10, 0.0, 64, True)
+
+
+@pytest.mark.gpu
+def test_forest_wrapper(dev):
+    """occgrid_raymarch_forest (mirror of the reference wrapper, occgrid_raymarch.py:223-272): packs per hit ray and per block run."""
+    from nr3d_lib_b200.bindings import _occ_grid as og
+    from nr3d_lib_b200.occgrid_raymarch import occgrid_raymarch_forest
+    c = FOREST_MARCH_CASES["basic"]
+    d = forest_inputs(**c["inp"])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    ret = occgrid_raymarch_forest(_forest_meta(og.ForestMeta, d, t), t(d["grid"]), t(d["rays_o"]), t(d["rays_d"]), t(d["near"]), t(d["far"]),
+                                  t(d["seg_block_inds"]), t(d["seg_entries"]), t(d["seg_exits"]), t(d["seg_pack_infos"]), step_size=c["step"],
+                                  max_steps=c["ms"])
+    o = _oracle(d, c["step"], c["mx"], c["gamma"], c["ms"])
+    hit = o["packed_info"][:, 1] > 0
+    assert ret.num_hit_rays == int(hit.sum()) and np.array_equal(ret.ridx_hit.cpu().numpy(), np.nonzero(hit)[0])
+    assert np.array_equal(ret.pack_infos.cpu().numpy(), o["packed_info"][hit].astype(np.int64))
+    assert np.array_equal(ret.blidx.cpu().numpy(), o["blidx"].astype(np.int64))
+    assert np.array_equal(ret.deltas.cpu().numpy(), o["t_ends"] - o["t_starts"])
+    want = torch.addcmul(torch.from_numpy(d["rays_o"])[o["ridx"].astype(np.int64)], torch.from_numpy(d["rays_d"])[o["ridx"].astype(np.int64)],
+                         torch.from_numpy(o["t_starts"]).unsqueeze(-1))
+    assert torch.equal(ret.samples.cpu(), want)
+    bpi = ret.blidx_pack_infos.cpu().numpy()
+    assert bpi[:, 1].sum() == o["blidx"].size and np.array_equal(bpi[:, 0], np.cumsum(bpi[:, 1]) - bpi[:, 1])
+    for b, n in bpi[:200]:
+        assert len(set(o["blidx"][b:b + n].tolist())) == 1
