@@ -111,6 +111,39 @@ int nr3d_lotd_grid_index(const nr3d_lotd_meta* meta, int32_t input_dtype, uint64
                          const int64_t* batch_inds, const int64_t* batch_offsets, uint32_t batch_data_size,
                          int32_t max_level, int64_t* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LoTD over a forest of blocks.  Replaces the `metas=(LoDMeta, ForestMeta)` overloads of
+ * lod_fwd / lod_bwd / lod_bwd_bwd_input (csrc/lotd/src/lotd.cpp:45-58 -> lod_forest_*, lotd_torch_api.cu:367-381,539-556,750-769;
+ * kernels csrc/lotd/include/lotd/lotd_forest.h).  `batch_inds` are the points' BLOCK indices (int64 [N], < 0 = skip),
+ * `x` their block-local coordinates in [0,1]^3; every block owns n_params parameters at batch_offsets[b] (or b * n_params).
+ * Corners on a block face belong to the neighbour block found through the octree (csrc/forest/forest.h:25-57); absent
+ * neighbours contribute zero.  D = 3; level types Dense / VM / NPlaneMul / CP / Hash.  Outputs are row-major.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct nr3d_forest_meta {          /* device views of ForestMeta's tensors, csrc/forest/forest_cpp_api.h:16-36 */
+    const uint8_t* octree;                 /* uint8 [n_nodes]   SPC octree bytes (kaolin layout) */
+    const int32_t* exsum;                  /* int32 [n_nodes+1] exclusive sum of the child counts */
+    const int16_t* block_ks;               /* int16 [n_trees,3] integer block coordinates */
+    uint32_t n_trees, level, level_poffset, continuity_enabled;
+} nr3d_forest_meta;
+
+/* == lod_forest_fwd.  y: [N, n_enc] param dtype; dy_dx: f32 [N, n_enc, 3] or NULL; both fully written. */
+int nr3d_lotd_forest_fwd(const nr3d_lotd_meta* meta, const nr3d_forest_meta* forest, int32_t input_dtype, int32_t param_dtype,
+                         uint64_t N, const void* x, const void* params, const int64_t* batch_inds, const int64_t* batch_offsets,
+                         uint32_t batch_data_size, int32_t max_level, void* y, void* dy_dx, void* stream);
+/* == lod_forest_bwd (dL/dparam) when dL_ddLdx == NULL, else the second-order d(dL/dx)/dparam . dL_ddLdx of
+ * lod_forest_bwd_bwd_input.  dL_dparam (param dtype, [n_blocks * n_params]) is ACCUMULATED into: zero it first.
+ * (dL/dx and dL/d(dL/dy) are contractions with dy_dx: use nr3d_lotd_bwd_input / nr3d_lotd_bwd_bwd_input with dL_dparam = dL_dx = NULL.) */
+int nr3d_lotd_forest_bwd_param(const nr3d_lotd_meta* meta, const nr3d_forest_meta* forest, int32_t input_dtype, int32_t param_dtype,
+                               uint64_t N, const void* dL_dy, int64_t dLdy_stride_n, int64_t dLdy_stride_f, const void* dL_ddLdx,
+                               const void* x, const void* params, const int64_t* batch_inds, const int64_t* batch_offsets,
+                               uint32_t batch_data_size, int32_t max_level, void* dL_dparam, void* stream);
+/* == the d(dL/dx)/dx . dL_ddLdx part of lod_forest_bwd_bwd_input (Dense / VM / Hash levels, lotd_forest.h:1022-1050).
+ * dL_dx: f32 [N,3], accumulated into (zero it first). */
+int nr3d_lotd_forest_bwd_bwd_dx(const nr3d_lotd_meta* meta, const nr3d_forest_meta* forest, int32_t input_dtype, int32_t param_dtype,
+                                uint64_t N, const void* dL_ddLdx, const void* dL_dy, int64_t dLdy_stride_n, int64_t dLdy_stride_f,
+                                const void* x, const void* params, const int64_t* batch_inds, const int64_t* batch_offsets,
+                                uint32_t batch_data_size, int32_t max_level, void* dL_dx, void* stream);
+
 /* B200 fast path for Dense/Hash-only metas (D = 3, 2 features per pseudo level, fp32 params, single scene).  No
  * reference counterpart: the shim uses it for lod_fwd / lod_bwd when LoDMeta.c_sort_points is set.
  *   sort_points : counting sort of the points by a 128^3 cell key (x fastest) into `xs`, float4 [N] records
@@ -182,7 +215,7 @@ int nr3d_forest_march_fill(uint64_t n_rays, const float* rays_o, const float* ra
 
 /* Post-processing of the marcher's output in one pass (replaces index_select x2 + addcmul + sub of
  * nr3d_lib/graphics/raymarch/occgrid_raymarch.py:96-107): samples[i] = rays_o[ridx[i]] + rays_d[ridx[i]] * t_starts[i]
- * (product rounded, then sum rounded -- bit-identical to torch.addcmul), deltas[i] = t_ends[i] - t_starts[i] (deltas / t_ends nullable).
+ * (one FMA per component -- bit-identical to torch.addcmul on CUDA), deltas[i] = t_ends[i] - t_starts[i] (deltas / t_ends nullable).
  * ridx: int32 or int64 [S] (ridx_dtype = NR3D_I32 / NR3D_I64). */
 int nr3d_march_samples(uint64_t S, const float* rays_o, const float* rays_d, const float* t_starts, const float* t_ends,
                        const void* ridx, int32_t ridx_dtype, float* samples, float* deltas, void* stream);

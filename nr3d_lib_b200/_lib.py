@@ -41,6 +41,12 @@ class LotdMetaStruct(ctypes.Structure):
     ]
 
 
+class ForestMetaStruct(ctypes.Structure):
+    """Mirror of ``nr3d_forest_meta``."""
+    _fields_ = [("octree", ctypes.c_void_p), ("exsum", ctypes.c_void_p), ("block_ks", ctypes.c_void_p), ("n_trees", ctypes.c_uint32),
+                ("level", ctypes.c_uint32), ("level_poffset", ctypes.c_uint32), ("continuity_enabled", ctypes.c_uint32)]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -48,6 +54,7 @@ _vp, _i32, _u32, _i64, _u64, _f32, _f64 = (ctypes.c_void_p, ctypes.c_int32, ctyp
                                            ctypes.c_uint64, ctypes.c_float, ctypes.c_double)
 _meta_p = ctypes.POINTER(LotdMetaStruct)
 _u64_p = ctypes.POINTER(ctypes.c_uint64)
+_forest_p = ctypes.POINTER(ForestMetaStruct)
 _f32_3 = ctypes.POINTER(ctypes.c_float)    # 3 host floats
 
 # name -> argtypes, exactly the declarations of include/nr3d_b200.h
@@ -59,6 +66,9 @@ SIGNATURES = {
     "nr3d_lotd_bwd_bwd_input": [_meta_p, _i32, _i32, _u64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _u32,
                                 _i32, _vp, _vp, _vp, _vp],
     "nr3d_lotd_grid_index": [_meta_p, _i32, _u64, _vp, _vp, _vp, _u32, _i32, _vp, _vp],
+    "nr3d_lotd_forest_fwd": [_meta_p, _forest_p, _i32, _i32, _u64, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp, _vp],
+    "nr3d_lotd_forest_bwd_param": [_meta_p, _forest_p, _i32, _i32, _u64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp],
+    "nr3d_lotd_forest_bwd_bwd_dx": [_meta_p, _forest_p, _i32, _i32, _u64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp],
     "nr3d_lotd_sort_points": [_u64, _vp, _vp, _vp, _u64_p, _vp],
     "nr3d_lotd_fwd_sorted": [_meta_p, _i32, _u64, _vp, _vp, _i32, _vp, _i64, _i64, _vp],
     "nr3d_lotd_bwd_param_sorted": [_meta_p, _i32, _u64, _vp, _vp, _i64, _i64, _i32, _vp, _vp],

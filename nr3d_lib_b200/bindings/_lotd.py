@@ -139,9 +139,40 @@ def _is_forest(meta):
     return isinstance(meta, (tuple, list))
 
 
-def _forest_unsupported():
-    raise RuntimeError("nr3d_lib_b200: forest (multi-block) LoTD overloads are not part of the B200 hot path yet "
-                       "(SURVEY.md section 8f, row n4).")
+def _split_metas(lod_meta, fn, input, batch_offsets):
+    """`metas=(LoDMeta, ForestMeta)` overloads (csrc/lotd/src/lotd.cpp:45-58): returns (LoDMeta, nr3d_forest_meta struct | None) after
+    the reference's forest argument checks (lotd_torch_api.cu:333-359)."""
+    if not _is_forest(lod_meta):
+        return lod_meta, None
+    if len(lod_meta) != 2:
+        raise RuntimeError(f"{fn}: expected metas=(LoDMeta, ForestMeta)")
+    meta, forest = lod_meta
+    if not isinstance(meta, LoDMeta):
+        raise RuntimeError(f"{fn}: incompatible function arguments: lod_meta must be a LoDMeta")
+    if meta.n_dims_to_encode != 3:
+        raise RuntimeError("LoTDEncoding::fwd: lotd-forest only supports `n_dims_to_encode`==3")
+    octree, exsum, block_ks = forest.octree, forest.exsum, forest.block_ks
+    for name, t, dim, dt in (("forest.octree", octree, 1, torch.uint8), ("forest.exsum", exsum, 1, torch.int32),
+                             ("forest.block_ks", block_ks, 2, torch.int16)):
+        if t is None or t.dim() != dim:
+            raise RuntimeError(f"{fn}: Expected {dim}-dimensional tensor for argument '{name}'")
+        if t.dtype != dt:
+            raise RuntimeError(f"{fn}: Expected '{name}' to have scalar type {dt}, got {t.dtype}")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{fn}: Expected contiguous tensor for argument '{name}'")
+    n_trees = int(forest.n_trees)
+    if tuple(block_ks.shape) != (n_trees, 3):
+        raise RuntimeError(f"{fn}: Expected tensor of size [{n_trees}, 3] for argument 'forest.block_ks', got {tuple(block_ks.shape)}")
+    _lib.require_cuda(input, octree, exsum, block_ks, who=fn)
+    if batch_offsets is not None and tuple(batch_offsets.shape) != (n_trees,):
+        raise RuntimeError(f"{fn}: Expected tensor of size [{n_trees}] for argument 'batch_offset'")
+    for tp in meta.level_types:
+        if tp not in (int(LoDType.Dense), int(LoDType.VectorMatrix), int(LoDType.NPlaneMul), int(LoDType.CP), int(LoDType.Hash)):
+            raise RuntimeError("LoTDEncoding: lotd-forest supports Dense / VM / NPlaneMul / CP / Hash levels only")
+    fm = _lib.ForestMetaStruct(octree.data_ptr(), exsum.data_ptr(), block_ks.data_ptr(), n_trees, int(forest.level), int(forest.level_poffset),
+                               1 if getattr(forest, "continuity_enabled", True) else 0)
+    fm._keepalive = (octree, exsum, block_ks)
+    return meta, fm
 
 
 def _check_common(fn, meta: LoDMeta, input, params, batch_inds, batch_offsets, batch_data_size):
@@ -232,10 +263,8 @@ def _dydx_view(dy_dx, N, meta):
 def lod_fwd(lod_meta, input: torch.Tensor, params: torch.Tensor, batch_inds: Optional[torch.Tensor] = None,
             batch_offsets: Optional[torch.Tensor] = None, batch_data_size: Optional[int] = None,
             max_level: Optional[int] = None, need_input_grad: Optional[bool] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """== lotd::torch::lod_fwd (csrc/lotd/src/lotd_torch_api.cu:232-395)."""
-    if _is_forest(lod_meta):
-        _forest_unsupported()
-    meta = lod_meta
+    """== lotd::torch::lod_fwd / lod_forest_fwd (csrc/lotd/src/lotd_torch_api.cu:232-395)."""
+    meta, forest = _split_metas(lod_meta, "fwd", input, batch_offsets)
     N, bds, dev = _check_common("fwd", meta, input, params, batch_inds, batch_offsets, batch_data_size)
     D, E = meta.n_dims_to_encode, meta.n_encoded_dims
     max_level = meta.n_levels if max_level is None else int(max_level)
@@ -244,6 +273,16 @@ def lod_fwd(lod_meta, input: torch.Tensor, params: torch.Tensor, batch_inds: Opt
         return (torch.zeros([N, E], dtype=params.dtype, device=dev), torch.zeros([N, E * D], dtype=input.dtype, device=dev))
     dy_dx = None
     ds_n = ds_f = 0
+    if forest is not None:   # row-major outputs (lotd_forest.h:198-207); every element is written by the kernel
+        with torch.cuda.device(dev):
+            y = torch.empty([N, E], dtype=params.dtype, device=dev)
+            if need_input_grad:
+                dy_dx = torch.empty([N, E * D], dtype=input.dtype, device=dev)
+            _lib.check(_lib.get_lib().nr3d_lotd_forest_fwd(
+                ctypes.byref(meta._c), ctypes.byref(forest), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, _lib.ptr(input),
+                _lib.ptr(params), _lib.ptr(batch_inds), _lib.ptr(batch_offsets), bds, max_level, y.data_ptr(), _lib.ptr(dy_dx),
+                _lib.stream_of(dev)))
+        return y, dy_dx
     with torch.cuda.device(dev):
         if not need_input_grad and _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
             xs = _sorted_points(input)
@@ -280,10 +319,8 @@ def lod_bwd(lod_meta, dL_dy: torch.Tensor, input: torch.Tensor, params: torch.Te
             batch_inds: Optional[torch.Tensor] = None, batch_offsets: Optional[torch.Tensor] = None,
             batch_data_size: Optional[int] = None, max_level: Optional[int] = None, need_input_grad: Optional[bool] = None,
             need_param_grad: Optional[bool] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """== lotd::torch::lod_bwd (csrc/lotd/src/lotd_torch_api.cu:397-573)."""
-    if _is_forest(lod_meta):
-        _forest_unsupported()
-    meta = lod_meta
+    """== lotd::torch::lod_bwd / lod_forest_bwd (csrc/lotd/src/lotd_torch_api.cu:397-573)."""
+    meta, forest = _split_metas(lod_meta, "bwd", input, batch_offsets)
     N, bds, dev = _check_common("bwd", meta, input, params, batch_inds, batch_offsets, batch_data_size)
     D, E = meta.n_dims_to_encode, meta.n_encoded_dims
     if dL_dy.dim() != 2 or tuple(dL_dy.shape) != (N, E):
@@ -313,7 +350,12 @@ def lod_bwd(lod_meta, dL_dy: torch.Tensor, input: torch.Tensor, params: torch.Te
             _lib.check(lib.nr3d_lotd_bwd_input(
                 ctypes.byref(meta._c), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, dL_dy.data_ptr(),
                 dL_dy.stride(0), dL_dy.stride(1), dv.data_ptr(), ds_n, ds_f, dL_dx.data_ptr(), st))
-        if need_param_grad and _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
+        if need_param_grad and forest is not None:
+            _lib.check(lib.nr3d_lotd_forest_bwd_param(
+                ctypes.byref(meta._c), ctypes.byref(forest), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, dL_dy.data_ptr(),
+                dL_dy.stride(0), dL_dy.stride(1), None, input.data_ptr(), params.data_ptr(), _lib.ptr(batch_inds), _lib.ptr(batch_offsets),
+                bds, max_level, dL_dparam.data_ptr(), st))
+        elif need_param_grad and _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
             xs = _sorted_points(input)
             _lib.check(lib.nr3d_lotd_bwd_param_sorted(
                 ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), dL_dy.data_ptr(),
@@ -331,10 +373,8 @@ def lod_bwd_bwd_input(lod_meta, dL_ddLdx: torch.Tensor, dL_dy: torch.Tensor, inp
                       batch_offsets: Optional[torch.Tensor] = None, batch_data_size: Optional[int] = None,
                       max_level: Optional[int] = None, need_dLdinput_ddLdoutput: Optional[bool] = None,
                       need_dLdinput_dparams: Optional[bool] = None, need_dLdinput_dinput: Optional[bool] = None):
-    """== lotd::torch::lod_bwd_bwd_input (csrc/lotd/src/lotd_torch_api.cu:575-769) -> (dL_ddLdy, dL_dparams, dL_dx)."""
-    if _is_forest(lod_meta):
-        _forest_unsupported()
-    meta = lod_meta
+    """== lotd::torch::lod_bwd_bwd_input / lod_forest_bwd_bwd_input (csrc/lotd/src/lotd_torch_api.cu:575-769) -> (dL_ddLdy, dL_dparams, dL_dx)."""
+    meta, forest = _split_metas(lod_meta, "bwd_bwd_input", input, batch_offsets)
     N, bds, dev = _check_common("bwd_bwd_input", meta, input, params, batch_inds, batch_offsets, batch_data_size)
     D, E = meta.n_dims_to_encode, meta.n_encoded_dims
     if dL_ddLdx.dim() != 2 or tuple(dL_ddLdx.shape) != (N, D) or not dL_ddLdx.is_contiguous():
@@ -368,11 +408,29 @@ def lod_bwd_bwd_input(lod_meta, dL_ddLdx: torch.Tensor, dL_dy: torch.Tensor, inp
         dv, ds_n, ds_f = (None, 0, 0)
         if need_dLdy:
             dv, ds_n, ds_f = _dydx_view(dy_dx, N, meta)
-        _lib.check(_lib.get_lib().nr3d_lotd_bwd_bwd_input(
-            ctypes.byref(meta._c), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, dL_ddLdx.data_ptr(),
+        lib, st = _lib.get_lib(), _lib.stream_of(dev)
+        idt, pdt = _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype)
+        if forest is not None:
+            if need_dLdy:      # contraction with dy_dx: the same kernel as the single-block encoder
+                _lib.check(lib.nr3d_lotd_bwd_bwd_input(
+                    ctypes.byref(meta._c), idt, pdt, N, dL_ddLdx.data_ptr(), dL_dy.data_ptr(), dL_dy.stride(0), dL_dy.stride(1), input.data_ptr(),
+                    params.data_ptr(), _lib.ptr(dv), ds_n, ds_f, None, None, 0, max_level, _lib.ptr(dL_ddLdy), None, None, st))
+            if need_param:
+                _lib.check(lib.nr3d_lotd_forest_bwd_param(
+                    ctypes.byref(meta._c), ctypes.byref(forest), idt, pdt, N, dL_dy.data_ptr(), dL_dy.stride(0), dL_dy.stride(1),
+                    dL_ddLdx.data_ptr(), input.data_ptr(), params.data_ptr(), _lib.ptr(batch_inds), _lib.ptr(batch_offsets), bds, max_level,
+                    dL_dparams.data_ptr(), st))
+            if need_input:
+                _lib.check(lib.nr3d_lotd_forest_bwd_bwd_dx(
+                    ctypes.byref(meta._c), ctypes.byref(forest), idt, pdt, N, dL_ddLdx.data_ptr(), dL_dy.data_ptr(), dL_dy.stride(0),
+                    dL_dy.stride(1), input.data_ptr(), params.data_ptr(), _lib.ptr(batch_inds), _lib.ptr(batch_offsets), bds, max_level,
+                    dL_dx.data_ptr(), st))
+            return dL_ddLdy, dL_dparams, dL_dx
+        _lib.check(lib.nr3d_lotd_bwd_bwd_input(
+            ctypes.byref(meta._c), idt, pdt, N, dL_ddLdx.data_ptr(),
             dL_dy.data_ptr(), dL_dy.stride(0), dL_dy.stride(1), input.data_ptr(), params.data_ptr(), _lib.ptr(dv), ds_n, ds_f,
             _lib.ptr(batch_inds), _lib.ptr(batch_offsets), bds, max_level, _lib.ptr(dL_ddLdy), _lib.ptr(dL_dparams),
-            _lib.ptr(dL_dx), _lib.stream_of(dev)))
+            _lib.ptr(dL_dx), st))
     return dL_ddLdy, dL_dparams, dL_dx
 
 

@@ -23,7 +23,7 @@ static bool all_divisible(const int32_t* v, int n, int k) {
     return true;
 }
 
-static int build_launch(const nr3d_lotd_meta* m, int32_t input_dtype, int32_t param_dtype, uint64_t N, const void* x,
+int build_launch(const nr3d_lotd_meta* m, int32_t input_dtype, int32_t param_dtype, uint64_t N, const void* x,
                         const void* params, const int64_t* batch_inds, const int64_t* batch_offsets,
                         uint32_t batch_data_size, int32_t max_level, void* stream, LotdLaunch& L) {
     NR3D_CHECK(m != nullptr, "LoTDEncoding: null meta");

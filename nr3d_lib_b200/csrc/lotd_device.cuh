@@ -260,6 +260,42 @@ __device__ __forceinline__ void corner_val(const Ctx<D>& c, const PT* __restrict
     }
 }
 
+// sum_f corner_value[f] * grad[f] for the level types with a second-order dL/dx (Dense / Hash / VM / VecZMatXoY).  VM keeps the
+// un-rounded products of the reference (calc_dLdx_dim_vm_impl, lotd_cuda.h:887-918).
+template <int D, int F, typename PT>
+__device__ __forceinline__ float corner_dot(const Ctx<D>& c, const PT* __restrict__ g, const uint32_t* pos, const float* grad, bool vec_ok) {
+    using C = Cvt<PT>;
+    float s = 0.f;
+    if (c.type == NR3D_LOD_VM) {
+        if constexpr (D == 3) {
+            uint32_t plx[D], lnx[D];
+            idx_vm<D>(c.res, pos, plx, lnx);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                PT a[F], b[F];
+                load_feats<F>(g + (uint64_t)plx[k] * c.n_feat + c.gfo, a, vec_ok);
+                load_feats<F>(g + (uint64_t)lnx[k] * c.n_feat + c.gfo, b, vec_ok);
+#pragma unroll
+                for (int f = 0; f < F; ++f) s += C::to_f(a[f]) * C::to_f(b[f]) * grad[f];
+            }
+        }
+    } else if (c.type == NR3D_LOD_VECZMATXOY) {
+        if constexpr (D == 3) {
+            PT a[F], b[F];
+            load_feats<F>(g + (uint64_t)(c.res[2] + pos[1] + pos[0] * c.res[0]) * c.n_feat + c.gfo, a, vec_ok);
+            load_feats<F>(g + (uint64_t)pos[2] * c.n_feat + c.gfo, b, vec_ok);
+#pragma unroll
+            for (int f = 0; f < F; ++f) s += C::to_f(a[f]) * C::to_f(b[f]) * grad[f];
+        }
+    } else {
+        PT v[F];
+        corner_val<D, F, PT>(c, g, pos, v, vec_ok);
+#pragma unroll
+        for (int f = 0; f < F; ++f) s += C::to_f(v[f]) * grad[f];
+    }
+    return s;
+}
+
 // ------------------------------------------------------------------------------------------------
 // gradient scatter
 // ------------------------------------------------------------------------------------------------

@@ -341,34 +341,7 @@ lotd_bwdbwd_input_kernel(const __grid_constant__ LotdTable tab, const LotdIn in,
         uint32_t pos[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) pos[d] = c.cell[d] + ((idx >> d) & 1);
-        float s = 0.f;
-        if (c.type == NR3D_LOD_VM) {
-            if constexpr (D == 3) {  // un-rounded products (calc_dLdx_dim_vm_impl, lotd_cuda.h:887-918)
-                uint32_t plx[D], lnx[D];
-                idx_vm<D>(c.res, pos, plx, lnx);
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    PT a[F], b[F];
-                    load_feats<F>(g + (uint64_t)plx[k] * c.n_feat + c.gfo, a, vec_ok);
-                    load_feats<F>(g + (uint64_t)lnx[k] * c.n_feat + c.gfo, b, vec_ok);
-#pragma unroll
-                    for (int f = 0; f < F; ++f) s += C::to_f(a[f]) * C::to_f(b[f]) * grad[f];
-                }
-            }
-        } else if (c.type == NR3D_LOD_VECZMATXOY) {
-            if constexpr (D == 3) {
-                PT a[F], b[F];
-                load_feats<F>(g + (uint64_t)(c.res[2] + pos[1] + pos[0] * c.res[0]) * c.n_feat + c.gfo, a, vec_ok);
-                load_feats<F>(g + (uint64_t)pos[2] * c.n_feat + c.gfo, b, vec_ok);
-#pragma unroll
-                for (int f = 0; f < F; ++f) s += C::to_f(a[f]) * C::to_f(b[f]) * grad[f];
-            }
-        } else {
-            PT v[F];
-            corner_val<D, F, PT>(c, g, pos, v, vec_ok);
-#pragma unroll
-            for (int f = 0; f < F; ++f) s += C::to_f(v[f]) * grad[f];
-        }
+        const float s = corner_dot<D, F, PT>(c, g, pos, grad, vec_ok);
         S[idx] = s;
     }
     float gin_other[D], gin_diag[D];
@@ -497,6 +470,11 @@ struct LotdLaunch {
     int half;       // param dtype: 0 float, 1 half
     cudaStream_t stream;
 };
+
+// fills L from the C-ABI arguments (defined in lotd_api.cu; shared with lotd_forest.cu)
+int build_launch(const nr3d_lotd_meta* m, int32_t input_dtype, int32_t param_dtype, uint64_t N, const void* x, const void* params,
+                 const int64_t* batch_inds, const int64_t* batch_offsets, uint32_t batch_data_size, int32_t max_level, void* stream,
+                 LotdLaunch& L);
 
 template <int D> int lotd_launch_fwd(const LotdLaunch& L, void* y, int64_t ys_n, int64_t ys_f, float* dydx, int64_t ds_n, int64_t ds_f);
 template <int D> int lotd_launch_bwd_param(const LotdLaunch& L, const void* dLdy, int64_t gs_n, int64_t gs_f, const float* ddx, void* grad_params);

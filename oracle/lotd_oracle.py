@@ -119,9 +119,10 @@ class OracleMeta:
 # ------------------------------------------------------------------------------------------------------------------
 # helpers
 # ------------------------------------------------------------------------------------------------------------------
-def _pos(x32: torch.Tensor, xd: torch.Tensor, R: List[int], smooth: bool):
-    """cell (int64 [N,D]) and (p, dp/dv) in xd's dtype; value path identical to the fp32 kernels, grad path exact."""
-    scale = torch.tensor([r - 2 for r in R], dtype=torch.float64)
+def _pos(x32: torch.Tensor, xd: torch.Tensor, R: List[int], smooth: bool, forest: bool = False):
+    """cell (int64 [N,D]) and (p, dp/dv) in xd's dtype; value path identical to the fp32 kernels, grad path exact.
+    forest=True: scale = res (lotd_forest.h:237-240), so cells run 0..res and corner 0 / res+1 belong to the neighbour blocks."""
+    scale = torch.tensor([r if forest else r - 2 for r in R], dtype=torch.float64)
     v32 = (x32.double() * scale + 0.5).float()          # == fmaf(x, scale, 0.5f): the double product/sum is exact before rounding
     cell = torch.floor(v32)
     f32 = (v32 - cell).to(xd.dtype)                      # exact in float32
@@ -283,6 +284,80 @@ def _level_value(tp, R, size, cell, p, G: _Gather):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# forest (multi-block) variant: csrc/lotd/include/lotd/lotd_forest.h:31-139 (forward), :319-407 (dL/dparam), csrc/forest/forest.h:25-97
+# ------------------------------------------------------------------------------------------------------------------
+class OracleForest:
+    """What the reference's ForestMetaRef carries (forest.h:59-97): SPC octree bytes, their exclusive child-count sums, the blocks'
+    integer coordinates and the octree level they live on."""
+
+    def __init__(self, octree, exsum, block_ks, level, level_poffset, continuity_enabled=True):
+        self.octree = np.asarray(octree, dtype=np.uint8)
+        self.exsum = np.asarray(exsum, dtype=np.int64)
+        self.block_ks = np.asarray(block_ks, dtype=np.int64)
+        self.level, self.level_poffset, self.continuity_enabled = int(level), int(level_poffset), bool(continuity_enabled)
+
+    def map_block_ind(self, k: np.ndarray) -> np.ndarray:
+        """== ForestMetaRef::map_block_ind / identify (forest.h:25-57,88-95), vectorised over k [M,3]: walk the octree from the root,
+        at every level test the child bit and jump to `exsum[ord] + (inclusive count of set bits up to the child)`; -1 if absent."""
+        k = np.asarray(k, dtype=np.int64)
+        M = k.shape[0]
+        maxval = (1 << self.level) - 1
+        ok = np.all((k >= 0) & (k <= maxval), axis=1)
+        ord_ = np.zeros(M, dtype=np.int64)
+        kk = np.where(ok[:, None], k, 0)
+        for l in range(self.level):
+            depth = self.level - l - 1
+            child = (((kk[:, 0] >> depth) & 1) << 2) | (((kk[:, 1] >> depth) & 1) << 1) | ((kk[:, 2] >> depth) & 1)
+            bits = self.octree[ord_].astype(np.int64)
+            has = ((bits >> child) & 1) == 1
+            masked = bits & ((2 << child) - 1)
+            cnt = np.zeros(M, dtype=np.int64)
+            for b in range(8):
+                cnt += (masked >> b) & 1
+            ok &= has
+            ord_ = np.where(ok, self.exsum[ord_] + cnt, 0)
+        return np.where(ok, ord_ - self.level_poffset, -1)
+
+
+def _forest_level_value(tp, R, size, cell, p, params64, b, forest: OracleForest, block_base_of, lvl_off, n_feat, gfo, F):
+    """n-linear value of one pseudo level with the cross-block continuity rule (lotd_forest.h:53-88): corner coordinate 0 is the
+    left neighbour's res-1, res+1 the right neighbour's 0, 1..res are the block's own 0..res-1; a corner whose block is not in
+    the forest (or any remapped corner when continuity is disabled) contributes zero."""
+    if tp not in (DENSE, HASH, VM, NPLANEMUL, CP):
+        raise RuntimeError("lotd-forest supports Dense / VM / NPlaneMul / CP / Hash levels only (lotd_forest.h:263-311)")
+    D, N = 3, cell.shape[0]
+    Rt = torch.tensor(R, dtype=torch.int64)
+    out = torch.zeros(N, F, dtype=p.dtype)
+    bk = torch.from_numpy(forest.block_ks)[b]                       # [N,3]
+    for bits in _corner_bits(D):
+        w = torch.ones(N, dtype=p.dtype)
+        pos = cell.clone()
+        for d in range(D):
+            if bits[d]:
+                w = w * p[:, d]
+                pos[:, d] += 1
+            else:
+                w = w * (1.0 - p[:, d])
+        left, right = pos == 0, pos == (Rt + 1)
+        kloc = bk - left.long() + right.long()
+        ploc = torch.where(left, Rt - 1, torch.where(right, torch.zeros_like(pos), pos - 1))
+        changed = (left | right).any(dim=1)
+        bl = b.clone()
+        valid = torch.ones(N, dtype=torch.bool)
+        if changed.any():
+            if not forest.continuity_enabled:
+                valid = ~changed
+            else:
+                nb = torch.from_numpy(forest.map_block_ind(kloc[changed].numpy()))
+                bl[changed] = nb.clamp_min(0)
+                valid[changed] = nb >= 0
+        G = _Gather(params64, block_base_of(bl) + lvl_off, n_feat, gfo, F)
+        val = _corner_value(tp, R, size, ploc, G)
+        out = out + (w * valid.to(p.dtype)).unsqueeze(-1) * val
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # public API
 # ------------------------------------------------------------------------------------------------------------------
 def _point_batches(N, batch_inds, batch_data_size):
@@ -297,7 +372,7 @@ def _point_batches(N, batch_inds, batch_data_size):
 
 
 def encode_levels(meta, x: torch.Tensor, params: torch.Tensor, batch_inds=None, batch_offsets=None, batch_data_size=0,
-                  max_level=None, dtype=torch.float64):
+                  max_level=None, dtype=torch.float64, forest: Optional["OracleForest"] = None):
     """Returns a list with one [N, F_pl] float64 tensor per pseudo level (differentiable w.r.t. x / params if they
     are float64 leaves requiring grad; otherwise they are promoted)."""
     D = meta.n_dims_to_encode
@@ -319,8 +394,14 @@ def encode_levels(meta, x: torch.Tensor, params: torch.Tensor, batch_inds=None, 
             continue
         R = list(meta.level_res_multidim[lvl])
         if lvl not in cache:
-            cache[lvl] = _pos(x32, xd, R, smooth)
+            cache[lvl] = _pos(x32, xd, R, smooth, forest is not None)
         cell, p = cache[lvl]
+        if forest is not None:
+            base_of = (lambda bl: batch_offsets.long()[bl]) if batch_offsets is not None else (lambda bl: bl * meta.n_params)
+            val = _forest_level_value(int(meta.level_types[lvl]), R, meta.level_sizes[lvl], cell, p, pd, b, forest, base_of,
+                                      meta.level_offsets[lvl], meta.level_n_feats[lvl], meta.map_cnt[pl] * F, F)
+            outs.append(val * valid.unsqueeze(-1))
+            continue
         G = _Gather(pd, boff + meta.level_offsets[lvl], meta.level_n_feats[lvl], meta.map_cnt[pl] * F, F)
         val = _level_value(int(meta.level_types[lvl]), R, meta.level_sizes[lvl], cell, p, G)
         outs.append(val * valid.unsqueeze(-1))
@@ -353,6 +434,7 @@ def bwd(meta, dL_dy, x, params, **kw):
 
 
 _SECOND_ORDER_DX_TYPES = (DENSE, HASH, VM, VECZMATXOY)  # lotd_encoding.h:1245-1284
+_SECOND_ORDER_DX_TYPES_FOREST = (DENSE, HASH, VM)       # lotd_forest.h:1022-1050
 
 
 def bwd_bwd_input(meta, dL_ddLdx, dL_dy, x, params, **kw):
@@ -371,7 +453,7 @@ def bwd_bwd_input(meta, dL_ddLdx, dL_dy, x, params, **kw):
         if dldx is None:
             continue
         total_dldx = total_dldx + dldx
-        if int(meta.level_types[meta.map_levels[pl]]) in _SECOND_ORDER_DX_TYPES:
+        if int(meta.level_types[meta.map_levels[pl]]) in (_SECOND_ORDER_DX_TYPES_FOREST if kw.get("forest") is not None else _SECOND_ORDER_DX_TYPES):
             dx_supported = dx_supported + dldx
     s_all = (total_dldx * dL_ddLdx.double()).sum()
     g_gy, g_p = torch.autograd.grad(s_all, [gy, pd], retain_graph=True, allow_unused=True)

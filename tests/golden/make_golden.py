@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from tests.util import FOREST_MARCH_CASES, LOTD_CONFIGS, forest_inputs, lotd_inputs, load_ref, march_inputs, meta_args, pack_inputs, pack_next_inputs, seg_inputs  # noqa: E402
+from tests.util import FOREST_LOTD_CONFIGS, FOREST_MARCH_CASES, LOTD_CONFIGS, forest_lotd_inputs, forest_inputs, lotd_inputs, load_ref, march_inputs, meta_args, pack_inputs, pack_next_inputs, seg_inputs  # noqa: E402
 
 dev = torch.device("cuda:0")
 
@@ -190,6 +190,39 @@ def make_forest_march(out_dir):
              **{k: np.asarray(v) for k, v in d.items()})
 
 
+def _ref_forest_meta(fm, f, t):
+    meta = fm.ForestMeta()
+    meta.octree, meta.exsum, meta.block_ks = t(f["octree"]), t(f["exsum"]), t(f["block_ks"])
+    meta.world_origin, meta.world_block_size = [float(v) for v in f["world_origin"]], [float(v) for v in f["world_block_size"]]
+    meta.n_trees, meta.level, meta.level_poffset = int(f["block_ks"].shape[0]), int(f["level"]), int(f["level_poffset"])
+    meta.resolution = [1 << int(f["level"])] * 3     # ForestMetaRef reads resolution[0..2] unconditionally (forest.h:77)
+    return meta
+
+
+def make_forest_lotd(out_dir):
+    """lod_bwd / lod_bwd_bwd_input with metas=(LoDMeta, ForestMeta) of the reference build.  The reference's forest FORWARD cannot
+    run at this commit (lod_fwd_common never allocates `output` / `dy_dx` on the forest branch, lotd_torch_api.cu:300-362), so the
+    fixtures hold what does run: dL/dparam, d(dL/dx)/dparam, d(dL/dx)/dx.  No dy_dx is passed (it would have to come from our side)."""
+    fm, ref = load_ref("_forest"), load_ref("_lotd")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    for name, cfg in FOREST_LOTD_CONFIGS.items():
+        meta = ref.LoDMeta(*meta_args(cfg))
+        for pdtype, tag in ((torch.float32, "f32"), (torch.float16, "f16")):
+            if tag == "f16" and name != "mixed":
+                continue
+            inp = forest_lotd_inputs(cfg, meta.n_params, N=256, seed=zlib.crc32(name.encode()) % 1000)
+            f = inp["forest"]
+            metas = (meta, _ref_forest_meta(fm, f, t))
+            x, params, dL_dy = inp["x"].to(dev), inp["params"].to(dev).to(pdtype), inp["dL_dy"].to(dev).to(pdtype)
+            ddx, bi = inp["dL_ddLdx"].to(dev), inp["batch_inds"].to(dev)
+            _, dL_dparam = ref.lod_bwd(metas, dL_dy, x, params, None, bi, None, None, None, False, True)
+            _, g_param2, g_x2 = ref.lod_bwd_bwd_input(metas, ddx, dL_dy, x, params, None, bi, None, None, None, False, True, True)
+            _, dL_dparam_ml = ref.lod_bwd(metas, dL_dy, x, params, None, bi, None, None, 1, False, True)
+            save(out_dir, f"forest_lotd_{name}_{tag}", x=npy(x), params=npy(params), dL_dy=npy(dL_dy), dL_ddLdx=npy(ddx), batch_inds=npy(bi),
+                 dL_dparam=npy(dL_dparam), dL_dparam2=npy(g_param2), dL_dx2=npy(g_x2), dL_dparam_maxlevel1=npy(dL_dparam_ml),
+                 octree=f["octree"], exsum=f["exsum"], block_ks=f["block_ks"], level=np.asarray(f["level"]), level_poffset=np.asarray(f["level_poffset"]))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.abspath(__file__))))
@@ -198,7 +231,7 @@ if __name__ == "__main__":
     os.makedirs(args.out, exist_ok=True)
     assert torch.cuda.is_available(), "golden vectors are produced by the reference CUDA build: a GPU is required"
     only = set(args.only.split(',')) if args.only else None
-    for fn in (make_lotd, make_pack, make_pack_next, make_pack_seg, make_march, make_forest_march):
+    for fn in (make_lotd, make_pack, make_pack_next, make_pack_seg, make_march, make_forest_march, make_forest_lotd):
         if only and fn.__name__ not in only:
             continue
         try:

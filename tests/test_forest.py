@@ -151,9 +151,9 @@ def test_forest_wrapper(dev):
     assert np.array_equal(ret.pack_infos.cpu().numpy(), o["packed_info"][hit].astype(np.int64))
     assert np.array_equal(ret.blidx.cpu().numpy(), o["blidx"].astype(np.int64))
     assert np.array_equal(ret.deltas.cpu().numpy(), o["t_ends"] - o["t_starts"])
-    want = torch.addcmul(torch.from_numpy(d["rays_o"])[o["ridx"].astype(np.int64)], torch.from_numpy(d["rays_d"])[o["ridx"].astype(np.int64)],
-                         torch.from_numpy(o["t_starts"]).unsqueeze(-1))
-    assert torch.equal(ret.samples.cpu(), want)
+    ridx = torch.from_numpy(o["ridx"].astype(np.int64)).to(dev)      # the reference composes the positions on the GPU (occgrid_raymarch.py:268)
+    want = torch.addcmul(t(d["rays_o"]).index_select(0, ridx), t(d["rays_d"]).index_select(0, ridx), t(o["t_starts"]).unsqueeze(-1))
+    assert torch.equal(ret.samples, want)
     bpi = ret.blidx_pack_infos.cpu().numpy()
     assert bpi[:, 1].sum() == o["blidx"].size and np.array_equal(bpi[:, 0], np.cumsum(bpi[:, 1]) - bpi[:, 1])
     for b, n in bpi[:200]:

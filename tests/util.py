@@ -308,3 +308,31 @@ FOREST_MARCH_CASES = {
     "maxsteps": dict(inp=dict(R=300, res=8, seed=33, level=1, n_blocks=7, occupancy=0.9, block_size=1.0), step=0.01, mx=1e10, gamma=0.0, ms=23),
     "sparse": dict(inp=dict(R=500, res=20, seed=34, level=3, n_blocks=60, occupancy=0.15, block_size=0.25), step=0.003, mx=1e10, gamma=0.0, ms=1024),
 }
+
+
+# forest LoTD: level zoo restricted to the types the reference's forest kernels implement (lotd_forest.h:263-311)
+FOREST_LOTD_CONFIGS = {
+    "mixed": dict(D=3, res=[4, 8, 6, 8, 12], feats=[2, 4, 2, 4, 2], types=["Dense", "VM", "NPlaneMul", "CP", "Hash"], T=2 ** 8, smooth=False,
+                  forest=dict(seed=51, level=2, n_blocks=24)),
+    "smooth": dict(D=3, res=[5, 16, 9], feats=[2, 2, 2], types=["Dense", "Hash", "VM"], T=2 ** 9, smooth=True, forest=dict(seed=52, level=3, n_blocks=70)),
+    "hash_f4": dict(D=3, res=[6, 20], feats=[4, 8], types=["Dense", "Hash"], T=2 ** 9, smooth=False, forest=dict(seed=53, level=1, n_blocks=5)),
+}
+
+
+def forest_lotd_inputs(cfg, n_params, N=256, seed=0):
+    """Block-local points for a forest LoTD: a good share hugs the block faces / edges / corners so that neighbour lookups
+    (present and absent neighbours) are exercised; 10 % of the points carry block index -1 (skipped)."""
+    rs = np.random.RandomState(seed)
+    f = forest_inputs(R=4, res=2, **cfg["forest"])
+    B, E = f["block_ks"].shape[0], sum(cfg["feats"])
+    x = rs.rand(N, 3).astype(np.float32)
+    edge = rs.rand(N, 3) < 0.3
+    side = rs.rand(N, 3) < 0.5
+    near = (rs.rand(N, 3) * 0.04).astype(np.float32)
+    x = np.where(edge, np.where(side, near, 1.0 - near), x).astype(np.float32)
+    x = np.clip(x, 1e-6, 1 - 1e-6)
+    bi = rs.randint(0, B, size=N).astype(np.int64)
+    bi[rs.rand(N) < 0.1] = -1
+    return dict(x=torch.from_numpy(x), params=torch.from_numpy((rs.randn(B * n_params) * 0.1).astype(np.float32)),
+                dL_dy=torch.from_numpy(rs.randn(N, E).astype(np.float32)), dL_ddLdx=torch.from_numpy(rs.randn(N, 3).astype(np.float32)),
+                batch_inds=torch.from_numpy(bi), forest=f)
