@@ -52,14 +52,23 @@ def _stash(ctx, meta, prefix, batch_data_size, loss_scale, max_level):
     ctx.meta, ctx.prefix, ctx.batch_data_size, ctx.loss_scale, ctx.max_level = meta, prefix, batch_data_size, loss_scale, max_level
 
 
+def _scaled(t, s):
+    """t * s without the extra pass over the [N, n_enc] gradient when the loss scale is 1 (fp32 tables): same values."""
+    return t if s == 1.0 else t * s
+
+
+def _unscaled(t, s):
+    return t if (t is None or s == 1.0) else t / s
+
+
 def _first_order_backward(ctx, dL_dy, need_dx: bool, need_dgrid: bool):
     x, grid, dy_dx, bidx, batch_offsets = ctx.saved_tensors
     ls = ctx.loss_scale
-    dL_dx, dL_dgrid = _backend.lod_bwd(ctx.meta, dL_dy.flatten(0, -2) * ls, x.flatten(0, -2), grid, dy_dx,
+    dL_dx, dL_dgrid = _backend.lod_bwd(ctx.meta, _scaled(dL_dy.flatten(0, -2), ls), x.flatten(0, -2), grid, dy_dx,
                                        None if bidx is None else bidx.flatten(), batch_offsets, ctx.batch_data_size, ctx.max_level,
                                        need_dx, need_dgrid)
-    dL_dx = None if dL_dx is None else dL_dx.unflatten(0, ctx.prefix) / ls
-    dL_dgrid = None if dL_dgrid is None else dL_dgrid / ls
+    dL_dx = None if dL_dx is None else _unscaled(dL_dx.unflatten(0, ctx.prefix), ls)
+    dL_dgrid = _unscaled(dL_dgrid, ls)
     return dL_dx, dL_dgrid
 
 
@@ -120,13 +129,13 @@ class LoTDFunctionBwdDydx(torch.autograd.Function):
     def forward(ctx: FunctionCtx, meta, dL_dy, x, grid, dy_dx, bidx, batch_offsets, batch_data_size, loss_scale, max_level, grad_guard):
         ctx.set_materialize_grads(False)
         prefix, x, bidx = _prep(x, bidx)
-        dL_dx, _ = _backend.lod_bwd(meta, dL_dy.flatten(0, -2) * loss_scale, x.flatten(0, -2), grid, dy_dx, bidx, batch_offsets,
+        dL_dx, _ = _backend.lod_bwd(meta, _scaled(dL_dy.flatten(0, -2), loss_scale), x.flatten(0, -2), grid, dy_dx, bidx, batch_offsets,
                                     batch_data_size, max_level, True, False)
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[3]:
             ctx.save_for_backward(dL_dy, x, grid, dy_dx.contiguous(), bidx, batch_offsets)
             _stash(ctx, meta, prefix, batch_data_size, loss_scale, max_level)
             ctx.grad_guard = grad_guard
-        return None if dL_dx is None else dL_dx.unflatten(0, prefix) / loss_scale
+        return None if dL_dx is None else _unscaled(dL_dx.unflatten(0, prefix), loss_scale)
 
     @staticmethod
     @once_differentiable
@@ -136,12 +145,12 @@ class LoTDFunctionBwdDydx(torch.autograd.Function):
             dL_dy, x, grid, dy_dx, bidx, batch_offsets = ctx.saved_tensors
             prefix, ls = x.shape[:-1], ctx.loss_scale
             g_dLdy, g_grid, g_x = _backend.lod_bwd_bwd_input(
-                ctx.meta, dL_ddLdx.flatten(0, -2), dL_dy.flatten(0, -2) * ls, x.flatten(0, -2), grid, dy_dx,
+                ctx.meta, dL_ddLdx.flatten(0, -2), _scaled(dL_dy.flatten(0, -2), ls), x.flatten(0, -2), grid, dy_dx,
                 None if bidx is None else bidx.flatten(), batch_offsets, ctx.batch_data_size, ctx.max_level,
                 ctx.needs_input_grad[1], ctx.needs_input_grad[3], False)
             g_dLdy = None if g_dLdy is None else g_dLdy.unflatten(0, prefix)
-            g_grid = None if g_grid is None else g_grid / ls
-            g_x = None if g_x is None else g_x.unflatten(0, prefix) / ls
+            g_grid = _unscaled(g_grid, ls)
+            g_x = None if g_x is None else _unscaled(g_x.unflatten(0, prefix), ls)
             if ctx.grad_guard is not None and (g_grid is not None or g_dLdy is not None):
                 ctx.grad_guard.custom_grad_clip_step(dL_ddLdx, dy_dx, g_grid, g_dLdy)
         return None, g_dLdy, g_x, g_grid, None, None, None, None, None, None, None
