@@ -397,6 +397,136 @@ __device__ __forceinline__ void corner_add_grad(const Ctx<D>& c, const PT* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Aggregated gradient scatter of one (point, pseudo level) for the n-linear level types, given the weight cw[c] of every lattice
+// corner c (bit d of c set -> cell[d] + 1).  Same sums as corner_add_grad over all corners (reference add_grid_gridient_*_impl,
+// lotd_cuda.h:494-829, called once per corner -- and once per corner per derivative dimension in the second-order pass,
+// lotd_encoding.h:764-1041), but contributions that land on the SAME table entry are summed in registers first:
+//   VM      a line entry is shared by the 4 corners with the same bit k, a plane entry by 2: 18 reductions / 18 loads instead of 48 / 96
+//   CP      a line entry is shared by 2^(D-1) corners:                                      2 D reductions instead of D 2^D
+//   NPlane  a plane entry is shared by 2 corners:                                           D 2^(D-1) instead of D 2^D
+// which matters most exactly where the reference is slowest: the tiny line / plane tables are same-address reduction hot spots.
+// ------------------------------------------------------------------------------------------------
+template <int D, int F, typename PT>
+__device__ __forceinline__ void nlinear_scatter(const Ctx<D>& c, const PT* __restrict__ g, PT* __restrict__ gg, const float* cw,
+                                                const float* grad, bool vec_ok) {
+    using C = Cvt<PT>;
+    if (c.type == NR3D_LOD_DENSE || c.type == NR3D_LOD_HASH) {
+#pragma unroll
+        for (int idx = 0; idx < (1 << D); ++idx) {
+            uint32_t pos[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) pos[d] = c.cell[d] + ((idx >> d) & 1);
+            float wg[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) wg[f] = grad[f] * cw[idx];
+            const uint32_t e = c.type == NR3D_LOD_DENSE ? idx_dense<D>(c.res, pos) : idx_hash<D>(pos, c.size);
+            scatter_add<F>(gg + (uint64_t)e * c.n_feat + c.gfo, wg, vec_ok);
+        }
+        return;
+    }
+    if (c.type == NR3D_LOD_VM) {
+        if constexpr (D == 3) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                // entries of line k (2) and plane k (4; plane k ignores dimension k)
+                uint64_t il[2], ip[4];
+                PT Lv[2][F], Pv[4][F];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    // corner with bit k = 0 and the two other bits taken from b (in increasing dimension order)
+                    uint32_t pos[D], pl[D], ln[D];
+                    int bb = 0;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        if (d == k) pos[d] = c.cell[d];
+                        else { pos[d] = c.cell[d] + ((b >> bb) & 1); ++bb; }
+                    }
+                    idx_vm<D>(c.res, pos, pl, ln);
+                    ip[b] = (uint64_t)pl[k] * c.n_feat + c.gfo;
+                    load_feats<F>(g + ip[b], Pv[b], vec_ok);
+                    if (b == 0) {
+                        il[0] = (uint64_t)ln[k] * c.n_feat + c.gfo;
+                        il[1] = (uint64_t)(ln[k] + 1u) * c.n_feat + c.gfo;
+                    }
+                }
+                load_feats<F>(g + il[0], Lv[0], vec_ok);
+                load_feats<F>(g + il[1], Lv[1], vec_ok);
+                float gl[2][F], gp[4][F];
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+                    gl[0][f] = gl[1][f] = 0.f;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) gp[b][f] = 0.f;
+                }
+#pragma unroll
+                for (int idx = 0; idx < (1 << D); ++idx) {
+                    const int a = (idx >> k) & 1;
+                    int b = 0, bb = 0;
+#pragma unroll
+                    for (int d = 0; d < D; ++d)
+                        if (d != k) { b |= ((idx >> d) & 1) << bb; ++bb; }
+#pragma unroll
+                    for (int f = 0; f < F; ++f) {
+                        const float t = cw[idx] * grad[f];
+                        gl[a][f] += t * C::to_f(Pv[b][f]);
+                        gp[b][f] += t * C::to_f(Lv[a][f]);
+                    }
+                }
+                scatter_add<F>(gg + il[0], gl[0], vec_ok);
+                scatter_add<F>(gg + il[1], gl[1], vec_ok);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) scatter_add<F>(gg + ip[b], gp[b], vec_ok);
+            }
+        }
+        return;
+    }
+    if (c.type == NR3D_LOD_CP) {
+        uint64_t il[D][2];
+        PT Lv[D][2][F];
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                il[k][a] = (uint64_t)idx_cp_line<D>(c.res, c.cell[k] + a, k) * c.n_feat + c.gfo;
+                load_feats<F>(g + il[k][a], Lv[k][a], vec_ok);
+            }
+        float acc[D][2][F];
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+#pragma unroll
+            for (int f = 0; f < F; ++f) acc[k][0][f] = acc[k][1][f] = 0.f;
+#pragma unroll
+        for (int idx = 0; idx < (1 << D); ++idx) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+#pragma unroll
+                for (int f = 0; f < F; ++f) {
+                    float t = cw[idx] * grad[f];
+#pragma unroll
+                    for (int k2 = 0; k2 < D; ++k2)
+                        if (k2 != k) t *= C::to_f(Lv[k2][(idx >> k2) & 1][f]);
+                    acc[k][(idx >> k) & 1][f] += t;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            scatter_add<F>(gg + il[k][0], acc[k][0], vec_ok);
+            scatter_add<F>(gg + il[k][1], acc[k][1], vec_ok);
+        }
+        return;
+    }
+    // NPlaneMul, VecZMatXoY (rare) and anything else: per corner
+#pragma unroll 1
+    for (int idx = 0; idx < (1 << D); ++idx) {
+        uint32_t pos[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) pos[d] = c.cell[d] + ((idx >> d) & 1);
+        corner_add_grad<D, F, PT>(c, g, gg, pos, grad, cw[idx], vec_ok);
+    }
+}
+
 // corner position for corner id `idx` (bit d set -> cell+1) and its n-linear weight
 template <int D>
 __device__ __forceinline__ float corner_weight(const Ctx<D>& c, int idx, uint32_t* pos) {

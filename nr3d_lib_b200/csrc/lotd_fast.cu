@@ -26,8 +26,8 @@
 namespace nr3d {
 
 // tunables (overridable with -D for A/B runs, see scripts/build_variants.py)
-#ifndef NR3D_BIN_RES
-#define NR3D_BIN_RES 128
+#ifndef NR3D_BIN_RES        // 0: chosen per call from the number of points (about two points per bin), else fixed (A/B runs)
+#define NR3D_BIN_RES 0
 #endif
 #ifndef NR3D_BIN_ORDER      // 0: x fastest, 1: z fastest
 #define NR3D_BIN_ORDER 0
@@ -47,24 +47,28 @@ namespace nr3d {
 #ifndef NR3D_FAST_PAIR      // 1: two lanes per point (default), 0: one thread per point (kept for A/B runs)
 #define NR3D_FAST_PAIR 1
 #endif
-constexpr uint32_t kBinRes = NR3D_BIN_RES;               // bins per axis of the point sort
-constexpr uint32_t kBins = kBinRes * kBinRes * kBinRes;  // 2 Mi bins (8 MB of counters)
+// bins per axis of the point sort.  The kernels like about two points per bin (A/B on B200: 4 Mi uniform points 128^3 > 64^3, 256^3;
+// 30 Mi ray samples 256^3 > 192^3 > 128^3, profiles/r1_ab_tunables.txt), so the resolution follows the point count.
+static inline uint32_t bin_res_for(uint64_t N) {
+    if (NR3D_BIN_RES) return NR3D_BIN_RES;
+    return N >= (12ull << 20) ? 256u : 128u;
+}
 constexpr int kFastThreads = NR3D_FWD_THREADS;
 constexpr int kBwdThreads = NR3D_BWD_THREADS;
 constexpr int kScanBlockF = 1024;
 
-__device__ __forceinline__ uint32_t bin_key(float x, float y, float z) {
-    const uint32_t bx = min(kBinRes - 1, (uint32_t)fmaxf(x * (float)kBinRes, 0.f));
-    const uint32_t by = min(kBinRes - 1, (uint32_t)fmaxf(y * (float)kBinRes, 0.f));
-    const uint32_t bz = min(kBinRes - 1, (uint32_t)fmaxf(z * (float)kBinRes, 0.f));
-    return NR3D_BIN_ORDER == 0 ? (bz * kBinRes + by) * kBinRes + bx : (bx * kBinRes + by) * kBinRes + bz;
+__device__ __forceinline__ uint32_t bin_key(float x, float y, float z, uint32_t res) {
+    const uint32_t bx = min(res - 1, (uint32_t)fmaxf(x * (float)res, 0.f));
+    const uint32_t by = min(res - 1, (uint32_t)fmaxf(y * (float)res, 0.f));
+    const uint32_t bz = min(res - 1, (uint32_t)fmaxf(z * (float)res, 0.f));
+    return NR3D_BIN_ORDER == 0 ? (bz * res + by) * res + bx : (bx * res + by) * res + bz;
 }
 
 // pass 1: bin key and rank of the point inside its bin (the rank makes the scatter pass atomic-free)
-__global__ void __launch_bounds__(256) sort_hist_kernel(uint64_t N, const float* __restrict__ x, uint32_t* __restrict__ hist, uint2* __restrict__ keyrank) {
+__global__ void __launch_bounds__(256) sort_hist_kernel(uint64_t N, uint32_t res, const float* __restrict__ x, uint32_t* __restrict__ hist, uint2* __restrict__ keyrank) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const uint32_t k = bin_key(x[i * 3], x[i * 3 + 1], x[i * 3 + 2]);
+    const uint32_t k = bin_key(x[i * 3], x[i * 3 + 1], x[i * 3 + 2], res);
     const uint32_t r = atomicAdd(hist + k, 1u);
     keyrank[i] = make_uint2(k, r);
 }
@@ -610,8 +614,10 @@ using namespace nr3d;
 extern "C" {
 
 int nr3d_lotd_sort_points(uint64_t N, const float* x, void* xs /* float4 [N] */, void* ws, uint64_t* ws_bytes, void* stream) {
-    const uint32_t nb = div_up<uint32_t>(kBins, kScanBlockF);
-    const uint64_t need = (uint64_t)kBins * 4 + (uint64_t)nb * 4 + 64 + N * 8;
+    const uint32_t res = bin_res_for(N);
+    const uint32_t bins = res * res * res;
+    const uint32_t nb = div_up<uint32_t>(bins, kScanBlockF);
+    const uint64_t need = (uint64_t)bins * 4 + (uint64_t)nb * 4 + 64 + N * 8;
     if (ws == nullptr) {
         NR3D_CHECK(ws_bytes != nullptr, "sort_points: null ws_bytes");
         *ws_bytes = need;
@@ -624,17 +630,17 @@ int nr3d_lotd_sort_points(uint64_t N, const float* x, void* xs /* float4 [N] */,
     NR3D_CHECK((reinterpret_cast<uintptr_t>(xs) & 15u) == 0 && (reinterpret_cast<uintptr_t>(ws) & 15u) == 0, "sort_points: xs / ws must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* hist = reinterpret_cast<uint32_t*>(ws);
-    uint32_t* bs = hist + kBins;
-    uint2* keyrank = reinterpret_cast<uint2*>(reinterpret_cast<char*>(ws) + (((uint64_t)kBins * 4 + (uint64_t)nb * 4 + 63) / 64) * 64);
-    cudaMemsetAsync(hist, 0, (size_t)kBins * 4, st);
+    uint32_t* bs = hist + bins;
+    uint2* keyrank = reinterpret_cast<uint2*>(reinterpret_cast<char*>(ws) + (((uint64_t)bins * 4 + (uint64_t)nb * 4 + 63) / 64) * 64);
+    cudaMemsetAsync(hist, 0, (size_t)bins * 4, st);
     const unsigned grid = (unsigned)div_up<uint64_t>(N, 256);
-    sort_hist_kernel<<<grid, 256, 0, st>>>(N, x, hist, keyrank);
+    sort_hist_kernel<<<grid, 256, 0, st>>>(N, res, x, hist, keyrank);
     NR3D_LAUNCH_CHECK("sort_hist");
-    scanu_block_sums<<<nb, kScanBlockF, 0, st>>>(kBins, hist, bs);
+    scanu_block_sums<<<nb, kScanBlockF, 0, st>>>(bins, hist, bs);
     NR3D_LAUNCH_CHECK("sort_scan1");
     scanu_of_sums<<<1, kScanBlockF, 0, st>>>(nb, bs);
     NR3D_LAUNCH_CHECK("sort_scan2");
-    scanu_apply<<<nb, kScanBlockF, 0, st>>>(kBins, hist, bs);
+    scanu_apply<<<nb, kScanBlockF, 0, st>>>(bins, hist, bs);
     NR3D_LAUNCH_CHECK("sort_scan3");
     sort_scatter_kernel<<<grid, 256, 0, st>>>(N, x, keyrank, hist, reinterpret_cast<float4*>(xs));
     NR3D_LAUNCH_CHECK("sort_scatter");

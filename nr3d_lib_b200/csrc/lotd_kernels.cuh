@@ -183,28 +183,31 @@ lotd_bwd_param_kernel(const __grid_constant__ LotdTable tab, const LotdIn in, co
         for (int d = 0; d < D; ++d) gin[d] = c.scale[d] * ddx[i * D + d] * c.dp[d];
     }
     if (is_nlinear(c.type)) {
-        if (!SECOND) {
-#pragma unroll 1
-            for (int idx = 0; idx < (1 << D); ++idx) {
-                uint32_t pos[D];
-                const float w = corner_weight<D>(c, idx, pos);
-                corner_add_grad<D, F, PT>(c, g, gg, pos, grad, w, vec_ok);
-            }
-        } else {
-#pragma unroll 1
-            for (int gd = 0; gd < D; ++gd) {
-#pragma unroll 1
-                for (int idx = 0; idx < (1 << (D - 1)); ++idx) {
-                    uint32_t pos[D];
-                    int li;
-                    const float w = face_weight<D>(c, gd, idx, gin[gd], pos, &li);
-                    pos[gd] = c.cell[gd];
-                    corner_add_grad<D, F, PT>(c, g, gg, pos, grad, -w, vec_ok);
-                    pos[gd] = c.cell[gd] + 1;
-                    corner_add_grad<D, F, PT>(c, g, gg, pos, grad, w, vec_ok);
+        // weight of every lattice corner: the n-linear weight (first order), or -- second order -- the sum over the derivative
+        // dimensions gd of  gin[gd] * (+1 right / -1 left of gd) * prod_{d != gd} w_d  (the reference walks the 2^(D-1) face
+        // corners of every gd and scatters left and right separately, lotd_encoding.h:764-1041: 3x the reductions)
+        float cw[1 << D];
+#pragma unroll
+        for (int idx = 0; idx < (1 << D); ++idx) {
+            if (!SECOND) {
+                float w = 1.0f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) w *= ((idx >> d) & 1) ? c.p[d] : 1.0f - c.p[d];
+                cw[idx] = w;
+            } else {
+                float acc = 0.f;
+#pragma unroll
+                for (int gd = 0; gd < D; ++gd) {
+                    float w = gin[gd];
+#pragma unroll
+                    for (int d = 0; d < D; ++d)
+                        if (d != gd) w *= ((idx >> d) & 1) ? c.p[d] : 1.0f - c.p[d];
+                    acc += ((idx >> gd) & 1) ? w : -w;
                 }
+                cw[idx] = acc;
             }
         }
+        nlinear_scatter<D, F, PT>(c, g, gg, cw, grad, vec_ok);
     } else if (c.type == NR3D_LOD_NPLANESUM) {
         if constexpr (D > 2) {
 #pragma unroll 1
