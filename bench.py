@@ -303,7 +303,8 @@ def main():
         del params_h, dL_dy_h, dL_dy, x
         torch.cuda.empty_cache()
         from scripts.m2_bench import run_m2
-        m2_block = run_m2(dev, rank, n_gpus, steps=3, warmup=1)
+        # configs[2]: 1024^2 rays on one GPU; configs[4]: 4096^2 rays over 8 GPUs = 2 Mi rays per GPU
+        m2_block = run_m2(dev, rank, n_gpus, rays=(4096 * 4096 // 8 if n_gpus == 8 else 1024 * 1024), steps=3, warmup=1)
 
     ndist.barrier()
     ndist.shutdown()

@@ -4,6 +4,7 @@ Same names, argument order, defaults, validation rules, returned shapes / dtypes
 reference's pybind module, implemented on top of the C-ABI library ``libnr3d_b200.so``.
 """
 import ctypes
+import os
 import enum
 from typing import List, Optional, Sequence, Tuple, Union
 
@@ -115,7 +116,9 @@ class LoDMeta:
         # B200-only knob (no reference counterpart): walk the points in cell-sorted order (lotd_fast.cu).  When it applies
         # (Dense/Hash-only, D=3, 2 features per pseudo level, fp32 params, single scene, no dy_dx requested) lod_fwd returns a
         # contiguous row-major [N, n_enc] tensor instead of the transposed feature-major view; values are the same.
-        object.__setattr__(self, "c_sort_points", False)
+        # Default off (identical strides to the reference); NR3D_B200_SORT_POINTS=1 turns it on for every meta, so an unmodified
+        # reference application gets the fast path without a code change.
+        object.__setattr__(self, "c_sort_points", os.environ.get("NR3D_B200_SORT_POINTS", "0") not in ("", "0", "false", "False"))
         object.__setattr__(self, "_ctor", (n_input_dims, res_md, lod_n_feats, lod_types, hashmap_size, use_smooth_step))
 
     def __setattr__(self, key, value):

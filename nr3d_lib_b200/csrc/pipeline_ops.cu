@@ -36,7 +36,10 @@ __device__ __forceinline__ float softplus1(float v) {  // == F.softplus(v) (beta
     return v > 20.0f ? v : log1pf(expf(v));
 }
 
-// G lanes per row (G = 8 for C = 32: each lane one float4), 32 / G rows per warp pass.
+// G lanes per row (G = 8 for C = 32: each lane one float4); a warp pass covers kU * 32 / G rows with kU independent loads per lane in
+// flight (the kernel is a pure HBM stream: memory-level parallelism is what it needs).
+constexpr int kU = 4;
+
 template <int G, bool VEC4>
 __global__ void __launch_bounds__(256)
 density_alpha_fwd_kernel(uint64_t S, uint32_t C, const float* __restrict__ h, int64_t h_stride, const float* __restrict__ deltas, float gain,
@@ -45,24 +48,36 @@ density_alpha_fwd_kernel(uint64_t S, uint32_t C, const float* __restrict__ h, in
     constexpr uint32_t kRows = 32 / G;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t row0 = warp * kRows; row0 < S; row0 += n_warps * kRows) {
-        const uint64_t row = row0 + rl;
-        float s = 0.f;
-        if (row < S) {
-            const float* hr = h + (int64_t)row * h_stride;
-            if (VEC4) {
-                for (uint32_t c = sub * 4; c < C; c += G * 4) {
-                    const float4 v = __ldcs(reinterpret_cast<const float4*>(hr + c));
-                    s += (v.x + v.y) + (v.z + v.w);
+    for (uint64_t row0 = warp * (kRows * kU); row0 < S; row0 += n_warps * (kRows * kU)) {
+        float s[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const uint64_t row = row0 + (uint64_t)u * kRows + rl;
+            s[u] = 0.f;
+            if (row < S) {
+                const float* hr = h + (int64_t)row * h_stride;
+                if (VEC4) {
+                    for (uint32_t c = sub * 4; c < C; c += G * 4) {
+                        const float4 v = __ldcs(reinterpret_cast<const float4*>(hr + c));
+                        s[u] += (v.x + v.y) + (v.z + v.w);
+                    }
+                } else {
+                    for (uint32_t c = sub; c < C; c += G) s[u] += __ldcs(hr + c);
                 }
-            } else {
-                for (uint32_t c = sub; c < C; c += G) s += __ldcs(hr + c);
             }
         }
 #pragma unroll
-        for (int m = G / 2; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-        if (row < S && sub == 0) {
-            const float sg = softplus1(s * gain);
+        for (int u = 0; u < kU; ++u) {
+#pragma unroll
+            for (int m = G / 2; m > 0; m >>= 1) s[u] += __shfl_xor_sync(0xffffffffu, s[u], m);
+        }
+        // lane `sub` < kU of every group finishes row u = sub of its group (spreads the transcendental work over the lanes)
+        float mine = s[0];
+#pragma unroll
+        for (int u = 1; u < kU; ++u) mine = (sub == (uint32_t)u) ? s[u] : mine;
+        const uint64_t row = row0 + (uint64_t)sub * kRows + rl;
+        if (sub < (uint32_t)kU && row < S) {
+            const float sg = softplus1(mine * gain);
             __stcs(sigma + row, sg);
             __stcs(alpha + row, 1.0f - expf(-sg * __ldcs(deltas + row)));
         }
@@ -78,21 +93,32 @@ density_alpha_bwd_kernel(uint64_t S, uint32_t C, const float* __restrict__ d_alp
     constexpr uint32_t kRows = 32 / G;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t row0 = warp * kRows; row0 < S; row0 += n_warps * kRows) {
-        const uint64_t row = row0 + rl;
-        if (row >= S) continue;
-        // alpha = 1 - exp(-sigma * delta):  d alpha / d sigma = delta * (1 - alpha)
-        // sigma = softplus(gain * s):       d sigma / d s     = gain * sigmoid(gain * s) = gain * (1 - exp(-sigma))
-        const float sg = __ldcs(sigma + row);
-        float g_sigma = __ldcs(d_alpha + row) * __ldcs(deltas + row) * (1.0f - __ldcs(alpha + row));
-        if (d_sigma_extra) g_sigma += __ldcs(d_sigma_extra + row);
-        const float sig = sg > 20.0f ? 1.0f : (1.0f - expf(-sg));
-        const float c = g_sigma * sig * gain;
-        float* dr = d_h + row * (uint64_t)C;
-        if (VEC4) {
-            for (uint32_t k = sub * 4; k < C; k += G * 4) __stcs(reinterpret_cast<float4*>(dr + k), make_float4(c, c, c, c));
-        } else {
-            for (uint32_t k = sub; k < C; k += G) __stcs(dr + k, c);
+    for (uint64_t row0 = warp * (kRows * kU); row0 < S; row0 += n_warps * (kRows * kU)) {
+        // lane `sub` < kU of every group computes the coefficient of row u = sub of its group, then the group shares them
+        float mine = 0.f;
+        {
+            const uint64_t row = row0 + (uint64_t)sub * kRows + rl;
+            if (sub < (uint32_t)kU && row < S) {
+                // alpha = 1 - exp(-sigma * delta):  d alpha / d sigma = delta * (1 - alpha)
+                // sigma = softplus(gain * s):       d sigma / d s     = gain * sigmoid(gain * s) = gain * (1 - exp(-sigma))
+                const float sg = __ldcs(sigma + row);
+                float g_sigma = __ldcs(d_alpha + row) * __ldcs(deltas + row) * (1.0f - __ldcs(alpha + row));
+                if (d_sigma_extra) g_sigma += __ldcs(d_sigma_extra + row);
+                const float sig = sg > 20.0f ? 1.0f : (1.0f - expf(-sg));
+                mine = g_sigma * sig * gain;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const float c = __shfl_sync(0xffffffffu, mine, (int)(rl * G + u));
+            const uint64_t row = row0 + (uint64_t)u * kRows + rl;
+            if (row >= S) continue;
+            float* dr = d_h + row * (uint64_t)C;
+            if (VEC4) {
+                for (uint32_t k = sub * 4; k < C; k += G * 4) __stcs(reinterpret_cast<float4*>(dr + k), make_float4(c, c, c, c));
+            } else {
+                for (uint32_t k = sub; k < C; k += G) __stcs(dr + k, c);
+            }
         }
     }
 }
@@ -121,7 +147,7 @@ int nr3d_density_alpha_fwd(uint64_t S, uint32_t C, const float* h, int64_t h_str
     if (S == 0) return 0;
     NR3D_CHECK(h && deltas && sigma && alpha && C > 0, "density_alpha_fwd: null argument");
     const bool vec4 = (C % 4 == 0) && (h_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(h) & 15u) == 0);
-    const unsigned grid = (unsigned)std::min<uint64_t>(div_up<uint64_t>(S, 4 * 8), (uint64_t)kSMs * 16);   // 8 warps x 4 rows per CTA pass
+    const unsigned grid = (unsigned)std::min<uint64_t>(div_up<uint64_t>(S, 4 * kU * 8), (uint64_t)kSMs * 8);   // 8 warps x 16 rows per CTA pass
     if (vec4) density_alpha_fwd_kernel<8, true><<<grid, 256, 0, (cudaStream_t)stream>>>(S, C, h, h_stride, deltas, gain, sigma, alpha);
     else density_alpha_fwd_kernel<8, false><<<grid, 256, 0, (cudaStream_t)stream>>>(S, C, h, h_stride, deltas, gain, sigma, alpha);
     NR3D_LAUNCH_CHECK("density_alpha_fwd");
@@ -133,7 +159,7 @@ int nr3d_density_alpha_bwd(uint64_t S, uint32_t C, const float* d_alpha, const f
     if (S == 0) return 0;
     NR3D_CHECK(d_alpha && sigma && alpha && deltas && d_h && C > 0, "density_alpha_bwd: null argument");
     const bool vec4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_h) & 15u) == 0);
-    const unsigned grid = (unsigned)std::min<uint64_t>(div_up<uint64_t>(S, 4 * 8), (uint64_t)kSMs * 16);
+    const unsigned grid = (unsigned)std::min<uint64_t>(div_up<uint64_t>(S, 4 * kU * 8), (uint64_t)kSMs * 8);
     if (vec4) density_alpha_bwd_kernel<8, true><<<grid, 256, 0, (cudaStream_t)stream>>>(S, C, d_alpha, d_sigma_extra, sigma, alpha, deltas, gain, d_h);
     else density_alpha_bwd_kernel<8, false><<<grid, 256, 0, (cudaStream_t)stream>>>(S, C, d_alpha, d_sigma_extra, sigma, alpha, deltas, gain, d_h);
     NR3D_LAUNCH_CHECK("density_alpha_bwd");

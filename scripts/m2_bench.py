@@ -81,7 +81,8 @@ def run_m2(dev, rank, world, rays=1024 * 1024, chunk=262144, grid_kind="random",
             "n_gpus": world, "ms_per_step": ms, "rays_per_gpu": rays, "samples_per_ray": total_samples / (world * rays),
             "Msamples_per_s": total_samples / ms / 1e3, "grid": grid_kind, "chunk": chunk, "steps": steps, "warmup": warmup,
             "sort_points": sort_points, "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
-            "workload": "configs[2]/[4]: occ_grid 128^3 march (step 0.01, <=512 steps) + 16L NGP LoTD + softplus density head + "
+            "workload": ("configs[4] (4096^2 rays over 8 GPUs)" if world * rays == 4096 * 4096 else "configs[2] shape (1024^2 rays per GPU)") +
+                        ": occ_grid 128^3 march (step 0.01, <=512 steps) + 16L NGP LoTD + softplus density head + "
                         "packed alpha-composite + per-ray sums, forward + backward to the LoTD parameters, rays sharded over the GPUs, "
                         "one NCCL all-reduce of dL/dparams per step"}
 
