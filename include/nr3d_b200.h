@@ -156,6 +156,16 @@ int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64
 int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* dL_dy,
                                int64_t dLdy_stride_n, int64_t dLdy_stride_f, int32_t max_level, void* dL_dparam, void* stream);
 
+/* The same fast path for callers that need the nablas (NeuS-style eikonal terms): forward with dy/dx and the second-order
+ * d(dL/dx)/dparam . dL_ddLdx scatter (reference kernel_lod_hash_only_with_dydx / kernel_lod_hashonly_backward_input_backward_grid,
+ * lotd_hash_only.h:164-378, 472-695).  y: [N, n_enc] param dtype, dy_dx: f32 [N, n_enc, 3], both row-major at the points'
+ * original indices and fully written.  dL_ddLdx: f32 [N, 3]; dL_dparam is accumulated into (zero it first). */
+int nr3d_lotd_fwd_dydx_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* params,
+                              int32_t max_level, void* y, void* dy_dx, void* stream);
+int nr3d_lotd_bwd_param2_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* dL_dy,
+                                int64_t dLdy_stride_n, int64_t dLdy_stride_f, const float* dL_ddLdx, int32_t max_level,
+                                void* dL_dparam, void* stream);
+
 /* Fused LoTD encode + density decoder, forward only.  Replaces the composition
  * LoTDNeRF.query_density (nr3d_lib/models/fields/nerf/lotd_nerf.py:169-178): encoding(x) -> Linear(32,64) -> ReLU ->
  * Linear(64, <=16) -> activation(out[...,0]), without writing the [N,32] features to HBM.  tcgen05 (bf16 operands, f32

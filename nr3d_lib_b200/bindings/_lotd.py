@@ -294,6 +294,15 @@ def lod_fwd(lod_meta, input: torch.Tensor, params: torch.Tensor, batch_inds: Opt
                 ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), params.data_ptr(), max_level,
                 y.data_ptr(), E, 1, _lib.stream_of(dev)))
             return y, None
+        if need_input_grad and _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
+            # fast path with the nablas: row-major y and dy_dx (same shapes as the reference returns, contiguous instead of permuted views)
+            xs = _sorted_points(input)
+            y = torch.empty([N, E], dtype=params.dtype, device=dev)
+            dy_dx = torch.empty([N, E, D] if meta.c_permute_dydx else [N, E * D], dtype=input.dtype, device=dev)
+            _lib.check(_lib.get_lib().nr3d_lotd_fwd_dydx_sorted(
+                ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), params.data_ptr(), max_level,
+                y.data_ptr(), dy_dx.data_ptr(), _lib.stream_of(dev)))
+            return y, dy_dx
         if meta.c_hash_only:
             # feature-major storage returned through a transposed view (lotd_torch_api.cu:303,317)
             y_store = torch.empty([E, N], dtype=params.dtype, device=dev)
@@ -429,11 +438,19 @@ def lod_bwd_bwd_input(lod_meta, dL_ddLdx: torch.Tensor, dL_dy: torch.Tensor, inp
                     dL_dy.stride(1), input.data_ptr(), params.data_ptr(), _lib.ptr(batch_inds), _lib.ptr(batch_offsets), bds, max_level,
                     dL_dx.data_ptr(), st))
             return dL_ddLdy, dL_dparams, dL_dx
-        _lib.check(lib.nr3d_lotd_bwd_bwd_input(
-            ctypes.byref(meta._c), idt, pdt, N, dL_ddLdx.data_ptr(),
-            dL_dy.data_ptr(), dL_dy.stride(0), dL_dy.stride(1), input.data_ptr(), params.data_ptr(), _lib.ptr(dv), ds_n, ds_f,
-            _lib.ptr(batch_inds), _lib.ptr(batch_offsets), bds, max_level, _lib.ptr(dL_ddLdy), _lib.ptr(dL_dparams),
-            _lib.ptr(dL_dx), st))
+        dparam_generic = dL_dparams
+        if need_param and _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
+            xs = _sorted_points(input)      # second-order scatter on the fast path; the two other outputs keep the generic kernels
+            _lib.check(lib.nr3d_lotd_bwd_param2_sorted(
+                ctypes.byref(meta._c), pdt, N, xs.data_ptr(), dL_dy.data_ptr(), dL_dy.stride(0), dL_dy.stride(1), dL_ddLdx.data_ptr(),
+                max_level, dL_dparams.data_ptr(), st))
+            dparam_generic = None
+        if need_dLdy or need_input or dparam_generic is not None:
+            _lib.check(lib.nr3d_lotd_bwd_bwd_input(
+                ctypes.byref(meta._c), idt, pdt, N, dL_ddLdx.data_ptr(),
+                dL_dy.data_ptr(), dL_dy.stride(0), dL_dy.stride(1), input.data_ptr(), params.data_ptr(), _lib.ptr(dv), ds_n, ds_f,
+                _lib.ptr(batch_inds), _lib.ptr(batch_offsets), bds, max_level, _lib.ptr(dL_ddLdy), _lib.ptr(dparam_generic),
+                _lib.ptr(dL_dx), st))
     return dL_ddLdy, dL_dparams, dL_dx
 
 

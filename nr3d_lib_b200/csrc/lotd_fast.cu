@@ -480,10 +480,13 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT*
     }
 }
 
-template <typename PT>
+// SECOND = false: dL/dparam.  SECOND = true: d(dL/dx)/dparam . dL_ddLdx (second-order backward of NeuS-style eikonal terms,
+// reference kernel_lod_hashonly_backward_input_backward_grid, lotd_hash_only.h:472-695): the same scatter with the corner weights
+// replaced by sum_d ddx[d] * dw[d][corner] (pair_geo_d), ddx = dL_ddLdx [N,3] read at the point's original index.
+template <typename PT, bool SECOND>
 __global__ void __launch_bounds__(kBwdThreads)
 lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, const PT* __restrict__ dLdy, int64_t gs_n, int64_t gs_f,
-                     PT* __restrict__ grad) {
+                     const float* __restrict__ ddx, PT* __restrict__ grad) {
     using C = Cvt<PT>;
     __shared__ __align__(16) float tile[kBwdThreads / 32][32 * kPairTileStride];
     __shared__ float rows[kBwdThreads / 32][16 * kPairRowStride];
@@ -501,6 +504,8 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
     const PT* grow = dLdy + (int64_t)i * gs_n;
     const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
     const bool staged = (gs_f == 1);
+    float gx[3] = {0.f, 0.f, 0.f};
+    if (SECOND && active) { gx[0] = __ldg(ddx + i * 3); gx[1] = __ldg(ddx + i * 3 + 1); gx[2] = __ldg(ddx + i * 3 + 2); }
     uint32_t chunk_base = 0;
     for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
         const uint32_t level = tab.map_level[pl];
@@ -527,7 +532,14 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
         if ((int32_t)level > in.max_level) continue;  // uniform
         const LevelDesc& L = tab.lv[level];
         Geo2 g;
-        pair_geo(L, (uint32_t)tab.map_cnt[pl] * 2u, smooth, x, yv, z, side, g);
+        if (SECOND) {
+            float dw[3][4];
+            pair_geo_d(L, (uint32_t)tab.map_cnt[pl] * 2u, smooth, x, yv, z, side, g, dw);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) g.w[q] = gx[0] * dw[0][q] + gx[1] * dw[1][q] + gx[2] * dw[2][q];
+        } else {
+            pair_geo(L, (uint32_t)tab.map_cnt[pl] * 2u, smooth, x, yv, z, side, g);
+        }
         // points of one run (consecutive points in the same cell) merge their contributions before touching L2
         const bool can_key = L.res[0] <= 1024u && L.res[1] <= 1024u && L.res[2] <= 1024u;
         uint32_t hmask = 0x55555555u;  // bit 2k set: point k starts a run
@@ -576,6 +588,89 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
                 for (int qq = 0; qq < 4; ++qq) PairIO<PT>::red2(grad + g.e[qq], g.w[qq] * g0, g.w[qq] * g1);
             }
             __syncwarp();
+        }
+    }
+}
+
+// Forward with dy/dx (NeuS-style callers need the nablas): same walk as lotd_pair_fwd_kernel plus, per (point, feature), the three
+// derivatives  dy/dx_d = sum_corners dw[d][corner] * value(corner)  (reference kernel_lod_hash_only_with_dydx, lotd_hash_only.h:
+// 164-378).  dy_dx is written row-major [N, n_enc, 3] at the point's original index through a second staged tile (96 floats per
+// point and 32 features = three coalesced 128-byte stores), accumulated in fp32 for either table type (INPUT_T in the reference).
+constexpr int kDydxThreads = 128;
+constexpr int kDChunk = 16;          // features per staged dy/dx tile (8 pseudo levels): 48 floats = 192 bytes per point and flush
+constexpr int kPairDRowStride = 50;  // floats per staged dy/dx row (48 used): lane (k, side) writes bank 18k + 3 side + const, conflict free
+
+template <typename PT>
+__global__ void __launch_bounds__(kDydxThreads)
+lotd_pair_fwd_dydx_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT* __restrict__ y, float* __restrict__ dydx) {
+    using C = Cvt<PT>;
+    const PT* params = reinterpret_cast<const PT*>(in.params);
+    __shared__ float rows[kDydxThreads / 32][16 * kPairRowStride];
+    __shared__ float drows[kDydxThreads / 32][16 * kPairDRowStride];
+    const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const bool active = p < in.N;
+    const int lane = threadIdx.x & 31;
+    const uint32_t side = lane & 1;
+    const int k = lane >> 1;
+    float* myrows = rows[threadIdx.x >> 5];
+    float* mydrows = drows[threadIdx.x >> 5];
+    float4 rec = make_float4(0.5f, 0.5f, 0.5f, 0.f);
+    if (active) rec = __ldcs(in.xs + p);
+    const float x = rec.x, yv = rec.y, z = rec.z;
+    const uint64_t i = __float_as_uint(rec.w);
+    const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
+    const uint32_t n_enc = tab.n_enc;
+    uint32_t chunk_base = 0, dchunk_base = 0;
+    for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
+        const uint32_t level = tab.map_level[pl];
+        float r0 = 0.f, r1 = 0.f;
+        float d0[3] = {0.f, 0.f, 0.f}, d1[3] = {0.f, 0.f, 0.f};
+        if ((int32_t)level <= in.max_level) {
+            Geo2 g;
+            float dw[3][4];
+            pair_geo_d(tab.lv[level], (uint32_t)tab.map_cnt[pl] * 2u, smooth, x, yv, z, side, g, dw);
+            float2 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = PairIO<PT>::load2(params + g.e[q]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                r0 = C::to_f(C::add(C::from_f(r0), C::from_f(g.w[q] * v[q].x)));
+                r1 = C::to_f(C::add(C::from_f(r1), C::from_f(g.w[q] * v[q].y)));
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { d0[d] += dw[d][q] * v[q].x; d1[d] += dw[d][q] * v[q].y; }
+            }
+            r0 = C::to_f(C::add(C::from_f(r0), C::from_f(__shfl_xor_sync(0xffffffffu, r0, 1))));
+            r1 = C::to_f(C::add(C::from_f(r1), C::from_f(__shfl_xor_sync(0xffffffffu, r1, 1))));
+            // lane `side` owns feature 2 * pl + side of its point: it needs its partner's partial sums of that feature only
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float give = side ? d0[d] : d1[d];                       // the partner's feature
+                const float take = __shfl_xor_sync(0xffffffffu, give, 1);
+                if (side) d1[d] += take; else d0[d] += take;
+            }
+        }
+        const uint32_t c = pl * 2u - chunk_base, dc = pl * 2u - dchunk_base;
+        myrows[k * kPairRowStride + c + side] = side ? r1 : r0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) mydrows[k * kPairDRowStride + (dc + side) * 3 + d] = side ? d1[d] : d0[d];
+        const bool last = (pl + 1 == tab.n_pseudo);
+        const bool flush_y = (c + 2 == 32) || last, flush_d = (dc + 2 == kDChunk) || last;
+        if (flush_d) {  // one coalesced y row (every second time) and one and a half coalesced dy/dx lines per point
+            const uint32_t ywidth = c + 2, dwidth = (dc + 2) * 3;
+            __syncwarp();
+#pragma unroll 2
+            for (int r = 0; r < 16; ++r) {
+                const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * r);
+                const bool ok = __shfl_sync(0xffffffffu, (int)active, 2 * r);
+                if (!ok) continue;
+                if (flush_y && (uint32_t)lane < ywidth) st_cs(y + ir * n_enc + chunk_base + lane, C::from_f(myrows[r * kPairRowStride + lane]));
+                float* drow = dydx + (ir * n_enc + dchunk_base) * 3;
+                if ((uint32_t)lane < dwidth) __stcs(drow + lane, mydrows[r * kPairDRowStride + lane]);
+                if ((uint32_t)lane + 32u < dwidth) __stcs(drow + 32 + lane, mydrows[r * kPairDRowStride + 32 + lane]);
+            }
+            __syncwarp();
+            dchunk_base += kDChunk;
+            if (flush_y) chunk_base += 32;
         }
     }
 }
@@ -676,13 +771,46 @@ int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, 
     FastIn in{N, reinterpret_cast<const float4*>(xs), nullptr, max_level, 1u};
 #if NR3D_FAST_PAIR
     const unsigned grid = (unsigned)div_up<uint64_t>(2 * N, kBwdThreads);
-    if (param_dtype == NR3D_F16) lotd_pair_bwd_kernel<__half><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const __half*)dL_dy, dLdy_stride_n, dLdy_stride_f, (__half*)dL_dparam);
-    else lotd_pair_bwd_kernel<float><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, (float*)dL_dparam);
+    if (param_dtype == NR3D_F16) lotd_pair_bwd_kernel<__half, false><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const __half*)dL_dy, dLdy_stride_n, dLdy_stride_f, nullptr, (__half*)dL_dparam);
+    else lotd_pair_bwd_kernel<float, false><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, nullptr, (float*)dL_dparam);
 #else
     lotd_fast_bwd_kernel<<<(unsigned)div_up<uint64_t>(N, kBwdThreads), kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, (float*)dL_dparam);
 #endif
     NR3D_LAUNCH_CHECK("lotd_fast_bwd");
     return 0;
 }
+
+#if NR3D_FAST_PAIR
+int nr3d_lotd_fwd_dydx_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* params,
+                              int32_t max_level, void* y, void* dy_dx, void* stream) {
+    if (int rc = check_fast(meta, param_dtype, N)) return rc;
+    if (N == 0) return 0;
+    NR3D_CHECK(xs && params && y && dy_dx, "LoTDEncoding::fwd_dydx_sorted: null argument");
+    LotdTable tab;
+    make_table(meta, tab);
+    FastIn in{N, reinterpret_cast<const float4*>(xs), params, max_level, (uint32_t)((reinterpret_cast<uintptr_t>(params) & 15u) == 0)};
+    const unsigned grid = (unsigned)div_up<uint64_t>(2 * N, kDydxThreads);
+    if (param_dtype == NR3D_F16) lotd_pair_fwd_dydx_kernel<__half><<<grid, kDydxThreads, 0, (cudaStream_t)stream>>>(tab, in, (__half*)y, (float*)dy_dx);
+    else lotd_pair_fwd_dydx_kernel<float><<<grid, kDydxThreads, 0, (cudaStream_t)stream>>>(tab, in, (float*)y, (float*)dy_dx);
+    NR3D_LAUNCH_CHECK("lotd_fast_fwd_dydx");
+    return 0;
+}
+
+int nr3d_lotd_bwd_param2_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* dL_dy,
+                                int64_t dLdy_stride_n, int64_t dLdy_stride_f, const float* dL_ddLdx, int32_t max_level, void* dL_dparam,
+                                void* stream) {
+    if (int rc = check_fast(meta, param_dtype, N)) return rc;
+    if (N == 0) return 0;
+    NR3D_CHECK(xs && dL_dy && dL_ddLdx && dL_dparam, "LoTDEncoding::bwd_param2_sorted: null argument");
+    LotdTable tab;
+    make_table(meta, tab);
+    FastIn in{N, reinterpret_cast<const float4*>(xs), nullptr, max_level, 1u};
+    const unsigned grid = (unsigned)div_up<uint64_t>(2 * N, kBwdThreads);
+    if (param_dtype == NR3D_F16) lotd_pair_bwd_kernel<__half, true><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const __half*)dL_dy, dLdy_stride_n, dLdy_stride_f, dL_ddLdx, (__half*)dL_dparam);
+    else lotd_pair_bwd_kernel<float, true><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, dL_ddLdx, (float*)dL_dparam);
+    NR3D_LAUNCH_CHECK("lotd_fast_bwd2");
+    return 0;
+}
+#endif
 
 }  // extern "C"

@@ -419,6 +419,44 @@ lotd_bwd_input_kernel(uint64_t N, uint32_t n_enc, const PT* __restrict__ dLdy, i
     for (int d = 0; d < D; ++d) dLdx[i * D + d] = acc[d];
 }
 
+// Same contraction for ROW-MAJOR dy_dx ([N, n_enc * D] contiguous: generic metas, forest, the sorted fast path): a thread per point
+// would read 32 different lines per load there, so a warp takes one point per pass and streams its n_enc * D derivatives with coalesced
+// 128-byte loads; the D partial sums meet through shuffles.  Bound: HBM stream of dy_dx (12 B per feature and point).
+template <int D, typename PT>
+__global__ void __launch_bounds__(kLotdThreads)
+lotd_bwd_input_rows_kernel(uint64_t N, uint32_t n_enc, const PT* __restrict__ dLdy, int64_t gs_n, const float* __restrict__ dydx,
+                           float* __restrict__ dLdx) {
+    using C = Cvt<PT>;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t width = n_enc * D;
+    for (uint64_t i = warp; i < N; i += n_warps) {
+        const float* dp = dydx + i * width;
+        const PT* gp = dLdy + (int64_t)i * gs_n;
+        float acc[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc[d] = 0.f;
+        for (uint32_t e = lane; e < width; e += 32) {
+            const float v = __ldcs(dp + e) * C::to_f(gp[e / D]);
+            const uint32_t dd = e % D;
+#pragma unroll
+            for (int d = 0; d < D; ++d) acc[d] += (dd == (uint32_t)d) ? v : 0.f;
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], m);
+        }
+        if (lane < (uint32_t)D) {
+            float out = acc[0];
+#pragma unroll
+            for (int d = 1; d < D; ++d) out = (lane == (uint32_t)d) ? acc[d] : out;
+            dLdx[i * D + lane] = out;
+        }
+    }
+}
+
 template <int D, typename PT>
 __global__ void __launch_bounds__(kLotdThreads)
 lotd_ddLdy_kernel(uint64_t N, uint32_t n_enc, const float* __restrict__ ddx, const float* __restrict__ dydx, int64_t ds_n,
@@ -529,6 +567,11 @@ template <int D> int lotd_launch_grid_index(const LotdLaunch& L, int64_t* out);
                                              const float* dydx, int64_t ds_n, int64_t ds_f, float* dLdx) {                \
         if (L.in.N == 0) return 0;                                                                                        \
         const unsigned grid = (unsigned)div_up<uint64_t>(L.in.N, kLotdThreads);                                           \
+        if (gs_f == 1 && ds_f == D && ds_n == (int64_t)L.tab.n_enc * D) { /* row-major dy_dx: warp per point */            \
+            const unsigned rgrid = (unsigned)(div_up<uint64_t>(L.in.N, kLotdThreads / 32) < (uint64_t)kSMs * 16 ? div_up<uint64_t>(L.in.N, kLotdThreads / 32) : (uint64_t)kSMs * 16); \
+            if (L.half) lotd_bwd_input_rows_kernel<D, __half><<<rgrid, kLotdThreads, 0, L.stream>>>(L.in.N, L.tab.n_enc, (const __half*)dLdy, gs_n, dydx, dLdx); \
+            else lotd_bwd_input_rows_kernel<D, float><<<rgrid, kLotdThreads, 0, L.stream>>>(L.in.N, L.tab.n_enc, (const float*)dLdy, gs_n, dydx, dLdx); \
+        } else                                                                                                            \
         if (L.half) lotd_bwd_input_kernel<D, __half><<<grid, kLotdThreads, 0, L.stream>>>(L.in.N, L.tab.n_enc, (const __half*)dLdy, gs_n, gs_f, dydx, ds_n, ds_f, dLdx); \
         else lotd_bwd_input_kernel<D, float><<<grid, kLotdThreads, 0, L.stream>>>(L.in.N, L.tab.n_enc, (const float*)dLdy, gs_n, gs_f, dydx, ds_n, ds_f, dLdx); \
         NR3D_LAUNCH_CHECK("lotd_bwd_input");                                                                              \

@@ -43,9 +43,49 @@ def test_sorted_path_matches_generic_and_oracle(name, N, dev):
     x.mul_(0.5)
     y2, _ = _lotd.lod_fwd(meta_s, x, p, need_input_grad=False)
     assert rel_err(y2.cpu(), O.encode(om, x.cpu(), inp["params"])) < 1e-5
-    # dy_dx requests fall back to the reference layout
+    # dy_dx requests stay on the fast path: same shapes as the reference returns, contiguous, values equal to the generic kernels
     y3, dy = _lotd.lod_fwd(meta_s, x, p, need_input_grad=True)
-    assert dy is not None and (N == 1 or not y3.is_contiguous())
+    y3g, dyg = _lotd.lod_fwd(meta_g, x, p, need_input_grad=True)
+    assert dy.shape == dyg.shape and dy.is_contiguous() and y3.is_contiguous() and torch.equal(y3, y2)
+    assert rel_err(dy.cpu(), dyg.cpu()) < 1e-5 and rel_err(y3.cpu(), y3g.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["ngp8", "ngp_smooth"])
+@pytest.mark.parametrize("pdtype", [torch.float32, torch.float16])
+def test_sorted_path_nablas_and_second_order(name, pdtype, dev):
+    """NeuS-style call pattern on the fast path: forward with dy/dx, dL/dx, and the second-order backward (dL_ddLdy, dparam, dx)
+    against the generic kernels and the float64 oracle."""
+    from nr3d_lib_b200.bindings import _lotd
+    from oracle import lotd_oracle as O
+    cfg = LOTD_CONFIGS[name]
+    meta_s, meta_g = _lotd.LoDMeta(*meta_args(cfg)), _lotd.LoDMeta(*meta_args(cfg))
+    meta_s.c_sort_points = True
+    N = 6000
+    inp = lotd_inputs(cfg, meta_g.n_params, N=N, seed=5)
+    x, p, gy, ddx = inp["x"].to(dev), inp["params"].to(dev).to(pdtype), inp["dL_dy"].to(dev).to(pdtype), inp["dL_ddLdx"].to(dev)
+    half = pdtype == torch.float16
+    tol, tol_at = (2e-3, 3e-2) if half else (1e-5, 2e-5)
+    out = {}
+    for tag, meta in (("s", meta_s), ("g", meta_g)):
+        _lotd.clear_sort_cache()
+        y, dydx = _lotd.lod_fwd(meta, x, p, need_input_grad=True)
+        dL_dx, dL_dp = _lotd.lod_bwd(meta, gy, x, p, dydx, need_input_grad=True, need_param_grad=True)
+        a, b, c = _lotd.lod_bwd_bwd_input(meta, ddx, gy, x, p, dydx, need_dLdinput_ddLdoutput=True, need_dLdinput_dparams=True,
+                                          need_dLdinput_dinput=True)
+        out[tag] = dict(y=y, dy_dx=dydx.reshape(N, -1, 3), dL_dx=dL_dx, dL_dparam=dL_dp, dL_ddLdy=a, dL_dparam2=b, dL_dx2=c)
+    for k in out["s"]:
+        t = tol_at if k in ("dL_dparam", "dL_dparam2", "dL_dx2") else tol
+        assert rel_err(out["s"][k].float().cpu(), out["g"][k].float().cpu()) < t, k
+    om = O.OracleMeta(*meta_args(cfg))
+    pp, gg = (inp["params"].half().float(), inp["dL_dy"].half().float()) if half else (inp["params"], inp["dL_dy"])
+    y_o, dydx_o = O.fwd_dydx(om, inp["x"], pp)
+    a_o, b_o, c_o = O.bwd_bwd_input(om, inp["dL_ddLdx"], gg, inp["x"], pp)
+    assert rel_err(out["s"]["y"].float().cpu(), y_o) < tol and rel_err(out["s"]["dy_dx"].cpu(), dydx_o) < tol
+    assert rel_err(out["s"]["dL_dparam2"].float().cpu(), b_o) < tol_at and rel_err(out["s"]["dL_ddLdy"].float().cpu(), a_o) < tol
+    # max_level and an empty batch
+    y1, d1 = _lotd.lod_fwd(meta_s, x, p, max_level=1, need_input_grad=True)
+    y1g, d1g = _lotd.lod_fwd(meta_g, x, p, max_level=1, need_input_grad=True)
+    assert rel_err(d1.reshape(N, -1, 3).cpu(), d1g.reshape(N, -1, 3).cpu()) < tol and rel_err(y1.float().cpu(), y1g.float().cpu()) < tol
 
 
 def test_sorted_path_clustered_points(dev):
