@@ -210,7 +210,7 @@ def main():
     # steps overlap the kernels (3 streams, double buffers).  `--e2e-serial` issues everything on one stream instead.
     from nr3d_lib_b200.pipeline import HostFedLoTDStep
     grad_host2 = [grad_host, torch.empty(meta.n_params, dtype=torch.float32).pin_memory()]
-    pipe = HostFedLoTDStep(meta, params, N, dev, grad_of_y=lambda y: y * 1.0e-4, world=n_gpus)   # y * 1e-4: stand-in for the decoder's backward
+    pipe = HostFedLoTDStep(meta, params, N, dev, grad_of_y=lambda y: y * 1.0e-4, world=n_gpus, rank=rank)   # y * 1e-4: stand-in for the decoder's backward
 
     def run_e2e(steps):
         if args.e2e_serial:
@@ -219,7 +219,8 @@ def main():
                 y, _ = _lotd.lod_fwd(meta, xd, params, need_input_grad=False)
                 _, g = _lotd.lod_bwd(meta, y * 1.0e-4, xd, params, None, need_input_grad=False, need_param_grad=True)
                 ndist.allreduce_param_grads(g, n_gpus)
-                grad_host2[k % 2].copy_(g, non_blocking=True)
+                lo, hi = ndist.shard_range(g.shape[0], rank, n_gpus)
+                grad_host2[k % 2][lo:hi].copy_(g[lo:hi], non_blocking=True)
             return
         pipe.prefetch(x_host)
         for k in range(steps):
@@ -316,9 +317,10 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(n_gpus), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(x_host.numel() * 4),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(x_host.numel() * 4) * n_gpus,
                     "d2h_bytes_per_step": int(grad_host.numel() * 4),
-                    "note": "x from pinned host memory each step, dL_dy derived on device from the step's y, dL/dparams read back to host; "
+                    "note": "whole-job bytes per step: every rank feeds its own 4 Mi points from pinned host memory, dL_dy is derived on device "
+                            "from the step's y, the (all-reduced) dL/dparams is read back to the host once -- each rank returns its 1/N slice; "
                             + ("single stream" if args.e2e_serial else "copies of neighbouring steps overlap the kernels (pipeline.HostFedLoTDStep)")},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "fp16_params": fp16_block, "m2": m2_block}
     sys.stdout.flush()

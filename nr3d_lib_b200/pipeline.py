@@ -108,12 +108,13 @@ class HostFedLoTDStep:
         pipe.drain()                    # the compute stream waits for the last device->host copy
 
     `x_host` / `grad_host` must be pinned.  `grad_of_y` stands for whatever turns the step's features into dL/dy on the
-    device (decoder + loss); with world > 1 the gradients are all-reduced (one NCCL call) before they leave the device.
+    device (decoder + loss); with world > 1 the gradients are all-reduced (one NCCL call) before they leave the device and every
+    rank writes only its own contiguous 1/world slice of `grad_host` (`dist.shard_range`), so the job returns the result once.
     """
 
-    def __init__(self, meta, params: torch.Tensor, n_points: int, device, grad_of_y, world: int = 1):
+    def __init__(self, meta, params: torch.Tensor, n_points: int, device, grad_of_y, world: int = 1, rank: int = 0):
         from .bindings import _lotd
-        self._lotd, self.meta, self.params, self.world, self.grad_of_y = _lotd, meta, params, world, grad_of_y
+        self._lotd, self.meta, self.params, self.world, self.rank, self.grad_of_y = _lotd, meta, params, world, rank, grad_of_y
         self.dev = torch.device(device)
         self.compute = torch.cuda.current_stream(self.dev)
         self.h2d, self.d2h = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
@@ -145,13 +146,17 @@ class HostFedLoTDStep:
         gy = self.grad_of_y(y)
         _, g = self._lotd.lod_bwd(self.meta, gy, x, self.params, None, need_input_grad=False, need_param_grad=True)
         self.x_free[b].record(self.compute)
+        lo, hi = 0, g.shape[0]
         if self.world > 1:
             ndist.allreduce_param_grads(g, self.world)
+            # every rank now holds the same summed gradient: each returns its own 1/world slice to the host, so the job reads the
+            # result back exactly once instead of `world` identical copies competing for the host's memory bandwidth
+            lo, hi = ndist.shard_range(g.shape[0], self.rank, self.world)
         done = torch.cuda.Event()
         done.record(self.compute)
         self.d2h.wait_event(done)
         with torch.cuda.stream(self.d2h):
-            grad_host.copy_(g, non_blocking=True)
+            grad_host[lo:hi].copy_(g[lo:hi], non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(self.d2h)
         g.record_stream(self.d2h)
