@@ -10,7 +10,7 @@ One step  = lod_fwd(need_input_grad=False) + lod_bwd(need_param_grad=True) throu
 `e2e`     = the same step driven from HOST buffers: x comes from pinned host memory every step (H2D inside the timed
             region), dL_dy is derived on the device from the step's own output y (stand-in for the decoder's backward),
             and the step's result dL/dparams is read back to the host (D2H inside the timed region).
-`--impl reference` times the CPU port of the reference's algorithm (oracle/lotd_oracle.py, fp32, all host threads) on a
+`--impl reference` times the CPU port of the reference's algorithm (oracle/lotd_port.c, plain C, fp32, OpenMP over all host threads) on a
             bounded sample of the same workload -- the reference has no CPU implementation of this path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
@@ -95,29 +95,29 @@ class ClockSampler(threading.Thread):
 # CPU arm: the reference algorithm restated for the host (kind "port"), all threads, bounded sample
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_fwd_bwd(steps, warmup, seed=42, budget_s=20.0):
-    """fp32 torch-CPU port of the reference algorithm on a bounded sample.  The sample size is chosen from a short probe
-    so that warmup + steps fit in `budget_s` seconds (torch's index ops scale poorly beyond ~32 threads, so the thread
-    count is capped there; `cores` reports the threads actually used)."""
-    from oracle import lotd_oracle as O
-    cores = max(1, min(os.cpu_count() or 1, 32))
-    torch.set_num_threads(cores)
+    """The reference's algorithm for this path on the host: plain-C fp32 port of its Dense/Hash kernels (oracle/lotd_port.c, pinned by
+    the golden vectors of the reference's CUDA build), OpenMP over all host threads, on a bounded sample of the workload.  The
+    sample size comes from a short probe so that warmup + steps fit in `budget_s` seconds."""
+    from oracle import lotd_oracle as O, lotd_port as P
+    cores = max(1, P.max_threads())
     meta = O.OracleMeta(*ngp_cfg())
-    g = torch.Generator().manual_seed(seed)
-    params = ((torch.rand(meta.n_params, generator=g) * 2 - 1) * 1e-4).requires_grad_(True)
+    rs = np.random.RandomState(seed)
+    params = ((rs.rand(meta.n_params).astype(np.float32) * 2 - 1) * 1e-4).astype(np.float32)
+    grad = np.zeros(meta.n_params, dtype=np.float32)
 
     def one(n):
-        x = torch.rand(n, 3, generator=g).clamp(1e-6, 1 - 1e-6)
-        dL_dy = torch.randn(n, meta.n_encoded_dims, generator=g) * 1e-4
+        x = np.clip(rs.rand(n, 3).astype(np.float32), 1e-6, 1 - 1e-6)
+        dL_dy = (rs.randn(n, meta.n_encoded_dims) * 1e-4).astype(np.float32)
         t0 = time.perf_counter()
-        y = O.encode(meta, x, params, dtype=torch.float32)
-        y.backward(dL_dy)
-        params.grad = None
+        grad[:] = 0.0                                  # the step's zero-init of dL/dparam is part of the algorithm (SURVEY 8d)
+        P.fwd(meta, x, params, cores)
+        P.bwd_param(meta, dL_dy, x, cores, out=grad)
         return time.perf_counter() - t0
 
     one(4096)                                  # page in / thread-pool start
-    probe = one(16384)
-    per_point = probe / 16384
-    sample = int(min(262144, max(8192, budget_s / max(1, warmup + steps) / per_point)))
+    probe = one(65536)
+    per_point = probe / 65536
+    sample = int(min(N_POINTS, max(65536, budget_s / max(1, warmup + steps) / per_point)))
     sample = 1 << (sample.bit_length() - 1)     # power of two <= estimate
     times = []
     for it in range(warmup + steps):
@@ -126,8 +126,8 @@ def cpu_fwd_bwd(steps, warmup, seed=42, budget_s=20.0):
             times.append(dt)
     sec = float(np.mean(times))
     return dict(value=sample / sec / 1e6, unit=UNIT, cores=cores, kind="port",
-                sample=f"{sample} of the {N_POINTS} points per step, {steps} steps after {warmup} warm-up, fp32, torch CPU ops "
-                       f"(oracle/lotd_oracle.py), {cores} threads"), sec, sample
+                sample=f"{sample} of the {N_POINTS} points per step, {steps} steps after {warmup} warm-up, fp32, plain-C port of the reference's "
+                       f"Dense/Hash kernels (oracle/lotd_port.c), OpenMP with {cores} threads"), sec, sample
 
 
 def run_reference_arm(args):

@@ -292,3 +292,27 @@ def test_march_oracle_properties():
     assert d["grid"][ijk[:, 0], ijk[:, 1], ijk[:, 2]].mean() > 0.999
     empty = MO.ray_marching(d["rays_o"], d["rays_d"], d["near"], d["far"], d["roi"], np.zeros_like(d["grid"]), 0, 0.02, 1e10, 0.0, 64)
     assert empty["packed_info"][:, 1].sum() == 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# plain-C fp32 port of the Dense/Hash kernels (oracle/lotd_port.c): the CPU baseline of bench.py and a second, op-order
+# faithful oracle.  Pinned by the reference build's golden vectors and by the float64 oracle.
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["ngp8", "ngp_smooth", "hash_f4"])
+def test_lotd_port_vs_golden_and_oracle(name):
+    from oracle import lotd_oracle as O, lotd_port as P
+    cfg = LOTD_CONFIGS[name]
+    om = O.OracleMeta(*meta_args(cfg))
+    g = golden(f"lotd_{name}_f32")
+    assert g is not None
+    y = P.fwd(om, g["x"], g["params"])
+    gp = P.bwd_param(om, g["dL_dy"], g["x"])
+    assert rel_err(y, g["y"]) < 1e-6 and rel_err(gp, g["dL_dparam"]) < 1e-6           # the reference's own CUDA outputs
+    inp = lotd_inputs(cfg, om.n_params, N=3000, seed=17)
+    y2 = P.fwd(om, inp["x"].numpy(), inp["params"].numpy(), n_threads=3)
+    assert rel_err(y2, O.encode(om, inp["x"], inp["params"])) < 1e-6
+    gp2 = P.bwd_param(om, inp["dL_dy"].numpy(), inp["x"].numpy(), n_threads=3)
+    assert rel_err(gp2, O.bwd(om, inp["dL_dy"], inp["x"], inp["params"])[1]) < 1e-5
+    assert abs(float((y2.astype(np.float64) * inp["dL_dy"].numpy()).sum() - (inp["params"].numpy().astype(np.float64) * gp2).sum())) < 1e-3   # adjoint
+    with pytest.raises(ValueError):
+        P.fwd(O.OracleMeta(*meta_args(LOTD_CONFIGS["mixed"])), g["x"], g["params"])
