@@ -157,6 +157,110 @@ march_kernel(const MarchArgs a, const int32_t* __restrict__ packed_info, int32_t
     if (!FILL) num_steps[i] = (int32_t)j;
 }
 
+// Fill pass with coalesced output.  One thread per ray writes t_starts[base + j] etc. with a different base per lane: every store
+// instruction of a warp touches 32 sectors for 128 useful bytes.  Here each lane parks up to kStage samples in a shared-memory row,
+// then the warp writes the rows out one ray at a time (consecutive lanes -> consecutive addresses, full sectors).  The march itself
+// is the loop of march_kernel, statement for statement (bit-exact outputs), only chunked.
+constexpr int kStage = 16;            // samples parked per ray and round
+constexpr int kStageStride = 17;      // row stride (floats): conflict-free when the lanes of a warp write the same column
+constexpr int kFillThreads = 128;
+
+__global__ void __launch_bounds__(kFillThreads)
+march_fill_staged_kernel(const MarchArgs a, const int32_t* __restrict__ packed_info, float* __restrict__ t_starts, float* __restrict__ t_ends,
+                         int32_t* __restrict__ ridx_out, int32_t* __restrict__ bidx_out, int32_t* __restrict__ gidx_out) {
+    __shared__ float s_t0[kFillThreads / 32][32 * kStageStride];
+    __shared__ float s_t1[kFillThreads / 32][32 * kStageStride];
+    __shared__ int32_t s_g[kFillThreads / 32][32 * kStageStride];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* my_t0 = s_t0[wid] + lane * kStageStride;
+    float* my_t1 = s_t1[wid] + lane * kStageStride;
+    int32_t* my_g = s_g[wid] + lane * kStageStride;
+    bool done = i >= a.n_rays;
+    uint32_t batch_ind = 0;
+    if (!done) {
+        if (a.batch_inds) {
+            const int32_t b = a.batch_inds[i];
+            if (b < 0) done = true; else batch_ind = (uint32_t)b;
+        } else if (a.batch_data_size) {
+            batch_ind = (uint32_t)(i / a.batch_data_size);
+        }
+    }
+    const uint32_t cells = (uint32_t)(a.res.x * a.res.y * a.res.z);
+    const uint32_t grid_offset = batch_ind * cells;
+    const uint8_t* __restrict__ grid = a.grid + grid_offset;
+    const float* roi = a.roi + (uint64_t)batch_ind * 6;
+    uint32_t max_steps = 0;
+    uint64_t base = 0;
+    if (!done) {
+        base = (uint32_t)packed_info[i * 2 + 0];
+        max_steps = (uint32_t)packed_info[i * 2 + 1];
+        if (max_steps == 0) done = true;
+    }
+    const uint64_t ic = done ? 0 : i;   // finished / padding lanes read ray 0's data and never use it
+    const F3 origin = F3{a.rays_o[ic * 3 + 0], a.rays_o[ic * 3 + 1], a.rays_o[ic * 3 + 2]};
+    const F3 dir = F3{a.rays_d[ic * 3 + 0], a.rays_d[ic * 3 + 1], a.rays_d[ic * 3 + 2]};
+    const F3 inv_dir = F3{1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z};
+    const float near = a.t_min[ic], far = a.t_max[ic];
+    const F3 lo = F3{roi[0], roi[1], roi[2]};
+    const F3 hi = F3{roi[3], roi[4], roi[5]};
+    const float dt_min = a.step_size, dt_max = a.max_step_size;
+
+    uint32_t j = 0, flushed = 0;
+    float t0 = near;
+    float dt = calc_dt(t0, a.dt_gamma, dt_min, dt_max);
+    float t1 = t0 + dt;
+    float t_mid = (t0 + t1) * 0.5f;
+    while (true) {
+        int pending = 0;
+        while (!done && pending < kStage) {
+            if (!((t_mid < far) && (j < max_steps))) { done = true; break; }
+            const F3 p = F3{origin.x + t_mid * dir.x, origin.y + t_mid * dir.y, origin.z + t_mid * dir.z};
+            int grid_idx = -1;
+            if (grid_occupied_at(p, lo, hi, a.type, a.res, grid, &grid_idx)) {
+                my_t0[pending] = t0;
+                my_t1[pending] = t1;
+                my_g[pending] = grid_idx + (int32_t)grid_offset;
+                ++pending;
+                ++j;
+                t0 = t1;
+                t1 = t0 + calc_dt(t0, a.dt_gamma, dt_min, dt_max);
+                t_mid = (t0 + t1) * 0.5f;
+            } else if (a.type == NR3D_CONTRACTION_AABB) {
+                t_mid = advance_to_next_voxel(t_mid, dt_min, p, dir, inv_dir, lo, hi, a.res);
+                dt = calc_dt(t_mid, a.dt_gamma, dt_min, dt_max);
+                t0 = t_mid - dt * 0.5f;
+                t1 = t_mid + dt * 0.5f;
+            } else {
+                t0 = t1;
+                t1 = t0 + calc_dt(t0, a.dt_gamma, dt_min, dt_max);
+                t_mid = (t0 + t1) * 0.5f;
+            }
+        }
+        __syncwarp();
+        // write the parked rows: ray by ray, lanes = consecutive samples of that ray
+        const uint32_t any = __ballot_sync(0xffffffffu, pending > 0);
+        for (uint32_t m = any; m; m &= m - 1) {
+            const int l = __ffs(m) - 1;
+            const int n = __shfl_sync(0xffffffffu, pending, l);
+            const uint64_t b = __shfl_sync(0xffffffffu, (unsigned long long)(base + flushed), l);
+            const int32_t ray = (int32_t)__shfl_sync(0xffffffffu, (unsigned long long)i, l);
+            const int32_t bat = (int32_t)__shfl_sync(0xffffffffu, batch_ind, l);
+            if (lane < n) {
+                const int src = l * kStageStride + lane;
+                t_starts[b + lane] = s_t0[wid][src];
+                t_ends[b + lane] = s_t1[wid][src];
+                ridx_out[b + lane] = ray;
+                if (bidx_out) bidx_out[b + lane] = bat;
+                if (gidx_out) gidx_out[b + lane] = s_g[wid][src];
+            }
+        }
+        flushed += (uint32_t)pending;
+        __syncwarp();
+        if (__all_sync(0xffffffffu, done)) break;
+    }
+}
+
 static int fill_args(MarchArgs& a, uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
                      const int32_t* batch_inds, uint32_t batch_data_size, int32_t n_batches, const float* roi, const uint8_t* grid,
                      int32_t rx, int32_t ry, int32_t rz, int32_t contraction, float step_size, float max_step_size, float dt_gamma,
@@ -321,7 +425,11 @@ int nr3d_march_fill(uint64_t n_rays, const float* rays_o, const float* rays_d, c
     if (int rc = fill_args(a, n_rays, rays_o, rays_d, t_min, t_max, batch_inds, batch_data_size, n_batches, roi, grid, rx, ry, rz,
                            contraction, step_size, max_step_size, dt_gamma, max_steps)) return rc;
     NR3D_CHECK(packed_info && t_starts && t_ends && ridx, "ray_marching: null output");
+#ifdef NR3D_MARCH_FILL_UNSTAGED   // thread-per-ray stores (kept for A/B runs)
     march_kernel<true><<<(unsigned)div_up<uint64_t>(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(a, packed_info, nullptr, t_starts, t_ends, ridx, bidx, gidx);
+#else
+    march_fill_staged_kernel<<<(unsigned)div_up<uint64_t>(n_rays, kFillThreads), kFillThreads, 0, (cudaStream_t)stream>>>(a, packed_info, t_starts, t_ends, ridx, bidx, gidx);
+#endif
     NR3D_LAUNCH_CHECK("ray_marching(fill)");
     return 0;
 }

@@ -243,3 +243,44 @@ def test_forest_lotd_through_autograd_wrappers(dev):
     om = O.OracleMeta(*meta_args(cfg))
     gx, gp = O.bwd(om, inp["dL_dy"], inp["x"], inp["params"], batch_inds=inp["batch_inds"], forest=_oracle_forest(inp["forest"]))
     assert rel_err(x.grad.cpu(), gx) < 1e-5 and rel_err(params.grad.cpu(), gp) < 2e-5
+
+
+@pytest.mark.gpu
+def test_forest_lotd_batch_data_size_and_offsets(dev):
+    """Block selection by `batch_data_size` (points grouped per block) and block tables addressed through `batch_offsets`
+    (lotd_forest.h:214-224): a permuted parameter storage must give the same features / gradients at the permuted places."""
+    from nr3d_lib_b200.bindings import _lotd, _occ_grid
+    from oracle import lotd_oracle as O
+    cfg = FOREST_LOTD_CONFIGS["hash_f4"]
+    meta = _lotd.LoDMeta(*meta_args(cfg))
+    om = O.OracleMeta(*meta_args(cfg))
+    inp = forest_lotd_inputs(cfg, meta.n_params, N=5 * 300, seed=21)
+    B = inp["forest"]["block_ks"].shape[0]
+    assert B == 5
+    fmeta = _forest_meta(_occ_grid.ForestMeta, inp["forest"], dev)
+    F = _oracle_forest(inp["forest"])
+    x, params, gy = inp["x"].to(dev), inp["params"].to(dev), inp["dL_dy"].to(dev)
+    # (1) batch_data_size: point i lies in block i // 300
+    y, dydx = _lotd.lod_fwd((meta, fmeta), x, params, None, None, 300, None, True)
+    _, gp = _lotd.lod_bwd((meta, fmeta), gy, x, params, dydx, None, None, 300, None, False, True)
+    y_o = O.encode(om, inp["x"], inp["params"], batch_data_size=300, forest=F)
+    _, gp_o = O.bwd(om, inp["dL_dy"], inp["x"], inp["params"], batch_data_size=300, forest=F)
+    assert rel_err(y.cpu(), y_o) < 1e-5 and rel_err(gp.cpu(), gp_o) < 2e-5
+    # (2) batch_offsets: block b's table stored at slot perm[b]
+    perm = torch.tensor([3, 0, 4, 1, 2])
+    offs = (perm * meta.n_params).to(dev)
+    p_perm = torch.empty_like(params)
+    for b in range(B):
+        p_perm[int(perm[b]) * meta.n_params:(int(perm[b]) + 1) * meta.n_params] = params[b * meta.n_params:(b + 1) * meta.n_params]
+    bi = inp["batch_inds"].to(dev)
+    y1, _ = _lotd.lod_fwd((meta, fmeta), x, params, bi, None, None, None, False)
+    y2, _ = _lotd.lod_fwd((meta, fmeta), x, p_perm, bi, offs, None, None, False)
+    assert rel_err(y2.cpu(), y1.cpu()) < 1e-6
+    _, g1 = _lotd.lod_bwd((meta, fmeta), gy, x, params, None, bi, None, None, None, False, True)
+    _, g2 = _lotd.lod_bwd((meta, fmeta), gy, x, p_perm, None, bi, offs, None, None, False, True)
+    for b in range(B):
+        a = g1[b * meta.n_params:(b + 1) * meta.n_params]
+        c = g2[int(perm[b]) * meta.n_params:(int(perm[b]) + 1) * meta.n_params]
+        assert rel_err(c.cpu(), a.cpu()) < 2e-5
+    with pytest.raises(RuntimeError):      # batch_offsets must have one entry per block
+        _lotd.lod_fwd((meta, fmeta), x, p_perm, bi, offs[:3], None, None, False)
