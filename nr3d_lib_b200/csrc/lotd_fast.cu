@@ -18,7 +18,7 @@
 //      and issue one reduction per corner per run;
 //   4. y and dL_dy are accessed as [N, n_enc] rows staged through shared memory (one coalesced 128-byte access per point),
 //      so the sort permutation costs no partial-sector traffic.
-// The thread-per-point kernels of the first iteration are kept behind NR3D_FAST_PAIR=0 for A/B runs (scripts/ab_bench.py).
+// (The thread-per-point kernels of the first iteration lost the A/B by 20 % -- profiles/r1_ab_pair_layout.txt -- and are gone.)
 // Results are identical to the generic kernels up to fp32 summation order (same index functions, same weights).
 #include "lotd_pair.cuh"
 #include <string.h>
@@ -43,9 +43,6 @@ namespace nr3d {
 #endif
 #ifndef NR3D_BWD_THREADS
 #define NR3D_BWD_THREADS 128
-#endif
-#ifndef NR3D_FAST_PAIR      // 1: two lanes per point (default), 0: one thread per point (kept for A/B runs)
-#define NR3D_FAST_PAIR 1
 #endif
 // bins per axis of the point sort.  The kernels like about two points per bin (A/B on B200: 4 Mi uniform points 128^3 > 64^3, 256^3;
 // 30 Mi ray samples 256^3 > 192^3 > 128^3, profiles/r1_ab_tunables.txt), so the resolution follows the point count.
@@ -150,246 +147,6 @@ __global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t N, const flo
 // ------------------------------------------------------------------------------------------------------------
 // per-(point, level) geometry shared by forward and backward
 // ------------------------------------------------------------------------------------------------------------
-
-#if !NR3D_FAST_PAIR  // ---- one thread per point (round-1 v3 kernels), compiled only for A/B runs ----
-constexpr int kRowStride = 33;  // floats per staged row (32 features + 1 pad: conflict-free for row and column access)
-
-// The 8 corners are handled as 4 pairs (a, b) of memory neighbours:
-//   Dense: pair q = (dx | dy << 1), a = (dx, dy, z), b = (dx, dy, z + 1);   Hash: pair q = (dy | dz << 1), a = (x, dy, dz), b = (x + 1, dy, dz)
-struct Geo {
-    uint32_t cx, cy, cz;
-    float wa[4], wb[4];     // n-linear weights of the two corners of each pair
-    uint64_t ea[4], eb[4];  // element offsets (floats) of the corners' feature pairs inside the level table
-    uint32_t pair_ok;       // bit q set: pair q may use one 16-byte access
-};
-
-__device__ __forceinline__ void fast_geo(const LevelDesc& L, uint32_t gfo, bool smooth, bool lvl_aligned, float x, float y, float z, Geo& g) {
-    const uint32_t Rx = L.res[0], Ry = L.res[1], Rz = L.res[2];
-    float p[3];
-    uint32_t c[3];
-    const float xv[3] = {x, y, z};
-    const uint32_t R[3] = {Rx, Ry, Rz};
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        const float sc = (float)(R[d] - 2u);
-        float v = xv[d] * sc + 0.5f;
-        const float fl = floorf(v);
-        c[d] = (uint32_t)fl;
-        v -= (float)c[d];
-        p[d] = smooth ? v * v * (3.0f - 2.0f * v) : v;
-    }
-    g.cx = c[0]; g.cy = c[1]; g.cz = c[2];
-    const float wx[2] = {1.0f - p[0], p[0]}, wy[2] = {1.0f - p[1], p[1]}, wz[2] = {1.0f - p[2], p[2]};
-    const uint32_t nf = L.n_feat;
-    g.pair_ok = 0;
-    if (L.type == NR3D_LOD_DENSE) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t dx = q & 1, dy = q >> 1;
-            const uint32_t c0 = ((c[0] + dx) * Ry + (c[1] + dy)) * Rz + c[2];  // uint32 arithmetic as in the reference
-            const uint64_t e0 = (uint64_t)c0 * nf + gfo;
-            g.ea[q] = e0;
-            g.eb[q] = (uint64_t)(c0 + 1u) * nf + gfo;
-            g.wa[q] = (wx[dx] * wy[dy]) * wz[0];
-            g.wb[q] = (wx[dx] * wy[dy]) * wz[1];
-            if (lvl_aligned && nf == 2 && ((e0 & 3u) == 0)) g.pair_ok |= 1u << q;
-        }
-    } else {  // Hash
-        const uint32_t size = L.size;
-        const bool pow2 = (size & (size - 1u)) == 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t dy = q & 1, dz = q >> 1;
-            const uint32_t hyz = ((c[1] + dy) * 2654435761u) ^ ((c[2] + dz) * 805459861u);
-            const uint32_t h0 = pow2 ? ((c[0] ^ hyz) & (size - 1u)) : ((c[0] ^ hyz) % size);
-            const uint32_t h1 = pow2 ? (((c[0] + 1u) ^ hyz) & (size - 1u)) : (((c[0] + 1u) ^ hyz) % size);
-            g.ea[q] = (uint64_t)h0 * nf + gfo;
-            g.eb[q] = (uint64_t)h1 * nf + gfo;
-            g.wa[q] = (wx[0] * wy[dy]) * wz[dz];
-            g.wb[q] = (wx[1] * wy[dy]) * wz[dz];
-            if (lvl_aligned && nf == 2 && ((h0 ^ h1) == 1u)) g.pair_ok |= 1u << q;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// forward: thread = one (sorted) point, loop over pseudo levels.
-// Row-major y: the warp stages its 32 rows (up to 32 features at a time) in shared memory and writes each point's row
-// with one fully coalesced 128-byte store -- 32 line-writes per warp instead of 8 x 32 partial-line stores.
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kFastThreads)
-lotd_fast_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, float* __restrict__ y, int64_t ys_n, int64_t ys_f) {
-    __shared__ float rows[kFastThreads / 32][32 * kRowStride];
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = p < in.N;
-    const int lane = threadIdx.x & 31;
-    float* myrows = rows[threadIdx.x >> 5];
-    float4 rec = make_float4(0.5f, 0.5f, 0.5f, 0.f);
-    if (active) rec = __ldcs(in.xs + p);
-    const float x = rec.x, yv = rec.y, z = rec.z;
-    const uint64_t i = __float_as_uint(rec.w);
-    const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
-    const bool staged = (ys_f == 1);
-    uint32_t chunk_base = 0;  // first feature of the chunk currently staged
-    constexpr int kFwdUnroll = NR3D_FWD_UNROLL;
-#pragma unroll kFwdUnroll
-    for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
-        const uint32_t level = tab.map_level[pl];
-        float r0 = 0.f, r1 = 0.f;
-        if ((int32_t)level <= in.max_level) {
-            const LevelDesc& L = tab.lv[level];
-            const bool lvl_aligned = in.base_aligned16 && ((L.offset & 3u) == 0);
-            Geo g;
-            fast_geo(L, (uint32_t)tab.map_cnt[pl] * 2u, smooth, lvl_aligned, x, yv, z, g);
-            const float* tbl = reinterpret_cast<const float*>(in.params) + L.offset;
-            float4 v[4];  // (a.f0, a.f1, b.f0, b.f1) per pair; all loads are issued before the first use
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (g.pair_ok & (1u << q)) {
-                    const bool a_first = g.ea[q] < g.eb[q];
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(tbl + (a_first ? g.ea[q] : g.eb[q])));
-                    v[q] = a_first ? t : make_float4(t.z, t.w, t.x, t.y);
-                } else {
-                    const float2 ta = __ldg(reinterpret_cast<const float2*>(tbl + g.ea[q]));
-                    const float2 tb = __ldg(reinterpret_cast<const float2*>(tbl + g.eb[q]));
-                    v[q] = make_float4(ta.x, ta.y, tb.x, tb.y);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                r0 += g.wa[q] * v[q].x; r1 += g.wa[q] * v[q].y;
-                r0 += g.wb[q] * v[q].z; r1 += g.wb[q] * v[q].w;
-            }
-        }
-        if (staged) {
-            const uint32_t c = pl * 2u - chunk_base;
-            myrows[lane * kRowStride + c] = r0;
-            myrows[lane * kRowStride + c + 1] = r1;
-            const bool last = (pl + 1 == tab.n_pseudo);
-            if (c + 2 == 32 || last) {  // flush the chunk: one coalesced row store per point of the warp
-                const uint32_t width = c + 2;
-                __syncwarp();
-                for (int r = 0; r < 32; ++r) {
-                    const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, r);
-                    const bool ok = __shfl_sync(0xffffffffu, (int)active, r);
-                    if (ok && (uint32_t)lane < width) __stcs(y + (int64_t)ir * ys_n + chunk_base + lane, myrows[r * kRowStride + lane]);
-                }
-                __syncwarp();
-                chunk_base += 32;
-            }
-        } else if (active) {
-            float* yrow = y + (int64_t)i * ys_n;
-            __stcs(yrow + (int64_t)(pl * 2) * ys_f, r0);
-            __stcs(yrow + (int64_t)(pl * 2 + 1) * ys_f, r1);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// backward (dL/dparam): thread = one (sorted) point, loop over levels, run-merged 16-byte reductions
-// ------------------------------------------------------------------------------------------------------------
-constexpr int kTileStride = 20;  // floats per lane in the run-merge tile: 16 used, padded so that STS.128 is conflict free
-
-__device__ __forceinline__ void scatter_pair(float* tbl, const Geo& g, int q, float4 c /* a.f0 a.f1 b.f0 b.f1 */) {
-    if (g.pair_ok & (1u << q)) {
-        if (g.ea[q] < g.eb[q]) red_add_v4_f32(tbl + g.ea[q], c.x, c.y, c.z, c.w);
-        else red_add_v4_f32(tbl + g.eb[q], c.z, c.w, c.x, c.y);
-    } else {
-        red_add_v2_f32(tbl + g.ea[q], c.x, c.y);
-        red_add_v2_f32(tbl + g.eb[q], c.z, c.w);
-    }
-}
-
-__global__ void __launch_bounds__(kBwdThreads)
-lotd_fast_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, const float* __restrict__ dLdy, int64_t gs_n, int64_t gs_f,
-                     float* __restrict__ grad) {
-    __shared__ __align__(16) float tile[kBwdThreads / 32][32 * kTileStride];
-    __shared__ float rows[kBwdThreads / 32][32 * kRowStride];
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = p < in.N;
-    const int lane = threadIdx.x & 31;
-    float* mytile = tile[threadIdx.x >> 5];
-    float* myrows = rows[threadIdx.x >> 5];
-    float4 rec = make_float4(0.5f, 0.5f, 0.5f, 0.f);
-    if (active) rec = __ldcs(in.xs + p);
-    const float x = rec.x, yv = rec.y, z = rec.z;
-    const uint64_t i = __float_as_uint(rec.w);
-    const float* grow = dLdy + (int64_t)i * gs_n;
-    const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
-    const bool staged = (gs_f == 1);
-    const bool grad_aligned = (reinterpret_cast<uintptr_t>(grad) & 15u) == 0;
-    uint32_t chunk_base = 0;
-    for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
-        const uint32_t level = tab.map_level[pl];
-        float g0 = 0.f, g1 = 0.f;
-        if (staged) {
-            if (pl * 2u == chunk_base + 32u) chunk_base += 32u;
-            if (pl * 2u == chunk_base) {  // stage the next (up to) 32 features of the warp's 32 rows: one coalesced 128-byte read per point
-                const uint32_t width = min(32u, tab.n_enc - chunk_base);
-                __syncwarp();
-                for (int r = 0; r < 32; ++r) {
-                    const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, r);
-                    const bool ok = __shfl_sync(0xffffffffu, (int)active, r);
-                    if (ok && (uint32_t)lane < width) myrows[r * kRowStride + lane] = __ldcs(dLdy + (int64_t)ir * gs_n + chunk_base + lane);
-                }
-                __syncwarp();
-            }
-            g0 = myrows[lane * kRowStride + pl * 2u - chunk_base];
-            g1 = myrows[lane * kRowStride + pl * 2u - chunk_base + 1];
-        } else if (active) {
-            g0 = grow[(int64_t)(pl * 2) * gs_f];
-            g1 = grow[(int64_t)(pl * 2 + 1) * gs_f];
-        }
-        if ((int32_t)level > in.max_level) continue;  // uniform
-        const LevelDesc& L = tab.lv[level];
-        const bool lvl_aligned = in.base_aligned16 && grad_aligned && ((L.offset & 3u) == 0);
-        Geo g;
-        fast_geo(L, (uint32_t)tab.map_cnt[pl] * 2u, smooth, lvl_aligned, x, yv, z, g);
-        float* tbl = grad + L.offset;
-        // lanes of one run (consecutive lanes in the same cell) merge their contributions before touching L2
-        const bool can_key = L.res[0] <= 1024u && L.res[1] <= 1024u && L.res[2] <= 1024u;
-        uint32_t heads = 0xffffffffu;
-        if (can_key) {
-            const uint32_t key = active ? (g.cx | (g.cy << 10) | (g.cz << 20)) : (0xffffffffu - (uint32_t)lane);
-            const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-            heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
-        }
-        if (__popc(heads) > NR3D_MERGE_MAX_HEADS) {  // (almost) nothing to merge: scatter directly
-            if (active) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    scatter_pair(tbl, g, q, make_float4(g.wa[q] * g0, g.wa[q] * g1, g.wb[q] * g0, g.wb[q] * g1));
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<float4*>(mytile + lane * kTileStride + q * 4) = make_float4(g.wa[q] * g0, g.wa[q] * g1, g.wb[q] * g0, g.wb[q] * g1);
-            __syncwarp();
-            const uint32_t le = heads & (0xffffffffu >> (31 - lane));  // heads at or below my lane
-            const int s = 31 - __clz(le);
-            const uint32_t above = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
-            const int e = above ? (__ffs(above) - 1) : 32;
-            const int r = e - s, j = lane - s;
-            if (active) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {  // position j of a run of length r owns pairs j, j + r, j + 2r, ...
-                    const int d = q - j;
-                    if (d == 0 || (d > 0 && (d == r || d == 2 * r || d == 3 * r))) {
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int m = s; m < e; ++m) {
-                            const float4 t = *reinterpret_cast<const float4*>(mytile + m * kTileStride + q * 4);
-                            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-                        }
-                        scatter_pair(tbl, g, q, acc);
-                    }
-                }
-            }
-            __syncwarp();
-        }
-    }
-}
-
-#endif  // !NR3D_FAST_PAIR
 
 // ------------------------------------------------------------------------------------------------------------
 // "pair" layout (default).  Measured on B200 (scripts/ubench_pair.cu -> profiles/r1_ubench_pair.txt): a warp-wide gather
@@ -691,11 +448,7 @@ int make_table_public(const nr3d_lotd_meta* m, LotdTable& tab) { return make_tab
 
 static int check_fast(const nr3d_lotd_meta* m, int32_t param_dtype, uint64_t N) {
     NR3D_CHECK(m != nullptr, "LoTDEncoding: null meta");
-#if NR3D_FAST_PAIR
     const bool dtype_ok = param_dtype == NR3D_F32 || param_dtype == NR3D_F16;
-#else
-    const bool dtype_ok = param_dtype == NR3D_F32;
-#endif
     NR3D_CHECK(m->hash_only && m->n_dims_to_encode == 3 && m->n_feat_per_pseudo_lvl == 2 && dtype_ok,
                "LoTDEncoding: the sorted fast path needs a Dense/Hash-only meta with D=3, 2 features per pseudo level and fp32 / fp16 params");
     NR3D_CHECK(N < (1ull << 32), "LoTDEncoding: batch_size must be < 2^32");
@@ -750,13 +503,9 @@ int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64
     LotdTable tab;
     make_table(meta, tab);
     FastIn in{N, reinterpret_cast<const float4*>(xs), params, max_level, (uint32_t)((reinterpret_cast<uintptr_t>(params) & 15u) == 0)};
-#if NR3D_FAST_PAIR
     const unsigned grid = (unsigned)div_up<uint64_t>(2 * N, kFastThreads);
     if (param_dtype == NR3D_F16) lotd_pair_fwd_kernel<__half><<<grid, kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (__half*)y, y_stride_n, y_stride_f);
     else lotd_pair_fwd_kernel<float><<<grid, kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (float*)y, y_stride_n, y_stride_f);
-#else
-    lotd_fast_fwd_kernel<<<(unsigned)div_up<uint64_t>(N, kFastThreads), kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (float*)y, y_stride_n, y_stride_f);
-#endif
     NR3D_LAUNCH_CHECK("lotd_fast_fwd");
     return 0;
 }
@@ -769,18 +518,13 @@ int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, 
     LotdTable tab;
     make_table(meta, tab);
     FastIn in{N, reinterpret_cast<const float4*>(xs), nullptr, max_level, 1u};
-#if NR3D_FAST_PAIR
     const unsigned grid = (unsigned)div_up<uint64_t>(2 * N, kBwdThreads);
     if (param_dtype == NR3D_F16) lotd_pair_bwd_kernel<__half, false><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const __half*)dL_dy, dLdy_stride_n, dLdy_stride_f, nullptr, (__half*)dL_dparam);
     else lotd_pair_bwd_kernel<float, false><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, nullptr, (float*)dL_dparam);
-#else
-    lotd_fast_bwd_kernel<<<(unsigned)div_up<uint64_t>(N, kBwdThreads), kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, (float*)dL_dparam);
-#endif
     NR3D_LAUNCH_CHECK("lotd_fast_bwd");
     return 0;
 }
 
-#if NR3D_FAST_PAIR
 int nr3d_lotd_fwd_dydx_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* params,
                               int32_t max_level, void* y, void* dy_dx, void* stream) {
     if (int rc = check_fast(meta, param_dtype, N)) return rc;
@@ -811,6 +555,5 @@ int nr3d_lotd_bwd_param2_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype,
     NR3D_LAUNCH_CHECK("lotd_fast_bwd2");
     return 0;
 }
-#endif
 
 }  // extern "C"

@@ -5,7 +5,6 @@ import json, os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 VARIANTS = {
     "base": [],                                   # pair layout (two lanes per point)
-    "nopair": ["NR3D_FAST_PAIR=0"],               # one thread per point (round-1 v3 kernels)
     "heads12": ["NR3D_MERGE_MAX_HEADS=12"],
     "heads28": ["NR3D_MERGE_MAX_HEADS=28"],
     "unroll1": ["NR3D_FWD_UNROLL=1"],

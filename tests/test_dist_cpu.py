@@ -44,6 +44,13 @@ def _worker(rank, world, port, out_dir):
     ro, rd, near, far, (rb, re_) = nd.shard_rays(torch.arange(30.).view(10, 3), torch.ones(10, 3), torch.zeros(10), torch.ones(10), r, w)
     assert ro.shape[0] == re_ - rb and float(ro[0, 0]) == 3.0 * rb
     assert nd.max_over_ranks(float(rank)) == float(world - 1)
+    assert nd.sum_over_ranks(float(rank + 1)) == float(world * (world + 1) // 2)        # e.g. the samples every rank marched
+    # host-fed read-back: every rank returns its own slice of the (identical) all-reduced gradient -> the host sees it exactly once
+    host = torch.zeros(meta.n_params, dtype=gp_local.dtype)
+    lo, hi = nd.shard_range(meta.n_params, r, w)
+    host[lo:hi] = gp_local[lo:hi]
+    torch.distributed.all_reduce(host)                                                  # (stands for the shared pinned host buffer)
+    assert torch.equal(host, gp_local)
     nd.barrier()
     np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([1]))
     torch.distributed.destroy_process_group()
