@@ -105,6 +105,16 @@ int nr3d_lotd_bwd_bwd_input(const nr3d_lotd_meta* meta, int32_t input_dtype, int
                             const int64_t* batch_inds, const int64_t* batch_offsets, uint32_t batch_data_size,
                             int32_t max_level, void* dL_ddLdy, void* dL_dparam, void* dL_dx, void* stream);
 
+/* dL/dparam (dL_ddLdx == NULL) or the second-order d(dL/dx)/dparam . dL_ddLdx (dL_ddLdx: f32 [N, D]) with the number of scenes
+ * behind `params` made explicit (n_batches = params.numel / n_params; 0 = unknown).  Same results as nr3d_lotd_bwd_param /
+ * the dL_dparam output of nr3d_lotd_bwd_bwd_input; knowing the scene count lets small Dense / CP tables and the lines of VM levels
+ * be accumulated in shared memory (one copy per scene and CTA) before they are added to dL_dparam -- the reference scatters every
+ * corner straight into these same-address hot spots (lotd_cuda.h:494-829).  dL_dparam is accumulated into: zero it first. */
+int nr3d_lotd_bwd_param_scenes(const nr3d_lotd_meta* meta, int32_t input_dtype, int32_t param_dtype, uint64_t N, const void* dL_dy,
+                               int64_t dLdy_stride_n, int64_t dLdy_stride_f, const void* dL_ddLdx, const void* x, const void* params,
+                               const int64_t* batch_inds, const int64_t* batch_offsets, uint32_t batch_data_size, uint32_t n_batches,
+                               int32_t max_level, void* dL_dparam, void* stream);
+
 /* == lod_get_grid_index, csrc/lotd/src/lotd_torch_api.cu:771-855 (kernel lotd_encoding.h:1300-1433).
  * out: int64 [N, n_enc, 2^D], MUST be zero-filled by the caller (skipped entries stay 0). Dense/Hash only. */
 int nr3d_lotd_grid_index(const nr3d_lotd_meta* meta, int32_t input_dtype, uint64_t N, const void* x,

@@ -62,6 +62,7 @@ SIGNATURES = {
     "nr3d_lotd_meta_create": [_i32, _i32, _vp, _vp, _vp, _u32, _i32, _meta_p],
     "nr3d_lotd_fwd": [_meta_p, _i32, _i32, _u64, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _i64, _i64, _vp, _i64, _i64, _vp],
     "nr3d_lotd_bwd_param": [_meta_p, _i32, _i32, _u64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp],
+    "nr3d_lotd_bwd_param_scenes": [_meta_p, _i32, _i32, _u64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _i32, _vp, _vp],
     "nr3d_lotd_bwd_input": [_meta_p, _i32, _i32, _u64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp],
     "nr3d_lotd_bwd_bwd_input": [_meta_p, _i32, _i32, _u64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _u32,
                                 _i32, _vp, _vp, _vp, _vp],

@@ -373,10 +373,10 @@ def lod_bwd(lod_meta, dL_dy: torch.Tensor, input: torch.Tensor, params: torch.Te
                 ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), dL_dy.data_ptr(),
                 dL_dy.stride(0), dL_dy.stride(1), max_level, dL_dparam.data_ptr(), st))
         elif need_param_grad:
-            _lib.check(lib.nr3d_lotd_bwd_param(
+            _lib.check(lib.nr3d_lotd_bwd_param_scenes(
                 ctypes.byref(meta._c), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, dL_dy.data_ptr(),
-                dL_dy.stride(0), dL_dy.stride(1), input.data_ptr(), params.data_ptr(), _lib.ptr(batch_inds),
-                _lib.ptr(batch_offsets), bds, max_level, dL_dparam.data_ptr(), st))
+                dL_dy.stride(0), dL_dy.stride(1), None, input.data_ptr(), params.data_ptr(), _lib.ptr(batch_inds),
+                _lib.ptr(batch_offsets), bds, params.shape[0] // meta.n_params, max_level, dL_dparam.data_ptr(), st))
     return dL_dx, dL_dparam
 
 
@@ -445,11 +445,16 @@ def lod_bwd_bwd_input(lod_meta, dL_ddLdx: torch.Tensor, dL_dy: torch.Tensor, inp
                 ctypes.byref(meta._c), pdt, N, xs.data_ptr(), dL_dy.data_ptr(), dL_dy.stride(0), dL_dy.stride(1), dL_ddLdx.data_ptr(),
                 max_level, dL_dparams.data_ptr(), st))
             dparam_generic = None
-        if need_dLdy or need_input or dparam_generic is not None:
+        if dparam_generic is not None:      # second-order scatter with the scene count made explicit (shared-memory privatisation)
+            _lib.check(lib.nr3d_lotd_bwd_param_scenes(
+                ctypes.byref(meta._c), idt, pdt, N, dL_dy.data_ptr(), dL_dy.stride(0), dL_dy.stride(1), dL_ddLdx.data_ptr(), input.data_ptr(),
+                params.data_ptr(), _lib.ptr(batch_inds), _lib.ptr(batch_offsets), bds, params.shape[0] // meta.n_params, max_level,
+                dparam_generic.data_ptr(), st))
+        if need_dLdy or need_input:
             _lib.check(lib.nr3d_lotd_bwd_bwd_input(
                 ctypes.byref(meta._c), idt, pdt, N, dL_ddLdx.data_ptr(),
                 dL_dy.data_ptr(), dL_dy.stride(0), dL_dy.stride(1), input.data_ptr(), params.data_ptr(), _lib.ptr(dv), ds_n, ds_f,
-                _lib.ptr(batch_inds), _lib.ptr(batch_offsets), bds, max_level, _lib.ptr(dL_ddLdy), _lib.ptr(dparam_generic),
+                _lib.ptr(batch_inds), _lib.ptr(batch_offsets), bds, max_level, _lib.ptr(dL_ddLdy), None,
                 _lib.ptr(dL_dx), st))
     return dL_ddLdy, dL_dparams, dL_dx
 

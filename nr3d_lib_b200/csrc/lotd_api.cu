@@ -198,6 +198,19 @@ int nr3d_lotd_bwd_param(const nr3d_lotd_meta* meta, int32_t input_dtype, int32_t
     NR3D_DISPATCH_DIM(meta, lotd_launch_bwd_param<D>(L, dL_dy, s_n, s_f, nullptr, dL_dparam));
 }
 
+int nr3d_lotd_bwd_param_scenes(const nr3d_lotd_meta* meta, int32_t input_dtype, int32_t param_dtype, uint64_t N, const void* dL_dy,
+                               int64_t s_n, int64_t s_f, const void* dL_ddLdx, const void* x, const void* params, const int64_t* batch_inds,
+                               const int64_t* batch_offsets, uint32_t batch_data_size, uint32_t n_batches, int32_t max_level,
+                               void* dL_dparam, void* stream) {
+    if (N == 0) return 0;
+    LotdLaunch L;
+    if (int rc = build_launch(meta, input_dtype, param_dtype, N, x, params, batch_inds, batch_offsets, batch_data_size, max_level, stream, L)) return rc;
+    NR3D_CHECK(dL_dy && dL_dparam, "LoTDEncoding::bwd: null argument");
+    L.in.vec_ok = L.in.vec_ok && ((reinterpret_cast<uintptr_t>(dL_dparam) & 7u) == 0);
+    L.n_batches = n_batches;
+    NR3D_DISPATCH_DIM(meta, lotd_launch_bwd_param<D>(L, dL_dy, s_n, s_f, (const float*)dL_ddLdx, dL_dparam));
+}
+
 int nr3d_lotd_bwd_input(const nr3d_lotd_meta* meta, int32_t input_dtype, int32_t param_dtype, uint64_t N, const void* dL_dy,
                         int64_t s_n, int64_t s_f, const void* dy_dx, int64_t ds_n, int64_t ds_f, void* dL_dx, void* stream) {
     if (N == 0) return 0;

@@ -40,7 +40,8 @@ struct Ctx {
     uint32_t cell[D];
     float scale[D], p[D], dp[D], d2p[D];
     uint32_t type, n_feat, size, gfo;
-    uint64_t base;  // element offset of this level's table inside `params`
+    uint32_t batch;  // scene (batch) index of the point
+    uint64_t base;   // element offset of this level's table inside `params`
 };
 
 // returns false when the (point, pseudo level) pair is skipped (level > max_level or batch index < 0)
@@ -59,6 +60,7 @@ __device__ __forceinline__ bool lotd_setup(const LotdTable& tab, const LotdIn& i
     const uint64_t batch_offset = in.batch_offsets ? (uint64_t)in.batch_offsets[batch_ind] : (uint64_t)batch_ind * tab.n_params;
     const LevelDesc& L = tab.lv[level];
     c.base = batch_offset + L.offset;
+    c.batch = batch_ind;
     c.type = L.type;
     c.n_feat = L.n_feat;
     c.size = L.size;
@@ -407,8 +409,33 @@ __device__ __forceinline__ void corner_add_grad(const Ctx<D>& c, const PT* __res
 //   NPlane  a plane entry is shared by 2 corners:                                           D 2^(D-1) instead of D 2^D
 // which matters most exactly where the reference is slowest: the tiny line / plane tables are same-address reduction hot spots.
 // ------------------------------------------------------------------------------------------------
-template <int D, int F, typename PT>
-__device__ __forceinline__ void nlinear_scatter(const Ctx<D>& c, const PT* __restrict__ g, PT* __restrict__ gg, const float* cw,
+// Where the summed contributions go.  GlobalSink: L2 reductions into the gradient table.  PrivSink: entries below `n_small` (the
+// whole table of a small Dense / CP level, the line part of a VM level) are accumulated in the CTA's shared-memory copy of the
+// table first -- these tiny sub-tables receive thousands of reductions per entry and serialise in the L2 slices otherwise.
+template <int F, typename PT>
+struct GlobalSink {
+    PT* gg;            // level base inside the gradient array
+    uint32_t n_feat, gfo;
+    bool vec_ok;
+    __device__ __forceinline__ void add(uint32_t entry, const float* v) const { scatter_add<F>(gg + (uint64_t)entry * n_feat + gfo, v, vec_ok); }
+};
+template <int F, typename PT>
+struct PrivSink {
+    GlobalSink<F, PT> g;
+    float* sm;         // this scene's slice of the shared-memory table: [n_small][F]
+    uint32_t n_small;
+    __device__ __forceinline__ void add(uint32_t entry, const float* v) const {
+        if (entry < n_small) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) atomicAdd(sm + entry * F + f, v[f]);
+        } else {
+            g.add(entry, v);
+        }
+    }
+};
+
+template <int D, int F, typename PT, typename Sink>
+__device__ __forceinline__ void nlinear_scatter(const Ctx<D>& c, const PT* __restrict__ g, PT* __restrict__ gg, const Sink& sink, const float* cw,
                                                 const float* grad, bool vec_ok) {
     using C = Cvt<PT>;
     if (c.type == NR3D_LOD_DENSE || c.type == NR3D_LOD_HASH) {
@@ -420,8 +447,7 @@ __device__ __forceinline__ void nlinear_scatter(const Ctx<D>& c, const PT* __res
             float wg[F];
 #pragma unroll
             for (int f = 0; f < F; ++f) wg[f] = grad[f] * cw[idx];
-            const uint32_t e = c.type == NR3D_LOD_DENSE ? idx_dense<D>(c.res, pos) : idx_hash<D>(pos, c.size);
-            scatter_add<F>(gg + (uint64_t)e * c.n_feat + c.gfo, wg, vec_ok);
+            sink.add(c.type == NR3D_LOD_DENSE ? idx_dense<D>(c.res, pos) : idx_hash<D>(pos, c.size), wg);
         }
         return;
     }
@@ -430,7 +456,7 @@ __device__ __forceinline__ void nlinear_scatter(const Ctx<D>& c, const PT* __res
 #pragma unroll
             for (int k = 0; k < D; ++k) {
                 // entries of line k (2) and plane k (4; plane k ignores dimension k)
-                uint64_t il[2], ip[4];
+                uint32_t el[2], ep[4];
                 PT Lv[2][F], Pv[4][F];
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
@@ -443,15 +469,12 @@ __device__ __forceinline__ void nlinear_scatter(const Ctx<D>& c, const PT* __res
                         else { pos[d] = c.cell[d] + ((b >> bb) & 1); ++bb; }
                     }
                     idx_vm<D>(c.res, pos, pl, ln);
-                    ip[b] = (uint64_t)pl[k] * c.n_feat + c.gfo;
-                    load_feats<F>(g + ip[b], Pv[b], vec_ok);
-                    if (b == 0) {
-                        il[0] = (uint64_t)ln[k] * c.n_feat + c.gfo;
-                        il[1] = (uint64_t)(ln[k] + 1u) * c.n_feat + c.gfo;
-                    }
+                    ep[b] = pl[k];
+                    load_feats<F>(g + (uint64_t)ep[b] * c.n_feat + c.gfo, Pv[b], vec_ok);
+                    if (b == 0) { el[0] = ln[k]; el[1] = ln[k] + 1u; }
                 }
-                load_feats<F>(g + il[0], Lv[0], vec_ok);
-                load_feats<F>(g + il[1], Lv[1], vec_ok);
+                load_feats<F>(g + (uint64_t)el[0] * c.n_feat + c.gfo, Lv[0], vec_ok);
+                load_feats<F>(g + (uint64_t)el[1] * c.n_feat + c.gfo, Lv[1], vec_ok);
                 float gl[2][F], gp[4][F];
 #pragma unroll
                 for (int f = 0; f < F; ++f) {
@@ -473,23 +496,23 @@ __device__ __forceinline__ void nlinear_scatter(const Ctx<D>& c, const PT* __res
                         gp[b][f] += t * C::to_f(Lv[a][f]);
                     }
                 }
-                scatter_add<F>(gg + il[0], gl[0], vec_ok);
-                scatter_add<F>(gg + il[1], gl[1], vec_ok);
+                sink.add(el[0], gl[0]);
+                sink.add(el[1], gl[1]);
 #pragma unroll
-                for (int b = 0; b < 4; ++b) scatter_add<F>(gg + ip[b], gp[b], vec_ok);
+                for (int b = 0; b < 4; ++b) sink.add(ep[b], gp[b]);
             }
         }
         return;
     }
     if (c.type == NR3D_LOD_CP) {
-        uint64_t il[D][2];
+        uint32_t el[D][2];
         PT Lv[D][2][F];
 #pragma unroll
         for (int k = 0; k < D; ++k)
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
-                il[k][a] = (uint64_t)idx_cp_line<D>(c.res, c.cell[k] + a, k) * c.n_feat + c.gfo;
-                load_feats<F>(g + il[k][a], Lv[k][a], vec_ok);
+                el[k][a] = idx_cp_line<D>(c.res, c.cell[k] + a, k);
+                load_feats<F>(g + (uint64_t)el[k][a] * c.n_feat + c.gfo, Lv[k][a], vec_ok);
             }
         float acc[D][2][F];
 #pragma unroll
@@ -512,12 +535,12 @@ __device__ __forceinline__ void nlinear_scatter(const Ctx<D>& c, const PT* __res
         }
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            scatter_add<F>(gg + il[k][0], acc[k][0], vec_ok);
-            scatter_add<F>(gg + il[k][1], acc[k][1], vec_ok);
+            sink.add(el[k][0], acc[k][0]);
+            sink.add(el[k][1], acc[k][1]);
         }
         return;
     }
-    // NPlaneMul, VecZMatXoY (rare) and anything else: per corner
+    // NPlaneMul, VecZMatXoY (rare) and anything else: per corner, straight to the table
 #pragma unroll 1
     for (int idx = 0; idx < (1 << D); ++idx) {
         uint32_t pos[D];
@@ -525,6 +548,16 @@ __device__ __forceinline__ void nlinear_scatter(const Ctx<D>& c, const PT* __res
         for (int d = 0; d < D; ++d) pos[d] = c.cell[d] + ((idx >> d) & 1);
         corner_add_grad<D, F, PT>(c, g, gg, pos, grad, cw[idx], vec_ok);
     }
+}
+
+// number of leading table entries of a level that are worth privatising in shared memory (0: none)
+__host__ __device__ inline uint32_t small_entries(uint32_t type, const uint32_t* res, int D, uint32_t size) {
+    uint32_t lines = 0;
+    for (int d = 0; d < D; ++d) lines += res[d];
+    if (type == NR3D_LOD_CP) return lines;          // the whole table
+    if (type == NR3D_LOD_VM) return lines;          // the lines; the planes follow
+    if (type == NR3D_LOD_DENSE) return size;        // the whole table (the launcher checks that it fits)
+    return 0;
 }
 
 // corner position for corner id `idx` (bit d set -> cell+1) and its n-linear weight

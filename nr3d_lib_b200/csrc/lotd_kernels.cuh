@@ -2,6 +2,7 @@
 // Instantiated per input dimension in lotd_d{2,3,4}.cu.  The Dense/Hash tuned kernels live in lotd_fast.cu.
 #pragma once
 #include "lotd_device.cuh"
+#include <string.h>
 
 namespace nr3d {
 
@@ -158,14 +159,51 @@ lotd_fwd_kernel(const __grid_constant__ LotdTable tab, const LotdIn in, PT* __re
 // SECOND = true adds the second-order term d(dL/dx)/dparam . dL_ddLdx instead
 // (kernel_lod_backward_input_backward_grid, lotd_encoding.h:764-1041).
 // =================================================================================================
+// Pseudo levels whose small sub-tables are accumulated in shared memory by lotd_bwd_param_priv_kernel (the plain kernel skips them).
+constexpr int kMaxPriv = 64;
+struct PrivPlan {
+    uint32_t n;                 // number of privatised pseudo levels
+    uint32_t n_batches;         // scenes with a shared-memory copy each
+    uint32_t skip[NR3D_MAX_PSEUDO_LEVELS / 32];   // bit pl set: pseudo level pl belongs to the privatised kernel
+    uint8_t pl[kMaxPriv];
+};
+
+// weight of every lattice corner: the n-linear weight (first order), or -- second order -- the sum over the derivative dimensions gd of
+// gin[gd] * (+1 right / -1 left of gd) * prod_{d != gd} w_d  (the reference walks the 2^(D-1) face corners of every gd and scatters
+// left and right separately, lotd_encoding.h:764-1041: 3x the reductions)
+template <int D, bool SECOND>
+__device__ __forceinline__ void corner_weights(const Ctx<D>& c, const float* gin, float* cw) {
+#pragma unroll
+    for (int idx = 0; idx < (1 << D); ++idx) {
+        if (!SECOND) {
+            float w = 1.0f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) w *= ((idx >> d) & 1) ? c.p[d] : 1.0f - c.p[d];
+            cw[idx] = w;
+        } else {
+            float acc = 0.f;
+#pragma unroll
+            for (int gd = 0; gd < D; ++gd) {
+                float w = gin[gd];
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+                    if (d != gd) w *= ((idx >> d) & 1) ? c.p[d] : 1.0f - c.p[d];
+                acc += ((idx >> gd) & 1) ? w : -w;
+            }
+            cw[idx] = acc;
+        }
+    }
+}
+
 template <int D, int F, typename PT, bool SECOND>
 __global__ void __launch_bounds__(kLotdThreads)
-lotd_bwd_param_kernel(const __grid_constant__ LotdTable tab, const LotdIn in, const PT* __restrict__ dLdy, int64_t gs_n,
-                      int64_t gs_f, const float* __restrict__ ddx, PT* __restrict__ grad_params) {
+lotd_bwd_param_kernel(const __grid_constant__ LotdTable tab, const LotdIn in, const __grid_constant__ PrivPlan plan, const PT* __restrict__ dLdy,
+                      int64_t gs_n, int64_t gs_f, const float* __restrict__ ddx, PT* __restrict__ grad_params) {
     using C = Cvt<PT>;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= in.N) return;
     const uint32_t pl = blockIdx.y;
+    if (plan.skip[pl >> 5] & (1u << (pl & 31))) return;   // handled by lotd_bwd_param_priv_kernel
     Ctx<D> c;
     if (!lotd_setup<D, F>(tab, in, i, pl, c)) return;
     const PT* g = reinterpret_cast<const PT*>(in.params) + c.base;
@@ -183,31 +221,9 @@ lotd_bwd_param_kernel(const __grid_constant__ LotdTable tab, const LotdIn in, co
         for (int d = 0; d < D; ++d) gin[d] = c.scale[d] * ddx[i * D + d] * c.dp[d];
     }
     if (is_nlinear(c.type)) {
-        // weight of every lattice corner: the n-linear weight (first order), or -- second order -- the sum over the derivative
-        // dimensions gd of  gin[gd] * (+1 right / -1 left of gd) * prod_{d != gd} w_d  (the reference walks the 2^(D-1) face
-        // corners of every gd and scatters left and right separately, lotd_encoding.h:764-1041: 3x the reductions)
         float cw[1 << D];
-#pragma unroll
-        for (int idx = 0; idx < (1 << D); ++idx) {
-            if (!SECOND) {
-                float w = 1.0f;
-#pragma unroll
-                for (int d = 0; d < D; ++d) w *= ((idx >> d) & 1) ? c.p[d] : 1.0f - c.p[d];
-                cw[idx] = w;
-            } else {
-                float acc = 0.f;
-#pragma unroll
-                for (int gd = 0; gd < D; ++gd) {
-                    float w = gin[gd];
-#pragma unroll
-                    for (int d = 0; d < D; ++d)
-                        if (d != gd) w *= ((idx >> d) & 1) ? c.p[d] : 1.0f - c.p[d];
-                    acc += ((idx >> gd) & 1) ? w : -w;
-                }
-                cw[idx] = acc;
-            }
-        }
-        nlinear_scatter<D, F, PT>(c, g, gg, cw, grad, vec_ok);
+        corner_weights<D, SECOND>(c, gin, cw);
+        nlinear_scatter<D, F, PT>(c, g, gg, GlobalSink<F, PT>{gg, c.n_feat, c.gfo, vec_ok}, cw, grad, vec_ok);
     } else if (c.type == NR3D_LOD_NPLANESUM) {
         if constexpr (D > 2) {
 #pragma unroll 1
@@ -310,6 +326,62 @@ lotd_bwd_param_kernel(const __grid_constant__ LotdTable tab, const LotdIn in, co
                 }
             }
         }
+    }
+}
+
+// =================================================================================================
+// dL/dparam for pseudo levels with tiny, heavily shared sub-tables (small Dense, CP, the lines of VM): a persistent grid of CTAs,
+// each with a shared-memory copy of the sub-table for every scene, walks the points; the copies are added to the gradient table
+// once per CTA at the end.  2 Mi points onto a 96-entry line table are ~90 000 reductions per entry when sent to L2 directly --
+// the L2 slice applies same-address reductions one after the other -- and a few hundred after privatisation.
+// grid = (persistent CTAs, privatised pseudo levels); dynamic shared memory = n_batches * n_small * F floats.
+// =================================================================================================
+template <int D, int F, typename PT, bool SECOND>
+__global__ void __launch_bounds__(kLotdThreads)
+lotd_bwd_param_priv_kernel(const __grid_constant__ LotdTable tab, const LotdIn in, const __grid_constant__ PrivPlan plan, const PT* __restrict__ dLdy,
+                           int64_t gs_n, int64_t gs_f, const float* __restrict__ ddx, PT* __restrict__ grad_params) {
+    using C = Cvt<PT>;
+    extern __shared__ float sm[];
+    const uint32_t pl = plan.pl[blockIdx.y];
+    const LevelDesc& L = tab.lv[tab.map_level[pl]];
+    const uint32_t n_small = small_entries(L.type, L.res, D, L.size);
+    const uint32_t n_slots = plan.n_batches * n_small * F;
+    for (uint32_t e = threadIdx.x; e < n_slots; e += blockDim.x) sm[e] = 0.f;
+    __syncthreads();
+    const bool vec_ok = in.vec_ok;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < in.N; i += (uint64_t)gridDim.x * blockDim.x) {
+        Ctx<D> c;
+        if (!lotd_setup<D, F>(tab, in, i, pl, c)) continue;
+        const PT* g = reinterpret_cast<const PT*>(in.params) + c.base;
+        PT* gg = grad_params + c.base;
+        float grad[F];
+        {
+            const PT* gp = dLdy + (int64_t)i * gs_n + (int64_t)(pl * F) * gs_f;
+#pragma unroll
+            for (int f = 0; f < F; ++f) grad[f] = C::to_f(gp[(int64_t)f * gs_f]);
+        }
+        float gin[D];
+        if (SECOND) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) gin[d] = c.scale[d] * ddx[i * D + d] * c.dp[d];
+        }
+        float cw[1 << D];
+        corner_weights<D, SECOND>(c, gin, cw);
+        const bool mine = c.batch < plan.n_batches;     // scenes beyond the planned count go straight to the table
+        const PrivSink<F, PT> sink{GlobalSink<F, PT>{gg, c.n_feat, c.gfo, vec_ok}, sm + (size_t)(mine ? c.batch : 0) * n_small * F, mine ? n_small : 0u};
+        nlinear_scatter<D, F, PT>(c, g, gg, sink, cw, grad, vec_ok);
+    }
+    __syncthreads();
+    const uint32_t gfo = (uint32_t)tab.map_cnt[pl] * F;
+    for (uint32_t e = threadIdx.x; e < plan.n_batches * n_small; e += blockDim.x) {
+        float v[F];
+        bool any = false;
+#pragma unroll
+        for (int f = 0; f < F; ++f) { v[f] = sm[e * F + f]; any |= (v[f] != 0.f); }
+        if (!any) continue;
+        const uint32_t b = e / n_small, ent = e - b * n_small;
+        const uint64_t boff = in.batch_offsets ? (uint64_t)in.batch_offsets[b] : (uint64_t)b * tab.n_params;
+        scatter_add<F>(grad_params + boff + L.offset + (uint64_t)ent * L.n_feat + gfo, v, vec_ok);
     }
 }
 
@@ -510,7 +582,32 @@ struct LotdLaunch {
     int fpl;        // 2, 4, 8
     int half;       // param dtype: 0 float, 1 half
     cudaStream_t stream;
+    uint32_t n_batches = 0;   // scenes behind `params` if the caller knows (0: unknown -> no shared-memory privatisation)
 };
+
+// which pseudo levels go to the privatised dL/dparam kernel (host side)
+template <int D>
+inline PrivPlan make_priv_plan(const LotdLaunch& L, int F, size_t* smem_bytes) {
+    PrivPlan plan;
+    memset(&plan, 0, sizeof(plan));
+    *smem_bytes = 0;
+    uint32_t B = L.n_batches;
+    if (B == 0 && !L.in.batch_inds) B = L.in.batch_data_size ? (uint32_t)(L.in.N / L.in.batch_data_size) : 1u;
+    if (B == 0) return plan;
+    plan.n_batches = B;
+    for (uint32_t pl = 0; pl < L.tab.n_pseudo && plan.n < (uint32_t)kMaxPriv; ++pl) {
+        const LevelDesc& lv = L.tab.lv[L.tab.map_level[pl]];
+        const uint32_t n_small = small_entries(lv.type, lv.res, D, lv.size);
+        if (n_small == 0 || (int32_t)L.tab.map_level[pl] > L.in.max_level) continue;
+        const size_t bytes = (size_t)B * n_small * F * sizeof(float);
+        // worth it when the points outnumber the privatised entries and every scene's copy fits the default shared-memory window
+        if (bytes > 48 * 1024 || L.in.N < 2ull * B * n_small) continue;
+        plan.pl[plan.n++] = (uint8_t)pl;
+        plan.skip[pl >> 5] |= 1u << (pl & 31);
+        if (bytes > *smem_bytes) *smem_bytes = bytes;
+    }
+    return plan;
+}
 
 // fills L from the C-ABI arguments (defined in lotd_api.cu; shared with lotd_forest.cu)
 int build_launch(const nr3d_lotd_meta* m, int32_t input_dtype, int32_t param_dtype, uint64_t N, const void* x, const void* params,
@@ -549,10 +646,22 @@ template <int D> int lotd_launch_grid_index(const LotdLaunch& L, int64_t* out);
                                              const float* ddx, void* gp) {                                                \
         if (L.in.N == 0) return 0;                                                                                        \
         const dim3 grid((unsigned)div_up<uint64_t>(L.in.N, kLotdThreads), L.tab.n_pseudo, 1);                             \
-        NR3D_LOTD_DISPATCH_F_PT(                                                                                          \
-            if (ddx) lotd_bwd_param_kernel<D, F, PT, true><<<grid, kLotdThreads, 0, L.stream>>>(L.tab, L.in, (const PT*)dLdy, gs_n, gs_f, ddx, (PT*)gp); \
-            else lotd_bwd_param_kernel<D, F, PT, false><<<grid, kLotdThreads, 0, L.stream>>>(L.tab, L.in, (const PT*)dLdy, gs_n, gs_f, nullptr, (PT*)gp)) \
-        NR3D_LAUNCH_CHECK("lotd_bwd_param");                                                                              \
+        size_t priv_smem = 0;                                                                                             \
+        const PrivPlan plan = make_priv_plan<D>(L, L.fpl, &priv_smem);                                                    \
+        if (plan.n < L.tab.n_pseudo) {                                                                                    \
+            NR3D_LOTD_DISPATCH_F_PT(                                                                                      \
+                if (ddx) lotd_bwd_param_kernel<D, F, PT, true><<<grid, kLotdThreads, 0, L.stream>>>(L.tab, L.in, plan, (const PT*)dLdy, gs_n, gs_f, ddx, (PT*)gp); \
+                else lotd_bwd_param_kernel<D, F, PT, false><<<grid, kLotdThreads, 0, L.stream>>>(L.tab, L.in, plan, (const PT*)dLdy, gs_n, gs_f, nullptr, (PT*)gp)) \
+            NR3D_LAUNCH_CHECK("lotd_bwd_param");                                                                          \
+        }                                                                                                                 \
+        if (plan.n) {                                                                                                     \
+            const uint64_t want = div_up<uint64_t>(L.in.N, kLotdThreads);                                                 \
+            const dim3 pgrid((unsigned)(want < (uint64_t)kSMs * 3 ? want : (uint64_t)kSMs * 3), plan.n, 1);               \
+            NR3D_LOTD_DISPATCH_F_PT(                                                                                      \
+                if (ddx) lotd_bwd_param_priv_kernel<D, F, PT, true><<<pgrid, kLotdThreads, priv_smem, L.stream>>>(L.tab, L.in, plan, (const PT*)dLdy, gs_n, gs_f, ddx, (PT*)gp); \
+                else lotd_bwd_param_priv_kernel<D, F, PT, false><<<pgrid, kLotdThreads, priv_smem, L.stream>>>(L.tab, L.in, plan, (const PT*)dLdy, gs_n, gs_f, nullptr, (PT*)gp)) \
+            NR3D_LAUNCH_CHECK("lotd_bwd_param_priv");                                                                     \
+        }                                                                                                                 \
         return 0;                                                                                                         \
     }                                                                                                                     \
     template <> int lotd_launch_bwdbwd_input<D>(const LotdLaunch& L, const void* dLdy, int64_t gs_n, int64_t gs_f,       \
