@@ -262,6 +262,78 @@ __device__ __forceinline__ void corner_val(const Ctx<D>& c, const PT* __restrict
     }
 }
 
+// values of all 2^D lattice corners of one (point, pseudo level).  Same arithmetic (and rounding points) as corner_val per corner,
+// but every distinct table entry is loaded once: a VM corner is sum_k plane_k * line_k with only 4 distinct plane entries and 2 distinct
+// line entries per k (18 loads instead of 48), a CP corner is the product of D line entries out of 2 D (6 loads instead of 24).
+template <int D, int F, typename PT>
+__device__ __forceinline__ void all_corner_vals(const Ctx<D>& c, const PT* __restrict__ g, PT (&v)[1 << D][F], bool vec_ok) {
+    using C = Cvt<PT>;
+    if (c.type == NR3D_LOD_VM) {
+        if constexpr (D == 3) {
+#pragma unroll
+            for (int idx = 0; idx < (1 << D); ++idx)
+#pragma unroll
+                for (int f = 0; f < F; ++f) v[idx][f] = C::zero();
+#pragma unroll
+            for (int k = 0; k < D; ++k) {      // k ascending: the same summation order as corner_val
+                PT Lv[2][F], Pv[4][F];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    uint32_t pos[D], pl[D], ln[D];
+                    int bb = 0;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        if (d == k) pos[d] = c.cell[d];
+                        else { pos[d] = c.cell[d] + ((b >> bb) & 1); ++bb; }
+                    }
+                    idx_vm<D>(c.res, pos, pl, ln);
+                    load_feats<F>(g + (uint64_t)pl[k] * c.n_feat + c.gfo, Pv[b], vec_ok);
+                    if (b == 0) {
+                        load_feats<F>(g + (uint64_t)ln[k] * c.n_feat + c.gfo, Lv[0], vec_ok);
+                        load_feats<F>(g + (uint64_t)(ln[k] + 1u) * c.n_feat + c.gfo, Lv[1], vec_ok);
+                    }
+                }
+#pragma unroll
+                for (int idx = 0; idx < (1 << D); ++idx) {
+                    const int a = (idx >> k) & 1;
+                    int b = 0, bb = 0;
+#pragma unroll
+                    for (int d = 0; d < D; ++d)
+                        if (d != k) { b |= ((idx >> d) & 1) << bb; ++bb; }
+#pragma unroll
+                    for (int f = 0; f < F; ++f) v[idx][f] = C::add(v[idx][f], C::from_f(C::to_f(Pv[b][f]) * C::to_f(Lv[a][f])));
+                }
+            }
+            return;
+        }
+    }
+    if (c.type == NR3D_LOD_CP) {
+        PT Lv[D][2][F];
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) load_feats<F>(g + (uint64_t)idx_cp_line<D>(c.res, c.cell[k] + a, k) * c.n_feat + c.gfo, Lv[k][a], vec_ok);
+#pragma unroll
+        for (int idx = 0; idx < (1 << D); ++idx) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                float r = C::to_f(Lv[0][idx & 1][f]);
+#pragma unroll
+                for (int k = 1; k < D; ++k) r *= C::to_f(Lv[k][(idx >> k) & 1][f]);
+                v[idx][f] = C::from_f(r);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int idx = 0; idx < (1 << D); ++idx) {
+        uint32_t pos[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) pos[d] = c.cell[d] + ((idx >> d) & 1);
+        corner_val<D, F, PT>(c, g, pos, v[idx], vec_ok);
+    }
+}
+
 // sum_f corner_value[f] * grad[f] for the level types with a second-order dL/dx (Dense / Hash / VM / VecZMatXoY).  VM keeps the
 // un-rounded products of the reference (calc_dLdx_dim_vm_impl, lotd_cuda.h:887-918).
 template <int D, int F, typename PT>

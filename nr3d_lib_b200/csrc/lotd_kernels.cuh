@@ -35,13 +35,7 @@ lotd_fwd_kernel(const __grid_constant__ LotdTable tab, const LotdIn in, PT* __re
         const bool vec_ok = in.vec_ok;
         if (is_nlinear(c.type)) {
             PT v[1 << D][F];
-#pragma unroll
-            for (int idx = 0; idx < (1 << D); ++idx) {
-                uint32_t pos[D];
-#pragma unroll
-                for (int d = 0; d < D; ++d) pos[d] = c.cell[d] + ((idx >> d) & 1);
-                corner_val<D, F, PT>(c, g, pos, v[idx], vec_ok);
-            }
+            all_corner_vals<D, F, PT>(c, g, v, vec_ok);
 #pragma unroll
             for (int idx = 0; idx < (1 << D); ++idx) {
                 uint32_t pos[D];
@@ -146,10 +140,17 @@ lotd_fwd_kernel(const __grid_constant__ LotdTable tab, const LotdIn in, PT* __re
     for (int f = 0; f < F; ++f) st_cs(yo + (int64_t)f * ys_f, r[f]);
     if (DYDX) {
         float* go = dydx + (int64_t)i * ds_n + (int64_t)ofo * ds_f;
+        if (ds_f == D && ((F * D) % 2 == 0) && ((reinterpret_cast<uintptr_t>(go) & 7u) == 0)) {
+            // the thread's F * D derivatives are contiguous (row-major dy_dx): 8-byte stores
+            const float* flat = &gr[0][0];
 #pragma unroll
-        for (int f = 0; f < F; ++f)
+            for (int e = 0; e < F * D; e += 2) __stcs(reinterpret_cast<float2*>(go + e), make_float2(flat[e], flat[e + 1]));
+        } else {
 #pragma unroll
-            for (int d = 0; d < D; ++d) st_cs(go + (int64_t)f * ds_f + d, gr[f][d]);
+            for (int f = 0; f < F; ++f)
+#pragma unroll
+                for (int d = 0; d < D; ++d) st_cs(go + (int64_t)f * ds_f + d, gr[f][d]);
+        }
     }
 }
 
@@ -676,7 +677,7 @@ template <int D> int lotd_launch_grid_index(const LotdLaunch& L, int64_t* out);
                                              const float* dydx, int64_t ds_n, int64_t ds_f, float* dLdx) {                \
         if (L.in.N == 0) return 0;                                                                                        \
         const unsigned grid = (unsigned)div_up<uint64_t>(L.in.N, kLotdThreads);                                           \
-        if (gs_f == 1 && ds_f == D && ds_n == (int64_t)L.tab.n_enc * D) { /* row-major dy_dx: warp per point */            \
+        if (gs_f == 1 && ds_f == D && ds_n == (int64_t)L.tab.n_enc * D && L.tab.n_enc * D >= 96) { /* wide row-major dy_dx: warp per point (measured: 2x at 96 floats per row, 0.5x at 60) */ \
             const unsigned rgrid = (unsigned)(div_up<uint64_t>(L.in.N, kLotdThreads / 32) < (uint64_t)kSMs * 16 ? div_up<uint64_t>(L.in.N, kLotdThreads / 32) : (uint64_t)kSMs * 16); \
             if (L.half) lotd_bwd_input_rows_kernel<D, __half><<<rgrid, kLotdThreads, 0, L.stream>>>(L.in.N, L.tab.n_enc, (const __half*)dLdy, gs_n, dydx, dLdx); \
             else lotd_bwd_input_rows_kernel<D, float><<<rgrid, kLotdThreads, 0, L.stream>>>(L.in.N, L.tab.n_enc, (const float*)dLdy, gs_n, dydx, dLdx); \
