@@ -16,7 +16,6 @@ Usage:  python oracle/build_ref.py [--jobs N] [--only lotd,pack_ops,occ_grid]
 """
 import argparse
 import os
-import re
 import shutil
 import subprocess
 import sys

@@ -8,7 +8,6 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from nr3d_lib_b200.bindings import _lotd as mine  # noqa: E402

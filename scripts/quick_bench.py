@@ -1,5 +1,5 @@
 """Quick kernel timing (mine vs the reference CUDA build) on the C2 config: 16-level NGP LoTD, 4M points."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from tests.util import load_ref
