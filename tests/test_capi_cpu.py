@@ -48,6 +48,9 @@ def test_struct_layout_matches_header():
     from nr3d_lib_b200 import _lib
     # nr3d_lotd_meta: 8 scalars + 32*4 + 4*32 + 33 + 2*256 uint32
     assert ctypes.sizeof(_lib.LotdMetaStruct) == 4 * (8 + 32 * 4 + 4 * 32 + 33 + 2 * 256)
+    # nr3d_forest_meta: three device pointers + four uint32 (forest_cpp_api.h:16-36 as device views)
+    assert ctypes.sizeof(_lib.ForestMetaStruct) == 3 * ctypes.sizeof(ctypes.c_void_p) + 4 * 4
+    assert [f[0] for f in _lib.ForestMetaStruct._fields_] == ["octree", "exsum", "block_ks", "n_trees", "level", "level_poffset", "continuity_enabled"]
 
 
 def test_errors_are_reported_without_gpu():
@@ -128,3 +131,19 @@ print("DROPIN_OK")
         if missing and all(not m.startswith("nr3d_lib_b200") for m in missing):
             pytest.skip(f"reference import chain needs unavailable third-party modules: {sorted(set(missing))}")
         raise AssertionError(r.stderr[-2000:])
+
+
+def test_sort_points_flag_default_and_env(monkeypatch):
+    """`LoDMeta.c_sort_points` (B200-only knob) is off by default -- identical strides to the reference -- and NR3D_B200_SORT_POINTS=1
+    turns it on for every meta so that an unmodified reference application can opt in without a code change."""
+    from nr3d_lib_b200.bindings import _lotd
+    args = (3, [16, 32], [2, 2], ["Dense", "Hash"], 2 ** 10, False)
+    monkeypatch.delenv("NR3D_B200_SORT_POINTS", raising=False)
+    assert _lotd.LoDMeta(*args).c_sort_points is False
+    monkeypatch.setenv("NR3D_B200_SORT_POINTS", "1")
+    m = _lotd.LoDMeta(*args)
+    assert m.c_sort_points is True
+    m.c_sort_points = 0
+    assert m.c_sort_points is False
+    monkeypatch.setenv("NR3D_B200_SORT_POINTS", "0")
+    assert _lotd.LoDMeta(*args).c_sort_points is False
