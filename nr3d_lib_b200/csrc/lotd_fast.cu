@@ -32,11 +32,8 @@ namespace nr3d {
 #ifndef NR3D_BIN_ORDER      // 0: x fastest, 1: z fastest
 #define NR3D_BIN_ORDER 0
 #endif
-#ifndef NR3D_MERGE_MAX_HEADS
-#define NR3D_MERGE_MAX_HEADS 20
-#endif
 #ifndef NR3D_FWD_UNROLL
-#define NR3D_FWD_UNROLL 2
+#define NR3D_FWD_UNROLL 1
 #endif
 #ifndef NR3D_FWD_THREADS
 #define NR3D_FWD_THREADS 256

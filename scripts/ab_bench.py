@@ -5,8 +5,6 @@ import json, os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 VARIANTS = {
     "base": [],                                   # pair layout (two lanes per point)
-    "heads12": ["NR3D_MERGE_MAX_HEADS=12"],
-    "heads28": ["NR3D_MERGE_MAX_HEADS=28"],
     "unroll1": ["NR3D_FWD_UNROLL=1"],
     "unroll4": ["NR3D_FWD_UNROLL=4"],
     "fwd128": ["NR3D_FWD_THREADS=128"],
@@ -22,7 +20,7 @@ else:
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for n in VARIANTS:
         env = dict(os.environ, NR3D_B200_LIB=os.path.join(root, "nr3d_lib_b200", "lib", "variants", n + ".so"))
-        out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "10", "--warmup", "3", "--no-cpu-baseline"],
+        out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "10", "--warmup", "3", "--no-cpu-baseline", "--no-m2"],
                              env=env, capture_output=True, text=True).stdout.strip().splitlines()
         try:
             d = json.loads(out[-1])
