@@ -12,6 +12,8 @@ namespace nr3d {
 
 constexpr int kNextThreads = 256;
 constexpr int kNextWarps = kNextThreads / 32;
+
+template <typename T> __device__ __forceinline__ T clamp_next(T v, T lo, T hi) { return v < lo ? lo : (hi < v ? hi : v); }
 constexpr unsigned kFullMask = 0xffffffffu;
 
 template <typename T> struct Num { static __device__ __forceinline__ float f(T v) { return (float)v; } };
@@ -225,8 +227,81 @@ pack_matmul_kernel(uint64_t P, uint32_t C, uint32_t Co, const T* __restrict__ fe
 // interleave_sample_step_wrt_depth_in_packed_segments (pack_ops_cuda.cu:606-795): depth-proportional stepping restricted to
 // the [entry, exit] segments of every ray.  Stepping is a serial recurrence per ray -> one thread per ray, two passes.
 // Quirks kept: the walk to a segment entry advances by min_step at least once per segment; max_steps bounds the ray total.
+// Fill pass with coalesced output (same idea as march_fill_staged_kernel in march.cu): every lane parks up to kSegStage samples of its
+// ray in a shared-memory row, then the warp writes the rows out ray by ray (consecutive lanes -> consecutive addresses).  The segment
+// walk of seg_sample_kernel is kept statement for statement, only made resumable (state: segment, t, step, inside-a-segment flag).
+constexpr int kSegStage = 8;
+constexpr int kSegStride = 9;
+constexpr int kSegThreads = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(kSegThreads)
+seg_sample_fill_staged_kernel(uint64_t P, T dt_gamma, T min_step, T max_step, const T* __restrict__ nears, const T* __restrict__ fars,
+                              const T* __restrict__ entries, const T* __restrict__ exits, const int64_t* __restrict__ seg_pack_infos,
+                              const int64_t* __restrict__ pack_infos, T* __restrict__ t_samples, T* __restrict__ deltas,
+                              int64_t* __restrict__ nidx, int64_t* __restrict__ sidx) {
+    __shared__ T s_t[kSegThreads / 32][32 * kSegStride];
+    __shared__ T s_d[kSegThreads / 32][32 * kSegStride];
+    __shared__ int64_t s_s[kSegThreads / 32][32 * kSegStride];
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    bool done = p >= P;
+    const uint64_t pc = done ? 0 : p;
+    const T near = nears[pc], far = fars[pc];
+    uint64_t i = (uint64_t)seg_pack_infos[2 * pc];
+    const uint64_t seg_end = i + (uint64_t)seg_pack_infos[2 * pc + 1];
+    const uint64_t begin = (uint64_t)pack_infos[2 * pc];
+    const uint32_t limit = done ? 0u : (uint32_t)pack_infos[2 * pc + 1];
+    if (limit == 0) done = true;
+    T t = near, exit_ = (T)0;
+    uint32_t step = 0, flushed = 0;
+    bool in_seg = false;
+    while (true) {
+        int pending = 0;
+        while (!done && pending < kSegStage) {
+            if (!in_seg) {
+                if (i >= seg_end) { done = true; break; }
+                const T entry = entries[i];
+                exit_ = exits[i];
+                if (entry >= far || exit_ <= near) { done = true; break; }
+                do { t += min_step; } while (t < entry);
+                in_seg = true;
+            }
+            if (t <= exit_ && t <= far && step < limit) {
+                const T dt = clamp_next<T>(t * dt_gamma, min_step, max_step);
+                s_t[wid][lane * kSegStride + pending] = t;
+                s_d[wid][lane * kSegStride + pending] = dt;
+                s_s[wid][lane * kSegStride + pending] = (int64_t)i;
+                ++pending;
+                t += dt;
+                step++;
+            } else {
+                in_seg = false;
+                ++i;
+            }
+        }
+        __syncwarp();
+        const uint32_t any = __ballot_sync(0xffffffffu, pending > 0);
+        for (uint32_t m = any; m; m &= m - 1) {
+            const int l = __ffs(m) - 1;
+            const int n = __shfl_sync(0xffffffffu, pending, l);
+            const uint64_t b = __shfl_sync(0xffffffffu, (unsigned long long)(begin + flushed), l);
+            const int64_t ray = (int64_t)__shfl_sync(0xffffffffu, (unsigned long long)p, l);
+            if (lane < n) {
+                const int src = l * kSegStride + lane;
+                t_samples[b + lane] = s_t[wid][src];
+                deltas[b + lane] = s_d[wid][src];
+                nidx[b + lane] = ray;
+                sidx[b + lane] = s_s[wid][src];
+            }
+        }
+        flushed += (uint32_t)pending;
+        __syncwarp();
+        if (__all_sync(0xffffffffu, done)) break;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
-template <typename T> __device__ __forceinline__ T clamp_next(T v, T lo, T hi) { return v < lo ? lo : (hi < v ? hi : v); }
 
 template <typename T, bool FILL>
 __global__ void __launch_bounds__(kNextThreads)
@@ -374,10 +449,10 @@ int nr3d_pack_seg_sample_fill(int32_t dtype, uint64_t P, const void* nears, cons
                               void* t_samples, void* deltas, int64_t* nidx, int64_t* sidx, void* stream) {
     if (P == 0) return 0;
     NR3D_CHECK(nears && fars && seg_pack_infos && pack_infos, "interleave_sample_step_wrt_depth_in_packed_segments: null argument");
-    const unsigned grid = (unsigned)div_up<uint64_t>(P, kNextThreads);
+    const unsigned grid = (unsigned)div_up<uint64_t>(P, kSegThreads);
     NR3D_NEXT_DISPATCH_FLOAT(dtype, "interleave_sample_step_wrt_depth_in_packed_segments",
-        (seg_sample_kernel<T, true><<<grid, kNextThreads, 0, (cudaStream_t)stream>>>(P, 0u, (T)dt_gamma, (T)min_step, (T)max_step, (const T*)nears,
-            (const T*)fars, (const T*)entries, (const T*)exits, seg_pack_infos, pack_infos, nullptr, (T*)t_samples, (T*)deltas, nidx, sidx)));
+        (seg_sample_fill_staged_kernel<T><<<grid, kSegThreads, 0, (cudaStream_t)stream>>>(P, (T)dt_gamma, (T)min_step, (T)max_step, (const T*)nears,
+            (const T*)fars, (const T*)entries, (const T*)exits, seg_pack_infos, pack_infos, (T*)t_samples, (T*)deltas, nidx, sidx)));
     NR3D_LAUNCH_CHECK("seg_sample_fill");
     return 0;
 }
