@@ -35,6 +35,9 @@ namespace nr3d {
 #ifndef NR3D_FWD_UNROLL
 #define NR3D_FWD_UNROLL 1
 #endif
+#ifndef NR3D_BWD_SHORTRUN     // 1: runs of 2-3 points in one cell are summed through two shuffle steps, the head of the run issues the reductions
+#define NR3D_BWD_SHORTRUN 1     // A/B on B200: 2083 -> 2203 Msamples/s (profiles/r1_ab_tunables.txt)
+#endif
 #ifndef NR3D_FWD_THREADS
 #define NR3D_FWD_THREADS 256
 #endif
@@ -309,11 +312,12 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
         const int e0 = above ? ((__ffs(above) - 1) >> 1) : 16;
         const int r = e0 - s0, j = k - s0;
         const bool longrun = active && r >= 4;  // shorter runs are not worth the detour through shared memory
+        // every lane ends up with at most four contributions (entry g.e[q], value pair); cv[q]: this lane issues corner q
+        float cx[4], cy[4];
+        bool cv[4];
         if (!__any_sync(0xffffffffu, longrun)) {
-            if (active) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) PairIO<PT>::red2(grad + g.e[q], g.w[q] * g0, g.w[q] * g1);
-            }
+            for (int q = 0; q < 4; ++q) { cx[q] = g.w[q] * g0; cy[q] = g.w[q] * g1; cv[q] = active; }
         } else {
             *reinterpret_cast<float4*>(mytile + lane * kPairTileStride) = make_float4(g.w[0] * g0, g.w[0] * g1, g.w[1] * g0, g.w[1] * g1);
             *reinterpret_cast<float4*>(mytile + lane * kPairTileStride + 4) = make_float4(g.w[2] * g0, g.w[2] * g1, g.w[3] * g0, g.w[3] * g1);
@@ -322,11 +326,11 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
             // s0 + c, s0 + c + nch, ... (c = j >> 2), the nch partial sums of a corner then meet through two shuffles and
             // positions 0..3 issue ONE reduction per corner for the whole run.
             const int nch = r >> 2;  // 1..4 groups of four positions
-            const int q = j & 3, c = j >> 2;
+            const int qj = j & 3, c = j >> 2;
             float2 acc = make_float2(0.f, 0.f);
             if (longrun && c < nch) {
                 for (int m = s0 + c; m < e0; m += nch) {
-                    const float2 t = *reinterpret_cast<const float2*>(mytile + (2 * m + side) * kPairTileStride + q * 2);
+                    const float2 t = *reinterpret_cast<const float2*>(mytile + (2 * m + side) * kPairTileStride + qj * 2);
                     acc.x += t.x; acc.y += t.y;
                 }
             }
@@ -335,14 +339,35 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
             if (longrun && j + 8 < lim) { acc.x += tx; acc.y += ty; }   // positions j + 8 (and, through them, j + 12)
             tx = __shfl_down_sync(0xffffffffu, acc.x, 8); ty = __shfl_down_sync(0xffffffffu, acc.y, 8);
             if (longrun && j < 4 && j + 4 < lim) { acc.x += tx; acc.y += ty; }
-            if (longrun) {
-                if (j < 4) PairIO<PT>::red2(grad + (q == 0 ? g.e[0] : (q == 1 ? g.e[1] : (q == 2 ? g.e[2] : g.e[3]))), acc.x, acc.y);
-            } else if (active) {
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) PairIO<PT>::red2(grad + g.e[qq], g.w[qq] * g0, g.w[qq] * g1);
+            for (int q = 0; q < 4; ++q) {
+                if (longrun) { cv[q] = (j < 4) && (q == qj); cx[q] = acc.x; cy[q] = acc.y; }
+                else { cv[q] = active; cx[q] = g.w[q] * g0; cy[q] = g.w[q] * g1; }
             }
             __syncwarp();
         }
+#if NR3D_BWD_SHORTRUN
+        // Runs of two or three points in one cell: the hardware does not merge lanes that hit the same entry, so they would cost one L2
+        // packet each.  Two shuffle steps towards the head of the run (the points of a run are neighbours in the warp) and only the head
+        // issues the four reductions.
+        const bool shortrun = active && (r == 2 || r == 3);
+        if (__any_sync(0xffffffffu, shortrun)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float ux = __shfl_down_sync(0xffffffffu, cx[q], 2), uy = __shfl_down_sync(0xffffffffu, cy[q], 2);
+                if (shortrun && j + 1 < r) { cx[q] += ux; cy[q] += uy; }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float ux = __shfl_down_sync(0xffffffffu, cx[q], 4), uy = __shfl_down_sync(0xffffffffu, cy[q], 4);
+                if (shortrun && j + 2 < r) { cx[q] += ux; cy[q] += uy; }
+                if (shortrun && j > 0) cv[q] = false;
+            }
+        }
+#endif
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (cv[q]) PairIO<PT>::red2(grad + g.e[q], cx[q], cy[q]);
     }
 }
 
