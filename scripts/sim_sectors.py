@@ -1,10 +1,14 @@
-"""How many 32-byte reduction sectors does the sorted pair layout HAVE to touch?  (CPU-only, numpy.)
+"""How many L2 reduction packets does the headline backward HAVE to issue?  (CPU-only, numpy.)
 
-Re-enacts the headline backward kernel's addressing on 4 Mi uniform points: counting sort by a 128^3 bin key (x fastest), 16 points per
-warp, lane pair = the two x-neighbour corners of a Hash level (z-neighbours of a Dense level), one reduction instruction per corner group
-q = 0..3.  Reports distinct sectors per point for every level if the hardware merged lanes over the whole warp / half / quarter warp,
-and what a software pre-reduction over 16 / 64 / 256 / 1024 consecutive points could reach.  Compare with the measured
-l1tex__t_sectors_pipe_lsu_mem_global_op_red / N of profiles/r1_s2_pair_ncu_summary.txt (62 sectors per point).
+Re-enacts the kernel's addressing on 4 Mi uniform points: counting sort by a 128^3 bin key (x fastest), 16 points per warp, lane pair =
+the two x-neighbour corners of a Hash level (z-neighbours of a Dense level), one reduction instruction per corner group q = 0..3.
+Cost model (scripts/ubench_redgroup.cu, profiles/r1_s2_ubench_redgroup.txt): lanes of one instruction that hit DIFFERENT entries of a
+32-byte sector share one packet, lanes that hit the SAME entry need one packet each.  Columns, in packets per point and level:
+  no merge          every lane issues its reduction
+  runs >= 4 merged  the shared-memory run merge (consecutive points in one cell) for runs of four and more  -- the build that ncu saw
+  all runs merged   + runs of two and three points through shuffles                                        -- the shipped build
+  distinct sectors  the floor if every repeated entry inside an instruction were merged for free
+Measured (ncu, profiles/r1_s2_pair_ncu_summary.txt): 260.8 M packets / 4 194 304 points = 62.2 for the "runs >= 4" build.
 
     python scripts/sim_sectors.py > profiles/r1_s2_sector_simulation.txt
 """
@@ -12,6 +16,7 @@ import numpy as np
 
 N = 1 << 22
 T = 1 << 19
+W = N // 16
 rs = np.random.RandomState(0)
 x = rs.rand(N, 3).astype(np.float32)
 res_list = (16 * 1.382 ** np.arange(16)).astype(int).tolist()
@@ -19,12 +24,43 @@ b = np.minimum((x * 128).astype(np.int64), 127)
 xs = x[np.argsort((b[:, 2] * 128 + b[:, 1]) * 128 + b[:, 0], kind="stable")]
 
 
-def level_sectors(R):
-    """[N, 8] sector ids (8-byte entries, 4 per sector) in instruction order q * 2 + side."""
+def packets(ent, valid):
+    """ent, valid: [W, 32].  Sum over duplicate ranks of the distinct sectors among the lanes of that rank."""
+    L = ent.shape[1]
+    idx = np.arange(L)[None, :].repeat(W, 0)
+    e = np.where(valid, ent, (np.int64(1) << 40) + idx)
+    o = np.argsort(e, axis=1, kind="stable")
+    es, vs = np.take_along_axis(e, o, 1), np.take_along_axis(valid, o, 1)
+    newa = np.ones((W, L), bool)
+    newa[:, 1:] = es[:, 1:] != es[:, :-1]
+    rank = idx - np.maximum.accumulate(np.where(newa, idx, 0), axis=1)
+    total = 0
+    for r in range(int(rank[vs].max()) + 1):
+        m = (rank == r) & vs
+        if not m.any():
+            break
+        ss = np.sort(np.where(m, es >> 2, -1 - idx), axis=1)
+        total += ((np.diff(ss, axis=1) != 0).sum(1) + 1 - (~m).sum(1)).sum()
+    return total
+
+
+print(f"# {N} uniform points, 16-level NGP LoTD (T = 2^19, F = 2), sorted by 128^3 bins (x fastest); L2 reduction packets per point")
+print("# level   res  type | no merge | runs >= 4 merged | all runs merged | distinct sectors")
+tot = np.zeros(4)
+for li, R in enumerate(res_list):
     dense = R ** 3 <= T
     c = np.floor(xs * np.float32(R - 2) + np.float32(0.5)).astype(np.int64)
-    out = []
+    key = (c[:, 0] | (c[:, 1] << 10) | (c[:, 2] << 20)).reshape(W, 16)
+    head = np.ones((W, 16), bool)
+    head[:, 1:] = key[:, 1:] != key[:, :-1]
+    run_id = np.cumsum(head, axis=1)
+    rl = np.zeros((W, 16), np.int64)
+    for r in range(1, 17):
+        m = run_id == r
+        rl += m * m.sum(1, keepdims=True)
+    res = np.zeros(4)
     for q in range(4):
+        ents = []
         for side in range(2):
             if dense:
                 dx, dy = q & 1, q >> 1
@@ -33,27 +69,16 @@ def level_sectors(R):
                 dy, dz = q & 1, q >> 1
                 hyz = (((c[:, 1] + dy) * 2654435761) ^ ((c[:, 2] + dz) * 805459861)) & 0xFFFFFFFF
                 e = ((c[:, 0] + side) ^ hyz) & (T - 1)
-            out.append(e >> 2)
-    return np.stack(out, 1)
-
-
-def distinct(a):
-    a = np.sort(a, axis=1)
-    return (np.diff(a, axis=1) != 0).sum() + a.shape[0]
-
-
-print(f"# {N} uniform points, 16-level NGP LoTD (T = 2^19, F = 2), sorted by 128^3 bins (x fastest); distinct 32-byte sectors per point")
-print("# level  res  type | per instruction, lanes merged over: warp(32)  half(16)  quarter(8) | software pre-reduction over: 16 pts   64    256   1024")
-tot = np.zeros(7)
-for li, R in enumerate(res_list):
-    S = level_sectors(R)
-    row = []
-    for lanes in (32, 16, 8):
-        pts = lanes // 2
-        row.append(sum(distinct(S[:, 2 * q:2 * q + 2].reshape(N // pts, lanes)) for q in range(4)) / N)
-    for P in (16, 64, 256, 1024):
-        row.append(distinct(S.reshape(N // P, P * 8)) / N)
-    tot += np.array(row)
-    print(f"  L{li:<2d} {R:5d}  {'Dense' if R ** 3 <= T else 'Hash '} | " + "  ".join(f"{v:7.3f}" for v in row[:3]) + "   | " + "  ".join(f"{v:6.3f}" for v in row[3:]))
-print("  total              | " + "  ".join(f"{v:7.3f}" for v in tot[:3]) + "   | " + "  ".join(f"{v:6.3f}" for v in tot[3:]))
-print("# measured on B200 (ncu, shipped kernel): 260.8 M sectors / 4 194 304 points = 62.2 per point at 212 G sectors/s (L2 reduction unit: 231 G/s)")
+            ents.append(e.reshape(W, 16))
+        ent = np.stack(ents, 2).reshape(W, 32)
+        res[0] += packets(ent, np.ones((W, 32), bool))
+        res[1] += packets(ent, np.repeat(head | (rl < 4), 2, axis=1))
+        res[2] += packets(ent, np.repeat(head, 2, axis=1))
+        s = np.sort(ent >> 2, axis=1)
+        res[3] += (np.diff(s, axis=1) != 0).sum() + W
+    res /= N
+    tot += res
+    print(f"  L{li:<2d}  {R:5d}  {'Dense' if dense else 'Hash '} | {res[0]:8.3f} | {res[1]:16.3f} | {res[2]:15.3f} | {res[3]:16.3f}")
+print(f"  total               | {tot[0]:8.3f} | {tot[1]:16.3f} | {tot[2]:15.3f} | {tot[3]:16.3f}")
+print("# measured on B200: 62.2 packets per point at 212 G/s for the 'runs >= 4' build (backward 1.268 ms); the shipped 'all runs' build runs the")
+print("# backward in 1.148 ms -- the time follows the packet count (61.6 -> 55.6 = -9.7 %, time -9.5 %): the kernel is bound by the L2 reduction unit.")
