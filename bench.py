@@ -99,7 +99,8 @@ def cpu_fwd_bwd(steps, warmup, seed=42, budget_s=20.0):
     the golden vectors of the reference's CUDA build), OpenMP over all host threads, on a bounded sample of the workload.  The
     sample size comes from a short probe so that warmup + steps fit in `budget_s` seconds."""
     from oracle import lotd_oracle as O, lotd_port as P
-    cores = max(1, P.max_threads())
+    # all host threads this process may use -- asked for explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
+    cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     meta = O.OracleMeta(*ngp_cfg())
     rs = np.random.RandomState(seed)
     params = ((rs.rand(meta.n_params).astype(np.float32) * 2 - 1) * 1e-4).astype(np.float32)
