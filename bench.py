@@ -5,7 +5,9 @@ Metric (BASELINE.json): "LoTD-Hash 16L fwd+bwd Msamples/s" on configs[1]: 16-lev
 T=2^19, F=2, fp32 params; nr3d_lib/models/grid_encodings/lotd/lotd_cfg.py:48-57), 4 Mi uniform random 3-D points per GPU.
 
 One step  = lod_fwd(need_input_grad=False) + lod_bwd(need_param_grad=True) through the reference-facing operator
-            surface (nr3d_lib_b200.bindings._lotd == nr3d_lib.bindings._lotd) [+ one NCCL all-reduce of dL/dparams if N > 1].
+            surface (nr3d_lib_b200.bindings._lotd == nr3d_lib.bindings._lotd) with its DEFAULT settings (the cell-sorted fast path is
+            what a drop-in user gets) [+ one NCCL all-reduce of dL/dparams if N > 1].  Consecutive steps see DIFFERENT points (two
+            point sets alternate), so every forward sorts and every backward reuses the forward's records after the on-device check.
 `value`   = whole-job samples/s with x and dL_dy already resident in HBM (device-timed, max over ranks).
 `e2e`     = the same step driven from HOST buffers: x comes from pinned host memory every step (H2D inside the timed
             region), dL_dy is derived on the device from the step's own output y (stand-in for the decoder's backward),
@@ -138,7 +140,7 @@ def run_reference_arm(args):
     base, sec, sample = cpu_fwd_bwd(args.steps, min(args.warmup, 2), budget_s=60.0)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus) | {"sample_points_per_step": sample},
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -167,6 +169,10 @@ def main():
     ap.add_argument("--e2e-serial", action="store_true", help="e2e leg without copy/compute overlap (single stream)")
     ap.add_argument("--no-sort", action="store_true", help="use the generic (unsorted, feature-major) kernels instead of lotd_fast.cu")
     ap.add_argument("--no-m2", action="store_true", help="skip the secondary M2 block (march + encode + composite rays/s)")
+    ap.add_argument("--allreduce", default="bucketed", choices=["bucketed", "allreduce"],
+                    help="N > 1: how dL/dparams is summed (dist.GradReducer): fine levels first with their all-reduce overlapping the coarse "
+                         "levels' scatter (default), or one blocking all-reduce after the scatter")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational legs (reference CUDA build, generic path, torch CPU baselines)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -186,24 +192,30 @@ def main():
     n_gpus = max(world, 1)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa = ndist.bind_to_gpu_numa(local)       # before any pinned allocation: staging buffers on the GPU's own NUMA node
 
     meta = _lotd.LoDMeta(*ngp_cfg())
-    meta.c_sort_points = not args.no_sort      # B200 fast path (lotd_fast.cu); the point sort is redone EVERY step (cache cleared)
+    if args.no_sort:
+        meta.c_sort_points = False             # reference strides + generic kernels (the default is the cell-sorted fast path)
     torch.manual_seed(42 + rank)
     N = N_POINTS
-    x = torch.rand(N, 3, device=dev).clamp(1e-6, 1 - 1e-6)
+    # two point sets alternate between steps: a training step never sees the previous step's points, so every forward sorts
+    xs = [torch.rand(N, 3, device=dev).clamp(1e-6, 1 - 1e-6) for _ in range(2)]
     gen = torch.Generator(device=dev).manual_seed(42)                      # parameters are replicated: same seed on every rank
     params = (torch.rand(meta.n_params, device=dev, generator=gen) * 2 - 1) * 1e-4
     dL_dy = torch.randn(N, meta.n_encoded_dims, device=dev) * 1e-4
-    x_host = x.cpu().pin_memory()
+    xs_host = [x.cpu().pin_memory() for x in xs]
     grad_host = torch.empty(meta.n_params, dtype=torch.float32).pin_memory()
     stream = torch.cuda.current_stream(dev)
+    reducer = ndist.GradReducer(meta, n_gpus, dev, mode=args.allreduce)
+    step_no = [0]
 
-    def step_resident():
-        _lotd.clear_sort_cache()               # a training step sees new points: never reuse the previous step's sort
-        y, _ = _lotd.lod_fwd(meta, x, params, need_input_grad=False)
-        _, g = _lotd.lod_bwd(meta, dL_dy, x, params, None, need_input_grad=False, need_param_grad=True)
-        ndist.allreduce_param_grads(g, n_gpus)
+    def step_resident(m=meta, p=params, gy=dL_dy):
+        x = xs[step_no[0] & 1]
+        step_no[0] += 1
+        y, _ = _lotd.lod_fwd(m, x, p, need_input_grad=False)
+        _, g = _lotd.lod_bwd(m, gy, x, p, None, need_input_grad=False, need_param_grad=True)
+        reducer.reduce(g)
         return y, g
 
     # e2e: the same step fed from / drained to HOST buffers through the public host-fed driver (pipeline.HostFedLoTDStep):
@@ -216,16 +228,16 @@ def main():
     def run_e2e(steps):
         if args.e2e_serial:
             for k in range(steps):
-                xd = x_host.to(dev, non_blocking=True)
+                xd = xs_host[k & 1].to(dev, non_blocking=True)
                 y, _ = _lotd.lod_fwd(meta, xd, params, need_input_grad=False)
                 _, g = _lotd.lod_bwd(meta, y * 1.0e-4, xd, params, None, need_input_grad=False, need_param_grad=True)
-                ndist.allreduce_param_grads(g, n_gpus)
-                lo, hi = ndist.shard_range(g.shape[0], rank, n_gpus)
-                grad_host2[k % 2][lo:hi].copy_(g[lo:hi], non_blocking=True)
+                out = pipe.reducer.reduce(g)
+                lo, hi = pipe.reducer.slice_range(g.shape[0], rank) if n_gpus > 1 else (0, g.shape[0])
+                grad_host2[k % 2][lo:hi].copy_(out[: hi - lo], non_blocking=True)
             return
-        pipe.prefetch(x_host)
+        pipe.prefetch(xs_host[0])
         for k in range(steps):
-            pipe.step(x_host if k + 1 < steps else None, grad_host2[k % 2])
+            pipe.step(xs_host[(k + 1) & 1] if k + 1 < steps else None, grad_host2[k % 2])
         pipe.drain()
 
     def timed(fn, steps, sampler=None):
@@ -267,11 +279,12 @@ def main():
             ts.append(a.elapsed_time(b))
         return float(np.mean(ts))
     it = max(3, min(args.steps, 10))
+    flip = [0]
     def fwd_with_sort():
-        _lotd.clear_sort_cache()
-        _lotd.lod_fwd(meta, x, params, need_input_grad=False)
+        flip[0] ^= 1
+        _lotd.lod_fwd(meta, xs[flip[0]], params, need_input_grad=False)          # new points: fingerprint + sort + gather
     ms_fwd = kernel_ms(fwd_with_sort, it)      # includes the per-step point sort of the fast path
-    ms_bwd = kernel_ms(lambda: _lotd.lod_bwd(meta, dL_dy, x, params, None, need_input_grad=False, need_param_grad=True), it)
+    ms_bwd = kernel_ms(lambda: _lotd.lod_bwd(meta, dL_dy, xs[flip[0]], params, None, need_input_grad=False, need_param_grad=True), it)   # fingerprint (hit) + scatter
     peak, peak_src = measured_peak_gbs()
     dom = "lod_bwd (dL/dparam scatter)" if ms_bwd >= ms_fwd else "lod_fwd (corner gather)"
     dom_ms, dom_bytes = (ms_bwd, BYTES_BWD + BYTES_TABLE) if ms_bwd >= ms_fwd else (ms_fwd, BYTES_FWD)
@@ -286,10 +299,7 @@ def main():
     # secondary number of metric M1: the same step with fp16 parameter tables (y, dL_dy and dL/dparams in half)
     params_h, dL_dy_h = params.half(), dL_dy.half()
     def step_half():
-        _lotd.clear_sort_cache()
-        _lotd.lod_fwd(meta, x, params_h, need_input_grad=False)
-        _, g = _lotd.lod_bwd(meta, dL_dy_h, x, params_h, None, need_input_grad=False, need_param_grad=True)
-        ndist.allreduce_param_grads(g, n_gpus)
+        step_resident(meta, params_h, dL_dy_h)
     for _ in range(3):
         step_half()
     ms_half = timed(step_half, args.steps) / args.steps
@@ -302,28 +312,67 @@ def main():
     # march -> LoTD -> density head -> alpha-composite, forward + backward, one all-reduce per step (scripts/m2_bench.py)
     m2_block = None
     if not args.no_m2:
-        del params_h, dL_dy_h, dL_dy, x
-        torch.cuda.empty_cache()
+        pass
         from scripts.m2_bench import run_m2
         # configs[2]: 1024^2 rays on one GPU; configs[4]: 4096^2 rays over 8 GPUs = 2 Mi rays per GPU
         m2_block = run_m2(dev, rank, n_gpus, rays=(4096 * 4096 // 8 if n_gpus == 8 else 1024 * 1024), steps=3, warmup=1)
 
+    # informational legs, outside every timed region above (N = 1, rank 0): the same step (a) with the fast path switched off -- the
+    # reference's strides and our generic kernels -- and (b) on the REFERENCE'S OWN CUDA KERNELS compiled for sm_100 (oracle/_ref/_lotd.so,
+    # "reported in every benchmark run, same process, same box"), on the same tensors
+    generic_block = ref_cuda_block = None
+    if n_gpus == 1 and not args.no_extras:
+        def fwd_bwd_ms(fwd, bwd, iters=5):
+            for _ in range(2):
+                fwd(); bwd()
+            return kernel_ms(fwd, iters), kernel_ms(bwd, iters)
+        meta_g = _lotd.LoDMeta(*ngp_cfg())
+        meta_g.c_sort_points = False
+        f_ms, b_ms = fwd_bwd_ms(lambda: _lotd.lod_fwd(meta_g, xs[0], params, need_input_grad=False),
+                                lambda: _lotd.lod_bwd(meta_g, dL_dy, xs[0], params, None, need_input_grad=False, need_param_grad=True))
+        generic_block = {"value": N / ((f_ms + b_ms) * 1e-3) / 1e6, "unit": UNIT, "ms": {"lod_fwd": f_ms, "lod_bwd": b_ms},
+                         "note": "LoDMeta.c_sort_points = False: reference strides (feature-major y), generic kernels"}
+        try:
+            ref_so = os.path.join(ROOT, "oracle", "_ref", "_lotd.so")
+            if os.path.exists(ref_so):
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("_lotd", ref_so)
+                ref = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(ref)
+                m_r = ref.LoDMeta(*ngp_cfg())
+                f_ms, b_ms = fwd_bwd_ms(lambda: ref.lod_fwd(m_r, xs[0], params, None, None, None, None, False),
+                                        lambda: ref.lod_bwd(m_r, dL_dy, xs[0], params, None, None, None, None, None, False, True))
+                ref_cuda_block = {"value": N / ((f_ms + b_ms) * 1e-3) / 1e6, "unit": UNIT, "ms": {"lod_fwd": f_ms, "lod_bwd": b_ms},
+                                  "note": "the reference's own hash-only CUDA kernels (csrc/lotd, unmodified, nvcc 12.9 -O3 sm_100 via oracle/build_ref.py), "
+                                          "same tensors, same process, CUDA events"}
+        except Exception as e:      # the checker build is optional on the box
+            ref_cuda_block = {"unavailable": str(e)[:200]}
+
+    reducer.close()
     ndist.barrier()
     ndist.shutdown()
     if rank != 0:
         return 0
-    cpu_base = None
+    cpu_base = torch_cpu = None
     if n_gpus == 1 and not args.no_cpu_baseline:
         cpu_base, _, _ = cpu_fwd_bwd(steps=5, warmup=1, budget_s=15.0)
+        if not args.no_extras:
+            # BASELINE.json north_star: "next to the reference's pure-PyTorch grid_sample / F.cumprod path timed on the box's own host
+            # cores (core count stated) in the same run as a reported baseline only" -- configs[0] and the dense-batch compositing
+            from oracle import torch_baselines as TB
+            torch_cpu = {"grid_sample_config0": TB.time_config0(), "cumprod_composite": TB.time_composite()}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(n_gpus), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(x_host.numel() * 4) * n_gpus,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(xs_host[0].numel() * 4) * n_gpus,
                     "d2h_bytes_per_step": int(grad_host.numel() * 4),
                     "note": "whole-job bytes per step: every rank feeds its own 4 Mi points from pinned host memory, dL_dy is derived on device "
-                            "from the step's y, the (all-reduced) dL/dparams is read back to the host once -- each rank returns its 1/N slice; "
+                            "from the step's y, the summed dL/dparams (one reduce-scatter) is read back to the host once -- each rank returns its 1/N slice; "
                             + ("single stream" if args.e2e_serial else "copies of neighbouring steps overlap the kernels (pipeline.HostFedLoTDStep)")},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "fp16_params": fp16_block, "m2": m2_block}
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "fp16_params": fp16_block, "m2": m2_block,
+            "collective": (None if n_gpus == 1 else {"value_leg": args.allreduce + (": all-reduce of levels 8-15 overlaps the scatter of levels 0-7" if args.allreduce == "bucketed" else ""),
+                                                     "e2e_leg": "reduce-scatter, each rank returns its slice"}),
+            "numa": numa, "generic_path": generic_block, "ref_cuda_build": ref_cuda_block, "torch_cpu_baselines": torch_cpu}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     return 0

@@ -154,26 +154,36 @@ int nr3d_lotd_forest_bwd_bwd_dx(const nr3d_lotd_meta* meta, const nr3d_forest_me
                                 const void* x, const void* params, const int64_t* batch_inds, const int64_t* batch_offsets,
                                 uint32_t batch_data_size, int32_t max_level, void* dL_dx, void* stream);
 
-/* B200 fast path for Dense/Hash-only metas (D = 3, 2 features per pseudo level, fp32 params, single scene).  No
- * reference counterpart: the shim uses it for lod_fwd / lod_bwd when LoDMeta.c_sort_points is set.
- *   sort_points : counting sort of the points by a 128^3 cell key (x fastest) into `xs`, float4 [N] records
- *                 (x, y, z, original index as raw uint32 bits).  Query the workspace size with ws == NULL.
+/* B200 fast path for Dense/Hash-only metas (D = 3, 2 / 4 / 8 features per pseudo level, fp32 or fp16 params, one scene or many).
+ * No reference counterpart: the shim uses it for lod_fwd / lod_bwd / lod_bwd_bwd_input whenever LoDMeta.c_sort_points is set (default)
+ * and the call is eligible; the reference's hash-only kernels (lotd_hash_only.h:15-695) serve the same set of configurations.
+ *   sort_points : counting sort of the points by (scene, cell bin) into `xs`, float4 [N] records (x, y, z, original index as raw uint32
+ *                 bits) and -- for batched calls -- `scenes`, uint16 [N] (0xffff = skipped point: batch_inds < 0).  batch_inds (int64 [N])
+ *                 / batch_data_size / n_scenes as in nr3d_lotd_fwd.  Query the workspace size with ws == NULL.
+ *                 The workspace is STATEFUL: zero-fill it before its first use and keep it with `xs`; every call fingerprints the points it
+ *                 is given (on the device, in stream order) and re-sorts only when they differ from the ones the records were built from
+ *                 (`force` != 0: always sort) -- lod_fwd and lod_bwd of one step share one sort without trusting host-side tensor identity.
  *   fwd_sorted  : same values as nr3d_lotd_fwd; y element (n, j) at y + n*y_stride_n + j*y_stride_f (row-major is fastest).
- *   bwd_param_sorted : same values as nr3d_lotd_bwd_param (up to fp32 summation order); dL_dparam zero-filled by caller. */
-int nr3d_lotd_sort_points(uint64_t N, const float* x, void* xs, void* ws, uint64_t* ws_bytes, void* stream);
-int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* params,
-                         int32_t max_level, void* y, int64_t y_stride_n, int64_t y_stride_f, void* stream);
-int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* dL_dy,
-                               int64_t dLdy_stride_n, int64_t dLdy_stride_f, int32_t max_level, void* dL_dparam, void* stream);
+ *   bwd_param_sorted : same values as nr3d_lotd_bwd_param (up to fp32 summation order); dL_dparam zero-filled by caller.  Only the pseudo
+ *                 levels [pl_begin, pl_end) are scattered (0, UINT32_MAX: all) -- multi-GPU callers launch the fine levels first and start
+ *                 the all-reduce of their part of the table while the coarse levels are still being scattered.
+ * params / dL_dparam must be 16-byte aligned; n_scenes * n_params < 2^32. */
+int nr3d_lotd_sort_points(uint64_t N, const float* x, const int64_t* batch_inds, uint32_t batch_data_size, uint32_t n_scenes, int32_t force,
+                          void* xs, uint16_t* scenes, void* ws, uint64_t* ws_bytes, void* stream);
+int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
+                         const void* params, int32_t max_level, void* y, int64_t y_stride_n, int64_t y_stride_f, void* stream);
+int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
+                               const void* dL_dy, int64_t dLdy_stride_n, int64_t dLdy_stride_f, int32_t max_level, uint32_t pl_begin, uint32_t pl_end,
+                               void* dL_dparam, void* stream);
 
 /* The same fast path for callers that need the nablas (NeuS-style eikonal terms): forward with dy/dx and the second-order
  * d(dL/dx)/dparam . dL_ddLdx scatter (reference kernel_lod_hash_only_with_dydx / kernel_lod_hashonly_backward_input_backward_grid,
  * lotd_hash_only.h:164-378, 472-695).  y: [N, n_enc] param dtype, dy_dx: f32 [N, n_enc, 3], both row-major at the points'
  * original indices and fully written.  dL_ddLdx: f32 [N, 3]; dL_dparam is accumulated into (zero it first). */
-int nr3d_lotd_fwd_dydx_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* params,
-                              int32_t max_level, void* y, void* dy_dx, void* stream);
-int nr3d_lotd_bwd_param2_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* dL_dy,
-                                int64_t dLdy_stride_n, int64_t dLdy_stride_f, const float* dL_ddLdx, int32_t max_level,
+int nr3d_lotd_fwd_dydx_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
+                              const void* params, int32_t max_level, void* y, void* dy_dx, void* stream);
+int nr3d_lotd_bwd_param2_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
+                                const void* dL_dy, int64_t dLdy_stride_n, int64_t dLdy_stride_f, const float* dL_ddLdx, int32_t max_level,
                                 void* dL_dparam, void* stream);
 
 /* Fused LoTD encode + density decoder, forward only.  Replaces the composition

@@ -6,6 +6,7 @@ reference's pybind module, implemented on top of the C-ABI library ``libnr3d_b20
 import ctypes
 import os
 import enum
+import threading
 from typing import List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -113,12 +114,12 @@ class LoDMeta:
         object.__setattr__(self, "c_bmm_backend", True)
         object.__setattr__(self, "c_prefetch", True)
         object.__setattr__(self, "c_permute_dydx", True)
-        # B200-only knob (no reference counterpart): walk the points in cell-sorted order (lotd_fast.cu).  When it applies
-        # (Dense/Hash-only, D=3, 2 features per pseudo level, fp32 params, single scene, no dy_dx requested) lod_fwd returns a
-        # contiguous row-major [N, n_enc] tensor instead of the transposed feature-major view; values are the same.
-        # Default off (identical strides to the reference); NR3D_B200_SORT_POINTS=1 turns it on for every meta, so an unmodified
-        # reference application gets the fast path without a code change.
-        object.__setattr__(self, "c_sort_points", os.environ.get("NR3D_B200_SORT_POINTS", "0") not in ("", "0", "false", "False"))
+        # B200-only knob (no reference counterpart): walk the points in cell-sorted order (lotd_fast.cu).  On by default: whenever a call
+        # is eligible (Dense/Hash-only meta, D=3, 2 / 4 / 8 features per pseudo level, fp32 points, no user `batch_offsets`) lod_fwd returns
+        # contiguous row-major [N, n_enc] / [N, n_enc, D] tensors instead of the reference's transposed feature-major views; values are the
+        # same.  `meta.c_sort_points = False` (or NR3D_B200_SORT_POINTS=0 in the environment) restores the reference's strides and the
+        # generic kernels for callers that depend on the memory layout.
+        object.__setattr__(self, "c_sort_points", os.environ.get("NR3D_B200_SORT_POINTS", "1") not in ("", "0", "false", "False"))
         object.__setattr__(self, "_ctor", (n_input_dims, res_md, lod_n_feats, lod_types, hashmap_size, use_smooth_step))
 
     def __setattr__(self, key, value):
@@ -216,40 +217,82 @@ def _check_common(fn, meta: LoDMeta, input, params, batch_inds, batch_offsets, b
     return N, bds, dev
 
 
-# one-slot cache of the point sort per device: lod_fwd and lod_bwd of one step see the same `x`.  The cache keeps a
-# reference to the tensor it sorted, so its memory cannot be recycled while the entry lives, and checks the version
-# counter, so in-place edits invalidate it.
+# Sorted records of the fast path.  lod_fwd and lod_bwd of one step see the same points, and the reference's autograd wrappers give us no way
+# to hand the records from one call to the other, so the shim keeps ONE set of buffers per (device, stream): sorted records, scene ids and the
+# sort's stateful workspace.  Whether the records still belong to the points of the current call is decided ON THE DEVICE by a fingerprint of
+# the points (nr3d_lotd_sort_points, lotd_sort.cu) -- tensor identity / version counters are not trusted, so `x.data.mul_()`, raw kernels
+# writing into the buffer or a re-clamped copy of the same points (lotd.py:211) all do the right thing.  Buffers are only reused on the
+# stream that produced them.  Memory held: 16 B + 4 B per point and 2 x 4 B per sort bin per (device, stream); clear_sort_cache() frees it.
 _sort_cache = {}
+_sort_lock = threading.Lock()
 
 
 def clear_sort_cache():
-    """Drop the cached point sort (a new batch of points always misses it; benchmarks call this to time the sort every step)."""
-    _sort_cache.clear()
+    """Free the sorted-record buffers (the next call sorts unconditionally)."""
+    with _sort_lock:
+        _sort_cache.clear()
+
+
+def _n_scenes(meta, params):
+    return params.shape[0] // meta.n_params if (params is not None and meta.n_params) else 1
 
 
 def _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
-    return (getattr(meta, "c_sort_points", False) and meta.c_hash_only and meta.n_dims_to_encode == 3
-            and meta.n_feat_per_pseudo_lvl == 2 and params is not None and params.dtype in (torch.float32, torch.float16)
-            and input.dtype == torch.float32 and batch_inds is None and batch_offsets is None and not bds
-            and (params.shape[0] == meta.n_params) and input.shape[0] > 0)
+    if not (getattr(meta, "c_sort_points", False) and meta.c_hash_only and meta.n_dims_to_encode == 3
+            and meta.n_feat_per_pseudo_lvl in (2, 4, 8) and params is not None and params.dtype in (torch.float32, torch.float16)
+            and input.dtype == torch.float32 and batch_offsets is None and input.shape[0] > 0):
+        return False
+    ns = _n_scenes(meta, params)
+    if ns < 1 or ns >= 65535 or ns * meta.n_params >= 2 ** 32 or params.data_ptr() % 16 != 0:
+        return False
+    if ns > 1 and batch_inds is None and not bds:
+        return False        # several tables but no scene assignment: the generic kernels read scene 0 like the reference
+    return True
 
 
-def _sorted_points(x: torch.Tensor):
+def _sorted_points(x: torch.Tensor, batch_inds: Optional[torch.Tensor] = None, bds: int = 0, n_scenes: int = 1):
+    """(xs, scenes): float4 records (x, y, z, original index) in (scene, cell) order and -- for batched calls -- the uint16 scene of every
+    record.  Sorts on the current stream unless the device-side fingerprint says the cached records belong to these very points."""
     dev = x.device
-    ent = _sort_cache.get(dev)
-    if ent is not None:
-        x_ref, ver, xs = ent
-        if x_ref.data_ptr() == x.data_ptr() and x_ref.shape == x.shape and x._version == ver and x_ref._version == ver:
-            return xs
     lib = _lib.get_lib()
     N = x.shape[0]
-    xs = torch.empty([N, 4], dtype=torch.float32, device=dev)      # (x, y, z, original index bits) per sorted point
-    nbytes = ctypes.c_uint64(0)
-    _lib.check(lib.nr3d_lotd_sort_points(N, None, None, None, ctypes.byref(nbytes), None))
-    ws = torch.empty([nbytes.value], dtype=torch.uint8, device=dev)
-    _lib.check(lib.nr3d_lotd_sort_points(N, x.data_ptr(), xs.data_ptr(), ws.data_ptr(), ctypes.byref(nbytes), _lib.stream_of(dev)))
-    _sort_cache[dev] = (x, x._version, xs)
-    return xs
+    st = _lib.stream_of(dev)
+    batched = batch_inds is not None or bool(bds)
+    ns = n_scenes if batched else 1
+    key = (dev.index, int(st or 0))
+    cfg = (N, ns, batched)
+    with _sort_lock:
+        ent = _sort_cache.get(key)
+        force = 0
+        if ent is None or ent[0] != cfg:
+            nbytes = ctypes.c_uint64(0)
+            _lib.check(lib.nr3d_lotd_sort_points(N, None, None, int(bds), ns, 1, None, None, None, ctypes.byref(nbytes), None))
+            xs = torch.empty([N, 4], dtype=torch.float32, device=dev)      # (x, y, z, original index bits) per sorted point
+            scenes = torch.empty([N], dtype=torch.int16, device=dev) if batched else None
+            ws = torch.zeros([nbytes.value], dtype=torch.uint8, device=dev)   # stateful: zero before first use
+            ent = (cfg, xs, scenes, ws, nbytes.value)
+            _sort_cache[key] = ent
+            force = 1
+        _, xs, scenes, ws, nb = ent
+        nbytes = ctypes.c_uint64(nb)
+        _lib.check(lib.nr3d_lotd_sort_points(N, x.data_ptr(), _lib.ptr(batch_inds), int(bds), ns, force, xs.data_ptr(), _lib.ptr(scenes),
+                                             ws.data_ptr(), ctypes.byref(nbytes), st))
+    return xs, scenes
+
+
+# Multi-GPU hook (no reference counterpart; the reference's DDP support is "discarded", nr3d_lib/config.py:74-75).  When set, an eligible
+# lod_bwd scatters the FINE levels first and calls `hook(dL_dparam, begin, end)` as soon as a contiguous part [begin, end) of the table is
+# final on the current stream, so that the caller (nr3d_lib_b200.dist.GradReducer) can start the all-reduce of that part while the
+# remaining levels are still being scattered.  The hook is called once per part; the parts cover the whole table.
+_grad_bucket_hook = None
+_grad_bucket_split = 8      # pseudo levels [split, n) form the first part; 8 * 2 features = 64 B = two full sectors of a dL_dy row
+
+
+def set_grad_bucket_hook(fn, split: Optional[int] = None):
+    global _grad_bucket_hook, _grad_bucket_split
+    _grad_bucket_hook = fn
+    if split is not None:
+        _grad_bucket_split = int(split)
 
 
 def _dydx_view(dy_dx, N, meta):
@@ -287,20 +330,19 @@ def lod_fwd(lod_meta, input: torch.Tensor, params: torch.Tensor, batch_inds: Opt
                 _lib.stream_of(dev)))
         return y, dy_dx
     with torch.cuda.device(dev):
-        if not need_input_grad and _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
-            xs = _sorted_points(input)
+        if _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
+            # fast path: row-major y (and dy_dx: same shapes as the reference returns, contiguous instead of permuted views)
+            ns = _n_scenes(meta, params)
+            xs, scenes = _sorted_points(input, batch_inds, bds, ns)
             y = torch.empty([N, E], dtype=params.dtype, device=dev)
-            _lib.check(_lib.get_lib().nr3d_lotd_fwd_sorted(
-                ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), params.data_ptr(), max_level,
-                y.data_ptr(), E, 1, _lib.stream_of(dev)))
-            return y, None
-        if need_input_grad and _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
-            # fast path with the nablas: row-major y and dy_dx (same shapes as the reference returns, contiguous instead of permuted views)
-            xs = _sorted_points(input)
-            y = torch.empty([N, E], dtype=params.dtype, device=dev)
+            if not need_input_grad:
+                _lib.check(_lib.get_lib().nr3d_lotd_fwd_sorted(
+                    ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), _lib.ptr(scenes), ns, params.data_ptr(), max_level,
+                    y.data_ptr(), E, 1, _lib.stream_of(dev)))
+                return y, None
             dy_dx = torch.empty([N, E, D] if meta.c_permute_dydx else [N, E * D], dtype=input.dtype, device=dev)
             _lib.check(_lib.get_lib().nr3d_lotd_fwd_dydx_sorted(
-                ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), params.data_ptr(), max_level,
+                ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), _lib.ptr(scenes), ns, params.data_ptr(), max_level,
                 y.data_ptr(), dy_dx.data_ptr(), _lib.stream_of(dev)))
             return y, dy_dx
         if meta.c_hash_only:
@@ -368,10 +410,21 @@ def lod_bwd(lod_meta, dL_dy: torch.Tensor, input: torch.Tensor, params: torch.Te
                 dL_dy.stride(0), dL_dy.stride(1), None, input.data_ptr(), params.data_ptr(), _lib.ptr(batch_inds), _lib.ptr(batch_offsets),
                 bds, max_level, dL_dparam.data_ptr(), st))
         elif need_param_grad and _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
-            xs = _sorted_points(input)
-            _lib.check(lib.nr3d_lotd_bwd_param_sorted(
-                ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), dL_dy.data_ptr(),
-                dL_dy.stride(0), dL_dy.stride(1), max_level, dL_dparam.data_ptr(), st))
+            ns = _n_scenes(meta, params)
+            xs, scenes = _sorted_points(input, batch_inds, bds, ns)
+            P = meta.n_pseudo_levels
+            hook, split = _grad_bucket_hook, _grad_bucket_split
+            groups = [(0, P)]
+            if hook is not None and ns == 1 and 0 < split < P and meta.map_levels[split] != meta.map_levels[split - 1]:
+                groups = [(split, P), (0, split)]         # fine levels first: their part of the table is reduced while the coarse levels run
+            for b, e in groups:
+                _lib.check(lib.nr3d_lotd_bwd_param_sorted(
+                    ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), _lib.ptr(scenes), ns, dL_dy.data_ptr(),
+                    dL_dy.stride(0), dL_dy.stride(1), max_level, b, e, dL_dparam.data_ptr(), st))
+                if hook is not None:
+                    lo = meta.level_offsets[meta.map_levels[b]] if len(groups) > 1 else 0
+                    hi = meta.level_offsets[meta.map_levels[e - 1] + 1] if len(groups) > 1 else dL_dparam.shape[0]
+                    hook(dL_dparam, lo, hi)
         elif need_param_grad:
             _lib.check(lib.nr3d_lotd_bwd_param_scenes(
                 ctypes.byref(meta._c), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, dL_dy.data_ptr(),
@@ -440,9 +493,10 @@ def lod_bwd_bwd_input(lod_meta, dL_ddLdx: torch.Tensor, dL_dy: torch.Tensor, inp
             return dL_ddLdy, dL_dparams, dL_dx
         dparam_generic = dL_dparams
         if need_param and _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
-            xs = _sorted_points(input)      # second-order scatter on the fast path; the two other outputs keep the generic kernels
+            ns = _n_scenes(meta, params)     # second-order scatter on the fast path; the two other outputs keep the generic kernels
+            xs, scenes = _sorted_points(input, batch_inds, bds, ns)
             _lib.check(lib.nr3d_lotd_bwd_param2_sorted(
-                ctypes.byref(meta._c), pdt, N, xs.data_ptr(), dL_dy.data_ptr(), dL_dy.stride(0), dL_dy.stride(1), dL_ddLdx.data_ptr(),
+                ctypes.byref(meta._c), pdt, N, xs.data_ptr(), _lib.ptr(scenes), ns, dL_dy.data_ptr(), dL_dy.stride(0), dL_dy.stride(1), dL_ddLdx.data_ptr(),
                 max_level, dL_dparams.data_ptr(), st))
             dparam_generic = None
         if dparam_generic is not None:      # second-order scatter with the scene count made explicit (shared-memory privatisation)

@@ -1,5 +1,6 @@
-// lotd_fast.cu -- B200 fast path of the LoTD encoder for the Dense/Hash ("hash-only") configuration, D = 3, F_pl = 2,
-// fp32 or fp16 parameters, single scene: the workload of BASELINE.json's headline metric.
+// lotd_fast.cu -- B200 fast path of the LoTD encoder for Dense/Hash ("hash-only") metas, D = 3, F = 2 / 4 / 8 features per pseudo level,
+// fp32 or fp16 parameters, one scene or many (batch indices / batch_data_size): the workload of BASELINE.json's headline metric and of the
+// reference's hash-only kernels (lotd_hash_only.h:15-695 serve the same set).
 //
 // What bounds this workload on B200 (measured, scripts/ubench_mem.cu, scripts/ubench_pair.cu -> profiles/r1_ubench_*.txt):
 //   * the 48.5 MB parameter table is L2 resident, so DRAM only sees x, y, dL_dy (about 1.3 GB per fwd+bwd step);
@@ -9,16 +10,16 @@
 //     460 G lanes/s when lane pairs share a chunk), f32 / v2.f32 / v4.f32 cost the same, and same-address reductions
 //     from different SMs serialise in the L2 slice (coarse levels: up to 4.5x slower).
 // So the levers are (1) lanes of one instruction sharing lines / sectors, (2) merging same-address contributions before they
-// reach L2, (3) fewer instructions (both kernels end up ~85 % issue-bound).  This file implements them:
-//   1. points are binned once per step by a 128^3 cell key (x fastest) with a counting sort; forward and backward walk
-//      the points in that order, so coarse and middle levels hit few lines per warp;
+// reach L2, (3) fewer instructions.  This file implements them:
+//   1. points are binned once per step by (scene, cell bin) with a counting sort (lotd_sort.cu; bricks of 8 x 4 x 2 bins, x fastest
+//      inside); forward and backward walk the points in that order, so coarse and middle levels hit few lines per warp;
 //   2. TWO ADJACENT LANES share one point (see "pair layout" below): the x-neighbour corners of a Hash level (z-neighbours
 //      of a Dense level) are fetched / scattered by the two lanes of a pair in the same instruction and coalesce in hardware;
-//   3. in the backward pass, runs of points in the same cell sum their corner contributions through a shared-memory tile
-//      and issue one reduction per corner per run;
+//   3. in the backward pass, runs of points in the same cell sum their corner contributions with a segmented shuffle reduction, and the
+//      CTA (128 points = about one brick of bins) sums what is left per table entry in SHARED-MEMORY TILES -- one tile per level whose corner
+//      bounding box fits -- that are flushed with ONE reduction per touched entry (scripts/sim_tiles.py: 55.6 -> 38.3 L2 packets per point);
 //   4. y and dL_dy are accessed as [N, n_enc] rows staged through shared memory (one coalesced 128-byte access per point),
 //      so the sort permutation costs no partial-sector traffic.
-// (The thread-per-point kernels of the first iteration lost the A/B by 20 % -- profiles/r1_ab_pair_layout.txt -- and are gone.)
 // Results are identical to the generic kernels up to fp32 summation order (same index functions, same weights).
 #include "lotd_pair.cuh"
 #include <string.h>
@@ -26,160 +27,59 @@
 namespace nr3d {
 
 // tunables (overridable with -D for A/B runs, see scripts/build_variants.py)
-#ifndef NR3D_BIN_RES        // 0: chosen per call from the number of points (about two points per bin), else fixed (A/B runs)
-#define NR3D_BIN_RES 0
-#endif
-#ifndef NR3D_BIN_ORDER      // 0: x fastest, 1: z fastest
-#define NR3D_BIN_ORDER 0
-#endif
 #ifndef NR3D_FWD_UNROLL
 #define NR3D_FWD_UNROLL 1
-#endif
-#ifndef NR3D_BWD_SHORTRUN     // 1: runs of 2-3 points in one cell are summed through two shuffle steps, the head of the run issues the reductions
-#define NR3D_BWD_SHORTRUN 1     // A/B on B200: 2083 -> 2203 Msamples/s (profiles/r1_ab_tunables.txt)
 #endif
 #ifndef NR3D_FWD_THREADS
 #define NR3D_FWD_THREADS 256
 #endif
-#ifndef NR3D_BWD_THREADS
-#define NR3D_BWD_THREADS 128
+#ifndef NR3D_BWD_THREADS      // 256 threads = 128 points per CTA: about one 8 x 4 x 2 brick of sort bins
+#define NR3D_BWD_THREADS 256
 #endif
-// bins per axis of the point sort.  The kernels like about two points per bin (A/B on B200: 4 Mi uniform points 128^3 > 64^3, 256^3;
-// 30 Mi ray samples 256^3 > 192^3 > 128^3, profiles/r1_ab_tunables.txt), so the resolution follows the point count.
-static inline uint32_t bin_res_for(uint64_t N) {
-    if (NR3D_BIN_RES) return NR3D_BIN_RES;
-    return N >= (12ull << 20) ? 256u : 128u;
-}
+#ifndef NR3D_BWD_TILES        // 1: CTA-level shared-memory tiles in the backward (0: every run head scatters to L2 directly)
+#define NR3D_BWD_TILES 0      // A/B on B200 (profiles/r2_ab_tiles.txt): OFF wins, 1.18 ms vs 2.45 - 3.6 ms -- see the note at smem_add2
+#endif
+#ifndef NR3D_TILE_FLOATS      // shared-memory floats per CTA for the backward tiles
+#define NR3D_TILE_FLOATS 6144
+#endif
+#ifndef NR3D_BWD_OCC          // resident threads per SM the F = 2 backward is compiled for (register cap through __launch_bounds__), 0: no cap
+#define NR3D_BWD_OCC 1536
+#endif
 constexpr int kFastThreads = NR3D_FWD_THREADS;
 constexpr int kBwdThreads = NR3D_BWD_THREADS;
-constexpr int kScanBlockF = 1024;
-
-__device__ __forceinline__ uint32_t bin_key(float x, float y, float z, uint32_t res) {
-    const uint32_t bx = min(res - 1, (uint32_t)fmaxf(x * (float)res, 0.f));
-    const uint32_t by = min(res - 1, (uint32_t)fmaxf(y * (float)res, 0.f));
-    const uint32_t bz = min(res - 1, (uint32_t)fmaxf(z * (float)res, 0.f));
-    return NR3D_BIN_ORDER == 0 ? (bz * res + by) * res + bx : (bx * res + by) * res + bz;
-}
-
-// pass 1: bin key and rank of the point inside its bin (the rank makes the scatter pass atomic-free)
-__global__ void __launch_bounds__(256) sort_hist_kernel(uint64_t N, uint32_t res, const float* __restrict__ x, uint32_t* __restrict__ hist, uint2* __restrict__ keyrank) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const uint32_t k = bin_key(x[i * 3], x[i * 3 + 1], x[i * 3 + 2], res);
-    const uint32_t r = atomicAdd(hist + k, 1u);
-    keyrank[i] = make_uint2(k, r);
-}
-
-// exclusive scan of `hist` in place (three launches, like pack_ops.cu's scan but for uint32)
-__global__ void __launch_bounds__(kScanBlockF) scanu_block_sums(uint32_t n, const uint32_t* __restrict__ v, uint32_t* __restrict__ bs) {
-    __shared__ uint32_t ws[32];
-    const uint32_t i = blockIdx.x * kScanBlockF + threadIdx.x;
-    uint32_t s = i < n ? v[i] : 0;
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        uint32_t t = ws[threadIdx.x];
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
-        if (threadIdx.x == 0) bs[blockIdx.x] = t;
-    }
-}
-__global__ void __launch_bounds__(kScanBlockF) scanu_of_sums(uint32_t nb, uint32_t* __restrict__ bs) {
-    __shared__ uint32_t ws[32];
-    __shared__ uint32_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < nb; base += kScanBlockF) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t x = i < nb ? bs[i] : 0;
-        uint32_t s = x;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, s, d); if ((threadIdx.x & 31) >= d) s += t; }
-        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = s;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t w = ws[threadIdx.x];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, d); if (threadIdx.x >= d) w += t; }
-            ws[threadIdx.x] = w;
-        }
-        __syncthreads();
-        const uint32_t off = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0;
-        const uint32_t carry = carry_s;
-        if (i < nb) bs[i] = carry + off + s - x;
-        __syncthreads();
-        if (threadIdx.x == kScanBlockF - 1) carry_s = carry + off + s;
-        __syncthreads();
-    }
-}
-__global__ void __launch_bounds__(kScanBlockF) scanu_apply(uint32_t n, uint32_t* __restrict__ v, const uint32_t* __restrict__ bs) {
-    __shared__ uint32_t ws[32];
-    const uint32_t i = blockIdx.x * kScanBlockF + threadIdx.x;
-    const uint32_t x = i < n ? v[i] : 0;
-    uint32_t s = x;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, s, d); if ((threadIdx.x & 31) >= d) s += t; }
-    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        uint32_t w = ws[threadIdx.x];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, d); if (threadIdx.x >= d) w += t; }
-        ws[threadIdx.x] = w;
-    }
-    __syncthreads();
-    const uint32_t off = bs[blockIdx.x] + ((threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0);
-    if (i < n) v[i] = off + s - x;
-}
-
-// pass 2: sorted record = (x, y, z, original index) written with ONE 16-byte store per point
-__global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t N, const float* __restrict__ x, const uint2* __restrict__ keyrank,
-                                                           const uint32_t* __restrict__ offsets, float4* __restrict__ xs) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const uint2 kr = keyrank[i];
-    const uint32_t pos = __ldg(offsets + kr.x) + kr.y;
-    xs[pos] = make_float4(x[i * 3 + 0], x[i * 3 + 1], x[i * 3 + 2], __uint_as_float((uint32_t)i));
-}
+constexpr int kBwdWarps = kBwdThreads / 32;
+constexpr int kTileFloats = NR3D_TILE_FLOATS;
+constexpr int kMaxTiledLevels = 32;   // pseudo levels that can own a tile (one lane of warp 0 plans each)
 
 // ------------------------------------------------------------------------------------------------------------
-// per-(point, level) geometry shared by forward and backward
-// ------------------------------------------------------------------------------------------------------------
-
-// ------------------------------------------------------------------------------------------------------------
-// "pair" layout (default).  Measured on B200 (scripts/ubench_pair.cu -> profiles/r1_ubench_pair.txt): a warp-wide gather
+// "pair" layout.  Measured on B200 (scripts/ubench_pair.cu -> profiles/r1_ubench_pair.txt): a warp-wide gather
 // costs one LSU slot per DISTINCT 128-BYTE LINE (two lanes in one line, even in different sectors: 572 G lanes/s vs 287),
 // a warp-wide red.global costs one L2 slot per DISTINCT 32-BYTE SECTOR (two lanes in one sector: 460 G lanes/s vs 231).
 // The two corners of a Hash level that differ in x sit at (x ^ h) and ((x+1) ^ h): the same 128-byte line 15/16 of the time
-// and the same sector 3/4 of the time, for odd x as well -- which the one-thread-per-point layout above can only exploit
+// and the same sector 3/4 of the time, for odd x as well -- which a one-thread-per-point layout can only exploit
 // for even x (16-byte accesses).  So here TWO ADJACENT LANES share one point: lane side s handles the four corners with
 // x + s (Hash) or z + s (Dense, z fastest), the pair's partial sums meet with one shuffle, and the hardware coalesces the
 // pair's accesses.  Hash-level cost drops from 6 to ~4.25 lines (gather) and from 6 to 5 sectors (reduction) per point.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kPairRowStride = 34;   // floats per staged row: row k starts at bank 2k -> conflict-free pair writes and row reads
-constexpr int kPairTileStride = 12;  // floats per lane in the run-merge tile (8 used): conflict-free 16-byte stores
 
+// scene (batch) of sorted record p: parameter base of the scene and whether the point takes part at all
+__device__ __forceinline__ bool point_scene(const FastIn& in, uint64_t p, bool active, uint32_t& scene, uint32_t& pbase) {
+    scene = 0; pbase = 0;
+    if (!active) return false;
+    if (in.scenes) {
+        scene = __ldg(in.scenes + p);
+        if (scene == 0xffffu) return false;   // batch_inds < 0: the point is skipped (zero output, no gradient)
+        pbase = scene * in.n_params;
+    }
+    return true;
+}
 
-// parameter-type specifics: fp32 tables accumulate in fp32; fp16 tables accumulate every term in half like the reference
-// (linear_interpolate.cuh:118) and scatter with packed-half reductions.
-template <typename PT> struct PairIO;
-template <> struct PairIO<float> {
-    static __device__ __forceinline__ float2 load2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-    static __device__ __forceinline__ float ldcs(const float* p) { return __ldcs(p); }
-    static __device__ __forceinline__ void red2(float* p, float a, float b) { red_add_v2_f32(p, a, b); }
-};
-template <> struct PairIO<__half> {
-    static __device__ __forceinline__ float2 load2(const __half* p) { return __half22float2(__ldg(reinterpret_cast<const __half2*>(p))); }
-    static __device__ __forceinline__ float ldcs(const __half* p) { return __half2float(__ldcs(p)); }
-    static __device__ __forceinline__ void red2(__half* p, float a, float b) { red_add_h2(p, __floats2half2_rn(a, b)); }
-};
-
-template <typename PT>
-__global__ void __launch_bounds__(kFastThreads)
+template <typename PT, int F>
+__global__ void __launch_bounds__(kFastThreads, F == 2 ? 2048 / kFastThreads : 1)
 lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT* __restrict__ y, int64_t ys_n, int64_t ys_f) {
     using C = Cvt<PT>;
+    constexpr int H = F / 2;   // features of a pseudo level that one lane of the pair writes out
     const PT* params = reinterpret_cast<const PT*>(in.params);
     __shared__ float rows[kFastThreads / 32][16 * kPairRowStride];
     const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
@@ -190,7 +90,9 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT*
     float* myrows = rows[threadIdx.x >> 5];
     float4 rec = make_float4(0.5f, 0.5f, 0.5f, 0.f);
     if (active) rec = __ldcs(in.xs + p);
-    const float x = rec.x, yv = rec.y, z = rec.z;
+    uint32_t scene, pbase;
+    const bool live = point_scene(in, p, active, scene, pbase);
+    const float x = live ? rec.x : 0.5f, yv = live ? rec.y : 0.5f, z = live ? rec.z : 0.5f;
     const uint64_t i = __float_as_uint(rec.w);
     const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
     const bool staged = (ys_f == 1);
@@ -199,176 +101,304 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT*
 #pragma unroll kFwdUnroll
     for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
         const uint32_t level = tab.map_level[pl];
-        float r0 = 0.f, r1 = 0.f;  // (for fp16 tables these always hold half-representable values)
+        float r[F];  // (for fp16 tables these always hold half-representable values)
+#pragma unroll
+        for (int f = 0; f < F; ++f) r[f] = 0.f;
         if ((int32_t)level <= in.max_level) {
             Geo2 g;
-            pair_geo(tab.lv[level], (uint32_t)tab.map_cnt[pl] * 2u, smooth, x, yv, z, side, g);
-            float2 v[4];  // all four loads are issued before the first use
+            pair_geo(tab.lv[level], (uint32_t)tab.map_cnt[pl] * F, smooth, x, yv, z, side, g);
+            float v[4][F];  // all four loads are issued before the first use
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = PairIO<PT>::load2(params + g.e[q]);
+            for (int q = 0; q < 4; ++q) load_feats<PT, F>(params + pbase + g.e[q], v[q]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                r0 = C::to_f(C::add(C::from_f(r0), C::from_f(g.w[q] * v[q].x)));
-                r1 = C::to_f(C::add(C::from_f(r1), C::from_f(g.w[q] * v[q].y)));
-            }
-            r0 = C::to_f(C::add(C::from_f(r0), C::from_f(__shfl_xor_sync(0xffffffffu, r0, 1))));
-            r1 = C::to_f(C::add(C::from_f(r1), C::from_f(__shfl_xor_sync(0xffffffffu, r1, 1))));
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int f = 0; f < F; ++f) r[f] = C::to_f(C::add(C::from_f(r[f]), C::from_f(g.w[q] * v[q][f])));
+#pragma unroll
+            for (int f = 0; f < F; ++f) r[f] = C::to_f(C::add(C::from_f(r[f]), C::from_f(__shfl_xor_sync(0xffffffffu, r[f], 1))));
         }
-        const float mine = side ? r1 : r0;  // lane `side` owns feature 2 * pl + side of its point
+        // lane `side` owns features pl * F + side * H + [0, H) of its point
+        float mine[H];
+#pragma unroll
+        for (int j = 0; j < H; ++j) mine[j] = live ? (side ? r[H + j] : r[j]) : 0.f;
         if (staged) {
-            const uint32_t c = pl * 2u - chunk_base;
-            myrows[k * kPairRowStride + c + side] = mine;
+            const uint32_t c = pl * F - chunk_base;
+#pragma unroll
+            for (int j = 0; j < H; ++j) myrows[k * kPairRowStride + c + side * H + j] = mine[j];
             const bool last = (pl + 1 == tab.n_pseudo);
-            if (c + 2 == 32 || last) {  // flush the chunk: one coalesced row store per point of the warp
-                const uint32_t width = c + 2;
+            if (c + F == 32 || last) {  // flush the chunk: one coalesced row store per point of the warp
+                const uint32_t width = c + F;
                 __syncwarp();
 #pragma unroll 4
-                for (int r = 0; r < 16; ++r) {
-                    const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * r);
-                    const bool ok = __shfl_sync(0xffffffffu, (int)active, 2 * r);
-                    if (ok && (uint32_t)lane < width) st_cs(y + (int64_t)ir * ys_n + chunk_base + lane, C::from_f(myrows[r * kPairRowStride + lane]));
+                for (int rr = 0; rr < 16; ++rr) {
+                    const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * rr);
+                    const bool ok = __shfl_sync(0xffffffffu, (int)active, 2 * rr);
+                    if (ok && (uint32_t)lane < width) st_cs(y + (int64_t)ir * ys_n + chunk_base + lane, C::from_f(myrows[rr * kPairRowStride + lane]));
                 }
                 __syncwarp();
                 chunk_base += 32;
             }
         } else if (active) {
-            st_cs(y + (int64_t)i * ys_n + (int64_t)(pl * 2 + side) * ys_f, C::from_f(mine));
+#pragma unroll
+            for (int j = 0; j < H; ++j) st_cs(y + (int64_t)i * ys_n + (int64_t)(pl * F + side * H + j) * ys_f, C::from_f(mine[j]));
         }
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// backward: dL/dparam scatter
+// ------------------------------------------------------------------------------------------------------------
+// fp32 pair added to a shared-memory tile entry: ONE 64-bit compare-and-swap loop (fp32 shared-memory atomics are CAS loops on sm_100a
+// anyway -- SASS ATOMS.CAST.SPIN -- so the pair costs the same as a single float).
+// MEASURED (profiles/r2_ab_tiles.txt, 4 Mi points): the tiles remove 31 % of the L2 reduction packets as simulated (scripts/sim_tiles.py)
+// and still LOSE by 2x: the backward goes from 1.18 ms to 2.45 ms (x-fastest bins) / 2.9 - 3.6 ms (bricks, 3072 - 12288 tile floats).
+// ATOMS.CAS.64 retires about one lane every two clocks per SM (9 tiled levels x ~100 lane operations x 1771 warps per SM = 2 ms), i.e.
+// a shared-memory float add costs ~3x what the L2 reduction unit charges for a whole packet (231 G packets/s = 1.26 clocks per SM).
+// The only cheap fp32 adder with conflict resolution on this chip is the L2 reduction unit; the code stays for the record (-DNR3D_BWD_TILES=1).
+__device__ __forceinline__ void smem_add2(float* addr, float a, float b) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(addr);
+    unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(p), assumed;
+    do {
+        assumed = old;
+        const float lo = __uint_as_float((uint32_t)assumed) + a, hi = __uint_as_float((uint32_t)(assumed >> 32)) + b;
+        old = atomicCAS(p, assumed, ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo));
+    } while (old != assumed);
+}
+
+struct TilePlan {                       // one entry per pseudo level, written by warp 0
+    int32_t off[kMaxTiledLevels];       // first float of the level's tile inside the CTA tile memory, -1: not tiled
+    uint32_t lo[kMaxTiledLevels][3];    // smallest corner coordinate of the CTA's points on the level
+    uint32_t n[kMaxTiledLevels][3];     // corners per axis
+};
+
 // SECOND = false: dL/dparam.  SECOND = true: d(dL/dx)/dparam . dL_ddLdx (second-order backward of NeuS-style eikonal terms,
 // reference kernel_lod_hashonly_backward_input_backward_grid, lotd_hash_only.h:472-695): the same scatter with the corner weights
 // replaced by sum_d ddx[d] * dw[d][corner] (pair_geo_d), ddx = dL_ddLdx [N,3] read at the point's original index.
-template <typename PT, bool SECOND>
-__global__ void __launch_bounds__(kBwdThreads)
+template <typename PT, int F, bool SECOND>
+__global__ void __launch_bounds__(kBwdThreads, (F == 2 && !SECOND && NR3D_BWD_OCC) ? NR3D_BWD_OCC / kBwdThreads : 1)
 lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, const PT* __restrict__ dLdy, int64_t gs_n, int64_t gs_f,
                      const float* __restrict__ ddx, PT* __restrict__ grad) {
     using C = Cvt<PT>;
-    __shared__ __align__(16) float tile[kBwdThreads / 32][32 * kPairTileStride];
-    __shared__ float rows[kBwdThreads / 32][16 * kPairRowStride];
+    extern __shared__ __align__(16) float smem[];
+    float* ctile = smem;                                                    // [kTileFloats] CTA tiles (NR3D_BWD_TILES)
+    float* myrows = smem + (NR3D_BWD_TILES ? kTileFloats : 0) + (threadIdx.x >> 5) * (16 * kPairRowStride);
+    __shared__ uint32_t s_box[8];   // min x, y, z bits | max x, y, z bits | min scene | max scene over the live points of the CTA
+    __shared__ TilePlan plan;
     const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     const bool active = p < in.N;
     const int lane = threadIdx.x & 31;
     const uint32_t side = lane & 1;
     const int k = lane >> 1;
-    float* mytile = tile[threadIdx.x >> 5];
-    float* myrows = rows[threadIdx.x >> 5];
     float4 rec = make_float4(0.5f, 0.5f, 0.5f, 0.f);
     if (active) rec = __ldcs(in.xs + p);
-    const float x = rec.x, yv = rec.y, z = rec.z;
+    uint32_t scene, pbase;
+    const bool live = point_scene(in, p, active, scene, pbase);
+    const float x = live ? rec.x : 0.5f, yv = live ? rec.y : 0.5f, z = live ? rec.z : 0.5f;
     const uint64_t i = __float_as_uint(rec.w);
     const PT* grow = dLdy + (int64_t)i * gs_n;
     const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
     const bool staged = (gs_f == 1);
     float gx[3] = {0.f, 0.f, 0.f};
-    if (SECOND && active) { gx[0] = __ldg(ddx + i * 3); gx[1] = __ldg(ddx + i * 3 + 1); gx[2] = __ldg(ddx + i * 3 + 2); }
-    uint32_t chunk_base = 0;
-    for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
+    if (SECOND && live) { gx[0] = __ldg(ddx + i * 3); gx[1] = __ldg(ddx + i * 3 + 1); gx[2] = __ldg(ddx + i * 3 + 2); }
+    // a point starts a new run on every level when its scene differs from the previous point's
+    const uint32_t scene_prev = __shfl_up_sync(0xffffffffu, scene, 2);
+    const bool scene_break = scene != scene_prev;
+
+#if NR3D_BWD_TILES
+    // ---- CTA bounding box of the live points (in unit-cube coordinates: 6 reductions instead of 6 per level) and the tile plan ----
+    if (threadIdx.x < 8) s_box[threadIdx.x] = (threadIdx.x < 3 || threadIdx.x == 6) ? 0xffffffffu : 0u;
+    for (int t = threadIdx.x; t < kTileFloats / 4; t += kBwdThreads) reinterpret_cast<float4*>(ctile)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    {
+        // non-negative floats order like their bit patterns; coordinates below 0 land in cell 0 like 0 does
+        const uint32_t ux = __float_as_uint(fmaxf(x, 0.f)), uy = __float_as_uint(fmaxf(yv, 0.f)), uz = __float_as_uint(fmaxf(z, 0.f));
+        const uint32_t mn[4] = {live ? ux : 0xffffffffu, live ? uy : 0xffffffffu, live ? uz : 0xffffffffu, live ? scene : 0xffffffffu};
+        const uint32_t mx[4] = {live ? ux : 0u, live ? uy : 0u, live ? uz : 0u, live ? scene : 0u};
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const uint32_t a = __reduce_min_sync(0xffffffffu, mn[d]), b = __reduce_max_sync(0xffffffffu, mx[d]);
+            if (lane == 0) { atomicMin(&s_box[d == 3 ? 6 : d], a); atomicMax(&s_box[d == 3 ? 7 : 3 + d], b); }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t pl = threadIdx.x;
+        uint32_t need = 0;   // floats of this level's tile (0: level not processed at all)
+        bool fits = false;
+        uint32_t lo[3] = {0, 0, 0}, n[3] = {0, 0, 0};
+        const bool one_scene = s_box[6] != 0xffffffffu && s_box[6] == s_box[7];
+        if (pl >= in.pl_begin && pl < in.pl_end && pl < kMaxTiledLevels && one_scene) {
+            const uint32_t level = tab.map_level[pl];
+            if ((int32_t)level <= in.max_level) {
+                const LevelDesc& L = tab.lv[level];
+                uint64_t size = 1;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    lo[d] = (uint32_t)floorf(cell_pos(__uint_as_float(s_box[d]), L.res[d]));
+                    const uint32_t hi = (uint32_t)floorf(cell_pos(__uint_as_float(s_box[3 + d]), L.res[d])) + 1u;
+                    n[d] = min(hi - lo[d] + 1u, 4096u);
+                    size *= n[d];
+                }
+                need = (uint32_t)min(size * F, (uint64_t)kTileFloats + 1);
+                fits = true;
+            }
+        }
+        uint32_t incl = need;   // inclusive prefix over the pseudo levels: tiles are handed out in level order while the memory lasts
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl = min(incl + t, 2u * kTileFloats); }
+        fits = fits && incl <= (uint32_t)kTileFloats;
+        plan.off[pl] = fits ? (int32_t)(incl - need) : -1;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { plan.lo[pl][d] = lo[d]; plan.n[pl][d] = n[d]; }
+    }
+    __syncthreads();
+#endif
+
+    uint32_t chunk_base = 0xffffffffu;   // first feature of the staged chunk (none yet)
+    for (uint32_t pl = in.pl_begin; pl < in.pl_end; ++pl) {
         const uint32_t level = tab.map_level[pl];
-        float g0 = 0.f, g1 = 0.f;
+        float gv[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) gv[f] = 0.f;
         if (staged) {
-            if (pl * 2u == chunk_base + 32u) chunk_base += 32u;
-            if (pl * 2u == chunk_base) {  // stage the next (up to) 32 features of the warp's 16 rows: one coalesced row read per point
-                const uint32_t width = min(32u, tab.n_enc - chunk_base);
+            const uint32_t want_base = (pl * (uint32_t)F) / 32u * 32u;
+            if (want_base != chunk_base) {  // stage the next (up to) 32 features of the warp's 16 rows: one coalesced row read per point
+                const uint32_t width = min(32u, tab.n_enc - want_base);
                 __syncwarp();
 #pragma unroll 4
-                for (int r = 0; r < 16; ++r) {
-                    const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * r);
-                    const bool ok = __shfl_sync(0xffffffffu, (int)active, 2 * r);
-                    if (ok && (uint32_t)lane < width) myrows[r * kPairRowStride + lane] = PairIO<PT>::ldcs(dLdy + (int64_t)ir * gs_n + chunk_base + lane);
+                for (int rr = 0; rr < 16; ++rr) {
+                    const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * rr);
+                    const bool ok = __shfl_sync(0xffffffffu, (int)live, 2 * rr);
+                    // (a level-group launch only touches the sectors of its own features)
+                    if (ok && (uint32_t)lane < width && want_base + lane >= in.pl_begin * F && want_base + lane < in.pl_end * F)
+                        myrows[rr * kPairRowStride + lane] = ldcs_f<PT>(dLdy + (int64_t)ir * gs_n + want_base + lane);
                 }
                 __syncwarp();
             }
-            g0 = myrows[k * kPairRowStride + pl * 2u - chunk_base];
-            g1 = myrows[k * kPairRowStride + pl * 2u - chunk_base + 1];
-        } else if (active) {
-            g0 = C::to_f(grow[(int64_t)(pl * 2) * gs_f]);
-            g1 = C::to_f(grow[(int64_t)(pl * 2 + 1) * gs_f]);
+            chunk_base = want_base;
+            if (live) {
+#pragma unroll
+                for (int f = 0; f < F; ++f) gv[f] = myrows[k * kPairRowStride + pl * F - chunk_base + f];
+            }
+        } else if (live) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) gv[f] = C::to_f(grow[(int64_t)(pl * F + f) * gs_f]);
         }
         if ((int32_t)level > in.max_level) continue;  // uniform
         const LevelDesc& L = tab.lv[level];
         Geo2 g;
         if (SECOND) {
             float dw[3][4];
-            pair_geo_d(L, (uint32_t)tab.map_cnt[pl] * 2u, smooth, x, yv, z, side, g, dw);
+            pair_geo_d(L, (uint32_t)tab.map_cnt[pl] * F, smooth, x, yv, z, side, g, dw);
 #pragma unroll
             for (int q = 0; q < 4; ++q) g.w[q] = gx[0] * dw[0][q] + gx[1] * dw[1][q] + gx[2] * dw[2][q];
         } else {
-            pair_geo(L, (uint32_t)tab.map_cnt[pl] * 2u, smooth, x, yv, z, side, g);
+            pair_geo(L, (uint32_t)tab.map_cnt[pl] * F, smooth, x, yv, z, side, g);
         }
-        // points of one run (consecutive points in the same cell) merge their contributions before touching L2
-        const bool can_key = L.res[0] <= 1024u && L.res[1] <= 1024u && L.res[2] <= 1024u;
-        uint32_t hmask = 0x55555555u;  // bit 2k set: point k starts a run
-        if (can_key) {
-            const uint32_t key = active ? g.key : (0xffffffffu - (uint32_t)k);
-            const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 2);
-            hmask = __ballot_sync(0xffffffffu, k == 0 || key != prev) & 0x55555555u;
-        }
-        // run of my point: points [s0, e0), length r, my position j
-        const uint32_t le = hmask & (0xffffffffu >> (31 - 2 * k));
-        const int s0 = (31 - __clz(le)) >> 1;
-        const uint32_t above = hmask & (0xffffffffu << (2 * k + 1));
-        const int e0 = above ? ((__ffs(above) - 1) >> 1) : 16;
-        const int r = e0 - s0, j = k - s0;
-        const bool longrun = active && r >= 4;  // shorter runs are not worth the detour through shared memory
-        // every lane ends up with at most four contributions (entry g.e[q], value pair); cv[q]: this lane issues corner q
-        float cx[4], cy[4];
-        bool cv[4];
-        if (!__any_sync(0xffffffffu, longrun)) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { cx[q] = g.w[q] * g0; cy[q] = g.w[q] * g1; cv[q] = active; }
-        } else {
-            *reinterpret_cast<float4*>(mytile + lane * kPairTileStride) = make_float4(g.w[0] * g0, g.w[0] * g1, g.w[1] * g0, g.w[1] * g1);
-            *reinterpret_cast<float4*>(mytile + lane * kPairTileStride + 4) = make_float4(g.w[2] * g0, g.w[2] * g1, g.w[3] * g0, g.w[3] * g1);
-            __syncwarp();
-            // A long run is reduced by its first 4 * nch positions: position j sums corner q = j & 3 over the points
-            // s0 + c, s0 + c + nch, ... (c = j >> 2), the nch partial sums of a corner then meet through two shuffles and
-            // positions 0..3 issue ONE reduction per corner for the whole run.
-            const int nch = r >> 2;  // 1..4 groups of four positions
-            const int qj = j & 3, c = j >> 2;
-            float2 acc = make_float2(0.f, 0.f);
-            if (longrun && c < nch) {
-                for (int m = s0 + c; m < e0; m += nch) {
-                    const float2 t = *reinterpret_cast<const float2*>(mytile + (2 * m + side) * kPairTileStride + qj * 2);
-                    acc.x += t.x; acc.y += t.y;
-                }
-            }
-            const int lim = nch << 2;
-            float tx = __shfl_down_sync(0xffffffffu, acc.x, 16), ty = __shfl_down_sync(0xffffffffu, acc.y, 16);
-            if (longrun && j + 8 < lim) { acc.x += tx; acc.y += ty; }   // positions j + 8 (and, through them, j + 12)
-            tx = __shfl_down_sync(0xffffffffu, acc.x, 8); ty = __shfl_down_sync(0xffffffffu, acc.y, 8);
-            if (longrun && j < 4 && j + 4 < lim) { acc.x += tx; acc.y += ty; }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (longrun) { cv[q] = (j < 4) && (q == qj); cx[q] = acc.x; cy[q] = acc.y; }
-                else { cv[q] = active; cx[q] = g.w[q] * g0; cy[q] = g.w[q] * g1; }
-            }
-            __syncwarp();
-        }
-#if NR3D_BWD_SHORTRUN
-        // Runs of two or three points in one cell: the hardware does not merge lanes that hit the same entry, so they would cost one L2
-        // packet each.  Two shuffle steps towards the head of the run (the points of a run are neighbours in the warp) and only the head
-        // issues the four reductions.
-        const bool shortrun = active && (r == 2 || r == 3);
-        if (__any_sync(0xffffffffu, shortrun)) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float ux = __shfl_down_sync(0xffffffffu, cx[q], 2), uy = __shfl_down_sync(0xffffffffu, cy[q], 2);
-                if (shortrun && j + 1 < r) { cx[q] += ux; cy[q] += uy; }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float ux = __shfl_down_sync(0xffffffffu, cx[q], 4), uy = __shfl_down_sync(0xffffffffu, cy[q], 4);
-                if (shortrun && j + 2 < r) { cx[q] += ux; cy[q] += uy; }
-                if (shortrun && j > 0) cv[q] = false;
-            }
-        }
-#endif
+        // every lane holds four contributions (entry g.e[q], F values)
+        float cx[4][F];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            if (cv[q]) PairIO<PT>::red2(grad + g.e[q], cx[q], cy[q]);
+#pragma unroll
+            for (int f = 0; f < F; ++f) cx[q][f] = g.w[q] * gv[f];
+        // Points of one run (consecutive points of the warp in the same cell of this level) merge their contributions before they leave the
+        // warp: the hardware merges different entries of a sector, not lanes that hit the same entry.  The cell key holds 10 bits per axis;
+        // finer levels have no runs worth merging (less than one point per cell).
+        bool issue = live;   // this lane issues its four contributions
+        const bool can_key = L.res[0] <= 1024u && L.res[1] <= 1024u && L.res[2] <= 1024u;
+        if (can_key) {
+            const uint32_t key = live ? g.key : (0xffffffffu - (uint32_t)k);
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 2);
+            const uint32_t hmask = __ballot_sync(0xffffffffu, k == 0 || key != prev || scene_break) & 0x55555555u;  // bit 2k set: point k starts a run
+            if (hmask != 0x55555555u) {
+                // run of my point: points [s0, e0), length r, my position j
+                const uint32_t le = hmask & (0xffffffffu >> (31 - 2 * k));
+                const int s0 = (31 - __clz(le)) >> 1;
+                const uint32_t above = hmask & (0xffffffffu << (2 * k + 1));
+                const int e0 = above ? ((__ffs(above) - 1) >> 1) : 16;
+                const int r = e0 - s0, j = k - s0;
+                const int rmax = __reduce_max_sync(0xffffffffu, r);
+                // segmented reduction towards the head of every run: after the step with distance d, position j holds the sum over
+                // positions [j, min(j + 2d, r)) -- the points of a run are neighbours in the warp, 2 lanes apart
+#pragma unroll
+                for (int d = 1; d < 16; d <<= 1) {
+                    if (d >= rmax) break;   // warp uniform
+                    const bool take = j + d < r;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int f = 0; f < F; ++f) {
+                            const float u = __shfl_down_sync(0xffffffffu, cx[q][f], 2 * d);
+                            if (take) cx[q][f] += u;
+                        }
+                }
+                issue = live && j == 0;
+            }
+        }
+#if NR3D_BWD_TILES
+        const int32_t toff = pl < kMaxTiledLevels ? plan.off[pl] : -1;   // CTA uniform
+        if (toff >= 0) {
+            // tile entry of corner (a, b, c): z fastest for Dense levels (as in the table), x fastest for Hash levels (x ^ h(y, z): the x
+            // neighbours of a cell share a sector 3 times out of 4), so that the flush below leaves in few packets
+            const uint32_t n0 = plan.n[pl][0], n1 = plan.n[pl][1], n2 = plan.n[pl][2];
+            const bool dense = L.type == NR3D_LOD_DENSE;
+            const uint32_t st0 = dense ? n1 * n2 : 1u, st1 = dense ? n2 : n0, st2 = dense ? 1u : n0 * n1;
+            const uint32_t l0 = (g.c[0] - plan.lo[pl][0]) * st0 + (g.c[1] - plan.lo[pl][1]) * st1 + (g.c[2] - plan.lo[pl][2]) * st2;
+            if (issue) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t lq = l0 + (dense ? (q & 1) * st0 + (q >> 1) * st1 + side * st2 : side * st0 + (q & 1) * st1 + (q >> 1) * st2);
+                    float* t = ctile + toff + lq * F;
+#pragma unroll
+                    for (int f = 0; f < F; f += 2) smem_add2(t + f, cx[q][f], cx[q][f + 1]);
+                }
+            }
+            continue;
+        }
+#endif
+        if (issue) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) red_feats<PT, F>(grad + pbase + g.e[q], cx[q]);
+        }
     }
+
+#if NR3D_BWD_TILES
+    // ---- flush the tiles: ONE reduction per touched entry and CTA, consecutive lanes on consecutive entries ----
+    __syncthreads();
+    const uint32_t tbase = s_box[6] == 0xffffffffu ? 0u : s_box[6] * in.n_params;   // the tiled CTA lives in one scene
+    const uint32_t npl = min(in.pl_end, (uint32_t)kMaxTiledLevels);
+    for (uint32_t pl = in.pl_begin; pl < npl; ++pl) {
+        const int32_t toff = plan.off[pl];
+        if (toff < 0) continue;
+        const LevelDesc& L = tab.lv[tab.map_level[pl]];
+        const uint32_t n0 = plan.n[pl][0], n1 = plan.n[pl][1], n2 = plan.n[pl][2];
+        const uint32_t size = n0 * n1 * n2;
+        const bool dense = L.type == NR3D_LOD_DENSE;
+        const bool pow2 = (L.size & (L.size - 1u)) == 0;
+        const uint32_t base = tbase + L.offset + (uint32_t)tab.map_cnt[pl] * F;
+        for (uint32_t e = threadIdx.x; e < size; e += kBwdThreads) {
+            float v[F];
+            bool any = false;
+#pragma unroll
+            for (int f = 0; f < F; f += 2) {
+                const float2 t = *reinterpret_cast<const float2*>(ctile + toff + e * F + f);
+                v[f] = t.x; v[f + 1] = t.y;
+                any = any || t.x != 0.f || t.y != 0.f;
+            }
+            if (!any) continue;   // untouched corner of the bounding box (or a sum that is exactly zero)
+            uint32_t idx;
+            if (dense) {
+                const uint32_t c = e % n2, ab = e / n2, b = ab % n1, a = ab / n1;
+                idx = ((plan.lo[pl][0] + a) * L.res[1] + plan.lo[pl][1] + b) * L.res[2] + plan.lo[pl][2] + c;
+            } else {
+                const uint32_t a = e % n0, bc = e / n0, b = bc % n1, c = bc / n1;
+                const uint32_t h = (plan.lo[pl][0] + a) ^ ((plan.lo[pl][1] + b) * 2654435761u) ^ ((plan.lo[pl][2] + c) * 805459861u);
+                idx = pow2 ? (h & (L.size - 1u)) : (h % L.size);
+            }
+            red_feats<PT, F>(grad + base + idx * L.n_feat, v);
+        }
+    }
+#endif
 }
 
 // Forward with dy/dx (NeuS-style callers need the nablas): same walk as lotd_pair_fwd_kernel plus, per (point, feature), the three
@@ -376,13 +406,14 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
 // 164-378).  dy_dx is written row-major [N, n_enc, 3] at the point's original index through a second staged tile (96 floats per
 // point and 32 features = three coalesced 128-byte stores), accumulated in fp32 for either table type (INPUT_T in the reference).
 constexpr int kDydxThreads = 128;
-constexpr int kDChunk = 16;          // features per staged dy/dx tile (8 pseudo levels): 48 floats = 192 bytes per point and flush
-constexpr int kPairDRowStride = 50;  // floats per staged dy/dx row (48 used): lane (k, side) writes bank 18k + 3 side + const, conflict free
+constexpr int kDChunk = 16;          // features per staged dy/dx tile: 48 floats = 192 bytes per point and flush
+constexpr int kPairDRowStride = 50;  // floats per staged dy/dx row (48 used): lane (k, side) writes bank 18k + 3 side + const, conflict free for F = 2
 
-template <typename PT>
+template <typename PT, int F>
 __global__ void __launch_bounds__(kDydxThreads)
 lotd_pair_fwd_dydx_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT* __restrict__ y, float* __restrict__ dydx) {
     using C = Cvt<PT>;
+    constexpr int H = F / 2;
     const PT* params = reinterpret_cast<const PT*>(in.params);
     __shared__ float rows[kDydxThreads / 32][16 * kPairRowStride];
     __shared__ float drows[kDydxThreads / 32][16 * kPairDRowStride];
@@ -395,57 +426,63 @@ lotd_pair_fwd_dydx_kernel(const __grid_constant__ LotdTable tab, const FastIn in
     float* mydrows = drows[threadIdx.x >> 5];
     float4 rec = make_float4(0.5f, 0.5f, 0.5f, 0.f);
     if (active) rec = __ldcs(in.xs + p);
-    const float x = rec.x, yv = rec.y, z = rec.z;
+    uint32_t scene, pbase;
+    const bool live = point_scene(in, p, active, scene, pbase);
+    const float x = live ? rec.x : 0.5f, yv = live ? rec.y : 0.5f, z = live ? rec.z : 0.5f;
     const uint64_t i = __float_as_uint(rec.w);
     const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
     const uint32_t n_enc = tab.n_enc;
     uint32_t chunk_base = 0, dchunk_base = 0;
     for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
         const uint32_t level = tab.map_level[pl];
-        float r0 = 0.f, r1 = 0.f;
-        float d0[3] = {0.f, 0.f, 0.f}, d1[3] = {0.f, 0.f, 0.f};
+        float r[F], dd[F][3];
+#pragma unroll
+        for (int f = 0; f < F; ++f) { r[f] = 0.f; dd[f][0] = dd[f][1] = dd[f][2] = 0.f; }
         if ((int32_t)level <= in.max_level) {
             Geo2 g;
             float dw[3][4];
-            pair_geo_d(tab.lv[level], (uint32_t)tab.map_cnt[pl] * 2u, smooth, x, yv, z, side, g, dw);
-            float2 v[4];
+            pair_geo_d(tab.lv[level], (uint32_t)tab.map_cnt[pl] * F, smooth, x, yv, z, side, g, dw);
+            float v[4][F];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = PairIO<PT>::load2(params + g.e[q]);
+            for (int q = 0; q < 4; ++q) load_feats<PT, F>(params + pbase + g.e[q], v[q]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                r0 = C::to_f(C::add(C::from_f(r0), C::from_f(g.w[q] * v[q].x)));
-                r1 = C::to_f(C::add(C::from_f(r1), C::from_f(g.w[q] * v[q].y)));
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int d = 0; d < 3; ++d) { d0[d] += dw[d][q] * v[q].x; d1[d] += dw[d][q] * v[q].y; }
-            }
-            r0 = C::to_f(C::add(C::from_f(r0), C::from_f(__shfl_xor_sync(0xffffffffu, r0, 1))));
-            r1 = C::to_f(C::add(C::from_f(r1), C::from_f(__shfl_xor_sync(0xffffffffu, r1, 1))));
-            // lane `side` owns feature 2 * pl + side of its point: it needs its partner's partial sums of that feature only
+                for (int f = 0; f < F; ++f) {
+                    r[f] = C::to_f(C::add(C::from_f(r[f]), C::from_f(g.w[q] * v[q][f])));
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) dd[f][d] += dw[d][q] * v[q][f];
+                }
+#pragma unroll
+            for (int f = 0; f < F; ++f) r[f] = C::to_f(C::add(C::from_f(r[f]), C::from_f(__shfl_xor_sync(0xffffffffu, r[f], 1))));
+        }
+        // lane `side` owns features pl * F + side * H + [0, H) of its point: it needs its partner's partial sums of those features only
+        const uint32_t c = pl * F - chunk_base, dc = pl * F - dchunk_base;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            myrows[k * kPairRowStride + c + side * H + j] = live ? (side ? r[H + j] : r[j]) : 0.f;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                const float give = side ? d0[d] : d1[d];                       // the partner's feature
+                const float give = side ? dd[j][d] : dd[H + j][d];                       // the partner's feature
                 const float take = __shfl_xor_sync(0xffffffffu, give, 1);
-                if (side) d1[d] += take; else d0[d] += take;
+                const float own = (side ? dd[H + j][d] : dd[j][d]) + take;
+                mydrows[k * kPairDRowStride + (dc + side * H + j) * 3 + d] = live ? own : 0.f;
             }
         }
-        const uint32_t c = pl * 2u - chunk_base, dc = pl * 2u - dchunk_base;
-        myrows[k * kPairRowStride + c + side] = side ? r1 : r0;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) mydrows[k * kPairDRowStride + (dc + side) * 3 + d] = side ? d1[d] : d0[d];
         const bool last = (pl + 1 == tab.n_pseudo);
-        const bool flush_y = (c + 2 == 32) || last, flush_d = (dc + 2 == kDChunk) || last;
+        const bool flush_y = (c + F == 32) || last, flush_d = (dc + F == kDChunk) || last;
         if (flush_d) {  // one coalesced y row (every second time) and one and a half coalesced dy/dx lines per point
-            const uint32_t ywidth = c + 2, dwidth = (dc + 2) * 3;
+            const uint32_t ywidth = c + F, dwidth = (dc + F) * 3;
             __syncwarp();
 #pragma unroll 2
-            for (int r = 0; r < 16; ++r) {
-                const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * r);
-                const bool ok = __shfl_sync(0xffffffffu, (int)active, 2 * r);
+            for (int rr = 0; rr < 16; ++rr) {
+                const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * rr);
+                const bool ok = __shfl_sync(0xffffffffu, (int)active, 2 * rr);
                 if (!ok) continue;
-                if (flush_y && (uint32_t)lane < ywidth) st_cs(y + ir * n_enc + chunk_base + lane, C::from_f(myrows[r * kPairRowStride + lane]));
+                if (flush_y && (uint32_t)lane < ywidth) st_cs(y + ir * n_enc + chunk_base + lane, C::from_f(myrows[rr * kPairRowStride + lane]));
                 float* drow = dydx + (ir * n_enc + dchunk_base) * 3;
-                if ((uint32_t)lane < dwidth) __stcs(drow + lane, mydrows[r * kPairDRowStride + lane]);
-                if ((uint32_t)lane + 32u < dwidth) __stcs(drow + 32 + lane, mydrows[r * kPairDRowStride + 32 + lane]);
+                if ((uint32_t)lane < dwidth) __stcs(drow + lane, mydrows[rr * kPairDRowStride + lane]);
+                if ((uint32_t)lane + 32u < dwidth) __stcs(drow + 32 + lane, mydrows[rr * kPairDRowStride + 32 + lane]);
             }
             __syncwarp();
             dchunk_base += kDChunk;
@@ -468,14 +505,63 @@ static int make_table(const nr3d_lotd_meta* m, LotdTable& tab) {
 }
 int make_table_public(const nr3d_lotd_meta* m, LotdTable& tab) { return make_table(m, tab); }  // for lotd_fused.cu
 
-static int check_fast(const nr3d_lotd_meta* m, int32_t param_dtype, uint64_t N) {
+static int check_fast(const nr3d_lotd_meta* m, int32_t param_dtype, uint64_t N, uint32_t n_scenes, const void* table) {
     NR3D_CHECK(m != nullptr, "LoTDEncoding: null meta");
     const bool dtype_ok = param_dtype == NR3D_F32 || param_dtype == NR3D_F16;
-    NR3D_CHECK(m->hash_only && m->n_dims_to_encode == 3 && m->n_feat_per_pseudo_lvl == 2 && dtype_ok,
-               "LoTDEncoding: the sorted fast path needs a Dense/Hash-only meta with D=3, 2 features per pseudo level and fp32 / fp16 params");
+    const uint32_t F = m->n_feat_per_pseudo_lvl;
+    NR3D_CHECK(m->hash_only && m->n_dims_to_encode == 3 && (F == 2 || F == 4 || F == 8) && dtype_ok,
+               "LoTDEncoding: the sorted fast path needs a Dense/Hash-only meta with D=3, 2 / 4 / 8 features per pseudo level and fp32 / fp16 params");
     NR3D_CHECK(N < (1ull << 32), "LoTDEncoding: batch_size must be < 2^32");
+    NR3D_CHECK((uint64_t)(n_scenes ? n_scenes : 1) * m->n_params < (1ull << 32), "LoTDEncoding: the sorted fast path indexes the tables with 32 bits (n_scenes * n_params < 2^32)");
+    NR3D_CHECK((reinterpret_cast<uintptr_t>(table) & 15u) == 0, "LoTDEncoding: the sorted fast path needs 16-byte aligned tables");
     return 0;
 }
+
+// shared memory of the backward kernel: CTA tiles + one staged [16, 32] row tile per warp
+constexpr size_t kBwdSmem = sizeof(float) * ((NR3D_BWD_TILES ? kTileFloats : 0) + kBwdWarps * 16 * kPairRowStride);
+
+template <typename PT, int F, bool SECOND>
+static int launch_bwd(const LotdTable& tab, const FastIn& in, const void* dL_dy, int64_t gs_n, int64_t gs_f, const float* ddx, void* grad, cudaStream_t st) {
+    auto kern = lotd_pair_bwd_kernel<PT, F, SECOND>;
+    static bool configured = false;   // per instantiation; racing threads would set the same value
+    if (!configured) {
+        NR3D_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem) == cudaSuccess, "lotd_fast_bwd: cannot reserve %d bytes of shared memory", (int)kBwdSmem);
+        configured = true;
+    }
+    const unsigned grid = (unsigned)div_up<uint64_t>(2 * in.N, kBwdThreads);
+    kern<<<grid, kBwdThreads, kBwdSmem, st>>>(tab, in, (const PT*)dL_dy, gs_n, gs_f, ddx, (PT*)grad);
+    NR3D_LAUNCH_CHECK(SECOND ? "lotd_fast_bwd2" : "lotd_fast_bwd");
+    return 0;
+}
+
+template <typename PT, int F>
+static int launch_fwd(const LotdTable& tab, const FastIn& in, void* y, int64_t ys_n, int64_t ys_f, cudaStream_t st) {
+    const unsigned grid = (unsigned)div_up<uint64_t>(2 * in.N, kFastThreads);
+    lotd_pair_fwd_kernel<PT, F><<<grid, kFastThreads, 0, st>>>(tab, in, (PT*)y, ys_n, ys_f);
+    NR3D_LAUNCH_CHECK("lotd_fast_fwd");
+    return 0;
+}
+
+template <typename PT, int F>
+static int launch_fwd_dydx(const LotdTable& tab, const FastIn& in, void* y, float* dy_dx, cudaStream_t st) {
+    const unsigned grid = (unsigned)div_up<uint64_t>(2 * in.N, kDydxThreads);
+    lotd_pair_fwd_dydx_kernel<PT, F><<<grid, kDydxThreads, 0, st>>>(tab, in, (PT*)y, dy_dx);
+    NR3D_LAUNCH_CHECK("lotd_fast_fwd_dydx");
+    return 0;
+}
+
+#define NR3D_DISPATCH_PT_F(PDT, FPL, CALL)                                                    \
+    do {                                                                                      \
+        if ((PDT) == NR3D_F16) {                                                              \
+            if ((FPL) == 2) { using PT = __half; constexpr int F = 2; CALL; }                 \
+            else if ((FPL) == 4) { using PT = __half; constexpr int F = 4; CALL; }            \
+            else { using PT = __half; constexpr int F = 8; CALL; }                            \
+        } else {                                                                              \
+            if ((FPL) == 2) { using PT = float; constexpr int F = 2; CALL; }                  \
+            else if ((FPL) == 4) { using PT = float; constexpr int F = 4; CALL; }             \
+            else { using PT = float; constexpr int F = 8; CALL; }                             \
+        }                                                                                     \
+    } while (0)
 
 }  // namespace nr3d
 
@@ -483,99 +569,64 @@ using namespace nr3d;
 
 extern "C" {
 
-int nr3d_lotd_sort_points(uint64_t N, const float* x, void* xs /* float4 [N] */, void* ws, uint64_t* ws_bytes, void* stream) {
-    const uint32_t res = bin_res_for(N);
-    const uint32_t bins = res * res * res;
-    const uint32_t nb = div_up<uint32_t>(bins, kScanBlockF);
-    const uint64_t need = (uint64_t)bins * 4 + (uint64_t)nb * 4 + 64 + N * 8;
-    if (ws == nullptr) {
-        NR3D_CHECK(ws_bytes != nullptr, "sort_points: null ws_bytes");
-        *ws_bytes = need;
-        return 0;
-    }
-    NR3D_CHECK(ws_bytes && *ws_bytes >= need, "sort_points: workspace too small");
-    NR3D_CHECK(N < (1ull << 32), "sort_points: N must be < 2^32");
-    if (N == 0) return 0;
-    NR3D_CHECK(x && xs, "sort_points: null argument");
-    NR3D_CHECK((reinterpret_cast<uintptr_t>(xs) & 15u) == 0 && (reinterpret_cast<uintptr_t>(ws) & 15u) == 0, "sort_points: xs / ws must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
-    uint32_t* hist = reinterpret_cast<uint32_t*>(ws);
-    uint32_t* bs = hist + bins;
-    uint2* keyrank = reinterpret_cast<uint2*>(reinterpret_cast<char*>(ws) + (((uint64_t)bins * 4 + (uint64_t)nb * 4 + 63) / 64) * 64);
-    cudaMemsetAsync(hist, 0, (size_t)bins * 4, st);
-    const unsigned grid = (unsigned)div_up<uint64_t>(N, 256);
-    sort_hist_kernel<<<grid, 256, 0, st>>>(N, res, x, hist, keyrank);
-    NR3D_LAUNCH_CHECK("sort_hist");
-    scanu_block_sums<<<nb, kScanBlockF, 0, st>>>(bins, hist, bs);
-    NR3D_LAUNCH_CHECK("sort_scan1");
-    scanu_of_sums<<<1, kScanBlockF, 0, st>>>(nb, bs);
-    NR3D_LAUNCH_CHECK("sort_scan2");
-    scanu_apply<<<nb, kScanBlockF, 0, st>>>(bins, hist, bs);
-    NR3D_LAUNCH_CHECK("sort_scan3");
-    sort_scatter_kernel<<<grid, 256, 0, st>>>(N, x, keyrank, hist, reinterpret_cast<float4*>(xs));
-    NR3D_LAUNCH_CHECK("sort_scatter");
-    return 0;
-}
-
-int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* params,
-                         int32_t max_level, void* y, int64_t y_stride_n, int64_t y_stride_f, void* stream) {
-    if (int rc = check_fast(meta, param_dtype, N)) return rc;
+int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
+                         const void* params, int32_t max_level, void* y, int64_t y_stride_n, int64_t y_stride_f, void* stream) {
+    if (int rc = check_fast(meta, param_dtype, N, n_scenes, params)) return rc;
     if (N == 0) return 0;
     NR3D_CHECK(xs && params && y, "LoTDEncoding::fwd_sorted: null argument");
     LotdTable tab;
     make_table(meta, tab);
-    FastIn in{N, reinterpret_cast<const float4*>(xs), params, max_level, (uint32_t)((reinterpret_cast<uintptr_t>(params) & 15u) == 0)};
-    const unsigned grid = (unsigned)div_up<uint64_t>(2 * N, kFastThreads);
-    if (param_dtype == NR3D_F16) lotd_pair_fwd_kernel<__half><<<grid, kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (__half*)y, y_stride_n, y_stride_f);
-    else lotd_pair_fwd_kernel<float><<<grid, kFastThreads, 0, (cudaStream_t)stream>>>(tab, in, (float*)y, y_stride_n, y_stride_f);
-    NR3D_LAUNCH_CHECK("lotd_fast_fwd");
-    return 0;
+    FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, params, max_level, meta->n_params, 0u, meta->n_pseudo_levels};
+    int rc = 0;
+    NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl, (rc = launch_fwd<PT, F>(tab, in, y, y_stride_n, y_stride_f, (cudaStream_t)stream)));
+    return rc;
 }
 
-int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* dL_dy,
-                               int64_t dLdy_stride_n, int64_t dLdy_stride_f, int32_t max_level, void* dL_dparam, void* stream) {
-    if (int rc = check_fast(meta, param_dtype, N)) return rc;
+int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
+                               const void* dL_dy, int64_t dLdy_stride_n, int64_t dLdy_stride_f, int32_t max_level, uint32_t pl_begin, uint32_t pl_end,
+                               void* dL_dparam, void* stream) {
+    if (int rc = check_fast(meta, param_dtype, N, n_scenes, dL_dparam)) return rc;
+    if (pl_begin >= pl_end) return 0;
     if (N == 0) return 0;
     NR3D_CHECK(xs && dL_dy && dL_dparam, "LoTDEncoding::bwd_sorted: null argument");
     LotdTable tab;
     make_table(meta, tab);
-    FastIn in{N, reinterpret_cast<const float4*>(xs), nullptr, max_level, 1u};
-    const unsigned grid = (unsigned)div_up<uint64_t>(2 * N, kBwdThreads);
-    if (param_dtype == NR3D_F16) lotd_pair_bwd_kernel<__half, false><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const __half*)dL_dy, dLdy_stride_n, dLdy_stride_f, nullptr, (__half*)dL_dparam);
-    else lotd_pair_bwd_kernel<float, false><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, nullptr, (float*)dL_dparam);
-    NR3D_LAUNCH_CHECK("lotd_fast_bwd");
-    return 0;
+    const uint32_t pl_stop = (pl_end < meta->n_pseudo_levels) ? pl_end : meta->n_pseudo_levels;
+    FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, nullptr, max_level, meta->n_params, pl_begin, pl_stop};
+    int rc = 0;
+    NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl,
+                       (rc = launch_bwd<PT, F, false>(tab, in, dL_dy, dLdy_stride_n, dLdy_stride_f, nullptr, dL_dparam, (cudaStream_t)stream)));
+    return rc;
 }
 
-int nr3d_lotd_fwd_dydx_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* params,
-                              int32_t max_level, void* y, void* dy_dx, void* stream) {
-    if (int rc = check_fast(meta, param_dtype, N)) return rc;
+int nr3d_lotd_fwd_dydx_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
+                              const void* params, int32_t max_level, void* y, void* dy_dx, void* stream) {
+    if (int rc = check_fast(meta, param_dtype, N, n_scenes, params)) return rc;
     if (N == 0) return 0;
     NR3D_CHECK(xs && params && y && dy_dx, "LoTDEncoding::fwd_dydx_sorted: null argument");
     LotdTable tab;
     make_table(meta, tab);
-    FastIn in{N, reinterpret_cast<const float4*>(xs), params, max_level, (uint32_t)((reinterpret_cast<uintptr_t>(params) & 15u) == 0)};
-    const unsigned grid = (unsigned)div_up<uint64_t>(2 * N, kDydxThreads);
-    if (param_dtype == NR3D_F16) lotd_pair_fwd_dydx_kernel<__half><<<grid, kDydxThreads, 0, (cudaStream_t)stream>>>(tab, in, (__half*)y, (float*)dy_dx);
-    else lotd_pair_fwd_dydx_kernel<float><<<grid, kDydxThreads, 0, (cudaStream_t)stream>>>(tab, in, (float*)y, (float*)dy_dx);
-    NR3D_LAUNCH_CHECK("lotd_fast_fwd_dydx");
-    return 0;
+    FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, params, max_level, meta->n_params, 0u, meta->n_pseudo_levels};
+    int rc = 0;
+    NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl, (rc = launch_fwd_dydx<PT, F>(tab, in, y, (float*)dy_dx, (cudaStream_t)stream)));
+    return rc;
 }
 
-int nr3d_lotd_bwd_param2_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const void* dL_dy,
-                                int64_t dLdy_stride_n, int64_t dLdy_stride_f, const float* dL_ddLdx, int32_t max_level, void* dL_dparam,
-                                void* stream) {
-    if (int rc = check_fast(meta, param_dtype, N)) return rc;
+int nr3d_lotd_bwd_param2_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
+                                const void* dL_dy, int64_t dLdy_stride_n, int64_t dLdy_stride_f, const float* dL_ddLdx, int32_t max_level,
+                                void* dL_dparam, void* stream) {
+    const uint32_t pl_begin = 0, pl_end = meta ? meta->n_pseudo_levels : 0;
+    if (int rc = check_fast(meta, param_dtype, N, n_scenes, dL_dparam)) return rc;
     if (N == 0) return 0;
     NR3D_CHECK(xs && dL_dy && dL_ddLdx && dL_dparam, "LoTDEncoding::bwd_param2_sorted: null argument");
     LotdTable tab;
     make_table(meta, tab);
-    FastIn in{N, reinterpret_cast<const float4*>(xs), nullptr, max_level, 1u};
-    const unsigned grid = (unsigned)div_up<uint64_t>(2 * N, kBwdThreads);
-    if (param_dtype == NR3D_F16) lotd_pair_bwd_kernel<__half, true><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const __half*)dL_dy, dLdy_stride_n, dLdy_stride_f, dL_ddLdx, (__half*)dL_dparam);
-    else lotd_pair_bwd_kernel<float, true><<<grid, kBwdThreads, 0, (cudaStream_t)stream>>>(tab, in, (const float*)dL_dy, dLdy_stride_n, dLdy_stride_f, dL_ddLdx, (float*)dL_dparam);
-    NR3D_LAUNCH_CHECK("lotd_fast_bwd2");
-    return 0;
+    const uint32_t pl_stop = (pl_end < meta->n_pseudo_levels) ? pl_end : meta->n_pseudo_levels;
+    FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, nullptr, max_level, meta->n_params, pl_begin, pl_stop};
+    int rc = 0;
+    NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl,
+                       (rc = launch_bwd<PT, F, true>(tab, in, dL_dy, dLdy_stride_n, dLdy_stride_f, dL_ddLdx, dL_dparam, (cudaStream_t)stream)));
+    return rc;
 }
 
 }  // extern "C"

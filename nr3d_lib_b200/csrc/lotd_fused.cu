@@ -245,7 +245,7 @@ extern "C" int nr3d_lotd_fused_density_fwd(const nr3d_lotd_meta* meta, uint64_t 
                "fused_density: packed weights / out16 must be 16-byte aligned");
     LotdTable tab;
     make_table_public(meta, tab);
-    FastIn in{N, reinterpret_cast<const float4*>(xs), params, max_level, 1u};
+    FastIn in{N, reinterpret_cast<const float4*>(xs), nullptr, params, max_level, meta->n_params, 0u, meta->n_pseudo_levels};
     FusedDec dec{reinterpret_cast<const uint4*>(w1_packed), reinterpret_cast<const uint4*>(w2_packed), b1, b2, activation};
     const uint64_t n_tiles = div_up<uint64_t>(N, 128);
     const unsigned grid = (unsigned)(n_tiles < (uint64_t)kSMs * kFusedCtasPerSm ? n_tiles : (uint64_t)kSMs * kFusedCtasPerSm);

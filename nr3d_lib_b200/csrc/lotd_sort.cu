@@ -1,0 +1,266 @@
+// lotd_sort.cu -- counting sort of the query points by (scene, cell bin) for the cell-sorted LoTD fast path (lotd_fast.cu), with a
+// device-side check of whether the records of an earlier call are still current.
+//
+// Why the check lives on the device: lod_fwd and lod_bwd of one training step see the same points, so the sort should run once per step.
+// The reference's autograd wrappers (nr3d_lib/models/grid_encodings/lotd/lotd.py:60-119) hand the same tensor to both calls but offer no
+// way to pass our sorted records along.  A host-side cache keyed on the tensor's address / version counter is blind to writes that do
+// not bump the counter (`x.data.mul_()`, raw kernels, dlpack aliases).  So every call fingerprints the points it was given (one pass over
+// x, 12 bytes per point) and compares with the fingerprint stored next to the records; the sort kernels return at once when it matches.
+// Nothing is read back to the host; everything is ordered on the caller's stream.
+//
+//   verify   1 launch   64-bit sum + xor of a per-point hash of (x, y, z, index, scene); last block: compare, set `skip`, clear the scan state
+//   hist     1 launch   bin key -> rank inside the bin (atomic counter), 4 bytes per point kept
+//   scan     1 launch   decoupled look-back exclusive scan of the bin counters; zeroes the counters for the next call
+//   scatter  1 launch   16-byte records (x, y, z, original index) [+ uint16 scene] written at offsets[key] + rank
+#include "lotd_pair.cuh"
+
+namespace nr3d {
+
+#ifndef NR3D_BIN_RES        // 0: chosen per call from the number of points (about two points per bin), else fixed (A/B runs)
+#define NR3D_BIN_RES 0
+#endif
+
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;                        // per thread
+constexpr int kScanTile = kScanThreads * kScanItems;   // counters per tile
+constexpr uint32_t kMaxTiles = 8192;                 // 2^25 counters
+constexpr uint64_t kHeaderBytes = 256;
+
+struct SortHeader {
+    unsigned long long fp_sum, fp_xor, fp_n;      // fingerprint (and point count / scene configuration) the records in `xs` were built from
+    unsigned long long acc_sum, acc_xor;          // accumulators of the running verify pass (zero between calls)
+    uint32_t blocks_done;                         // last-block detection (zero between calls)
+    uint32_t skip;                                // verdict of the last verify pass: 1 = records are current
+    uint32_t tile_counter;                        // scan: dynamic tile ids (zero at scan start)
+    uint32_t pad;
+};
+
+// bins per axis: about two points per bin (A/B on B200: 4 Mi uniform points 128^3 > 64^3, 256^3; 30 Mi ray samples 256^3 > 192^3 > 128^3,
+// profiles/r1_ab_tunables.txt); with several scenes every scene gets its own bin grid.
+static inline uint32_t bin_res_for(uint64_t N, uint32_t n_scenes) {
+    if (NR3D_BIN_RES) return NR3D_BIN_RES;
+    const uint64_t per = N / (n_scenes ? n_scenes : 1);
+    if (per >= (12ull << 20)) return 256u;
+    if (per >= (1536ull << 10)) return 128u;
+    if (per >= (192ull << 10)) return 64u;
+    return 32u;
+}
+
+__device__ __forceinline__ uint32_t bin_key(float x, float y, float z, uint32_t res) {
+    const uint32_t bx = min(res - 1, (uint32_t)fmaxf(x * (float)res, 0.f));
+    const uint32_t by = min(res - 1, (uint32_t)fmaxf(y * (float)res, 0.f));
+    const uint32_t bz = min(res - 1, (uint32_t)fmaxf(z * (float)res, 0.f));
+    return bin_order(bx, by, bz, res);
+}
+
+// scene of point i: 0 for single-scene calls, 0xffff for skipped points (batch_inds < 0 or out of range)
+__device__ __forceinline__ uint32_t scene_of(uint64_t i, const int64_t* __restrict__ batch_inds, uint32_t bds, uint32_t n_scenes) {
+    if (batch_inds) {
+        const int64_t b = __ldg(batch_inds + i);
+        return (b < 0 || b >= (int64_t)n_scenes) ? 0xffffu : (uint32_t)b;
+    }
+    if (bds) {
+        const uint64_t b = i / bds;
+        return b >= n_scenes ? 0xffffu : (uint32_t)b;
+    }
+    return 0u;
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {  // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) sort_verify_kernel(uint64_t N, const float* __restrict__ x, const int64_t* __restrict__ batch_inds, uint32_t bds,
+                                                          uint32_t n_scenes, uint32_t res, int force, SortHeader* __restrict__ hdr,
+                                                          unsigned long long* __restrict__ status, uint32_t n_tiles) {
+    __shared__ unsigned long long s_sum, s_xor;
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) { s_sum = 0; s_xor = 0; }
+    __syncthreads();
+    unsigned long long sum = 0, xr = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t a = __float_as_uint(__ldcs(x + i * 3)), b = __float_as_uint(__ldcs(x + i * 3 + 1)), c = __float_as_uint(__ldcs(x + i * 3 + 2));
+        const uint32_t sc = scene_of(i, batch_inds, bds, n_scenes);
+        const unsigned long long h = mix64((((unsigned long long)a << 32) | b) ^ mix64((((unsigned long long)c << 32) | (uint32_t)i) + ((unsigned long long)sc << 48) + 0x9e3779b97f4a7c15ull));
+        sum += h; xr ^= h;
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, m);
+        xr ^= __shfl_xor_sync(0xffffffffu, xr, m);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_sum, sum); atomicXor(&s_xor, xr); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(&hdr->acc_sum, s_sum);
+        atomicXor(&hdr->acc_xor, s_xor);
+        __threadfence();
+        s_last = atomicAdd(&hdr->blocks_done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    __shared__ bool s_same;
+    if (threadIdx.x == 0) {
+        const unsigned long long fs = atomicAdd(&hdr->acc_sum, 0ull), fx = atomicAdd(&hdr->acc_xor, 0ull);
+        const unsigned long long fn = N ^ ((unsigned long long)n_scenes << 40) ^ ((unsigned long long)res << 52);
+        const bool same = !force && fs == hdr->fp_sum && fx == hdr->fp_xor && fn == hdr->fp_n;
+        hdr->fp_sum = fs; hdr->fp_xor = fx; hdr->fp_n = fn;
+        hdr->skip = same ? 1u : 0u;
+        hdr->acc_sum = 0; hdr->acc_xor = 0; hdr->blocks_done = 0; hdr->tile_counter = 0;
+        s_same = same;
+    }
+    __syncthreads();
+    if (!s_same)
+        for (uint32_t t = threadIdx.x; t < n_tiles; t += blockDim.x) status[t] = 0ull;
+}
+
+// pass 1: rank of the point inside its bin (the rank makes the scatter pass atomic-free)
+__global__ void __launch_bounds__(256) sort_hist_kernel(uint64_t N, uint32_t res, uint32_t n_scenes, const float* __restrict__ x,
+                                                        const int64_t* __restrict__ batch_inds, uint32_t bds, const SortHeader* __restrict__ hdr,
+                                                        uint32_t* __restrict__ hist, uint32_t* __restrict__ rank) {
+    if (hdr->skip) return;
+    const uint32_t bins = res * res * res;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t sc = scene_of(i, batch_inds, bds, n_scenes);
+        const uint32_t k = sc == 0xffffu ? n_scenes * bins : sc * bins + bin_key(x[i * 3], x[i * 3 + 1], x[i * 3 + 2], res);
+        rank[i] = atomicAdd(hist + k, 1u);
+    }
+}
+
+// single-pass exclusive scan (decoupled look-back): hist -> offsets; the counters are zeroed on the way for the next call
+constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kFlagMask = 3ull << 62;
+__global__ void __launch_bounds__(kScanThreads) sort_scan_kernel(uint32_t n, SortHeader* __restrict__ hdr, uint32_t* __restrict__ hist,
+                                                                 uint32_t* __restrict__ offsets, unsigned long long* __restrict__ status) {
+    if (hdr->skip) return;
+    __shared__ uint32_t s_tile, s_prefix, ws[32];
+    if (threadIdx.x == 0) s_tile = atomicAdd(&hdr->tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    if (base + kScanItems <= n) {
+        const uint4 t = *reinterpret_cast<const uint4*>(hist + base);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        *reinterpret_cast<uint4*>(hist + base) = make_uint4(0, 0, 0, 0);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            v[k] = base + k < n ? hist[base + k] : 0u;
+            if (base + k < n) hist[base + k] = 0u;
+        }
+    }
+    const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+    uint32_t s = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, s, d); if ((threadIdx.x & 31) >= d) s += t; }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = ws[threadIdx.x];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, d); if (threadIdx.x >= d) w += t; }
+        ws[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const uint32_t excl = ((threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0u) + s - mine;  // exclusive prefix of this thread inside the tile
+    if (threadIdx.x == 0) {
+        const uint32_t total = ws[31];
+        uint32_t run = 0;
+        if (tile == 0) {
+            atomicExch(status, kFlagPrefix | total);
+        } else {
+            atomicExch(status + tile, kFlagAgg | total);
+            for (int j = (int)tile - 1; j >= 0; --j) {
+                unsigned long long st;
+                do { st = *reinterpret_cast<volatile unsigned long long*>(status + j); } while ((st & kFlagMask) == 0ull);
+                run += (uint32_t)st;
+                if ((st & kFlagMask) == kFlagPrefix) break;
+            }
+            atomicExch(status + tile, kFlagPrefix | (unsigned long long)(run + total));
+        }
+        s_prefix = run;
+    }
+    __syncthreads();
+    uint32_t o = s_prefix + excl;
+    if (base + kScanItems <= n) {
+        uint4 t;
+        t.x = o; o += v[0]; t.y = o; o += v[1]; t.z = o; o += v[2]; t.w = o;
+        *reinterpret_cast<uint4*>(offsets + base) = t;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) { if (base + k < n) offsets[base + k] = o; o += v[k]; }
+    }
+}
+
+// pass 2: sorted record = (x, y, z, original index) written with ONE 16-byte store per point (+ the scene for batched calls)
+__global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t N, uint32_t res, uint32_t n_scenes, const float* __restrict__ x,
+                                                           const int64_t* __restrict__ batch_inds, uint32_t bds, const SortHeader* __restrict__ hdr,
+                                                           const uint32_t* __restrict__ rank, const uint32_t* __restrict__ offsets,
+                                                           float4* __restrict__ xs, uint16_t* __restrict__ scenes) {
+    if (hdr->skip) return;
+    const uint32_t bins = res * res * res;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float px = x[i * 3], py = x[i * 3 + 1], pz = x[i * 3 + 2];
+        const uint32_t sc = scene_of(i, batch_inds, bds, n_scenes);
+        const uint32_t k = sc == 0xffffu ? n_scenes * bins : sc * bins + bin_key(px, py, pz, res);
+        const uint32_t pos = __ldg(offsets + k) + __ldcs(rank + i);
+        xs[pos] = make_float4(px, py, pz, __uint_as_float((uint32_t)i));
+        if (scenes) scenes[pos] = (uint16_t)sc;
+    }
+}
+
+}  // namespace nr3d
+
+using namespace nr3d;
+
+extern "C" {
+
+int nr3d_lotd_sort_points(uint64_t N, const float* x, const int64_t* batch_inds, uint32_t batch_data_size, uint32_t n_scenes, int32_t force,
+                          void* xs /* float4 [N] */, uint16_t* scenes /* [N] or NULL */, void* ws, uint64_t* ws_bytes, void* stream) {
+    if (n_scenes == 0) n_scenes = 1;
+    NR3D_CHECK(n_scenes < 0xffffu, "sort_points: at most 65534 scenes");
+    const uint32_t res = bin_res_for(N, n_scenes);
+    const uint64_t n_cnt64 = (uint64_t)n_scenes * res * res * res + 1;   // one extra bucket for skipped points
+    NR3D_CHECK(n_cnt64 <= (uint64_t)kMaxTiles * kScanTile, "sort_points: too many scenes for the bin grid (%llu counters)", (unsigned long long)n_cnt64);
+    const uint32_t n_cnt = (uint32_t)n_cnt64;
+    const uint32_t n_tiles = div_up<uint32_t>(n_cnt, kScanTile);
+    const uint64_t cnt_bytes = div_up<uint64_t>((uint64_t)n_cnt * 4, 256) * 256;
+    const uint64_t need = kHeaderBytes + (uint64_t)kMaxTiles * 8 + 2 * cnt_bytes + div_up<uint64_t>(N * 4, 256) * 256;
+    if (ws == nullptr) {
+        NR3D_CHECK(ws_bytes != nullptr, "sort_points: null ws_bytes");
+        *ws_bytes = need;
+        return 0;
+    }
+    NR3D_CHECK(ws_bytes && *ws_bytes >= need, "sort_points: workspace too small");
+    NR3D_CHECK(N < (1ull << 32), "sort_points: N must be < 2^32");
+    if (N == 0) return 0;
+    NR3D_CHECK(x && xs, "sort_points: null argument");
+    NR3D_CHECK((batch_inds == nullptr && batch_data_size == 0 && n_scenes == 1) || scenes != nullptr, "sort_points: batched calls need the `scenes` output");
+    NR3D_CHECK((reinterpret_cast<uintptr_t>(xs) & 15u) == 0 && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "sort_points: xs must be 16-byte, ws 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w = reinterpret_cast<char*>(ws);
+    SortHeader* hdr = reinterpret_cast<SortHeader*>(w);
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(w + kHeaderBytes);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(w + kHeaderBytes + (uint64_t)kMaxTiles * 8);
+    uint32_t* offsets = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(hist) + cnt_bytes);
+    uint32_t* rank = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(offsets) + cnt_bytes);
+    // a few CTAs per SM with grid-stride loops: when the records are current, the three sort kernels cost an (almost) empty launch each
+    const uint64_t gwant = div_up<uint64_t>(N, 256);
+    const unsigned grid = (unsigned)(gwant < (uint64_t)kSMs * 16 ? gwant : (uint64_t)kSMs * 16);
+    const uint64_t vwant = div_up<uint64_t>(N, 256 * 8);
+    const unsigned vgrid = (unsigned)(vwant < (uint64_t)kSMs * 8 ? vwant : (uint64_t)kSMs * 8);
+    sort_verify_kernel<<<vgrid, 256, 0, st>>>(N, x, batch_inds, batch_data_size, n_scenes, res, force, hdr, status, n_tiles);
+    NR3D_LAUNCH_CHECK("sort_verify");
+    sort_hist_kernel<<<grid, 256, 0, st>>>(N, res, n_scenes, x, batch_inds, batch_data_size, hdr, hist, rank);
+    NR3D_LAUNCH_CHECK("sort_hist");
+    sort_scan_kernel<<<n_tiles, kScanThreads, 0, st>>>(n_cnt, hdr, hist, offsets, status);
+    NR3D_LAUNCH_CHECK("sort_scan");
+    sort_scatter_kernel<<<grid, 256, 0, st>>>(N, res, n_scenes, x, batch_inds, batch_data_size, hdr, rank, offsets, reinterpret_cast<float4*>(xs), scenes);
+    NR3D_LAUNCH_CHECK("sort_scatter");
+    return 0;
+}
+
+}  // extern "C"

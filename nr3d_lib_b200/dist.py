@@ -52,6 +52,123 @@ def allreduce_param_grads(grad: torch.Tensor, world: Optional[int] = None, async
     return dist.all_reduce(grad, op=dist.ReduceOp.SUM, async_op=async_op)
 
 
+class GradReducer:
+    """Sum of dL/dparams over the ranks, once per step, in one of three ways (`mode`):
+
+      "allreduce"  one blocking all-reduce of the whole table after the scatter (round 1; SURVEY.md 8e baseline)
+      "bucketed"   the scatter runs fine levels first; the all-reduce of their part of the table (2/3 of the bytes for the NGP ladder)
+                   is issued asynchronously and overlaps the scatter of the coarse levels; only the coarse part's all-reduce is exposed
+      "scatter"    reduce-scatter: every rank ends with ITS contiguous 1/world slice of the summed table (what a sharded optimizer or the
+                   host-fed driver needs: pipeline.HostFedLoTDStep returns each slice to the host from its own rank) -- half the NVLink bytes
+
+    Usage per step:  (lod_bwd runs, the hook fires)  ->  out = reducer.reduce(grad)   # "scatter": out is the rank's slice, else `grad`.
+    The hook is installed with `bindings._lotd.set_grad_bucket_hook`; call close() to remove it."""
+
+    def __init__(self, meta, world: int, device, mode: str = "bucketed"):
+        from .bindings import _lotd
+        self._lotd, self.meta, self.world, self.mode, self.device = _lotd, meta, int(world), mode, device
+        self.pending = []
+        self.active = self.world > 1 and dist.is_available() and dist.is_initialized()
+        if mode not in ("allreduce", "bucketed", "scatter"):
+            raise RuntimeError(f"GradReducer: unknown mode {mode!r}")
+        if self.active and mode == "bucketed":
+            _lotd.set_grad_bucket_hook(self._on_part)
+        self._slice = None
+
+    def _on_part(self, grad, lo, hi):
+        # issued on NCCL's stream behind everything already queued on the current stream: overlaps what the caller launches next
+        self.pending.append((lo, hi, dist.all_reduce(grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True)))
+
+    def reduce(self, grad: torch.Tensor) -> torch.Tensor:
+        if not self.active:
+            return grad
+        if self.mode == "bucketed":
+            covered = sorted((lo, hi) for lo, hi, _ in self.pending)
+            pos = 0
+            for lo, hi in covered:
+                if lo != pos:
+                    break
+                pos = hi
+            if pos != grad.shape[0]:        # the hook did not fire (generic path / batched call): reduce the whole table now
+                for _, _, w in self.pending:
+                    w.wait()
+                self.pending = []
+                dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+                return grad
+            for _, _, w in self.pending:
+                w.wait()                    # the current stream waits for the collective; the host does not block
+            self.pending = []
+            return grad
+        if self.mode == "scatter":
+            n = grad.shape[0]
+            per = (n + self.world - 1) // self.world
+            if per * self.world != n:       # pad to a multiple of the world size (the NGP table divides evenly for 2 / 4 / 8 ranks)
+                g = torch.zeros(per * self.world, dtype=grad.dtype, device=grad.device)
+                g[:n] = grad
+            else:
+                g = grad
+            out = torch.empty(per, dtype=grad.dtype, device=grad.device)
+            dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM)
+            return out
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+        return grad
+
+    def slice_range(self, n: int, rank: int):
+        """[begin, end) of the table that `reduce` returns on `rank` in "scatter" mode."""
+        per = (n + self.world - 1) // self.world
+        return rank * per, min(n, (rank + 1) * per)
+
+    def close(self):
+        if self.active and self.mode == "bucketed":
+            self._lotd.set_grad_bucket_hook(None)
+
+
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Run this process (and allocate its pinned host buffers) on the NUMA node the GPU hangs off: with 8 ranks on one box the default
+    placement puts every rank's staging buffers on node 0 and half of the host<->device traffic crosses the socket interconnect.
+    Tries, in order, CPU affinity (first-touch then allocates locally) and a MPOL_PREFERRED memory policy.  Returns what it did (for the
+    bench line); never raises."""
+    info = {"gpu": int(local_rank), "node": None, "cpu_affinity": None, "mempolicy": None}
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bus is None:
+            import subprocess
+            bus = subprocess.run(["nvidia-smi", f"--id={local_rank}", "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True,
+                                 text=True, timeout=10).stdout.strip()
+        bus = str(bus).lower()
+        if len(bus.split(":")[0]) == 8:      # nvidia-smi prints an 8-digit domain, sysfs uses 4
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        want = cpus & allowed
+        if want:
+            os.sched_setaffinity(0, want)
+            info["cpu_affinity"] = f"{len(want)} cpus of node {node}"
+        else:
+            info["cpu_affinity"] = f"node {node} cpus not in the allowed set ({len(allowed)} cpus)"
+        try:
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            MPOL_PREFERRED, SYS_set_mempolicy = 1, 238      # x86-64
+            rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))
+            info["mempolicy"] = "preferred node %d" % node if rc == 0 else "set_mempolicy failed (errno %d)" % ctypes.get_errno()
+        except Exception as e:  # pragma: no cover
+            info["mempolicy"] = f"unavailable ({e})"
+    except Exception as e:
+        info["error"] = str(e)[:200]
+    return info
+
+
 def max_over_ranks(value: float, device=None) -> float:
     """max of a python float over all ranks (device-side timing is reported as the slowest rank's)."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:

@@ -63,7 +63,7 @@ class FusedDensityDecoder:
             sigma = torch.empty([N], dtype=torch.float32, device=dev)
             out16 = torch.empty([N, 16], dtype=torch.float32, device=dev) if return_output else None
             if N:
-                xs = _lotd._sorted_points(x)
+                xs, _ = _lotd._sorted_points(x)
                 _lib.check(_lib.get_lib().nr3d_lotd_fused_density_fwd(
                     ctypes.byref(self.meta._c), N, xs.data_ptr(), params.data_ptr(), ml, self.w1p.data_ptr(), _lib.ptr(self.b1),
                     self.w2p.data_ptr(), self.b2.data_ptr(), self.activation, sigma.data_ptr(), _lib.ptr(out16), _lib.stream_of(dev)))

@@ -107,9 +107,12 @@ class HostFedLoTDStep:
             pipe.step(x_host[i + 1] if i + 1 < steps else None, grad_host[i % 2])
         pipe.drain()                    # the compute stream waits for the last device->host copy
 
-    `x_host` / `grad_host` must be pinned.  `grad_of_y` stands for whatever turns the step's features into dL/dy on the
-    device (decoder + loss); with world > 1 the gradients are all-reduced (one NCCL call) before they leave the device and every
-    rank writes only its own contiguous 1/world slice of `grad_host` (`dist.shard_range`), so the job returns the result once.
+    `x_host` / `grad_host` must be pinned (allocate them after `dist.bind_to_gpu_numa`, so that they live on the GPU's NUMA node).
+    `grad_of_y` stands for whatever turns the step's features into dL/dy on the device (decoder + loss); with world > 1 the gradients are
+    summed with ONE reduce-scatter (`dist.GradReducer(mode="scatter")`): every rank ends with its own contiguous 1/world slice of the
+    summed table and writes exactly that slice of `grad_host`, so the job returns the result once and NVLink carries half the bytes of an
+    all-reduce.  Consecutive steps must bring different points (a trainer always does): the forward sorts them, the backward reuses the
+    records after the on-device fingerprint check (bindings/_lotd.py).
     """
 
     def __init__(self, meta, params: torch.Tensor, n_points: int, device, grad_of_y, world: int = 1, rank: int = 0):
@@ -123,6 +126,8 @@ class HostFedLoTDStep:
         self.x_free = [torch.cuda.Event(), torch.cuda.Event()]      # kernels reading buffer b finished
         self.inflight = []                                          # (event, grad tensor) of pending device->host copies
         self.slot = 0
+        from . import dist as ndist
+        self.reducer = ndist.GradReducer(meta, world, self.dev, mode="scatter")
         for e in self.x_free:
             e.record(self.compute)
 
@@ -141,27 +146,26 @@ class HostFedLoTDStep:
             self.prefetch(next_x_host)                              # goes into the other buffer, overlaps the kernels below
         self.compute.wait_event(self.x_ready[b])
         x = self.xbuf[b]
-        self._lotd.clear_sort_cache()
         y, _ = self._lotd.lod_fwd(self.meta, x, self.params, need_input_grad=False)
         gy = self.grad_of_y(y)
         _, g = self._lotd.lod_bwd(self.meta, gy, x, self.params, None, need_input_grad=False, need_param_grad=True)
         self.x_free[b].record(self.compute)
         lo, hi = 0, g.shape[0]
+        out = g
         if self.world > 1:
-            ndist.allreduce_param_grads(g, self.world)
-            # every rank now holds the same summed gradient: each returns its own 1/world slice to the host, so the job reads the
-            # result back exactly once instead of `world` identical copies competing for the host's memory bandwidth
-            lo, hi = ndist.shard_range(g.shape[0], self.rank, self.world)
+            # reduce-scatter: this rank now holds the summed gradient of its own 1/world slice and returns exactly that slice to the host
+            out = self.reducer.reduce(g)
+            lo, hi = self.reducer.slice_range(g.shape[0], self.rank)
         done = torch.cuda.Event()
         done.record(self.compute)
         self.d2h.wait_event(done)
         with torch.cuda.stream(self.d2h):
-            grad_host[lo:hi].copy_(g[lo:hi], non_blocking=True)
+            grad_host[lo:hi].copy_(out[: hi - lo], non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(self.d2h)
-        g.record_stream(self.d2h)
-        self.inflight = [(e, t) for (e, t) in self.inflight if not e.query()] + [(copied, g)]
-        return g
+        out.record_stream(self.d2h)
+        self.inflight = [(e, t) for (e, t) in self.inflight if not e.query()] + [(copied, out)]
+        return out
 
     def drain(self):
         for e, _ in self.inflight:

@@ -105,6 +105,33 @@ def ext_specs(scratch):
     }
 
 
+# The reference's own PYTHON wrappers of the hot path (autograd Functions, pack helpers, marcher post-processing) and the two pure-torch
+# baselines BASELINE.json names.  They are staged VERBATIM into the git-ignored oracle/_ref/pyref/ (like the compiled .so files: out of
+# history, shipped to the GPU box by gpurun) so that the GPU tests can run the UNMODIFIED reference files on top of the injected
+# nr3d_lib.bindings.* shims (tests/util.py:reference_wrappers) -- /root/reference itself does not exist on the GPU box.
+PY_STAGE = ["nr3d_lib/profile.py", "nr3d_lib/fmt.py", "nr3d_lib/distributed.py",
+            "nr3d_lib/models/grid_encodings/lotd/lotd.py", "nr3d_lib/models/grid_encodings/lotd/lotd_helpers.py",
+            "nr3d_lib/graphics/pack_ops/__init__.py", "nr3d_lib/graphics/pack_ops/pack_ops.py",
+            "nr3d_lib/graphics/raymarch/__init__.py", "nr3d_lib/graphics/raymarch/occgrid_raymarch.py",
+            "nr3d_lib/graphics/nerf/nerf_utils.py"]
+
+
+def stage_python():
+    dst_root = os.path.join(OUT, "pyref")
+    n = 0
+    for rel in PY_STAGE:
+        src = os.path.join(REF, rel)
+        if not os.path.exists(src):
+            print(f"[build_ref] stage-python: {src} missing")
+            continue
+        dst = os.path.join(dst_root, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(src, dst)
+        n += 1
+    print(f"[build_ref] staged {n} reference python files (verbatim) under {dst_root}")
+    return 0
+
+
 def run(cmd, log):
     t0 = time.time()
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -117,12 +144,23 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--jobs", type=int, default=min(8, os.cpu_count() or 4))
     ap.add_argument("--only", default="lotd,pack_ops,occ_grid,forest")
+    ap.add_argument("--variant", default="", help="checker build of _lotd with extra flags for the generic-kernel TUs (compile_split_*.cu): "
+                    "'O1' = -Xptxas -O1, 'O0' = -Xptxas -O0, 'G' = -G; written to oracle/_ref/_lotd__<variant>.so (module name stays _lotd)")
     args = ap.parse_args()
+    variant_flags = {"": [], "O1": ["-Xptxas", "-O1"], "O0": ["-Xptxas", "-O0"], "G": ["-G"], "O2": ["-Xptxas", "-O2"]}[args.variant]
+    ap_stage_only = args.only == "python"
+    if args.variant:
+        args.only = "lotd"
     if not os.path.isdir(CSRC):
         print(f"[build_ref] {CSRC} not present - nothing to build (GPU box uses the prebuilt oracle/_ref/*.so)")
         return 0
     os.makedirs(OUT, exist_ok=True)
+    stage_python()
+    if ap_stage_only:
+        return 0
     scratch = tempfile.mkdtemp(prefix="nr3d_ref_build_")
+    keep = os.path.join(tempfile.gettempdir(), "nr3d_ref_objs")      # objects of the stock build are kept for the variant links
+    os.makedirs(keep, exist_ok=True)
     inc, defs, link = torch_flags()
     specs = ext_specs(scratch)
     want = {"_" + s.strip() for s in args.only.split(",") if s.strip()}
@@ -131,10 +169,15 @@ def main():
         if name not in want:
             continue
         for src in sp["sources"]:
-            obj = os.path.join(scratch, name + "__" + os.path.basename(src) + ".o")
+            is_generic_tu = args.variant and os.path.basename(src).startswith("compile_split_")
+            obj = os.path.join(keep, name + "__" + os.path.basename(src) + (("." + args.variant) if is_generic_tu else "") + ".o")
             incs = ["-I" + d for d in sp["includes"]]
+            if os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src) and not src.startswith(scratch):
+                jobs.append((name, src, obj, ["true"]))
+                continue
             if src.endswith(".cu"):
-                cmd = ["nvcc"] + sp["nvcc"] + incs + inc + defs + [f"-DTORCH_EXTENSION_NAME={name}", "-c", src, "-o", obj]
+                extra = variant_flags if is_generic_tu else []
+                cmd = ["nvcc"] + sp["nvcc"] + extra + incs + inc + defs + [f"-DTORCH_EXTENSION_NAME={name}", "-c", src, "-o", obj]
             else:
                 cmd = ["g++"] + sp["cxx"] + incs + inc + defs + [f"-DTORCH_EXTENSION_NAME={name}", "-c", src, "-o", obj]
             jobs.append((name, src, obj, cmd))
@@ -169,7 +212,7 @@ def main():
             print(f"[build_ref] {name}: NOT linked, failed units: {[os.path.basename(s) for s, _ in failed]} (logs in {scratch})")
             status = 1
             continue
-        so = os.path.join(OUT, name + ".so")
+        so = os.path.join(OUT, name + (("__" + args.variant) if args.variant else "") + ".so")
         rc, _ = run(["g++", "-shared", "-o", so] + [o for _, o in objs] + link, so + ".link.log")
         print(f"[build_ref] link {name}: {'ok' if rc == 0 else 'FAIL'} -> {so}")
         status |= rc

@@ -499,3 +499,59 @@ def grid_sample_dense_reference(param: torch.Tensor, x01: torch.Tensor, R: int) 
     vol = param.permute(3, 0, 1, 2).unsqueeze(0)
     out = F_.grid_sample(vol, grid, align_corners=True, padding_mode="zeros")
     return out.view(param.shape[-1], -1).t()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# float64 arbiter for full-size gradient tables (Dense / Hash levels): bincount instead of autograd
+# ------------------------------------------------------------------------------------------------------------------
+def bwd_param_hash_f64(meta, dL_dy, x, chunk=1 << 19, batch_inds=None, batch_data_size=0, n_scenes=1):
+    """dL/dparam [n_scenes * n_params] in float64 for Dense / Hash-only metas plus, per entry, the sum of |terms| that met there.
+
+    Same maths as `bwd` (reference scatter lotd_cuda.h:494-829 over the n-linear weights of linear_interpolate.cuh:92-150; cell and
+    fraction from the fp32 `_pos` path), evaluated with np.bincount so that BASELINE.json's full sizes (4 Mi points) take seconds.
+    The |term| sum bounds what fp32 accumulation ORDER can change: |fl32(sum) - sum| <= n * eps32 * sum|terms| -- the element-wise
+    tolerance the full-size tests grant a build on top of its distance to this table."""
+    assert meta.c_hash_only
+    D, F = meta.n_dims_to_encode, meta.n_feat_per_pseudo_lvl
+    xn = x.detach().float()
+    g64 = dL_dy.detach().double().numpy()
+    N = xn.shape[0]
+    total = meta.n_params * n_scenes
+    out, mag = np.zeros(total, dtype=np.float64), np.zeros(total, dtype=np.float64)
+    smooth = meta.interpolation_type == 1
+    for s in range(0, N, chunk):
+        xs = xn[s:s + chunk]
+        n = xs.shape[0]
+        if batch_inds is not None:
+            sc = np.asarray(batch_inds[s:s + chunk]).astype(np.int64)
+        elif batch_data_size:
+            sc = (np.arange(s, s + n) // batch_data_size).astype(np.int64)
+        else:
+            sc = np.zeros(n, dtype=np.int64)
+        live = sc >= 0
+        for pl, lvl in enumerate(meta.map_levels):
+            R, size, nf = meta.level_res_multidim[lvl], meta.level_sizes[lvl], meta.level_n_feats[lvl]
+            cell, p = _pos(xs, xs.double(), R, smooth)
+            cell, p = cell.numpy(), p.numpy()
+            lnp = meta.level_n_params[lvl]
+            acc, acc_mag = np.zeros(n_scenes * lnp, dtype=np.float64), np.zeros(n_scenes * lnp, dtype=np.float64)
+            for bits in _corner_bits(D):
+                w = np.ones(n, dtype=np.float64)
+                pos = cell.copy()
+                for d in range(D):
+                    if bits[d]:
+                        w = w * p[:, d]
+                        pos[:, d] += 1
+                    else:
+                        w = w * (1.0 - p[:, d])
+                tpos = torch.from_numpy(pos)
+                idx = (_idx_dense(R, tpos) if meta.level_types[lvl] == DENSE else _idx_hash(tpos, size)).numpy()
+                flat = (sc * lnp + idx * nf + meta.map_cnt[pl] * F)[live]
+                for f in range(F):
+                    t = (w * g64[s:s + n, pl * F + f])[live]
+                    acc += np.bincount(flat + f, weights=t, minlength=n_scenes * lnp)
+                    acc_mag += np.bincount(flat + f, weights=np.abs(t), minlength=n_scenes * lnp)
+            o = meta.level_offsets[lvl]
+            out.reshape(n_scenes, meta.n_params)[:, o:o + lnp] += acc.reshape(n_scenes, lnp)
+            mag.reshape(n_scenes, meta.n_params)[:, o:o + lnp] += acc_mag.reshape(n_scenes, lnp)
+    return out, mag

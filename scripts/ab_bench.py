@@ -4,12 +4,15 @@
 import json, os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 VARIANTS = {
-    "base": [],                                   # pair layout (two lanes per point)
-    "unroll1": ["NR3D_FWD_UNROLL=1"],
-    "unroll4": ["NR3D_FWD_UNROLL=4"],
+    "base": [],                                   # x-fastest bins, no CTA tiles, 256-thread backward CTAs compiled for 1536 threads / SM
+    "bwd128": ["NR3D_BWD_THREADS=128"],
+    "bwd256_nocap": ["NR3D_BWD_OCC=0"],
+    "bwd128_nocap": ["NR3D_BWD_THREADS=128", "NR3D_BWD_OCC=0"],
+    "bwd128_occ2048": ["NR3D_BWD_THREADS=128", "NR3D_BWD_OCC=2048"],
     "fwd128": ["NR3D_FWD_THREADS=128"],
-    "bwd256": ["NR3D_BWD_THREADS=256"],
-    "bwd64": ["NR3D_BWD_THREADS=64"],
+    # round-2 experiments that lost (profiles/r2_ab_tiles.txt): CTA tiles through shared-memory CAS, brick order of the sort bins
+    "tiles_brick": ["NR3D_BWD_TILES=1", "NR3D_BIN_ORDER=2", "NR3D_BWD_OCC=0"],
+    "brick": ["NR3D_BIN_ORDER=2"],
 }
 if sys.argv[1] == "build":
     from nr3d_lib_b200.csrc import build as B
@@ -18,12 +21,10 @@ if sys.argv[1] == "build":
         print(n, B.build_variant(n, d))
 else:
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for n in VARIANTS:
+    names = sys.argv[2].split(",") if len(sys.argv) > 2 else list(VARIANTS)
+    for n in names:
         env = dict(os.environ, NR3D_B200_LIB=os.path.join(root, "nr3d_lib_b200", "lib", "variants", n + ".so"))
-        out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "10", "--warmup", "3", "--no-cpu-baseline", "--no-m2"],
-                             env=env, capture_output=True, text=True).stdout.strip().splitlines()
-        try:
-            d = json.loads(out[-1])
-            print(f"{n:10s} {d['value']:8.1f} Msamples/s  step {d['ms_per_step']:.3f} ms  fwd+sort {d['roofline']['ms']['lod_fwd']:.3f}  bwd {d['roofline']['ms']['lod_bwd']:.3f}", flush=True)
-        except Exception as e:
-            print(n, "FAILED", e, out[-3:])
+        for extra in ([], ["--half"]):
+            r = subprocess.run([sys.executable, os.path.join(root, "scripts", "step_probe.py"), "--tag", n] + extra, env=env, capture_output=True, text=True)
+            line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ("FAILED " + r.stderr[-400:])
+            print(line, flush=True)

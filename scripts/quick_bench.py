@@ -10,11 +10,15 @@ def ngp_cfg(min_res=16, n_levels=16, scale=1.382, log2_T=19, F=2):
     types = ["Dense" if r ** 3 <= 2 ** log2_T else "Hash" for r in res]
     return (3, res, [F] * n_levels, types, 2 ** log2_T, False)
 
-def timeit(fn, iters=10, warm=3):
-    for _ in range(warm): fn()
+def timeit(fn, iters=10, warm=3, pre=None):
+    """median device time of fn(); `pre` runs untimed before every call (e.g. to sort another point set so that fn re-sorts)."""
+    for _ in range(warm):
+        if pre: pre()
+        fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
+        if pre: pre()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     return float(np.median(ts))

@@ -134,16 +134,16 @@ print("DROPIN_OK")
 
 
 def test_sort_points_flag_default_and_env(monkeypatch):
-    """`LoDMeta.c_sort_points` (B200-only knob) is off by default -- identical strides to the reference -- and NR3D_B200_SORT_POINTS=1
-    turns it on for every meta so that an unmodified reference application can opt in without a code change."""
+    """`LoDMeta.c_sort_points` (B200-only knob) is ON by default -- a drop-in user gets the fast path -- and NR3D_B200_SORT_POINTS=0 (or
+    `meta.c_sort_points = False`) restores the reference's strides / the generic kernels."""
     from nr3d_lib_b200.bindings import _lotd
     args = (3, [16, 32], [2, 2], ["Dense", "Hash"], 2 ** 10, False)
     monkeypatch.delenv("NR3D_B200_SORT_POINTS", raising=False)
-    assert _lotd.LoDMeta(*args).c_sort_points is False
-    monkeypatch.setenv("NR3D_B200_SORT_POINTS", "1")
-    m = _lotd.LoDMeta(*args)
-    assert m.c_sort_points is True
-    m.c_sort_points = 0
-    assert m.c_sort_points is False
+    assert _lotd.LoDMeta(*args).c_sort_points is True
     monkeypatch.setenv("NR3D_B200_SORT_POINTS", "0")
-    assert _lotd.LoDMeta(*args).c_sort_points is False
+    m = _lotd.LoDMeta(*args)
+    assert m.c_sort_points is False
+    m.c_sort_points = 1
+    assert m.c_sort_points is True
+    monkeypatch.setenv("NR3D_B200_SORT_POINTS", "1")
+    assert _lotd.LoDMeta(*args).c_sort_points is True

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import rel_err
+from tests.util import C4_ARGS, c4_inputs, elementwise_excess, load_ref, rel_err, run_ref_worker
 
 pytestmark = pytest.mark.gpu
 
@@ -73,22 +73,44 @@ def test_config2_march_and_composite_at_1024x1024_rays(dev):
 def test_config3_batched_mixed_second_order_at_2Mi_points(dev):
     from nr3d_lib_b200.bindings import _lotd
     from oracle import lotd_oracle as O
-    args = (3, [8, 16, 32, 64, 128, 256], [4, 4, 4, 4, 2, 2], ["Dense", "Dense", "VM", "VM", "CP", "CP"], None, False)
+    args = C4_ARGS
     meta, om = _lotd.LoDMeta(*args), O.OracleMeta(*args)
     N, B = 2 * 1024 * 1024, 8
-    g = torch.Generator().manual_seed(11)
-    x = torch.rand(N, 3, generator=g).clamp(1e-6, 1 - 1e-6)
-    bi = torch.randint(0, B, (N,), generator=g)
-    bi[torch.rand(N, generator=g) < 0.01] = -1
-    params = torch.randn(B * meta.n_params, generator=g) * 0.1
-    gy = torch.randn(N, meta.n_encoded_dims, generator=g)
-    ddx = torch.randn(N, 3, generator=g)
+    inp = c4_inputs(N, meta.n_params, seed=11, B=B)
+    x, bi, params, gy, ddx = inp["x"], inp["batch_inds"], inp["params"], inp["dL_dy"], inp["dL_ddLdx"]
+    g = torch.Generator().manual_seed(12)
     xd, bd, pd, gd, dd = x.to(dev), bi.to(dev), params.to(dev), gy.to(dev), ddx.to(dev)
     kw = dict(batch_inds=bd, batch_offsets=None, batch_data_size=None, max_level=None)
     y, dydx = _lotd.lod_fwd(meta, xd, pd, need_input_grad=True, **kw)
     dL_dx, dL_dp = _lotd.lod_bwd(meta, gd, xd, pd, dydx, need_input_grad=True, need_param_grad=True, **kw)
     a, b, c = _lotd.lod_bwd_bwd_input(meta, dd, gd, xd, pd, dydx, need_dLdinput_ddLdoutput=True, need_dLdinput_dparams=True,
                                       need_dLdinput_dinput=True, **kw)
+    # ---- table against table: the reference's own CUDA kernels on the same 2 Mi points (first order: stock build, live) ----
+    ref = load_ref("_lotd")
+    if ref is not None:
+        m_r = ref.LoDMeta(*args)
+        y_r, _ = ref.lod_fwd(m_r, xd, pd, need_input_grad=False, **kw)
+        assert rel_err(y, y_r) < 1e-5
+        _, gp_r = ref.lod_bwd(m_r, gd, xd, pd, None, need_input_grad=False, need_param_grad=True, **kw)
+        # sum of |terms| per entry (all weights and factor products are taken positive): what fp32 summation order may change
+        _, mag = _lotd.lod_bwd(meta, gd.abs(), xd, pd.abs(), None, need_input_grad=False, need_param_grad=True, **kw)
+        bad, worst = elementwise_excess(dL_dp.cpu().numpy(), gp_r.cpu().numpy(), mag.cpu().numpy(), rel=1e-5, c_eps=16.0)
+        assert bad == 0, f"first-order dL/dparam vs the reference build, element-wise: {bad} entries out of tolerance (worst x{worst:.2f})"
+        del y_r, gp_r, mag
+    # ---- second order against the -G build of the reference's generic kernels (subprocess; per-level max-norm 5e-5) ----
+    chk = run_ref_worker([dict(name="c4", dtype="f32", N=N, seed=11, keys=["dL_dparam2", "dL_ddLdy", "dy_dx", "dL_dx"])], variant="G", timeout=3000)
+    if chk is not None:
+        chk = chk[0]
+        off = list(meta.level_offsets)
+        g2 = b.view(B, -1).cpu()
+        r2 = torch.from_numpy(chk["dL_dparam2"]).view(B, -1)
+        for lvl in range(meta.n_levels):
+            e = rel_err(g2[:, off[lvl]:off[lvl + 1]], r2[:, off[lvl]:off[lvl + 1]])
+            # line / plane tables of 96 - 1536 entries per scene receive 2 Mi x 24 fp32 terms in arbitrary order in BOTH builds
+            assert e < 5e-5, ("dL_dparam2 level", lvl, e)
+        assert rel_err(a.cpu(), chk["dL_ddLdy"]) < 1e-5 and rel_err(dL_dx.cpu(), chk["dL_dx"]) < 1e-5
+        assert rel_err(dydx.view(N, -1, 3).cpu(), chk["dy_dx"]) < 1e-5
+        del chk, g2, r2
     # per-point outputs of a random subset against the float64 oracle
     sub = torch.sort(torch.randperm(N, generator=g)[:4000]).values
     okw = dict(batch_inds=bi[sub])

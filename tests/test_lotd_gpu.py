@@ -4,6 +4,10 @@ Three checkers, in decreasing authority:
   1. golden vectors produced by the reference's own CUDA build (tests/golden/lotd_*.npz);
   2. the reference's own CUDA build run live on the same inputs (oracle/_ref/_lotd.so), incl. larger sizes;
   3. the float64 CPU oracle (oracle/lotd_oracle.py).
+No output is masked.  The reference's GENERIC kernels are miscompiled by nvcc 12.9 -O3 for sm_100 (dy/dx and what derives from it, n-linear
+level types, D >= 3 -- profiles/r2_ref_build_variants.txt); for exactly those outputs the checker is the same source built with -G
+(oracle/_ref/_lotd__G.so, `oracle/build_ref.py --variant G`), which passes finite differences of its own forward: its vectors are in the
+goldens (make_golden.py:make_lotd_checker) and it runs live through tests/ref_worker.py.
 Tolerances: fp32 params 1e-5 relative to the tensor's max magnitude (BASELINE.json north_star), fp16 params 2e-3
 (the reference accumulates in half); grid indices bit-exact.
 """
@@ -11,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import LOTD_CONFIGS, golden, load_ref, lotd_inputs, meta_args, rel_err
+from tests.util import LOTD_CONFIGS, golden, load_ref, lotd_inputs, meta_args, rel_err, run_ref_worker
 
 pytestmark = pytest.mark.gpu
 
@@ -48,32 +52,14 @@ def _run_all(backend, meta, inp, dev, pdtype, second_dx=True):
     return out
 
 
-def _ref_valid_masks(meta, n_batches):
-    """Which outputs of the reference's sm_100 build can serve as a checker.
-
-    The reference's GENERIC kernels (kernel_lod / kernel_lod_backward_input_backward_grid, lotd_encoding.h:113-428,764-1041)
-    built with nvcc 12.9 for sm_100 return dy/dx and d(dL/dx)/dparam that contradict (a) the same reference's hash-only
-    kernels on Dense levels and (b) finite differences of the reference's own forward output, for the n-linear level types
-    Dense / VM / VecZMatXoY / CP / NPlaneMul when D >= 3 (see DESIGN.md "reference build defect" and
-    test_reference_generic_dydx_defect below).  Hash, CPfast and NPlaneSum levels, D == 2, the forward output,
-    first-order dL/dparam and the second-order dL/dx are unaffected.  Affected entries are masked out here and are
-    pinned by the finite-difference identities instead (the reference's own test strategy, lotd/tests/math_test.py:99-171).
-    """
-    E = meta.n_encoded_dims
-    if meta.c_hash_only or meta.n_dims_to_encode == 2:
-        return torch.ones(E, dtype=torch.bool), torch.ones(meta.n_params * n_batches, dtype=torch.bool), True
-    ok_types = (7, 4, 6)  # Hash, CPfast, NPlaneSum
-    F = meta.n_feat_per_pseudo_lvl
-    feat = torch.zeros(E, dtype=torch.bool)
-    par = torch.zeros(meta.n_params, dtype=torch.bool)
-    for pl, lvl in enumerate(meta.map_levels):
-        feat[pl * F:(pl + 1) * F] = int(meta.level_types[lvl]) in ok_types
-    for lvl in range(meta.n_levels):
-        par[meta.level_offsets[lvl]:meta.level_offsets[lvl + 1]] = int(meta.level_types[lvl]) in ok_types
-    return feat, par.repeat(n_batches), bool(feat.all())
+CHECKER_KEYS = ("dy_dx", "dL_dx", "dL_ddLdy", "dL_dparam2")   # what the stock -O3 build of the generic kernels gets wrong (see module docstring)
 
 
-def _compare(got, want, pdtype, what, masks=None):
+def _stock_build_wrong(meta):
+    return (not meta.c_hash_only) and meta.n_dims_to_encode >= 3
+
+
+def _compare(got, want, pdtype, what):
     bad = []
     for k, w in want.items():
         if k not in got or got[k] is None or w is None:
@@ -85,16 +71,6 @@ def _compare(got, want, pdtype, what, masks=None):
             if not torch.equal(g, w):
                 bad.append((k, "indices differ", int((g != w).sum())))
             continue
-        if masks is not None:
-            feat, par, all_ok = masks
-            if k in ("dy_dx", "dL_ddLdy"):
-                g, w = g[:, feat], w[:, feat]
-            elif k == "dL_dparam2":
-                g, w = g[par], w[par]
-            elif k == "dL_dx" and not all_ok:
-                continue
-            if g.numel() == 0:
-                continue
         tol = TOL_ATOMIC[pdtype] if k in ("dL_dparam", "dL_dparam2", "dL_dx2") else TOL[pdtype]
         e = rel_err(g.float(), w.float())
         if not (e <= tol):
@@ -118,32 +94,61 @@ def test_lotd_vs_golden(name, dev):
                    dL_ddLdx=torch.from_numpy(g["dL_ddLdx"]), batch_inds=torch.from_numpy(g["batch_inds"]) if "batch_inds" in g else None)
         got = _run_all(mine, meta, inp, dev, pdtype)
         want = {k: g[k] for k in ("y", "dy_dx", "dL_dx", "dL_dparam", "dL_ddLdy", "dL_dparam2", "dL_dx2", "y_maxlevel1", "grid_index") if k in g}
-        _compare(got, want, pdtype, f"golden:{name}:{tag}", _ref_valid_masks(meta, cfg["B"]))
+        if _stock_build_wrong(meta):
+            assert "checker_build" in g, "golden fixture predates the -G checker pass: python tests/golden/make_golden.py --only make_lotd_checker"
+        _compare(got, want, pdtype, f"golden:{name}:{tag}")
     if not ran:
         pytest.skip("golden fixture not generated yet")
 
 
+_GENERIC_3D = [n for n, c in LOTD_CONFIGS.items() if c["D"] >= 3 and any(t not in ("Dense", "Hash") for t in c["types"])]
+
+
+@pytest.fixture(scope="module")
+def checker_outputs():
+    """dy_dx / dL_dx / dL_ddLdy / dL_dparam2 of the generic-path configurations from the -G build of the reference, one subprocess for all."""
+    jobs = [dict(name=n, dtype=t, N=20000 if LOTD_CONFIGS[n]["B"] == 1 else 19998, seed=11, keys=list(CHECKER_KEYS))
+            for n in _GENERIC_3D for t in ("f32", "f16")]
+    res = run_ref_worker(jobs, variant="G")
+    if res is None:
+        return None
+    return {(j["name"], j["dtype"]): res[i] for i, j in enumerate(jobs)}
+
+
+@pytest.mark.parametrize("fast", [True, False])
 @pytest.mark.parametrize("name", list(LOTD_CONFIGS))
 @pytest.mark.parametrize("pdtype", [torch.float32, torch.float16])
-def test_lotd_vs_reference_build(name, pdtype, dev):
-    """B200 kernels vs the reference's own CUDA kernels, live, on 20k seeded points."""
+def test_lotd_vs_reference_build(name, pdtype, fast, dev, checker_outputs):
+    """B200 kernels vs the reference's own CUDA kernels, live, on 20k seeded points -- every output, with the cell-sorted fast path on
+    (default) and off (reference strides)."""
     ref = load_ref("_lotd")
     if ref is None:
         pytest.skip("oracle/_ref/_lotd.so not built")
     mine = _mine()
     cfg = LOTD_CONFIGS[name]
     m_ref, m_mine = ref.LoDMeta(*meta_args(cfg)), mine.LoDMeta(*meta_args(cfg))
+    m_mine.c_sort_points = fast
+    if fast and not (m_mine.c_hash_only and m_mine.n_dims_to_encode == 3):
+        pytest.skip("the fast path does not apply to this meta: covered by fast=False")
     inp = lotd_inputs(cfg, m_mine.n_params, N=20000 if cfg["B"] == 1 else 19998, seed=11)
     want = _run_all(ref, m_ref, inp, dev, pdtype)
     got = _run_all(mine, m_mine, inp, dev, pdtype)
-    # stride contract of the fast path: feature-major storage behind transposed / permuted views
-    assert got["y"].stride() == want["y"].stride()
+    if fast:
+        assert got["y"].is_contiguous() and got["dy_dx"].is_contiguous()
+    else:   # stride contract of the reference: feature-major storage behind transposed / permuted views for Dense/Hash-only metas
+        assert got["y"].stride() == want["y"].stride()
+    if _stock_build_wrong(m_mine):
+        if checker_outputs is None:
+            pytest.skip("oracle/_ref/_lotd__G.so not built (python oracle/build_ref.py --variant G)")
+        chk = checker_outputs[(name, "f16" if pdtype == torch.float16 else "f32")]
+        for k in CHECKER_KEYS:
+            want[k] = torch.from_numpy(chk[k])
     if pdtype == torch.float16:
         # half2 atomics round after every add: both builds carry order-dependent noise, so the gradient tables are
         # compared against the float64 oracle (below) instead of against each other
         for k in ("dL_dparam", "dL_dparam2"):
             want.pop(k)
-    _compare(got, want, pdtype, f"ref:{name}:{pdtype}", _ref_valid_masks(m_mine, cfg["B"]))
+    _compare(got, want, pdtype, f"ref:{name}:{pdtype}:fast={fast}")
     if pdtype == torch.float16:
         from oracle import lotd_oracle as O
         om = O.OracleMeta(*meta_args(cfg))
@@ -256,22 +261,23 @@ def test_lotd_autograd_wrappers(dev):
     assert rel_err(p2.grad.cpu(), g_p2) < 2e-5
 
 
-def _central_diff(backend, meta, x, params, h, dev):
+def _central_diff(backend, meta, x, params, h, dev, kw=None):
     """dy/dx by central differences of the backend's own forward output: [N, E, D] (exact inside a cell for linear interp)."""
     cols = []
     for d in range(x.shape[1]):
         e = torch.zeros_like(x)
         e[:, d] = h
-        yp, _ = backend.lod_fwd(meta, (x + e).contiguous(), params, need_input_grad=False)
-        ym, _ = backend.lod_fwd(meta, (x - e).contiguous(), params, need_input_grad=False)
+        yp, _ = backend.lod_fwd(meta, (x + e).contiguous(), params, need_input_grad=False, **(kw or {}))
+        ym, _ = backend.lod_fwd(meta, (x - e).contiguous(), params, need_input_grad=False, **(kw or {}))
         cols.append((yp.double() - ym.double()) / ((x + e)[:, d:d + 1].double() - (x - e)[:, d:d + 1].double()))
     return torch.stack(cols, -1)
 
 
-@pytest.mark.parametrize("name", ["mixed", "cuboid_vm", "d4"])
-def test_dydx_matches_finite_differences_and_reference_defect(name, dev):
-    """(1) Our dy/dx equals central differences of our forward output (the reference's own check, math_test.py:99-102).
-    (2) Evidence for the masked golden entries: the reference's sm_100 build FAILS the same identity on its generic path."""
+@pytest.mark.parametrize("name", ["mixed", "cuboid_vm", "d4", "batched"])
+def test_dydx_matches_finite_differences(name, dev):
+    """Our dy/dx equals central differences of our forward output (the reference's own check, lotd/tests/math_test.py:99-102).  That the
+    -G build of the reference passes the same identity while its -O3 / ptxas -O0 / -O1 builds do not is recorded by
+    scripts/ref_variant_check.py in profiles/r2_ref_build_variants.txt; test_lotd_vs_reference_build compares us with the -G build."""
     mine = _mine()
     cfg = LOTD_CONFIGS[name]
     meta = mine.LoDMeta(*meta_args(cfg))
@@ -282,21 +288,13 @@ def test_dydx_matches_finite_differences_and_reference_defect(name, dev):
     for R in meta.level_res_multidim:  # keep points whose +-h neighbours stay in the same cell on every level
         s = torch.tensor([r - 2 for r in R], dtype=torch.float64)
         keep &= (torch.floor((x.double() + 2 * h) * s + 0.5) == torch.floor((x.double() - 2 * h) * s + 0.5)).all(-1)
+    kw = {}
+    if inp["batch_inds"] is not None:
+        kw = dict(batch_inds=inp["batch_inds"][keep].to(dev).contiguous())
     x = x[keep].to(dev).contiguous()
     params = inp["params"].to(dev)
     N, E, D = x.shape[0], meta.n_encoded_dims, meta.n_dims_to_encode
-    _, dy = mine.lod_fwd(meta, x, params, need_input_grad=True)
-    fd = _central_diff(mine, meta, x, params, h, dev)
+    _, dy = mine.lod_fwd(meta, x, params, need_input_grad=True, **kw)
+    fd = _central_diff(mine, meta, x, params, h, dev, kw)
     e_mine = rel_err(dy.reshape(N, E, D).double().cpu(), fd.cpu())
-    assert e_mine < 2e-2, f"our dy_dx vs finite differences: {e_mine}"
-    ref = load_ref("_lotd")
-    if ref is None:
-        return
-    m_ref = ref.LoDMeta(*meta_args(cfg))
-    _, dy_r = ref.lod_fwd(m_ref, x, params, need_input_grad=True)
-    fd_r = _central_diff(ref, m_ref, x, params, h, dev)
-    assert rel_err(fd_r.cpu(), fd.cpu()) < 1e-3          # the two forward passes agree ...
-    e_ref = rel_err(dy_r.reshape(N, E, D).double().cpu(), fd_r.cpu())
-    print(f"[defect evidence] {name}: dy_dx vs finite differences of own forward: ours {e_mine:.2e}, reference sm_100 build {e_ref:.2e}")
-    if e_ref < 2e-2:
-        pytest.fail("the reference build no longer shows the generic-path dy_dx defect: remove the masks in _ref_valid_masks")
+    assert e_mine < 2e-3, f"our dy_dx vs finite differences: {e_mine}"

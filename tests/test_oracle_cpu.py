@@ -89,7 +89,7 @@ def _golden_inputs(g):
 @pytest.mark.parametrize("name", list(LOTD_CONFIGS))
 def test_lotd_oracle_vs_golden(name):
     """The float64 oracle reproduces what the reference's CUDA build produced on a B200 (fp32 params: 1e-5)."""
-    from tests.test_lotd_gpu import _compare, _ref_valid_masks
+    from tests.test_lotd_gpu import _compare
     g = golden(f"lotd_{name}_f32")
     if g is None:
         pytest.skip("golden fixture missing")
@@ -106,19 +106,15 @@ def test_lotd_oracle_vs_golden(name):
         got["grid_index"] = O.grid_index(om, inp["x"], **kw)
     want = {k: g[k] for k in got if k in g}
 
-    class _M:  # _ref_valid_masks only reads these attributes
-        pass
-    mm = _M()
-    for a in ("n_encoded_dims", "c_hash_only", "n_dims_to_encode", "n_feat_per_pseudo_lvl", "n_params", "map_levels", "level_types",
-              "n_levels", "level_offsets"):
-        setattr(mm, a, getattr(om, a))
-    _compare(got, want, torch.float32, f"oracle-vs-golden:{name}", _ref_valid_masks(mm, cfg["B"]))
+    if not om.c_hash_only and cfg["D"] >= 3:
+        assert "checker_build" in g, "fixture predates the -G checker pass (tests/golden/make_golden.py:make_lotd_checker)"
+    _compare(got, want, torch.float32, f"oracle-vs-golden:{name}")      # every output, nothing masked
 
 
 @pytest.mark.parametrize("name", ["mixed", "mixed_smooth", "cuboid_vm", "d4", "batched"])
 def test_lotd_oracle_gradients_vs_finite_differences(name):
     """Analytic (autograd) derivatives of the oracle vs central differences in float64 -- pins dy/dx and the second-order
-    products for the level types whose reference sm_100 outputs are masked (see tests/test_lotd_gpu.py::_ref_valid_masks)."""
+    products independently of any build of the reference (its -O3 build of the generic kernels is miscompiled there, tests/test_lotd_gpu.py)."""
     cfg = LOTD_CONFIGS[name]
     om = O.OracleMeta(*meta_args(cfg))
     inp = lotd_inputs(cfg, om.n_params, N=64, seed=2)

@@ -112,17 +112,22 @@ def march_inputs(R=512, res=32, seed=0, B=1, occupancy=0.5, shell=False):
 _ref_cache = {}
 
 
-def load_ref(name):
-    """Load one of the reference's own CUDA extensions built by oracle/build_ref.py (None if absent)."""
+def load_ref(name, variant=""):
+    """Load one of the reference's own CUDA extensions built by oracle/build_ref.py (None if absent).  `variant` selects a checker build
+    of _lotd (oracle/build_ref.py --variant); pybind registers the reference's types per process, so only ONE _lotd build can be loaded
+    into a process -- tests reach the other one through tests/ref_worker.py."""
     if name in _ref_cache:
+        if _ref_cache[name] is not None and getattr(_ref_cache[name], "_nr3d_variant", "") != variant:
+            raise RuntimeError(f"reference build {name} already loaded as variant {_ref_cache[name]._nr3d_variant!r}, cannot load {variant!r}")
         return _ref_cache[name]
-    path = os.path.join(REF_DIR, name + ".so")
+    path = os.path.join(REF_DIR, name + (("__" + variant) if variant else "") + ".so")
     mod = None
     if os.path.exists(path):
         try:
             spec = importlib.util.spec_from_file_location(name, path)
             mod = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(mod)
+            mod._nr3d_variant = variant
         except Exception as e:  # pragma: no cover
             print(f"[tests] could not load reference build {path}: {e}")
             mod = None
@@ -336,3 +341,106 @@ def forest_lotd_inputs(cfg, n_params, N=256, seed=0):
     return dict(x=torch.from_numpy(x), params=torch.from_numpy((rs.randn(B * n_params) * 0.1).astype(np.float32)),
                 dL_dy=torch.from_numpy(rs.randn(N, E).astype(np.float32)), dL_ddLdx=torch.from_numpy(rs.randn(N, 3).astype(np.float32)),
                 batch_inds=torch.from_numpy(bi), forest=f)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# the reference's own python wrappers, UNMODIFIED, on top of this package's shims
+# --------------------------------------------------------------------------------------------------------------
+_refpy_cache = {}
+
+
+def reference_wrappers():
+    """Import the reference's unmodified `lotd.py`, `pack_ops.py` and `occgrid_raymarch.py` with `nr3d_lib.bindings.*` provided by
+    nr3d_lib_b200 (install()).  The files come from /root/reference when it exists (this container) and otherwise from the verbatim staging
+    copy `oracle/_ref/pyref/` that oracle/build_ref.py makes (git-ignored, shipped to the GPU box like the compiled reference .so files).
+    Parent packages are namespace shells: their own __init__ files pull in the whole model zoo and third-party deps that are out of scope.
+    Returns a dict(lotd=..., pack_ops=..., occgrid_raymarch=..., root=...) or None when neither location is available."""
+    if "mods" in _refpy_cache:
+        return _refpy_cache["mods"]
+    import types
+    root = None
+    for cand in ("/root/reference/nr3d_lib", os.path.join(REF_DIR, "pyref", "nr3d_lib")):
+        if os.path.isfile(os.path.join(cand, "models", "grid_encodings", "lotd", "lotd.py")):
+            root = cand
+            break
+    if root is None:
+        _refpy_cache["mods"] = None
+        return None
+    from nr3d_lib_b200.install import install
+
+    def shell(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+        return m
+    shell("nr3d_lib", root)
+    shell("nr3d_lib.models", root + "/models")
+    shell("nr3d_lib.models.grid_encodings", root + "/models/grid_encodings")
+    shell("nr3d_lib.models.grid_encodings.lotd", root + "/models/grid_encodings/lotd")
+    shell("nr3d_lib.graphics", root + "/graphics")
+    install()
+    import importlib
+    mods = dict(root=root,
+                lotd=importlib.import_module("nr3d_lib.models.grid_encodings.lotd.lotd"),
+                pack_ops=importlib.import_module("nr3d_lib.graphics.pack_ops.pack_ops"),
+                occgrid_raymarch=importlib.import_module("nr3d_lib.graphics.raymarch.occgrid_raymarch"))
+    for m in (mods["lotd"], mods["pack_ops"], mods["occgrid_raymarch"]):
+        assert os.path.abspath(m.__file__).startswith(os.path.abspath(root)), m.__file__       # the reference's files, not our mirrors
+    _refpy_cache["mods"] = mods
+    return mods
+
+
+def run_ref_worker(jobs, variant="G", timeout=1200):
+    """Run LoTD jobs on another build of the reference's _lotd in a subprocess (tests/ref_worker.py).  jobs: list of dicts
+    (name, dtype 'f32'|'f16', N, seed[, batch_mode]).  Returns {job_index: {output name: numpy array}} or None if that build is absent."""
+    import json
+    import subprocess
+    import tempfile
+    so = os.path.join(REF_DIR, "_lotd" + (("__" + variant) if variant else "") + ".so")
+    if not os.path.exists(so):
+        return None
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "out.npz")
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_worker.py"), variant, json.dumps(jobs), out],
+                           capture_output=True, text=True, timeout=timeout)
+        if r.returncode != 0 or not os.path.exists(out):
+            raise RuntimeError("ref_worker failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
+        z = np.load(out, allow_pickle=False)
+        res = {}
+        for k in z.files:
+            j, key = k.split("/", 1)
+            res.setdefault(int(j), {})[key] = z[k]
+        return res
+
+
+C4_ARGS = (3, [8, 16, 32, 64, 128, 256], [4, 4, 4, 4, 2, 2], ["Dense", "Dense", "VM", "VM", "CP", "CP"], None, False)   # BASELINE.json configs[3]
+
+
+def c4_inputs(N, n_params, seed=11, B=8):
+    """BASELINE.json configs[3]: B scenes, mixed Dense / VM / CP levels, per-point batch indices (1 % = -1).  CPU torch generator:
+    identical in the test process and in tests/ref_worker.py."""
+    g = torch.Generator().manual_seed(int(seed))
+    x = torch.rand(N, 3, generator=g).clamp(1e-6, 1 - 1e-6)
+    bi = torch.randint(0, B, (N,), generator=g)
+    bi[torch.rand(N, generator=g) < 0.01] = -1
+    params = torch.randn(B * n_params, generator=g) * 0.1
+    E = sum(C4_ARGS[2])
+    return dict(x=x, batch_inds=bi, params=params, dL_dy=torch.randn(N, E, generator=g), dL_ddLdx=torch.randn(N, 3, generator=g), batch_data_size=0)
+
+
+EPS32 = 2.0 ** -24
+
+
+def elementwise_excess(ours, f64, mag, ref=None, k=2.0, rel=1e-5, c_eps=8.0):
+    """Element-wise arbiter check of an atomically accumulated fp32 table against its float64 value:
+
+        |ours - f64|  <=  k * |ref - f64|  +  rel * |f64|  +  c_eps * eps32 * mag
+
+    `mag` = sum of |terms| per entry: what fp32 summation ORDER may change; `ref` (optional) = the reference build's table, whose own
+    distance to the float64 value is granted k-fold.  Returns (number of violating entries, worst ratio error / tolerance)."""
+    o, t = np.asarray(ours, dtype=np.float64), np.asarray(f64, dtype=np.float64)
+    tol = rel * np.abs(t) + c_eps * EPS32 * np.asarray(mag, dtype=np.float64) + 1e-300
+    if ref is not None:
+        tol = tol + k * np.abs(np.asarray(ref, dtype=np.float64) - t)
+    ratio = np.abs(o - t) / tol
+    return int((ratio > 1.0).sum()), float(ratio.max())
