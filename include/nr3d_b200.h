@@ -186,6 +186,16 @@ int nr3d_lotd_bwd_param2_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype,
                                 const void* dL_dy, int64_t dLdy_stride_n, int64_t dLdy_stride_f, const float* dL_ddLdx, int32_t max_level,
                                 void* dL_dparam, void* stream);
 
+/* Sorted fast path with the M2 workload's density head fused in (no reference counterpart; replaces the composition
+ * encoding(x) -> softplus(gain * sum_c h) -> alpha = 1 - exp(-sigma * delta) of the render step, nr3d_lib/graphics/nerf/nerf_ray_query.py:182,
+ * and its autograd chain).  Forward: sigma, alpha f32 [N] at the points' original indices; the [N, n_enc] features are never written.
+ * Backward: dL/dalpha f32 [N] (+ the saved sigma / alpha / deltas) -> dL/dparam, accumulated (zero it first); dL/dy is never materialised. */
+int nr3d_lotd_density_head_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
+                                      const void* params, int32_t max_level, const float* deltas, float gain, float* sigma, float* alpha, void* stream);
+int nr3d_lotd_density_head_bwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
+                                      const float* d_alpha, const float* sigma, const float* alpha, const float* deltas, float gain, int32_t max_level,
+                                      void* dL_dparam, void* stream);
+
 /* Fused LoTD encode + density decoder, forward only.  Replaces the composition
  * LoTDNeRF.query_density (nr3d_lib/models/fields/nerf/lotd_nerf.py:169-178): encoding(x) -> Linear(32,64) -> ReLU ->
  * Linear(64, <=16) -> activation(out[...,0]), without writing the [N,32] features to HBM.  tcgen05 (bf16 operands, f32

@@ -75,6 +75,8 @@ SIGNATURES = {
     "nr3d_lotd_bwd_param_sorted": [_meta_p, _i32, _u64, _vp, _vp, _u32, _vp, _i64, _i64, _i32, _u32, _u32, _vp, _vp],
     "nr3d_lotd_fwd_dydx_sorted": [_meta_p, _i32, _u64, _vp, _vp, _u32, _vp, _i32, _vp, _vp, _vp],
     "nr3d_lotd_bwd_param2_sorted": [_meta_p, _i32, _u64, _vp, _vp, _u32, _vp, _i64, _i64, _vp, _i32, _vp, _vp],
+    "nr3d_lotd_density_head_fwd_sorted": [_meta_p, _i32, _u64, _vp, _vp, _u32, _vp, _i32, _vp, _f32, _vp, _vp, _vp],
+    "nr3d_lotd_density_head_bwd_sorted": [_meta_p, _i32, _u64, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _vp],
     "nr3d_march_count": [_u64, _vp, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _u32,
                          _vp, _vp],
     "nr3d_march_pack": [_u64, _vp, _vp, _vp, _vp, _u64_p, _vp],

@@ -184,12 +184,17 @@ __device__ __forceinline__ void load_feats(const float* g, float* v, bool vec_ok
     }
 }
 template <int F>
-__device__ __forceinline__ void load_feats(const __half* g, __half* v, bool /*vec_ok*/) {
+__device__ __forceinline__ void load_feats(const __half* g, __half* v, bool vec_ok) {
+    if (vec_ok) {
 #pragma unroll
-    for (int f = 0; f < F; f += 2) {  // offsets are always even -> 4-byte aligned
-        const __half2 t = __ldg(reinterpret_cast<const __half2*>(g + f));
-        v[f] = __low2half(t);
-        v[f + 1] = __high2half(t);
+        for (int f = 0; f < F; f += 2) {  // level / scene offsets are even -> 4-byte aligned
+            const __half2 t = __ldg(reinterpret_cast<const __half2*>(g + f));
+            v[f] = __low2half(t);
+            v[f + 1] = __high2half(t);
+        }
+    } else {  // user-supplied batch_offsets may be odd: scalar accesses
+#pragma unroll
+        for (int f = 0; f < F; ++f) v[f] = __ldg(g + f);
     }
 }
 
@@ -384,9 +389,14 @@ __device__ __forceinline__ void scatter_add(float* addr, const float* v, bool ve
     }
 }
 template <int F>
-__device__ __forceinline__ void scatter_add(__half* addr, const float* v, bool /*vec_ok*/) {
+__device__ __forceinline__ void scatter_add(__half* addr, const float* v, bool vec_ok) {
+    if (vec_ok) {
 #pragma unroll
-    for (int f = 0; f < F; f += 2) red_add_h2(addr + f, __halves2half2(__float2half_rn(v[f]), __float2half_rn(v[f + 1])));
+        for (int f = 0; f < F; f += 2) red_add_h2(addr + f, __halves2half2(__float2half_rn(v[f]), __float2half_rn(v[f + 1])));
+    } else {  // possibly odd element offset: one half atomic per feature (same rounding per element as the packed reduction)
+#pragma unroll
+        for (int f = 0; f < F; ++f) atomicAdd(addr + f, __float2half_rn(v[f]));
+    }
 }
 
 // d(corner value)/d(params) * (grad * weight) for the n-linear types (reference: add_grid_gridient_*_impl)

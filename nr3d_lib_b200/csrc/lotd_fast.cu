@@ -75,9 +75,18 @@ __device__ __forceinline__ bool point_scene(const FastIn& in, uint64_t p, bool a
     return true;
 }
 
-template <typename PT, int F>
+// Density head fused into the encoder (HEAD = true; row "glue" of DESIGN.md, the M2 workload): the stand-in decoder of the render step is
+//   sigma = softplus(gain * sum_c y[c]),  alpha = 1 - exp(-sigma * delta)          (csrc/pipeline_ops.cu, nerf_ray_query.py:182)
+// so the forward only needs the feature SUM of a point and the backward's dL/dy row is one scalar repeated n_enc times: the [S, n_enc]
+// features and their gradient never reach HBM (4 x 128 B per sample of the M2 step).
+struct HeadFwd { const float* deltas; float gain; float* sigma; float* alpha; };
+struct HeadBwd { const float* d_alpha; const float* sigma; const float* alpha; const float* deltas; float gain; };
+
+__device__ __forceinline__ float softplus_head(float v) { return v > 20.0f ? v : log1pf(expf(v)); }   // == F.softplus (beta 1, threshold 20)
+
+template <typename PT, int F, bool HEAD = false>
 __global__ void __launch_bounds__(kFastThreads, F == 2 ? 2048 / kFastThreads : 1)
-lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT* __restrict__ y, int64_t ys_n, int64_t ys_f) {
+lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT* __restrict__ y, int64_t ys_n, int64_t ys_f, const HeadFwd hd) {
     using C = Cvt<PT>;
     constexpr int H = F / 2;   // features of a pseudo level that one lane of the pair writes out
     const PT* params = reinterpret_cast<const PT*>(in.params);
@@ -97,6 +106,7 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT*
     const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
     const bool staged = (ys_f == 1);
     uint32_t chunk_base = 0;
+    float hsum = 0.f;   // HEAD: sum of the point's features, level after level
     constexpr int kFwdUnroll = NR3D_FWD_UNROLL;
 #pragma unroll kFwdUnroll
     for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
@@ -116,6 +126,11 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT*
                 for (int f = 0; f < F; ++f) r[f] = C::to_f(C::add(C::from_f(r[f]), C::from_f(g.w[q] * v[q][f])));
 #pragma unroll
             for (int f = 0; f < F; ++f) r[f] = C::to_f(C::add(C::from_f(r[f]), C::from_f(__shfl_xor_sync(0xffffffffu, r[f], 1))));
+        }
+        if (HEAD) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) hsum += r[f];
+            continue;
         }
         // lane `side` owns features pl * F + side * H + [0, H) of its point
         float mine[H];
@@ -142,6 +157,11 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT*
 #pragma unroll
             for (int j = 0; j < H; ++j) st_cs(y + (int64_t)i * ys_n + (int64_t)(pl * F + side * H + j) * ys_f, C::from_f(mine[j]));
         }
+    }
+    if (HEAD && active && side == 0) {   // skipped points (batch_inds < 0) have all-zero features like in the unfused path
+        const float sg = softplus_head((live ? hsum : 0.f) * hd.gain);
+        __stcs(hd.sigma + i, sg);
+        __stcs(hd.alpha + i, 1.0f - expf(-sg * __ldcs(hd.deltas + i)));
     }
 }
 
@@ -174,10 +194,11 @@ struct TilePlan {                       // one entry per pseudo level, written b
 // SECOND = false: dL/dparam.  SECOND = true: d(dL/dx)/dparam . dL_ddLdx (second-order backward of NeuS-style eikonal terms,
 // reference kernel_lod_hashonly_backward_input_backward_grid, lotd_hash_only.h:472-695): the same scatter with the corner weights
 // replaced by sum_d ddx[d] * dw[d][corner] (pair_geo_d), ddx = dL_ddLdx [N,3] read at the point's original index.
-template <typename PT, int F, bool SECOND>
+// HEAD = true: dL/dy[i, :] = g_i for every feature, g_i = dL/dalpha_i * delta_i * (1 - alpha_i) * gain * sigmoid(gain * s_i) (HeadBwd).
+template <typename PT, int F, bool SECOND, bool HEAD = false>
 __global__ void __launch_bounds__(kBwdThreads, (F == 2 && !SECOND && NR3D_BWD_OCC) ? NR3D_BWD_OCC / kBwdThreads : 1)
 lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, const PT* __restrict__ dLdy, int64_t gs_n, int64_t gs_f,
-                     const float* __restrict__ ddx, PT* __restrict__ grad) {
+                     const float* __restrict__ ddx, PT* __restrict__ grad, const HeadBwd hd) {
     using C = Cvt<PT>;
     extern __shared__ __align__(16) float smem[];
     float* ctile = smem;                                                    // [kTileFloats] CTA tiles (NR3D_BWD_TILES)
@@ -197,7 +218,14 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
     const uint64_t i = __float_as_uint(rec.w);
     const PT* grow = dLdy + (int64_t)i * gs_n;
     const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
-    const bool staged = (gs_f == 1);
+    const bool staged = !HEAD && (gs_f == 1);
+    float ghead = 0.f;
+    if (HEAD && live) {
+        // alpha = 1 - exp(-sigma * delta): d alpha / d sigma = delta * (1 - alpha);  sigma = softplus(gain * s): d sigma / d s = gain * (1 - exp(-sigma))
+        const float sg = __ldcs(hd.sigma + i);
+        const float g_sigma = __ldcs(hd.d_alpha + i) * __ldcs(hd.deltas + i) * (1.0f - __ldcs(hd.alpha + i));
+        ghead = C::to_f(C::from_f(g_sigma * (sg > 20.0f ? 1.0f : (1.0f - expf(-sg))) * hd.gain));
+    }
     float gx[3] = {0.f, 0.f, 0.f};
     if (SECOND && live) { gx[0] = __ldg(ddx + i * 3); gx[1] = __ldg(ddx + i * 3 + 1); gx[2] = __ldg(ddx + i * 3 + 2); }
     // a point starts a new run on every level when its scene differs from the previous point's
@@ -259,8 +287,9 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
         const uint32_t level = tab.map_level[pl];
         float gv[F];
 #pragma unroll
-        for (int f = 0; f < F; ++f) gv[f] = 0.f;
-        if (staged) {
+        for (int f = 0; f < F; ++f) gv[f] = HEAD ? ghead : 0.f;
+        if (HEAD) {
+        } else if (staged) {
             const uint32_t want_base = (pl * (uint32_t)F) / 32u * 32u;
             if (want_base != chunk_base) {  // stage the next (up to) 32 features of the warp's 16 rows: one coalesced row read per point
                 const uint32_t width = min(32u, tab.n_enc - want_base);
@@ -520,16 +549,17 @@ static int check_fast(const nr3d_lotd_meta* m, int32_t param_dtype, uint64_t N, 
 // shared memory of the backward kernel: CTA tiles + one staged [16, 32] row tile per warp
 constexpr size_t kBwdSmem = sizeof(float) * ((NR3D_BWD_TILES ? kTileFloats : 0) + kBwdWarps * 16 * kPairRowStride);
 
-template <typename PT, int F, bool SECOND>
-static int launch_bwd(const LotdTable& tab, const FastIn& in, const void* dL_dy, int64_t gs_n, int64_t gs_f, const float* ddx, void* grad, cudaStream_t st) {
-    auto kern = lotd_pair_bwd_kernel<PT, F, SECOND>;
+template <typename PT, int F, bool SECOND, bool HEAD = false>
+static int launch_bwd(const LotdTable& tab, const FastIn& in, const void* dL_dy, int64_t gs_n, int64_t gs_f, const float* ddx, void* grad, cudaStream_t st,
+                      const HeadBwd hd = HeadBwd{}) {
+    auto kern = lotd_pair_bwd_kernel<PT, F, SECOND, HEAD>;
     static bool configured = false;   // per instantiation; racing threads would set the same value
     if (!configured) {
         NR3D_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem) == cudaSuccess, "lotd_fast_bwd: cannot reserve %d bytes of shared memory", (int)kBwdSmem);
         configured = true;
     }
     const unsigned grid = (unsigned)div_up<uint64_t>(2 * in.N, kBwdThreads);
-    kern<<<grid, kBwdThreads, kBwdSmem, st>>>(tab, in, (const PT*)dL_dy, gs_n, gs_f, ddx, (PT*)grad);
+    kern<<<grid, kBwdThreads, kBwdSmem, st>>>(tab, in, (const PT*)dL_dy, gs_n, gs_f, ddx, (PT*)grad, hd);
     NR3D_LAUNCH_CHECK(SECOND ? "lotd_fast_bwd2" : "lotd_fast_bwd");
     return 0;
 }
@@ -537,8 +567,16 @@ static int launch_bwd(const LotdTable& tab, const FastIn& in, const void* dL_dy,
 template <typename PT, int F>
 static int launch_fwd(const LotdTable& tab, const FastIn& in, void* y, int64_t ys_n, int64_t ys_f, cudaStream_t st) {
     const unsigned grid = (unsigned)div_up<uint64_t>(2 * in.N, kFastThreads);
-    lotd_pair_fwd_kernel<PT, F><<<grid, kFastThreads, 0, st>>>(tab, in, (PT*)y, ys_n, ys_f);
+    lotd_pair_fwd_kernel<PT, F><<<grid, kFastThreads, 0, st>>>(tab, in, (PT*)y, ys_n, ys_f, HeadFwd{});
     NR3D_LAUNCH_CHECK("lotd_fast_fwd");
+    return 0;
+}
+
+template <typename PT, int F>
+static int launch_fwd_head(const LotdTable& tab, const FastIn& in, const HeadFwd& hd, cudaStream_t st) {
+    const unsigned grid = (unsigned)div_up<uint64_t>(2 * in.N, kFastThreads);
+    lotd_pair_fwd_kernel<PT, F, true><<<grid, kFastThreads, 0, st>>>(tab, in, (PT*)nullptr, 0, 0, hd);
+    NR3D_LAUNCH_CHECK("lotd_fast_fwd_head");
     return 0;
 }
 
@@ -596,6 +634,36 @@ int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, 
     int rc = 0;
     NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl,
                        (rc = launch_bwd<PT, F, false>(tab, in, dL_dy, dLdy_stride_n, dLdy_stride_f, nullptr, dL_dparam, (cudaStream_t)stream)));
+    return rc;
+}
+
+int nr3d_lotd_density_head_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
+                                      const void* params, int32_t max_level, const float* deltas, float gain, float* sigma, float* alpha, void* stream) {
+    if (int rc = check_fast(meta, param_dtype, N, n_scenes, params)) return rc;
+    if (N == 0) return 0;
+    NR3D_CHECK(xs && params && deltas && sigma && alpha, "LoTDEncoding::density_head_fwd_sorted: null argument");
+    LotdTable tab;
+    make_table(meta, tab);
+    FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, params, max_level, meta->n_params, 0u, meta->n_pseudo_levels};
+    const HeadFwd hd{deltas, gain, sigma, alpha};
+    int rc = 0;
+    NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl, (rc = launch_fwd_head<PT, F>(tab, in, hd, (cudaStream_t)stream)));
+    return rc;
+}
+
+int nr3d_lotd_density_head_bwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
+                                      const float* d_alpha, const float* sigma, const float* alpha, const float* deltas, float gain, int32_t max_level,
+                                      void* dL_dparam, void* stream) {
+    if (int rc = check_fast(meta, param_dtype, N, n_scenes, dL_dparam)) return rc;
+    if (N == 0) return 0;
+    NR3D_CHECK(xs && d_alpha && sigma && alpha && deltas && dL_dparam, "LoTDEncoding::density_head_bwd_sorted: null argument");
+    LotdTable tab;
+    make_table(meta, tab);
+    FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, nullptr, max_level, meta->n_params, 0u, meta->n_pseudo_levels};
+    const HeadBwd hd{d_alpha, sigma, alpha, deltas, gain};
+    int rc = 0;
+    NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl,
+                       (rc = launch_bwd<PT, F, false, true>(tab, in, nullptr, 0, 0, nullptr, dL_dparam, (cudaStream_t)stream, hd)));
     return rc;
 }
 

@@ -78,6 +78,7 @@ struct MarchArgs {
     const float *rays_o, *rays_d, *t_min, *t_max;
     const int32_t* batch_inds;
     uint32_t batch_data_size;
+    uint32_t n_batches;   // rays whose batch index is outside [0, n_batches) are skipped (count 0) instead of reading grid / roi out of bounds
     const float* roi;
     const uint8_t* grid;
     int3 res;
@@ -95,13 +96,17 @@ march_kernel(const MarchArgs a, const int32_t* __restrict__ packed_info, int32_t
     uint32_t batch_ind = 0;
     if (a.batch_inds) {
         const int32_t b = a.batch_inds[i];
-        if (b < 0) {
+        if (b < 0 || (uint32_t)b >= a.n_batches) {
             if (!FILL) num_steps[i] = 0;
             return;
         }
         batch_ind = (uint32_t)b;
     } else if (a.batch_data_size) {
         batch_ind = (uint32_t)(i / a.batch_data_size);
+        if (batch_ind >= a.n_batches) {
+            if (!FILL) num_steps[i] = 0;
+            return;
+        }
     }
     const uint32_t cells = (uint32_t)(a.res.x * a.res.y * a.res.z);
     const uint32_t grid_offset = batch_ind * cells;
@@ -181,9 +186,10 @@ march_fill_staged_kernel(const MarchArgs a, const int32_t* __restrict__ packed_i
     if (!done) {
         if (a.batch_inds) {
             const int32_t b = a.batch_inds[i];
-            if (b < 0) done = true; else batch_ind = (uint32_t)b;
+            if (b < 0 || (uint32_t)b >= a.n_batches) done = true; else batch_ind = (uint32_t)b;
         } else if (a.batch_data_size) {
             batch_ind = (uint32_t)(i / a.batch_data_size);
+            if (batch_ind >= a.n_batches) { done = true; batch_ind = 0; }
         }
     }
     const uint32_t cells = (uint32_t)(a.res.x * a.res.y * a.res.z);
@@ -273,7 +279,7 @@ static int fill_args(MarchArgs& a, uint64_t n_rays, const float* rays_o, const f
                (unsigned long long)n_rays);
     NR3D_CHECK(n_rays < (1ull << 31), "ray_marching: n_rays must be < 2^31");
     a.n_rays = n_rays; a.rays_o = rays_o; a.rays_d = rays_d; a.t_min = t_min; a.t_max = t_max;
-    a.batch_inds = batch_inds; a.batch_data_size = batch_data_size; a.roi = roi; a.grid = grid;
+    a.batch_inds = batch_inds; a.batch_data_size = batch_data_size; a.n_batches = (uint32_t)n_batches; a.roi = roi; a.grid = grid;
     a.res = make_int3(rx, ry, rz); a.type = contraction;
     a.step_size = step_size; a.max_step_size = max_step_size; a.dt_gamma = dt_gamma; a.max_steps = max_steps;
     return 0;

@@ -38,7 +38,7 @@ class FusedDensityDecoder:
             raise RuntimeError("FusedDensityDecoder: needs a Dense/Hash-only LoDMeta with D=3, F=2 and 32 encoded dims")
         if tuple(w1.shape) != (64, 32) or w2.dim() != 2 or w2.shape[1] != 64 or not (1 <= w2.shape[0] <= 16):
             raise RuntimeError(f"FusedDensityDecoder: expected w1 [64, 32] and w2 [<=16, 64], got {tuple(w1.shape)} and {tuple(w2.shape)}")
-        self.dev = _lib.require_cuda(w1, w2, who="FusedDensityDecoder")
+        self.dev = _lib.require_cuda(w1, w2, b1, b2, who="FusedDensityDecoder")
         self.meta, self.activation, self.n_out = meta, _ACT[activation], w2.shape[0]
         self.w1p, self.w2p = pack_kmajor_bf16(w1, 64), pack_kmajor_bf16(w2, 16)
         self.b1 = None if b1 is None else b1.detach().float().contiguous()
@@ -56,14 +56,16 @@ class FusedDensityDecoder:
             raise RuntimeError(f"{fn}: expected a contiguous fp32 [N, 3] tensor for `x`")
         if params.dtype != torch.float32 or params.shape[0] != self.meta.n_params or not params.is_contiguous():
             raise RuntimeError(f"{fn}: expected contiguous fp32 params of size n_params={self.meta.n_params}")
-        dev = _lib.require_cuda(x, params, who=fn)
+        dev = _lib.require_cuda(x, params, self.w1p, self.b2, self.b1, who=fn)    # ... and on the decoder's device
         N = x.shape[0]
         ml = self.meta.n_levels if max_level is None else int(max_level)
         with torch.cuda.device(dev):
             sigma = torch.empty([N], dtype=torch.float32, device=dev)
             out16 = torch.empty([N, 16], dtype=torch.float32, device=dev) if return_output else None
             if N:
-                xs, _ = _lotd._sorted_points(x)
+                # same clamp as the unfused path (reference lotd.py:211 / nr3d_lib_b200/lotd.py): points on or outside the box boundary index
+                # the last cell instead of reading Dense levels out of bounds
+                xs, _ = _lotd._sorted_points(x.clamp(1.0e-6, 1.0 - 1.0e-6))
                 _lib.check(_lib.get_lib().nr3d_lotd_fused_density_fwd(
                     ctypes.byref(self.meta._c), N, xs.data_ptr(), params.data_ptr(), ml, self.w1p.data_ptr(), _lib.ptr(self.b1),
                     self.w2p.data_ptr(), self.b2.data_ptr(), self.activation, sigma.data_ptr(), _lib.ptr(out16), _lib.stream_of(dev)))

@@ -25,12 +25,14 @@ err_msg_empty_occ = ("Occupancy grid becomes empty during training. Your model/a
 _scratch = {}
 
 
-def _scratch_for(dev, n):
-    """uint32 scratch, zero between calls (nr3d_occ_apply resets what nr3d_occ_scatter_max touched)."""
-    key = (dev.index, n)
+def _scratch_for(dev, n, stream):
+    """uint32 scratch, zero between calls (nr3d_occ_apply resets what nr3d_occ_scatter_max touched).  One buffer per (device, stream, size):
+    two grids of equal size updated on different streams never share it.  A failed update zeroes it again (see the caller)."""
+    key = (dev.index, int(stream or 0), n)
     buf = _scratch.get(key)
     if buf is None:
-        _scratch.clear()   # one grid shape at a time is the common case; do not hoard
+        for k in [k for k in _scratch if k[:2] == key[:2]]:
+            del _scratch[k]   # one grid shape at a time per stream is the common case; do not hoard
         buf = torch.zeros([n], dtype=torch.int32, device=dev)
         _scratch[key] = buf
     return buf
@@ -117,19 +119,23 @@ def _update(fn, grid, *, pts=None, gidx=None, bidx=None, batch_data_size=0, occ_
     n_cells = grid.numel()
     with torch.cuda.device(dev):
         st = _lib.stream_of(dev)
-        scratch = _scratch_for(dev, n_cells)
-        _lib.check(lib.nr3d_occ_scatter_max(N, _lib.ptr(pts), _lib.ptr(gidx), _lib.ptr(bidx), int(batch_data_size), occ_val.data_ptr(), int(B),
-                                            _res_array(res3), scratch.data_ptr(), st))
-        if extra is not None:
-            e_gidx, e_bidx, e_val = extra
-            e_gidx, e_val = e_gidx.reshape(-1, 3).long().contiguous(), e_val.flatten().to(grid).contiguous()
-            e_bidx = None if e_bidx is None else e_bidx.flatten().long().contiguous()
-            _lib.check(lib.nr3d_occ_scatter_max(e_val.shape[0], None, e_gidx.data_ptr(), _lib.ptr(e_bidx), 0, e_val.data_ptr(), int(B),
+        scratch = _scratch_for(dev, n_cells, st)
+        try:
+            _lib.check(lib.nr3d_occ_scatter_max(N, _lib.ptr(pts), _lib.ptr(gidx), _lib.ptr(bidx), int(batch_data_size), occ_val.data_ptr(), int(B),
                                                 _res_array(res3), scratch.data_ptr(), st))
-        fused = occ_out is not None and not consider_mean
-        total = torch.zeros([1], dtype=torch.float64, device=dev) if (occ_out is not None and consider_mean) else None
-        _lib.check(lib.nr3d_occ_apply(n_cells, grid.data_ptr(), scratch.data_ptr(), float(ema_decay), int(fused), float(occ_thre),
-                                      _lib.ptr(occ_out) if fused else None, _lib.ptr(total), st))
+            if extra is not None:
+                e_gidx, e_bidx, e_val = extra
+                e_gidx, e_val = e_gidx.reshape(-1, 3).long().contiguous(), e_val.flatten().to(grid).contiguous()
+                e_bidx = None if e_bidx is None else e_bidx.flatten().long().contiguous()
+                _lib.check(lib.nr3d_occ_scatter_max(e_val.shape[0], None, e_gidx.data_ptr(), _lib.ptr(e_bidx), 0, e_val.data_ptr(), int(B),
+                                                    _res_array(res3), scratch.data_ptr(), st))
+            fused = occ_out is not None and not consider_mean
+            total = torch.zeros([1], dtype=torch.float64, device=dev) if (occ_out is not None and consider_mean) else None
+            _lib.check(lib.nr3d_occ_apply(n_cells, grid.data_ptr(), scratch.data_ptr(), float(ema_decay), int(fused), float(occ_thre),
+                                          _lib.ptr(occ_out) if fused else None, _lib.ptr(total), st))
+        except BaseException:
+            scratch.zero_()   # nr3d_occ_apply did not run (or failed): do not leave stale maxima for the next update
+            raise
         if total is not None:
             _lib.check(lib.nr3d_occ_binarize(n_cells, grid.data_ptr(), float(occ_thre), 1, float(eps), total.data_ptr(), occ_out.data_ptr(), st))
 

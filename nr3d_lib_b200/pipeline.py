@@ -77,16 +77,80 @@ def density_alpha(features: torch.Tensor, deltas: torch.Tensor, gain: float = 20
     return _DensityAlpha.apply(features, deltas, gain)
 
 
+class _EncodeDensityAlpha(torch.autograd.Function):
+    """encode + density head in ONE kernel each way (csrc/lotd_fast.cu, HEAD = true): alpha, sigma = head(LoTD(x)) without the [S, n_enc]
+    features or their gradient ever reaching HBM.  Same values as `density_alpha(encoder(x, params), deltas, gain)` up to the summation
+    order of the features (tests/test_pipeline_gpu.py).  Differentiable w.r.t. `params` through alpha."""
+
+    @staticmethod
+    def forward(ctx, meta, x01, params, deltas, gain, max_level):
+        import ctypes
+        from . import _lib
+        from .bindings import _lotd
+        dev = _lib.require_cuda(x01, params, deltas, who="encode_density_alpha")
+        x = x01.detach().clamp(1.0e-6, 1.0 - 1.0e-6).contiguous()          # as LoTDFunction does (reference lotd.py:211)
+        deltas = deltas.detach().float().contiguous().flatten()
+        N = x.shape[0]
+        ml = meta.n_levels if max_level is None else int(max_level)
+        with torch.cuda.device(dev):
+            sigma = torch.empty(N, dtype=torch.float32, device=dev)
+            alpha = torch.empty(N, dtype=torch.float32, device=dev)
+            if N:
+                xs, scenes = _lotd._sorted_points(x)
+                _lib.check(_lib.get_lib().nr3d_lotd_density_head_fwd_sorted(
+                    ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), _lib.ptr(scenes), 1, params.data_ptr(), ml,
+                    deltas.data_ptr(), float(gain), sigma.data_ptr(), alpha.data_ptr(), _lib.stream_of(dev)))
+        ctx.save_for_backward(x, sigma, alpha, deltas)
+        ctx.meta, ctx.gain, ctx.ml, ctx.pshape, ctx.pdtype = meta, float(gain), ml, params.shape, params.dtype
+        ctx.mark_non_differentiable(sigma)
+        return alpha, sigma
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_alpha, _d_sigma):
+        import ctypes
+        from . import _lib
+        from .bindings import _lotd
+        x, sigma, alpha, deltas = ctx.saved_tensors
+        if d_alpha is None or not ctx.needs_input_grad[2]:
+            return None, None, None, None, None, None
+        d_alpha = d_alpha.float().contiguous()
+        dev, N = x.device, x.shape[0]
+        with torch.cuda.device(dev):
+            g = torch.zeros(ctx.pshape, dtype=ctx.pdtype, device=dev)
+            if N:
+                xs, scenes = _lotd._sorted_points(x)      # the forward's records unless other points were sorted on this stream in between
+                _lib.check(_lib.get_lib().nr3d_lotd_density_head_bwd_sorted(
+                    ctypes.byref(ctx.meta._c), _lib.dtype_code(ctx.pdtype), N, xs.data_ptr(), _lib.ptr(scenes), 1, d_alpha.data_ptr(), sigma.data_ptr(),
+                    alpha.data_ptr(), deltas.data_ptr(), ctx.gain, ctx.ml, g.data_ptr(), _lib.stream_of(dev)))
+        return None, None, g, None, None, None
+
+
+def encode_density_alpha(encoder: LoTD, x01: torch.Tensor, params: torch.Tensor, deltas: torch.Tensor, gain: float = 20.0, max_level=None):
+    """(alpha, sigma) of the stand-in density head applied to the LoTD features of `x01`; one fused kernel each way when the encoder is
+    eligible for the cell-sorted fast path (Dense/Hash, D = 3, single scene), the two-kernel composition otherwise."""
+    from .bindings import _lotd
+    meta = encoder.meta
+    p = params.to(encoder.dtype)
+    if _lotd._sorted_eligible(meta, x01, p, None, None, 0) and x01.dim() == 2 and p.shape[0] == meta.n_params:
+        return _EncodeDensityAlpha.apply(meta, x01, p, deltas, gain, max_level)
+    return density_alpha(encoder(x01, params, max_level=max_level).float(), deltas, gain)
+
+
 def march_encode_composite(encoder: LoTD, params: torch.Tensor, occ_grid: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor,
                            near: torch.Tensor, far: torch.Tensor, *, step_size: float = 0.01, max_steps: int = 512, gain: float = 20.0,
-                           early_stop_eps: float = 1e-4, alpha_thre: float = 0.0) -> RenderOut:
-    """One differentiable render step for rays already intersected with the [-1,1]^3 box (near / far given)."""
+                           early_stop_eps: float = 1e-4, alpha_thre: float = 0.0, fuse_head: bool = True) -> RenderOut:
+    """One differentiable render step for rays already intersected with the [-1,1]^3 box (near / far given).  `fuse_head=False` keeps the
+    [S, n_enc] features in HBM between the encoder and the density head (the composition the reference's callers run)."""
     ret = occgrid_raymarch(occ_grid, rays_o, rays_d, near, far, step_size=step_size, max_steps=max_steps)
     if ret.num_hit_rays == 0:
         return RenderOut(ret, None, None, None)
     x01 = ret.samples * 0.5 + 0.5                      # [-1,1] -> [0,1]  (LoTDEncoding.forward, lotd_encoding.py:162)
-    h = encoder(x01, params)                           # [S, n_enc]
-    alpha, _sigma = density_alpha(h.float(), ret.deltas, gain)   # softplus head + (1 - exp(-sigma * delta)), nerf_ray_query.py:182
+    if fuse_head:
+        alpha, _sigma = encode_density_alpha(encoder, x01, params, ret.deltas, gain)
+    else:
+        h = encoder(x01, params)                       # [S, n_enc]
+        alpha, _sigma = density_alpha(h.float(), ret.deltas, gain)   # softplus head + (1 - exp(-sigma * delta)), nerf_ray_query.py:182
     w = packed_alpha_to_vw(alpha, ret.pack_infos, early_stop_eps, alpha_thre)
     depth = packed_sum(w * ret.depth_samples, ret.pack_infos)
     acc = packed_sum(w, ret.pack_infos)

@@ -203,6 +203,15 @@ def test_lotd_batch_data_size_and_offsets(dev):
     _, g_a = mine.lod_bwd(meta, dL_dy, x, params, None, batch_inds=bi, need_input_grad=False, need_param_grad=True)
     _, g_c = mine.lod_bwd(meta, dL_dy, x, params2, None, batch_inds=bi, batch_offsets=off, need_input_grad=False, need_param_grad=True)
     assert rel_err(g_c[pad:pad + params.numel()].cpu(), g_a.cpu()) < 1e-5 and g_c[:pad].abs().max() == 0
+    # fp16 tables behind an ODD element offset: 2-byte aligned only, the kernels must not use packed-half loads / reductions
+    ph, ph2, gyh = params.half(), params2.half(), dL_dy.half()
+    y_h, _ = mine.lod_fwd(meta, x, ph, batch_inds=bi, need_input_grad=False)
+    y_ho, dydx_ho = mine.lod_fwd(meta, x, ph2, batch_inds=bi, batch_offsets=off, need_input_grad=True)
+    assert torch.equal(y_h, y_ho)
+    _, g_h = mine.lod_bwd(meta, gyh, x, ph, None, batch_inds=bi, need_input_grad=False, need_param_grad=True)
+    _, g_ho = mine.lod_bwd(meta, gyh, x, ph2, None, batch_inds=bi, batch_offsets=off, need_input_grad=False, need_param_grad=True)
+    torch.cuda.synchronize(dev)
+    assert rel_err(g_ho[pad:pad + params.numel()].float().cpu(), g_h.float().cpu()) < 2e-2 and g_ho[:pad].abs().max() == 0
 
 
 def test_lotd_edge_cases(dev):

@@ -15,8 +15,8 @@ def _ngp(levels=10, T=2 ** 14):
     return dict(in_features=3, lod_res=res, lod_n_feats=[2] * levels, lod_types=["Dense" if r ** 3 <= T else "Hash" for r in res], hashmap_size=T)
 
 
-@pytest.mark.parametrize("sort_points", [False, True])
-def test_march_encode_composite_matches_oracles(sort_points, dev):
+@pytest.mark.parametrize("sort_points,fuse_head", [(False, False), (True, False), (True, True)])
+def test_march_encode_composite_matches_oracles(sort_points, fuse_head, dev):
     from nr3d_lib_b200.lotd import LoTD
     from nr3d_lib_b200.pipeline import march_encode_composite
     from oracle import lotd_oracle as O, march_oracle as MO, pack_oracle as PO
@@ -28,7 +28,8 @@ def test_march_encode_composite_matches_oracles(sort_points, dev):
     rs = np.random.RandomState(1)
     p_host = torch.from_numpy((rs.randn(enc.n_params) * 0.05).astype(np.float32))
     params = p_host.to(dev).requires_grad_(True)
-    out = march_encode_composite(enc, params, t(d["grid"]), t(d["rays_o"]), t(d["rays_d"]), t(d["near"]), t(d["far"]), step_size=0.02, max_steps=256)
+    out = march_encode_composite(enc, params, t(d["grid"]), t(d["rays_o"]), t(d["rays_d"]), t(d["near"]), t(d["far"]), step_size=0.02, max_steps=256,
+                                 fuse_head=fuse_head)
     assert out.march.num_hit_rays > 100
     loss = (out.depth ** 2).sum() + out.acc.sum()
     loss.backward()
@@ -109,6 +110,51 @@ def test_density_alpha_matches_torch_composition(C, dev):
         assert rel_err(a.grad, b.grad) < 1e-5
     with pytest.raises(RuntimeError):
         density_alpha(h.cpu(), deltas.cpu(), 20.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pdtype", [torch.float32, torch.float16])
+def test_fused_density_head_matches_composition(pdtype, dev):
+    """encode + density head fused into the pair kernels (lotd_fast.cu, HEAD) == density_alpha(LoTD(x)): alpha, sigma and dL/dparams."""
+    from nr3d_lib_b200 import _lib
+    from nr3d_lib_b200.lotd import LoTD
+    from nr3d_lib_b200.pipeline import density_alpha, encode_density_alpha
+    from oracle import lotd_oracle as O
+    cfg = _ngp()
+    enc = LoTD(dtype=pdtype, **cfg)
+    g = torch.Generator().manual_seed(8)
+    S = 30011
+    x = torch.rand(S, 3, generator=g)
+    x[:3] = torch.tensor([[0.0, 1.0, 0.5], [1.0, 1.0, 1.0], [0.0, 0.0, 0.0]])          # box boundary: clamped like the unfused path
+    p_host = (torch.randn(enc.n_params, generator=g) * 0.05).to(pdtype)
+    deltas = (torch.rand(S, generator=g) * 0.05).to(dev)
+    w = torch.randn(S, generator=g).to(dev)
+    xd = x.to(dev)
+    pa = p_host.to(dev).requires_grad_(True)
+    n0 = _lib.launch_count()
+    alpha, sigma = encode_density_alpha(enc, xd, pa, deltas, 2.0)
+    (alpha * w).sum().backward()
+    fused_launches = _lib.launch_count() - n0
+    pb = p_host.to(dev).requires_grad_(True)
+    alpha_u, sigma_u = density_alpha(enc(xd, pb).float(), deltas, 2.0)
+    (alpha_u * w).sum().backward()
+    tol = 1e-5 if pdtype == torch.float32 else 2e-3
+    assert rel_err(sigma, sigma_u) < tol and rel_err(alpha.detach(), alpha_u.detach()) < tol
+    assert rel_err(pa.grad.float(), pb.grad.float()) < (2e-5 if pdtype == torch.float32 else 3e-2)
+    assert fused_launches <= 8, fused_launches          # sort (<= 5) + head forward + memset-free head backward (+ fingerprint)
+    if pdtype == torch.float32:                          # and against the float64 oracle
+        om = O.OracleMeta(3, cfg["lod_res"], cfg["lod_n_feats"], cfg["lod_types"], cfg["hashmap_size"])
+        pd = p_host.double().requires_grad_(True)
+        h = O.encode(om, x.clamp(1e-6, 1 - 1e-6), pd)
+        sig = F.softplus(h.sum(-1) * 2.0)
+        al = 1.0 - torch.exp(-sig * deltas.cpu().double())
+        (al * w.cpu().double()).sum().backward()
+        assert rel_err(sigma.cpu(), sig.detach()) < 1e-5 and rel_err(alpha.detach().cpu(), al.detach()) < 1e-5
+        assert rel_err(pa.grad.cpu(), pd.grad) < 2e-5
+    enc.meta.c_sort_points = False                       # not eligible: falls back to the two-kernel composition, same values
+    pc = p_host.to(dev).requires_grad_(True)
+    alpha_g, _ = encode_density_alpha(enc, xd, pc, deltas, 2.0)
+    assert rel_err(alpha_g.detach(), alpha_u.detach()) < tol
 
 
 @pytest.mark.gpu
