@@ -169,9 +169,10 @@ def main():
     ap.add_argument("--e2e-serial", action="store_true", help="e2e leg without copy/compute overlap (single stream)")
     ap.add_argument("--no-sort", action="store_true", help="use the generic (unsorted, feature-major) kernels instead of lotd_fast.cu")
     ap.add_argument("--no-m2", action="store_true", help="skip the secondary M2 block (march + encode + composite rays/s)")
-    ap.add_argument("--allreduce", default="bucketed", choices=["bucketed", "allreduce"],
-                    help="N > 1: how dL/dparams is summed (dist.GradReducer): fine levels first with their all-reduce overlapping the coarse "
-                         "levels' scatter (default), or one blocking all-reduce after the scatter")
+    ap.add_argument("--allreduce", default="allreduce", choices=["bucketed", "allreduce"],
+                    help="N > 1: how dL/dparams is summed (dist.GradReducer): one NCCL all-reduce after the scatter (default), or fine levels first "
+                         "with their all-reduce overlapping the coarse levels' scatter (measured slower: 2.47 vs 2.15 ms / step at 2 GPUs, "
+                         "profiles/r2_bench_2gpu_*.json)")
     ap.add_argument("--no-extras", action="store_true", help="skip the informational legs (reference CUDA build, generic path, torch CPU baselines)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -264,6 +265,7 @@ def main():
     ms_step = ms_total / args.steps
     value = n_gpus * N / (ms_step * 1e-3) / 1e6
 
+    reducer.close()        # ("bucketed": the level-group hook must not fire inside the e2e leg, which has its own reduce-scatter)
     run_e2e(2)
     ms_e2e = timed(lambda: run_e2e(args.steps), 1) / args.steps
     e2e_value = n_gpus * N / (ms_e2e * 1e-3) / 1e6
@@ -370,7 +372,7 @@ def main():
                             "from the step's y, the summed dL/dparams (one reduce-scatter) is read back to the host once -- each rank returns its 1/N slice; "
                             + ("single stream" if args.e2e_serial else "copies of neighbouring steps overlap the kernels (pipeline.HostFedLoTDStep)")},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "fp16_params": fp16_block, "m2": m2_block,
-            "collective": (None if n_gpus == 1 else {"value_leg": args.allreduce + (": all-reduce of levels 8-15 overlaps the scatter of levels 0-7" if args.allreduce == "bucketed" else ""),
+            "collective": (None if n_gpus == 1 else {"value_leg": ("bucketed: all-reduce of levels 8-15 overlaps the scatter of levels 0-7" if args.allreduce == "bucketed" else "one NCCL all-reduce (sum) of the 48.5 MB fp32 dL/dparams after the scatter, on the step's stream"),
                                                      "e2e_leg": "reduce-scatter, each rank returns its slice"}),
             "numa": numa, "generic_path": generic_block, "ref_cuda_build": ref_cuda_block, "torch_cpu_baselines": torch_cpu}
     sys.stdout.flush()

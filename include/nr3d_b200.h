@@ -162,7 +162,8 @@ int nr3d_lotd_forest_bwd_bwd_dx(const nr3d_lotd_meta* meta, const nr3d_forest_me
  *                 / batch_data_size / n_scenes as in nr3d_lotd_fwd.  Query the workspace size with ws == NULL.
  *                 The workspace is STATEFUL: zero-fill it before its first use and keep it with `xs`; every call fingerprints the points it
  *                 is given (on the device, in stream order) and re-sorts only when they differ from the ones the records were built from
- *                 (`force` != 0: always sort) -- lod_fwd and lod_bwd of one step share one sort without trusting host-side tensor identity.
+ *                 (`force` != 0: always sort, the fingerprint is taken inside the histogram pass -- what a forward call with new points wants) --
+ *                 lod_fwd and lod_bwd of one step share one sort without trusting host-side tensor identity.
  *   fwd_sorted  : same values as nr3d_lotd_fwd; y element (n, j) at y + n*y_stride_n + j*y_stride_f (row-major is fastest).
  *   bwd_param_sorted : same values as nr3d_lotd_bwd_param (up to fp32 summation order); dL_dparam zero-filled by caller.  Only the pseudo
  *                 levels [pl_begin, pl_end) are scattered (0, UINT32_MAX: all) -- multi-GPU callers launch the fine levels first and start
@@ -206,6 +207,18 @@ int nr3d_lotd_density_head_bwd_sorted(const nr3d_lotd_meta* meta, int32_t param_
 int nr3d_lotd_fused_density_fwd(const nr3d_lotd_meta* meta, uint64_t N, const void* xs, const void* params, int32_t max_level,
                                 const void* w1_packed, const float* b1, const void* w2_packed, const float* b2, int32_t activation,
                                 float* sigma, float* out16, void* stream);
+
+/* Backward of the fused encoder + decoder (training through LoTDNeRF.forward_density, lotd_nerf.py:136-178, and models/blocks/mlp.py):
+ * one persistent kernel re-gathers the features, recomputes the hidden layer and runs  dH = G W2,  dF = (dH . relu') W1,
+ * dW2 += G^T H,  [dW1 | db1] += (dH . relu')^T [F | 1]  on tcgen05 (weight-gradient accumulators stay in TMEM for the whole kernel), then
+ * scatters dF into dL_dparam with the run-merged reductions of the sorted fast path.  G = dL/d(decoder output) [N, 16]:
+ * column 0 = d_sigma * activation'(out0) (derived from the forward's `sigma`) + d_out16[:, 0], the other columns d_out16 (either may be NULL).
+ * w2t_packed = W2^T [64, 16], w1t_packed = W1^T [32, 64], both bf16 K-major core-matrix order like w1_packed.
+ * Outputs are ACCUMULATED (zero them first): dL_dparam [n_params] f32, dW1 [64, 32], db1 [64], dW2 [16, 64], db2 [16] f32.  No dL/dx. */
+int nr3d_lotd_fused_density_bwd(const nr3d_lotd_meta* meta, uint64_t N, const void* xs, const void* params, int32_t max_level,
+                                const void* w1_packed, const void* w2t_packed, const void* w1t_packed, const float* b1, int32_t activation,
+                                const float* sigma, const float* d_sigma, const float* d_out16, float* dL_dparam, float* dW1, float* db1,
+                                float* dW2, float* db2, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------------
@@ -300,8 +313,10 @@ int nr3d_occ_query(uint64_t N, const float* pts, const int64_t* bidx, uint64_t b
  * pack_ops (replaces nr3d_lib.bindings._pack_ops, csrc/pack_ops/pack_ops.cpp:20-58)
  * pack_infos: int64 [P, 2] = (first index, length).  feats: [S, C] contiguous (C = 1 for 1-D tensors).
  * ---------------------------------------------------------------------------------------------- */
-/* == packed_sum, pack_ops_cuda.cu:798-861.  out [P, C] fully written (0 for empty packs). */
-int nr3d_pack_sum(int32_t dtype, uint64_t P, uint32_t C, const void* feats, const int64_t* pack_infos, void* out, void* stream);
+/* == packed_sum, pack_ops_cuda.cu:798-861.  out [P, C] fully written (0 for empty packs).  S = rows of `feats` (the tensor's size, which
+ * the reference's pybind entry knows too): lets the staged kernels (TMA bulk copies of whole sample windows, pack_staged.cu) stay inside the
+ * array; S = 0 selects the warp-per-pack kernels. */
+int nr3d_pack_sum(int32_t dtype, uint64_t P, uint32_t C, uint64_t S, const void* feats, const int64_t* pack_infos, void* out, void* stream);
 /* == packed_cumsum / packed_cumprod, pack_ops_cuda.cu:864-1095.  out [S, C] must be zero-filled where elements
  * are not covered by any pack. exclusive cumprod implements the DOCUMENTED semantics (leading 1,
  * nr3d_lib/graphics/pack_ops/pack_ops.py:149); bug_compat=1 reproduces the reference CUDA output (all zeros). */
@@ -319,12 +334,14 @@ int nr3d_pack_backward_diff(int32_t dtype, uint64_t P, uint32_t C, const void* f
 int nr3d_pack_binary(int32_t op, int32_t dtype, uint64_t P, uint32_t C, const void* feats, const void* other,
                      const int64_t* pack_infos, void* out, void* stream);
 /* == packed_alpha_to_vw_forward, pack_ops_cuda.cu:1735-1793,1850-1911.  weights (nullable) must be zero-filled;
- * num_steps (nullable, int64 [P]) fully written; selector (nullable, bool [S]) must be zero-filled. */
-int nr3d_pack_alpha_to_vw_fwd(int32_t dtype, uint64_t P, const void* alphas, const int64_t* pack_infos,
+ * num_steps (nullable, int64 [P]) fully written; selector (nullable, bool [S]) must be zero-filled.  S = number of samples in `alphas`
+ * (see nr3d_pack_sum).  Weights, selectors and counts are bit-identical to the reference's for every dtype. */
+int nr3d_pack_alpha_to_vw_fwd(int32_t dtype, uint64_t P, uint64_t S, const void* alphas, const int64_t* pack_infos,
                               float early_stop_eps, float alpha_thre, void* weights, int64_t* num_steps,
                               uint8_t* selector, void* stream);
-/* == packed_alpha_to_vw_backward, pack_ops_cuda.cu:1795-1848,1914-1958. grad_alphas must be zero-filled. */
-int nr3d_pack_alpha_to_vw_bwd(int32_t dtype, uint64_t P, const void* weights, const void* grad_weights,
+/* == packed_alpha_to_vw_backward, pack_ops_cuda.cu:1795-1848,1914-1958. grad_alphas must be zero-filled.  fp32 / fp64 results are
+ * bit-identical to the reference build's (same sequential order, same fused multiply-adds). */
+int nr3d_pack_alpha_to_vw_bwd(int32_t dtype, uint64_t P, uint64_t S, const void* weights, const void* grad_weights,
                               const void* alphas, const int64_t* pack_infos, float early_stop_eps, float alpha_thre,
                               void* grad_alphas, void* stream);
 /* int64 exclusive scan helper: pack_infos[P,2] = (exclusive cumsum(n), n); total[0] = sum.  Replaces the

@@ -89,14 +89,14 @@ SIGNATURES = {
     "nr3d_march_samples": [_u64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "nr3d_density_alpha_fwd": [_u64, _u32, _vp, _i64, _vp, _f32, _vp, _vp, _vp],
     "nr3d_density_alpha_bwd": [_u64, _u32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp],
-    "nr3d_pack_sum": [_i32, _u64, _u32, _vp, _vp, _vp, _vp],
+    "nr3d_pack_sum": [_i32, _u64, _u32, _u64, _vp, _vp, _vp, _vp],
     "nr3d_pack_cumsum": [_i32, _u64, _u32, _vp, _vp, _i32, _i32, _vp, _vp],
     "nr3d_pack_cumprod": [_i32, _u64, _u32, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
     "nr3d_pack_diff": [_i32, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp],
     "nr3d_pack_backward_diff": [_i32, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp],
     "nr3d_pack_binary": [_i32, _i32, _u64, _u32, _vp, _vp, _vp, _vp, _vp],
-    "nr3d_pack_alpha_to_vw_fwd": [_i32, _u64, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp],
-    "nr3d_pack_alpha_to_vw_bwd": [_i32, _u64, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp],
+    "nr3d_pack_alpha_to_vw_fwd": [_i32, _u64, _u64, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp],
+    "nr3d_pack_alpha_to_vw_bwd": [_i32, _u64, _u64, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp],
     "nr3d_pack_infos_from_counts": [_u64, _vp, _vp, _vp, _vp, _u64_p, _vp],
     "nr3d_pack_interleave_linstep": [_i32, _u64, _vp, _vp, _vp, _f64, _f64, _vp, _vp, _vp],
     "nr3d_pack_sample_step_count": [_i32, _u64, _vp, _vp, _u32, _f64, _f64, _f64, _vp, _vp],
@@ -108,6 +108,7 @@ SIGNATURES = {
     "nr3d_pack_sort": [_i32, _u64, _vp, _vp, _vp, _vp],
     "nr3d_pack_matmul": [_i32, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp],
     "nr3d_lotd_fused_density_fwd": [_vp, _u64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
+    "nr3d_lotd_fused_density_bwd": [_vp, _u64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "nr3d_occ_scatter_max": [_u64, _vp, _vp, _vp, _u64, _vp, _u32, _vp, _vp, _vp],
     "nr3d_occ_apply": [_u64, _vp, _vp, _f32, _i32, _f32, _vp, _vp, _vp],
     "nr3d_occ_binarize": [_u64, _vp, _f32, _i32, _f32, _vp, _vp, _vp],

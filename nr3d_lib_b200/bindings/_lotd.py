@@ -250,9 +250,11 @@ def _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
     return True
 
 
-def _sorted_points(x: torch.Tensor, batch_inds: Optional[torch.Tensor] = None, bds: int = 0, n_scenes: int = 1):
+def _sorted_points(x: torch.Tensor, batch_inds: Optional[torch.Tensor] = None, bds: int = 0, n_scenes: int = 1, expect_new: bool = False):
     """(xs, scenes): float4 records (x, y, z, original index) in (scene, cell) order and -- for batched calls -- the uint16 scene of every
-    record.  Sorts on the current stream unless the device-side fingerprint says the cached records belong to these very points."""
+    record.  Sorts on the current stream unless the device-side fingerprint says the cached records belong to these very points.
+    `expect_new` (forward calls: a step brings new points): sort unconditionally and take the fingerprint inside the histogram pass, which
+    saves the separate fingerprint pass; the backward of the step then finds the records current."""
     dev = x.device
     lib = _lib.get_lib()
     N = x.shape[0]
@@ -263,7 +265,7 @@ def _sorted_points(x: torch.Tensor, batch_inds: Optional[torch.Tensor] = None, b
     cfg = (N, ns, batched)
     with _sort_lock:
         ent = _sort_cache.get(key)
-        force = 0
+        force = 1 if expect_new else 0
         if ent is None or ent[0] != cfg:
             nbytes = ctypes.c_uint64(0)
             _lib.check(lib.nr3d_lotd_sort_points(N, None, None, int(bds), ns, 1, None, None, None, ctypes.byref(nbytes), None))
@@ -333,7 +335,7 @@ def lod_fwd(lod_meta, input: torch.Tensor, params: torch.Tensor, batch_inds: Opt
         if _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
             # fast path: row-major y (and dy_dx: same shapes as the reference returns, contiguous instead of permuted views)
             ns = _n_scenes(meta, params)
-            xs, scenes = _sorted_points(input, batch_inds, bds, ns)
+            xs, scenes = _sorted_points(input, batch_inds, bds, ns, expect_new=True)
             y = torch.empty([N, E], dtype=params.dtype, device=dev)
             if not need_input_grad:
                 _lib.check(_lib.get_lib().nr3d_lotd_fwd_sorted(

@@ -60,7 +60,7 @@ def packed_sum(feats: torch.Tensor, pack_infos: torch.Tensor) -> torch.Tensor:
     dev, P, C = _check_feats("packed_sum", feats, pack_infos)
     with torch.cuda.device(dev):
         out = torch.empty([P] if feats.dim() == 1 else [P, C], dtype=feats.dtype, device=dev)
-        _lib.check(_lib.get_lib().nr3d_pack_sum(_lib.dtype_code(feats.dtype), P, C, feats.data_ptr(), pack_infos.data_ptr(),
+        _lib.check(_lib.get_lib().nr3d_pack_sum(_lib.dtype_code(feats.dtype), P, C, feats.shape[0], feats.data_ptr(), pack_infos.data_ptr(),
                                                 out.data_ptr(), _lib.stream_of(dev)))
     return out
 
@@ -168,14 +168,14 @@ def packed_alpha_to_vw_forward(alphas: torch.Tensor, pack_infos: torch.Tensor, e
         if compression:
             num_steps = torch.zeros([P], dtype=torch.int64, device=dev)
             compact_selector = torch.zeros([alphas.shape[0]], dtype=torch.bool, device=dev)
-            _lib.check(lib.nr3d_pack_alpha_to_vw_fwd(_lib.dtype_code(alphas.dtype), P, alphas.data_ptr(), pack_infos.data_ptr(),
+            _lib.check(lib.nr3d_pack_alpha_to_vw_fwd(_lib.dtype_code(alphas.dtype), P, alphas.shape[0], alphas.data_ptr(), pack_infos.data_ptr(),
                                                      float(early_stop_eps), float(alpha_thre), None, num_steps.data_ptr(),
                                                      compact_selector.data_ptr(), st))
             # the reference builds this with cumsum(at::kInt) + stack => an int32 [P,2] tensor (pack_ops_cuda.cu:1874-1875)
             compact_pack_info = _pack_infos_from_counts(num_steps)[0].to(torch.int32)
         else:
             weights = torch.zeros_like(alphas)
-            _lib.check(lib.nr3d_pack_alpha_to_vw_fwd(_lib.dtype_code(alphas.dtype), P, alphas.data_ptr(), pack_infos.data_ptr(),
+            _lib.check(lib.nr3d_pack_alpha_to_vw_fwd(_lib.dtype_code(alphas.dtype), P, alphas.shape[0], alphas.data_ptr(), pack_infos.data_ptr(),
                                                      float(early_stop_eps), float(alpha_thre), weights.data_ptr(), None, None, st))
     return weights, compact_pack_info, compact_selector
 
@@ -197,7 +197,7 @@ def packed_alpha_to_vw_backward(weights: torch.Tensor, grad_weights: torch.Tenso
     with torch.cuda.device(dev):
         grad_alphas = torch.zeros_like(alphas)
         _lib.check(_lib.get_lib().nr3d_pack_alpha_to_vw_bwd(
-            _lib.dtype_code(weights.dtype), P, weights.data_ptr(), grad_weights.data_ptr(), alphas.data_ptr(), pack_infos.data_ptr(),
+            _lib.dtype_code(weights.dtype), P, alphas.shape[0], weights.data_ptr(), grad_weights.data_ptr(), alphas.data_ptr(), pack_infos.data_ptr(),
             float(early_stop_eps), float(alpha_thre), grad_alphas.data_ptr(), _lib.stream_of(dev)))
     return grad_alphas
 

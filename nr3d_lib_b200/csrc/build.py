@@ -19,7 +19,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-Xcompiler", "-fPIC", "-DNR3D_BUILDING", "-cudart", "static"]
 FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
 
-SOURCES = ["lotd_api.cu", "lotd_d2.cu", "lotd_d3.cu", "lotd_d4.cu", "lotd_fast.cu", "lotd_sort.cu", "lotd_fused.cu", "lotd_forest.cu", "pack_ops.cu", "pack_next.cu", "march.cu", "occ_update.cu", "pipeline_ops.cu"]
+SOURCES = ["lotd_api.cu", "lotd_d2.cu", "lotd_d3.cu", "lotd_d4.cu", "lotd_fast.cu", "lotd_sort.cu", "lotd_fused.cu", "lotd_fused_bwd.cu", "lotd_forest.cu", "pack_ops.cu", "pack_staged.cu", "pack_next.cu", "march.cu", "occ_update.cu", "pipeline_ops.cu"]
 
 
 def _deps():

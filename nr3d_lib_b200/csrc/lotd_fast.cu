@@ -36,6 +36,9 @@ namespace nr3d {
 #ifndef NR3D_BWD_THREADS      // 256 threads = 128 points per CTA: about one 8 x 4 x 2 brick of sort bins
 #define NR3D_BWD_THREADS 256
 #endif
+#ifndef NR3D_FWD_TMA          // 1: A/B variant of the forward that stages the Dense levels' corner boxes with TMA bulk copies (see below)
+#define NR3D_FWD_TMA 0
+#endif
 #ifndef NR3D_BWD_TILES        // 1: CTA-level shared-memory tiles in the backward (0: every run head scatters to L2 directly)
 #define NR3D_BWD_TILES 0      // A/B on B200 (profiles/r2_ab_tiles.txt): OFF wins, 1.18 ms vs 2.45 - 3.6 ms -- see the note at smem_add2
 #endif
@@ -120,18 +123,36 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT*
             float v[4][F];  // all four loads are issued before the first use
 #pragma unroll
             for (int q = 0; q < 4; ++q) load_feats<PT, F>(params + pbase + g.e[q], v[q]);
+            if constexpr (std::is_same<PT, __half>::value) {
+                // fp16 tables: every product is rounded to half and accumulated in half like the reference (linear_interpolate.cuh:118);
+                // two features per packed instruction (cvt.rn.f16x2.f32 + HADD2) -- same values as the scalar chain, a third of the issue slots
+                __half2 acc[F / 2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+                for (int j = 0; j < F / 2; ++j) acc[j] = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
-                for (int f = 0; f < F; ++f) r[f] = C::to_f(C::add(C::from_f(r[f]), C::from_f(g.w[q] * v[q][f])));
+                for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int f = 0; f < F; ++f) r[f] = C::to_f(C::add(C::from_f(r[f]), C::from_f(__shfl_xor_sync(0xffffffffu, r[f], 1))));
+                    for (int j = 0; j < F / 2; ++j) acc[j] = __hadd2(acc[j], __floats2half2_rn(g.w[q] * v[q][2 * j], g.w[q] * v[q][2 * j + 1]));
+#pragma unroll
+                for (int j = 0; j < F / 2; ++j) {
+                    const uint32_t mine_bits = *reinterpret_cast<const uint32_t*>(&acc[j]);
+                    const uint32_t other_bits = __shfl_xor_sync(0xffffffffu, mine_bits, 1);
+                    const float2 t = __half22float2(__hadd2(acc[j], as_half2(other_bits)));
+                    r[2 * j] = t.x; r[2 * j + 1] = t.y;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int f = 0; f < F; ++f) r[f] = C::to_f(C::add(C::from_f(r[f]), C::from_f(g.w[q] * v[q][f])));
+#pragma unroll
+                for (int f = 0; f < F; ++f) r[f] = C::to_f(C::add(C::from_f(r[f]), C::from_f(__shfl_xor_sync(0xffffffffu, r[f], 1))));
+            }
         }
-        if (HEAD) {
+        if constexpr (HEAD) {
 #pragma unroll
             for (int f = 0; f < F; ++f) hsum += r[f];
-            continue;
-        }
+        } else {
         // lane `side` owns features pl * F + side * H + [0, H) of its point
         float mine[H];
 #pragma unroll
@@ -157,6 +178,7 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT*
 #pragma unroll
             for (int j = 0; j < H; ++j) st_cs(y + (int64_t)i * ys_n + (int64_t)(pl * F + side * H + j) * ys_f, C::from_f(mine[j]));
         }
+        }   // !HEAD
     }
     if (HEAD && active && side == 0) {   // skipped points (batch_inds < 0) have all-zero features like in the unfused path
         const float sg = softplus_head((live ? hsum : 0.f) * hd.gain);
@@ -164,6 +186,175 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT*
         __stcs(hd.alpha + i, 1.0f - expf(-sg * __ldcs(hd.deltas + i)));
     }
 }
+
+#if NR3D_FWD_TMA
+// ------------------------------------------------------------------------------------------------------------
+// A/B VARIANT (-DNR3D_FWD_TMA=1, scripts/ab_bench.py "fwd_tma*"): TMA staging of the Dense levels' corner tiles (BASELINE.json north_star:
+// "TMA staging of grid-corner tiles into shared memory").  After the sort a CTA's 128 points sit on one x pencil of bins, so on a Dense
+// level their corners form a small box [n0 x n1 x n2] of the z-fastest table.  Warp 0 plans one shared-memory tile per Dense level from the
+// CTA's bounding box, every thread issues `cp.async.bulk.shared::cluster.global` copies (SASS UBLKCP; one per (x, y) row of the box:
+// the rows are the only contiguous pieces, 16 - 48 bytes each), the CTA waits on an mbarrier and the gather loop reads those levels'
+// corners from shared memory instead of L1 / L2.  Hash levels have no box to fetch (corners are scattered by the hash).
+// MEASURED: see profiles/r2_ab_fwd_tma.txt -- kept out of the shipped build.
+// ------------------------------------------------------------------------------------------------------------
+#ifndef NR3D_FWD_TMA_FLOATS
+#define NR3D_FWD_TMA_FLOATS 6144
+#endif
+constexpr int kTmaLevels = 8;                  // pseudo levels 0 .. 7 may own a tile (the NGP ladder has 6 Dense levels)
+constexpr int kTmaFloats = NR3D_FWD_TMA_FLOATS;
+
+struct TmaPlan {
+    int32_t off[kTmaLevels];        // first float of the level's tile, -1: not staged
+    uint32_t lo[kTmaLevels][3];     // smallest corner coordinate of the CTA's points on the level
+    uint32_t n0[kTmaLevels], n1[kTmaLevels], rs[kTmaLevels];   // box rows along x, y; row stride in entries (covers n2 + alignment slack)
+};
+
+__global__ void __launch_bounds__(kFastThreads, 6)
+lotd_pair_fwd_tma_kernel(const __grid_constant__ LotdTable tab, const FastIn in, float* __restrict__ y, int64_t ys_n) {
+    constexpr int F = 2;
+    const float* params = reinterpret_cast<const float*>(in.params);
+    __shared__ float rows[kFastThreads / 32][16 * kPairRowStride];
+    __shared__ __align__(128) float tile[kTmaFloats];
+    __shared__ uint32_t s_box[6];
+    __shared__ TmaPlan plan;
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_total;
+    const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const bool active = p < in.N;
+    const int lane = threadIdx.x & 31;
+    const uint32_t side = lane & 1;
+    const int k = lane >> 1;
+    float* myrows = rows[threadIdx.x >> 5];
+    float4 rec = make_float4(0.5f, 0.5f, 0.5f, 0.f);
+    if (active) rec = __ldcs(in.xs + p);
+    const float x = rec.x, yv = rec.y, z = rec.z;
+    const uint64_t i = __float_as_uint(rec.w);
+    const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    // ---- bounding box of the CTA's points (unit-cube coordinates; cell_pos is monotone, so it bounds the cells on every level) ----
+    if (threadIdx.x < 6) s_box[threadIdx.x] = threadIdx.x < 3 ? 0xffffffffu : 0u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    {
+        const uint32_t u[3] = {__float_as_uint(fmaxf(x, 0.f)), __float_as_uint(fmaxf(yv, 0.f)), __float_as_uint(fmaxf(z, 0.f))};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const uint32_t a = __reduce_min_sync(0xffffffffu, active ? u[d] : 0xffffffffu), b = __reduce_max_sync(0xffffffffu, active ? u[d] : 0u);
+            if (lane == 0) { atomicMin(&s_box[d], a); atomicMax(&s_box[3 + d], b); }
+        }
+    }
+    __syncthreads();
+    // ---- plan: lane pl of warp 0 sizes the tile of pseudo level pl ----
+    if (threadIdx.x < 32) {
+        const uint32_t pl = threadIdx.x;
+        uint32_t need = 0, lo[3] = {0, 0, 0}, n[3] = {0, 0, 0}, rs = 0;
+        if (pl < (uint32_t)kTmaLevels && pl < tab.n_pseudo && s_box[0] != 0xffffffffu) {
+            const uint32_t level = tab.map_level[pl];
+            const LevelDesc& L = tab.lv[level];
+            if ((int32_t)level <= in.max_level && L.type == NR3D_LOD_DENSE && L.n_feat == 2u && (L.offset & 1u) == 0u) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    lo[d] = (uint32_t)floorf(cell_pos(__uint_as_float(s_box[d]), L.res[d]));
+                    n[d] = (uint32_t)floorf(cell_pos(__uint_as_float(s_box[3 + d]), L.res[d])) + 2u - lo[d];
+                }
+                rs = (n[2] + 2u) & ~1u;     // entries per staged row: n2 plus one entry of alignment slack, even
+                const uint64_t sz = (uint64_t)n[0] * n[1] * rs * 2u;
+                need = (uint32_t)min(sz, (uint64_t)kTmaFloats + 1);
+            }
+        }
+        uint32_t incl = need;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl = min(incl + t, 2u * kTmaFloats); }
+        const bool fits = need > 0 && incl <= (uint32_t)kTmaFloats;
+        if (pl < (uint32_t)kTmaLevels) {
+            plan.off[pl] = fits ? (int32_t)(incl - need) : -1;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) plan.lo[pl][d] = lo[d];
+            plan.n0[pl] = n[0]; plan.n1[pl] = n[1]; plan.rs[pl] = rs;
+        }
+        uint32_t bytes = fits ? need * 4u : 0u;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, m);
+        if (lane == 0) {
+            s_total = bytes;
+            if (bytes) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        }
+    }
+    __syncthreads();
+    // ---- bulk copies: one per (x, y) row of every staged box ----
+    for (uint32_t pl = 0; pl < (uint32_t)kTmaLevels; ++pl) {
+        const int32_t off = plan.off[pl];
+        if (off < 0) continue;
+        const LevelDesc& L = tab.lv[tab.map_level[pl]];
+        const uint32_t n0 = plan.n0[pl], n1 = plan.n1[pl], rs = plan.rs[pl];
+        for (uint32_t r = threadIdx.x; r < n0 * n1; r += kFastThreads) {
+            const uint32_t a = r / n1, b = r - a * n1;
+            const uint32_t ge = (L.offset >> 1) + ((plan.lo[pl][0] + a) * L.res[1] + plan.lo[pl][1] + b) * L.res[2] + plan.lo[pl][2];   // 8-byte entries
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + off + r * rs * 2u);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst), "l"(params + (uint64_t)(ge & ~1u) * 2u), "r"(rs * 8u), "r"(bar) : "memory");
+        }
+    }
+    if (s_total) {
+        uint32_t ok = 0;
+        for (uint32_t spin = 0; !ok; ++spin) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
+            if (spin > (1u << 26)) __trap();
+        }
+    }
+    // ---- gather loop: staged Dense levels read their corners from the tile ----
+    uint32_t chunk_base = 0;
+    for (uint32_t pl = 0; pl < tab.n_pseudo; ++pl) {
+        const uint32_t level = tab.map_level[pl];
+        float r[F] = {0.f, 0.f};
+        if ((int32_t)level <= in.max_level) {
+            const LevelDesc& L = tab.lv[level];
+            Geo2 g;
+            pair_geo(L, (uint32_t)tab.map_cnt[pl] * F, smooth, x, yv, z, side, g);
+            float2 v[4];
+            const int32_t off = pl < (uint32_t)kTmaLevels ? plan.off[pl] : -1;
+            if (off >= 0) {
+                const uint32_t n1 = plan.n1[pl], rs = plan.rs[pl];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {      // corner (c0 + (q & 1), c1 + (q >> 1), c2 + side), see pair_geo
+                    const uint32_t cx = g.c[0] + (q & 1), cy = g.c[1] + (q >> 1);
+                    const uint32_t row = (cx - plan.lo[pl][0]) * n1 + (cy - plan.lo[pl][1]);
+                    const uint32_t row_ge = (L.offset >> 1) + (cx * L.res[1] + cy) * L.res[2] + plan.lo[pl][2];
+                    const uint32_t col = g.c[2] + side - plan.lo[pl][2] + (row_ge & 1u);
+                    v[q] = *reinterpret_cast<const float2*>(tile + off + (row * rs + col) * 2u);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float2*>(params + g.e[q]));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { r[0] += g.w[q] * v[q].x; r[1] += g.w[q] * v[q].y; }
+#pragma unroll
+            for (int f = 0; f < F; ++f) r[f] += __shfl_xor_sync(0xffffffffu, r[f], 1);
+        }
+        const float mine = active ? (side ? r[1] : r[0]) : 0.f;
+        const uint32_t c = pl * F - chunk_base;
+        myrows[k * kPairRowStride + c + side] = mine;
+        const bool last = (pl + 1 == tab.n_pseudo);
+        if (c + F == 32 || last) {
+            const uint32_t width = c + F;
+            __syncwarp();
+#pragma unroll 4
+            for (int rr = 0; rr < 16; ++rr) {
+                const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * rr);
+                const bool ok = __shfl_sync(0xffffffffu, (int)active, 2 * rr);
+                if (ok && (uint32_t)lane < width) __stcs(y + (int64_t)ir * ys_n + chunk_base + lane, myrows[rr * kPairRowStride + lane]);
+            }
+            __syncwarp();
+            chunk_base += 32;
+        }
+    }
+}
+#endif  // NR3D_FWD_TMA
 
 // ------------------------------------------------------------------------------------------------------------
 // backward: dL/dparam scatter
@@ -201,10 +392,12 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
                      const float* __restrict__ ddx, PT* __restrict__ grad, const HeadBwd hd) {
     using C = Cvt<PT>;
     extern __shared__ __align__(16) float smem[];
+#if NR3D_BWD_TILES
     float* ctile = smem;                                                    // [kTileFloats] CTA tiles (NR3D_BWD_TILES)
-    float* myrows = smem + (NR3D_BWD_TILES ? kTileFloats : 0) + (threadIdx.x >> 5) * (16 * kPairRowStride);
     __shared__ uint32_t s_box[8];   // min x, y, z bits | max x, y, z bits | min scene | max scene over the live points of the CTA
     __shared__ TilePlan plan;
+#endif
+    float* myrows = smem + (NR3D_BWD_TILES ? kTileFloats : 0) + (threadIdx.x >> 5) * (16 * kPairRowStride);
     const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
     const bool active = p < in.N;
     const int lane = threadIdx.x & 31;
@@ -567,6 +760,15 @@ static int launch_bwd(const LotdTable& tab, const FastIn& in, const void* dL_dy,
 template <typename PT, int F>
 static int launch_fwd(const LotdTable& tab, const FastIn& in, void* y, int64_t ys_n, int64_t ys_f, cudaStream_t st) {
     const unsigned grid = (unsigned)div_up<uint64_t>(2 * in.N, kFastThreads);
+#if NR3D_FWD_TMA
+    if constexpr (std::is_same<PT, float>::value && F == 2) {
+        if (in.scenes == nullptr && ys_f == 1) {
+            lotd_pair_fwd_tma_kernel<<<grid, kFastThreads, 0, st>>>(tab, in, (float*)y, ys_n);
+            NR3D_LAUNCH_CHECK("lotd_fast_fwd_tma");
+            return 0;
+        }
+    }
+#endif
     lotd_pair_fwd_kernel<PT, F><<<grid, kFastThreads, 0, st>>>(tab, in, (PT*)y, ys_n, ys_f, HeadFwd{});
     NR3D_LAUNCH_CHECK("lotd_fast_fwd");
     return 0;

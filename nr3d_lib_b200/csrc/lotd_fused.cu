@@ -17,8 +17,7 @@
 // Operands are bf16 with fp32 accumulation: results match an fp32 MLP fed with bf16-rounded operands to ~1e-3 (test tolerance
 // 2e-2 against the plain fp32 reference).  Completion is tracked with mbarriers (tcgen05.commit); every wait is bounded and
 // traps instead of hanging.
-#include "lotd_pair.cuh"
-#include <cuda_bf16.h>
+#include "lotd_umma.cuh"
 
 namespace nr3d {
 
@@ -36,46 +35,6 @@ constexpr uint32_t kOffIdx = kOffB2 + 64;        // 128 u32: original index per 
 constexpr uint32_t kOffBar = kOffIdx + 512;      // 2 mbarriers
 constexpr uint32_t kOffTmem = kOffBar + 16;      // TMEM base address
 constexpr uint32_t kFusedSmem = kOffTmem + 16;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major, no swizzle: element (row, k) lives at  (k / 8) * LBO + (row / 8) * SBO + (row % 8) * 16 + (k % 8) * 2  bytes
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
-}
-// instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, shape M x N
-__device__ __forceinline__ constexpr uint32_t umma_idesc(uint32_t M, uint32_t N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                 :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    for (uint32_t spin = 0; !ok; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1u << 26)) __trap();  // never hang the device: a lost arrival becomes a launch error
-    }
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-#define NR3D_TMEM_LD16(taddr, v)                                                                                         \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),   \
-                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                     \
-                 : "r"(taddr))
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&t);
-}
 
 struct FusedDec {
     const uint4* w1c;   // W1 [64, 32] bf16 in core-matrix order (4096 B)

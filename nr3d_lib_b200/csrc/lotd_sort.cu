@@ -9,6 +9,7 @@
 // Nothing is read back to the host; everything is ordered on the caller's stream.
 //
 //   verify   1 launch   64-bit sum + xor of a per-point hash of (x, y, z, index, scene); last block: compare, set `skip`, clear the scan state
+//                       (skipped for `force` calls -- forward passes, whose points are new: the histogram pass takes the fingerprint instead)
 //   hist     1 launch   bin key -> rank inside the bin (atomic counter), 4 bytes per point kept
 //   scan     1 launch   decoupled look-back exclusive scan of the bin counters; zeroes the counters for the next call
 //   scatter  1 launch   16-byte records (x, y, z, original index) [+ uint16 scene] written at offsets[key] + rank
@@ -72,20 +73,19 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {  // 
     return z ^ (z >> 31);
 }
 
-__global__ void __launch_bounds__(256) sort_verify_kernel(uint64_t N, const float* __restrict__ x, const int64_t* __restrict__ batch_inds, uint32_t bds,
-                                                          uint32_t n_scenes, uint32_t res, int force, SortHeader* __restrict__ hdr,
-                                                          unsigned long long* __restrict__ status, uint32_t n_tiles) {
+__device__ __forceinline__ unsigned long long point_hash(const float* __restrict__ x, uint64_t i, uint32_t sc) {
+    const uint32_t a = __float_as_uint(__ldcs(x + i * 3)), b = __float_as_uint(__ldcs(x + i * 3 + 1)), c = __float_as_uint(__ldcs(x + i * 3 + 2));
+    return mix64((((unsigned long long)a << 32) | b) ^ mix64((((unsigned long long)c << 32) | (uint32_t)i) + ((unsigned long long)sc << 48) + 0x9e3779b97f4a7c15ull));
+}
+
+// Block-level end of a fingerprint pass: adds the block's partial sums to the header; the LAST block compares with the stored fingerprint,
+// stores the new one, sets `skip` and re-arms the scan state.  Returns (to every thread of the last block) whether it was the last block.
+__device__ __forceinline__ bool fingerprint_finish(unsigned long long sum, unsigned long long xr, uint64_t N, uint32_t n_scenes, uint32_t res, int force,
+                                                   SortHeader* __restrict__ hdr, unsigned long long* __restrict__ status, uint32_t n_tiles) {
     __shared__ unsigned long long s_sum, s_xor;
-    __shared__ bool s_last;
+    __shared__ bool s_last, s_same;
     if (threadIdx.x == 0) { s_sum = 0; s_xor = 0; }
     __syncthreads();
-    unsigned long long sum = 0, xr = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t a = __float_as_uint(__ldcs(x + i * 3)), b = __float_as_uint(__ldcs(x + i * 3 + 1)), c = __float_as_uint(__ldcs(x + i * 3 + 2));
-        const uint32_t sc = scene_of(i, batch_inds, bds, n_scenes);
-        const unsigned long long h = mix64((((unsigned long long)a << 32) | b) ^ mix64((((unsigned long long)c << 32) | (uint32_t)i) + ((unsigned long long)sc << 48) + 0x9e3779b97f4a7c15ull));
-        sum += h; xr ^= h;
-    }
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) {
         sum += __shfl_xor_sync(0xffffffffu, sum, m);
@@ -100,9 +100,8 @@ __global__ void __launch_bounds__(256) sort_verify_kernel(uint64_t N, const floa
         s_last = atomicAdd(&hdr->blocks_done, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) return false;
     __threadfence();
-    __shared__ bool s_same;
     if (threadIdx.x == 0) {
         const unsigned long long fs = atomicAdd(&hdr->acc_sum, 0ull), fx = atomicAdd(&hdr->acc_xor, 0ull);
         const unsigned long long fn = N ^ ((unsigned long long)n_scenes << 40) ^ ((unsigned long long)res << 52);
@@ -115,19 +114,38 @@ __global__ void __launch_bounds__(256) sort_verify_kernel(uint64_t N, const floa
     __syncthreads();
     if (!s_same)
         for (uint32_t t = threadIdx.x; t < n_tiles; t += blockDim.x) status[t] = 0ull;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) sort_verify_kernel(uint64_t N, const float* __restrict__ x, const int64_t* __restrict__ batch_inds, uint32_t bds,
+                                                          uint32_t n_scenes, uint32_t res, int force, SortHeader* __restrict__ hdr,
+                                                          unsigned long long* __restrict__ status, uint32_t n_tiles) {
+    unsigned long long sum = 0, xr = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long h = point_hash(x, i, scene_of(i, batch_inds, bds, n_scenes));
+        sum += h; xr ^= h;
+    }
+    fingerprint_finish(sum, xr, N, n_scenes, res, force, hdr, status, n_tiles);
 }
 
 // pass 1: rank of the point inside its bin (the rank makes the scatter pass atomic-free)
+// FP = true ("the points are new", forward calls): no verify pass ran; this kernel sorts unconditionally and records the fingerprint of the
+// points on the way (same pass over x), so that a later verify pass -- the backward of the same step -- finds the records current.
+template <bool FP>
 __global__ void __launch_bounds__(256) sort_hist_kernel(uint64_t N, uint32_t res, uint32_t n_scenes, const float* __restrict__ x,
-                                                        const int64_t* __restrict__ batch_inds, uint32_t bds, const SortHeader* __restrict__ hdr,
-                                                        uint32_t* __restrict__ hist, uint32_t* __restrict__ rank) {
-    if (hdr->skip) return;
+                                                        const int64_t* __restrict__ batch_inds, uint32_t bds, SortHeader* __restrict__ hdr,
+                                                        uint32_t* __restrict__ hist, uint32_t* __restrict__ rank,
+                                                        unsigned long long* __restrict__ status, uint32_t n_tiles) {
+    if (!FP && hdr->skip) return;
     const uint32_t bins = res * res * res;
+    unsigned long long sum = 0, xr = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t sc = scene_of(i, batch_inds, bds, n_scenes);
         const uint32_t k = sc == 0xffffu ? n_scenes * bins : sc * bins + bin_key(x[i * 3], x[i * 3 + 1], x[i * 3 + 2], res);
         rank[i] = atomicAdd(hist + k, 1u);
+        if (FP) { const unsigned long long h = point_hash(x, i, sc); sum += h; xr ^= h; }
     }
+    if (FP) fingerprint_finish(sum, xr, N, n_scenes, res, /*force=*/1, hdr, status, n_tiles);
 }
 
 // single-pass exclusive scan (decoupled look-back): hist -> offsets; the counters are zeroed on the way for the next call
@@ -166,22 +184,31 @@ __global__ void __launch_bounds__(kScanThreads) sort_scan_kernel(uint32_t n, Sor
     }
     __syncthreads();
     const uint32_t excl = ((threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0u) + s - mine;  // exclusive prefix of this thread inside the tile
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {   // warp 0: publish the tile aggregate, then look back 32 predecessors at a time until an inclusive prefix shows up
+        const uint32_t lane = threadIdx.x;
         const uint32_t total = ws[31];
         uint32_t run = 0;
         if (tile == 0) {
-            atomicExch(status, kFlagPrefix | total);
+            if (lane == 0) atomicExch(status, kFlagPrefix | total);
         } else {
-            atomicExch(status + tile, kFlagAgg | total);
-            for (int j = (int)tile - 1; j >= 0; --j) {
-                unsigned long long st;
-                do { st = *reinterpret_cast<volatile unsigned long long*>(status + j); } while ((st & kFlagMask) == 0ull);
-                run += (uint32_t)st;
-                if ((st & kFlagMask) == kFlagPrefix) break;
+            if (lane == 0) atomicExch(status + tile, kFlagAgg | total);
+            for (int j0 = (int)tile - 1; ; j0 -= 32) {
+                const int j = j0 - (int)lane;
+                unsigned long long st = kFlagPrefix;             // before tile 0: an (empty) inclusive prefix
+                if (j >= 0) {
+                    do { st = *reinterpret_cast<volatile unsigned long long*>(status + j); } while ((st & kFlagMask) == 0ull);
+                }
+                const uint32_t pmask = __ballot_sync(0xffffffffu, (st & kFlagMask) == kFlagPrefix);
+                const int first = pmask ? (__ffs(pmask) - 1) : 31;   // nearest predecessor that already holds an inclusive prefix
+                uint32_t v = ((int)lane <= first) ? (uint32_t)st : 0u;
+#pragma unroll
+                for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+                run += v;
+                if (pmask) break;
             }
-            atomicExch(status + tile, kFlagPrefix | (unsigned long long)(run + total));
+            if (lane == 0) atomicExch(status + tile, kFlagPrefix | (unsigned long long)(run + total));
         }
-        s_prefix = run;
+        if (lane == 0) s_prefix = run;
     }
     __syncthreads();
     uint32_t o = s_prefix + excl;
@@ -252,9 +279,13 @@ int nr3d_lotd_sort_points(uint64_t N, const float* x, const int64_t* batch_inds,
     const unsigned grid = (unsigned)(gwant < (uint64_t)kSMs * 16 ? gwant : (uint64_t)kSMs * 16);
     const uint64_t vwant = div_up<uint64_t>(N, 256 * 8);
     const unsigned vgrid = (unsigned)(vwant < (uint64_t)kSMs * 8 ? vwant : (uint64_t)kSMs * 8);
-    sort_verify_kernel<<<vgrid, 256, 0, st>>>(N, x, batch_inds, batch_data_size, n_scenes, res, force, hdr, status, n_tiles);
-    NR3D_LAUNCH_CHECK("sort_verify");
-    sort_hist_kernel<<<grid, 256, 0, st>>>(N, res, n_scenes, x, batch_inds, batch_data_size, hdr, hist, rank);
+    if (force) {   // new points (forward calls, first use of the buffers): sort unconditionally, the fingerprint is taken inside the histogram pass
+        sort_hist_kernel<true><<<grid, 256, 0, st>>>(N, res, n_scenes, x, batch_inds, batch_data_size, hdr, hist, rank, status, n_tiles);
+    } else {       // probably the points of the previous call (the backward of a step): fingerprint first, the sort kernels return at once on a match
+        sort_verify_kernel<<<vgrid, 256, 0, st>>>(N, x, batch_inds, batch_data_size, n_scenes, res, 0, hdr, status, n_tiles);
+        NR3D_LAUNCH_CHECK("sort_verify");
+        sort_hist_kernel<false><<<grid, 256, 0, st>>>(N, res, n_scenes, x, batch_inds, batch_data_size, hdr, hist, rank, status, n_tiles);
+    }
     NR3D_LAUNCH_CHECK("sort_hist");
     sort_scan_kernel<<<n_tiles, kScanThreads, 0, st>>>(n_cnt, hdr, hist, offsets, status);
     NR3D_LAUNCH_CHECK("sort_scan");

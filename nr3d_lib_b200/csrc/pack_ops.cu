@@ -473,6 +473,17 @@ __global__ void mark_boundaries_kernel(uint64_t n, const T* __restrict__ ids, in
     out[i] = (i == 0) ? 1 : (ids[i - 1] == ids[i] ? 0 : 1);
 }
 
+// staged thread-per-pack kernels (pack_staged.cu): bit-identical to the reference's sequential loops, coalesced through shared memory
+int staged_alpha_fwd(int32_t dtype, uint64_t P, uint64_t total, const void* alphas, const int64_t* pack_infos, float eps, float thre, void* weights,
+                     int64_t* num_steps, uint8_t* selector, cudaStream_t st);
+int staged_alpha_bwd(int32_t dtype, uint64_t P, uint64_t total, const void* alphas, const void* weights, const void* grad_weights,
+                     const int64_t* pack_infos, float eps, float thre, void* grad_alphas, cudaStream_t st);
+int staged_pack_sum(int32_t dtype, uint64_t P, uint64_t total, const void* in, const int64_t* pack_infos, void* out, cudaStream_t st);
+
+#ifndef NR3D_PACK_STAGED      // 0: the warp-per-pack kernels of this file serve every call (A/B runs)
+#define NR3D_PACK_STAGED 1
+#endif
+
 static inline unsigned warp_grid(uint64_t warps) { return (unsigned)div_up<uint64_t>(warps, kWarpsPerBlock); }
 
 #define NR3D_PACK_DISPATCH(dtype, NAME, ...)                                                        \
@@ -497,9 +508,13 @@ using namespace nr3d;
 
 extern "C" {
 
-int nr3d_pack_sum(int32_t dtype, uint64_t P, uint32_t C, const void* feats, const int64_t* pack_infos, void* out, void* stream) {
+int nr3d_pack_sum(int32_t dtype, uint64_t P, uint32_t C, uint64_t S, const void* feats, const int64_t* pack_infos, void* out, void* stream) {
     if (P == 0) return 0;
     NR3D_CHECK(feats && pack_infos && out && C > 0, "packed_sum: null argument");
+    if (NR3D_PACK_STAGED && C == 1 && S > 0 && staged_pack_sum(dtype, P, S, feats, pack_infos, out, (cudaStream_t)stream) == 0) {
+        NR3D_LAUNCH_CHECK("packed_sum");
+        return 0;
+    }
     NR3D_PACK_DISPATCH(dtype, "packed_sum",
         (pack_sum_kernel<T><<<warp_grid(P), kPackThreads, 0, (cudaStream_t)stream>>>(P, C, (const T*)feats, pack_infos, (T*)out)));
     NR3D_LAUNCH_CHECK("packed_sum");
@@ -564,20 +579,28 @@ int nr3d_pack_binary(int32_t op, int32_t dtype, uint64_t P, uint32_t C, const vo
     return 0;
 }
 
-int nr3d_pack_alpha_to_vw_fwd(int32_t dtype, uint64_t P, const void* alphas, const int64_t* pack_infos, float early_stop_eps,
+int nr3d_pack_alpha_to_vw_fwd(int32_t dtype, uint64_t P, uint64_t S, const void* alphas, const int64_t* pack_infos, float early_stop_eps,
                               float alpha_thre, void* weights, int64_t* num_steps, uint8_t* selector, void* stream) {
     if (P == 0) return 0;
     NR3D_CHECK(alphas && pack_infos, "packed_alpha_to_vw_forward: null argument");
+    if (NR3D_PACK_STAGED && S > 0 && staged_alpha_fwd(dtype, P, S, alphas, pack_infos, early_stop_eps, alpha_thre, weights, num_steps, selector, (cudaStream_t)stream) == 0) {
+        NR3D_LAUNCH_CHECK("packed_alpha_to_vw_forward");
+        return 0;
+    }
     NR3D_PACK_DISPATCH_FLOAT(dtype, "packed_alpha_to_vw_forward",
         (alpha_to_vw_fwd_kernel<T><<<warp_grid(P), kPackThreads, 0, (cudaStream_t)stream>>>(P, (const T*)alphas, pack_infos, early_stop_eps, alpha_thre, (T*)weights, num_steps, selector)));
     NR3D_LAUNCH_CHECK("packed_alpha_to_vw_forward");
     return 0;
 }
 
-int nr3d_pack_alpha_to_vw_bwd(int32_t dtype, uint64_t P, const void* weights, const void* grad_weights, const void* alphas,
+int nr3d_pack_alpha_to_vw_bwd(int32_t dtype, uint64_t P, uint64_t S, const void* weights, const void* grad_weights, const void* alphas,
                               const int64_t* pack_infos, float early_stop_eps, float alpha_thre, void* grad_alphas, void* stream) {
     if (P == 0) return 0;
     NR3D_CHECK(weights && grad_weights && alphas && pack_infos && grad_alphas, "packed_alpha_to_vw_backward: null argument");
+    if (NR3D_PACK_STAGED && S > 0 && staged_alpha_bwd(dtype, P, S, alphas, weights, grad_weights, pack_infos, early_stop_eps, alpha_thre, grad_alphas, (cudaStream_t)stream) == 0) {
+        NR3D_LAUNCH_CHECK("packed_alpha_to_vw_backward");
+        return 0;
+    }
     NR3D_PACK_DISPATCH_FLOAT(dtype, "packed_alpha_to_vw_backward",
         (alpha_to_vw_bwd_kernel<T><<<warp_grid(P), kPackThreads, 0, (cudaStream_t)stream>>>(P, (const T*)alphas, (const T*)weights, (const T*)grad_weights, pack_infos, early_stop_eps, alpha_thre, (T*)grad_alphas)));
     NR3D_LAUNCH_CHECK("packed_alpha_to_vw_backward");

@@ -55,16 +55,18 @@ def allreduce_param_grads(grad: torch.Tensor, world: Optional[int] = None, async
 class GradReducer:
     """Sum of dL/dparams over the ranks, once per step, in one of three ways (`mode`):
 
-      "allreduce"  one blocking all-reduce of the whole table after the scatter (round 1; SURVEY.md 8e baseline)
+      "allreduce"  one all-reduce of the whole table after the scatter, on the step's stream (default)
       "bucketed"   the scatter runs fine levels first; the all-reduce of their part of the table (2/3 of the bytes for the NGP ladder)
-                   is issued asynchronously and overlaps the scatter of the coarse levels; only the coarse part's all-reduce is exposed
+                   is issued asynchronously and overlaps the scatter of the coarse levels.  MEASURED SLOWER on B200 (2 GPUs: 2.47 vs 2.15 ms
+                   per step, profiles/r2_bench_2gpu_*.json): two scatter launches re-read the records and dL_dy rows, and NCCL's CTAs take
+                   SMs from the scatter they overlap -- the whole all-reduce is only 0.1 - 0.2 ms.  Kept for the record / other shapes.
       "scatter"    reduce-scatter: every rank ends with ITS contiguous 1/world slice of the summed table (what a sharded optimizer or the
                    host-fed driver needs: pipeline.HostFedLoTDStep returns each slice to the host from its own rank) -- half the NVLink bytes
 
     Usage per step:  (lod_bwd runs, the hook fires)  ->  out = reducer.reduce(grad)   # "scatter": out is the rank's slice, else `grad`.
     The hook is installed with `bindings._lotd.set_grad_bucket_hook`; call close() to remove it."""
 
-    def __init__(self, meta, world: int, device, mode: str = "bucketed"):
+    def __init__(self, meta, world: int, device, mode: str = "allreduce"):
         from .bindings import _lotd
         self._lotd, self.meta, self.world, self.mode, self.device = _lotd, meta, int(world), mode, device
         self.pending = []
@@ -130,14 +132,18 @@ def bind_to_gpu_numa(local_rank: int) -> dict:
     bench line); never raises."""
     info = {"gpu": int(local_rank), "node": None, "cpu_affinity": None, "mempolicy": None}
     try:
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
-        if bus is None:
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = None
+        if all(hasattr(props, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            # torch exposes the three numbers, sysfs wants "dddd:bb:dd.f"
+            bus = f"{int(props.pci_domain_id):04x}:{int(props.pci_bus_id):02x}:{int(props.pci_device_id):02x}.0"
+        if bus is None or not os.path.exists(f"/sys/bus/pci/devices/{bus}/numa_node"):
             import subprocess
             bus = subprocess.run(["nvidia-smi", f"--id={local_rank}", "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True,
-                                 text=True, timeout=10).stdout.strip()
-        bus = str(bus).lower()
-        if len(bus.split(":")[0]) == 8:      # nvidia-smi prints an 8-digit domain, sysfs uses 4
-            bus = bus[4:]
+                                 text=True, timeout=10).stdout.strip().lower()
+            if len(bus.split(":")[0]) == 8:      # nvidia-smi prints an 8-digit domain, sysfs uses 4
+                bus = bus[4:]
+        info["pci"] = bus
         with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
             node = int(f.read().strip())
         info["node"] = node

@@ -96,7 +96,7 @@ class _EncodeDensityAlpha(torch.autograd.Function):
             sigma = torch.empty(N, dtype=torch.float32, device=dev)
             alpha = torch.empty(N, dtype=torch.float32, device=dev)
             if N:
-                xs, scenes = _lotd._sorted_points(x)
+                xs, scenes = _lotd._sorted_points(x, expect_new=True)
                 _lib.check(_lib.get_lib().nr3d_lotd_density_head_fwd_sorted(
                     ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), _lib.ptr(scenes), 1, params.data_ptr(), ml,
                     deltas.data_ptr(), float(gain), sigma.data_ptr(), alpha.data_ptr(), _lib.stream_of(dev)))

@@ -13,6 +13,10 @@ VARIANTS = {
     # round-2 experiments that lost (profiles/r2_ab_tiles.txt): CTA tiles through shared-memory CAS, brick order of the sort bins
     "tiles_brick": ["NR3D_BWD_TILES=1", "NR3D_BIN_ORDER=2", "NR3D_BWD_OCC=0"],
     "brick": ["NR3D_BIN_ORDER=2"],
+    # round-2 A/B of TMA staging for the Dense levels of the forward (profiles/r2_ab_fwd_tma.txt)
+    "fwd_tma": ["NR3D_FWD_TMA=1"],
+    "fwd_tma_12k": ["NR3D_FWD_TMA=1", "NR3D_FWD_TMA_FLOATS=3072"],
+    "fwd_tma_brick": ["NR3D_FWD_TMA=1", "NR3D_BIN_ORDER=2"],
 }
 if sys.argv[1] == "build":
     from nr3d_lib_b200.csrc import build as B

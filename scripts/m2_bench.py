@@ -32,7 +32,7 @@ def make_rays(n, dev, seed):
     return o.contiguous(), d.contiguous(), near.contiguous(), far.contiguous()
 
 
-def run_m2(dev, rank, world, rays=1024 * 1024, chunk=262144, grid_kind="random", steps=3, warmup=1, sort_points=True):
+def run_m2(dev, rank, world, rays=1024 * 1024, chunk=262144, grid_kind="random", steps=3, warmup=1, sort_points=True, fuse_head=True):
     """Times `steps` M2 steps (after `warmup`) on this rank's ray shard; returns the result dict (max over ranks inside)."""
     _, res, feats, types, T, _ = ngp_cfg()
     enc = LoTD(3, res, feats, types, hashmap_size=T, dtype=torch.float)
@@ -55,7 +55,7 @@ def run_m2(dev, rank, world, rays=1024 * 1024, chunk=262144, grid_kind="random",
         n_samples = 0
         for b in range(0, rays, chunk):
             o, d, near, far = (r[b:b + chunk] for r in ray_set)
-            out = march_encode_composite(enc, params, grid, o, d, near, far, step_size=0.01, max_steps=512, gain=2.0)
+            out = march_encode_composite(enc, params, grid, o, d, near, far, step_size=0.01, max_steps=512, gain=2.0, fuse_head=fuse_head)
             if out.depth is None:
                 continue
             n_samples += out.weights.numel()
@@ -79,7 +79,7 @@ def run_m2(dev, rank, world, rays=1024 * 1024, chunk=262144, grid_kind="random",
     return {"metric": "full march+encode+composite fwd+bwd Mrays/s", "value": world * rays / ms / 1e3, "unit": "Mrays/s",
             "n_gpus": world, "ms_per_step": ms, "rays_per_gpu": rays, "samples_per_ray": total_samples / (world * rays),
             "Msamples_per_s": total_samples / ms / 1e3, "grid": grid_kind, "chunk": chunk, "steps": steps, "warmup": warmup,
-            "sort_points": sort_points, "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+            "sort_points": sort_points, "fuse_head": bool(fuse_head and sort_points), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
             "workload": ("configs[4] (4096^2 rays over 8 GPUs)" if world * rays == 4096 * 4096 else "configs[2] shape (1024^2 rays per GPU)") +
                         ": occ_grid 128^3 march (step 0.01, <=512 steps) + 16L NGP LoTD + softplus density head + "
                         "packed alpha-composite + per-ray sums, forward + backward to the LoTD parameters, rays sharded over the GPUs, "
@@ -94,11 +94,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--no-sort", action="store_true")
+    ap.add_argument("--no-fuse-head", action="store_true", help="keep the [S, 32] features in HBM between the encoder and the density head")
     args = ap.parse_args()
     rank, world, local = ndist.init_from_env("nccl")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    out = run_m2(dev, rank, world, args.rays, args.chunk, args.grid, args.steps, args.warmup, not args.no_sort)
+    out = run_m2(dev, rank, world, args.rays, args.chunk, args.grid, args.steps, args.warmup, not args.no_sort, not args.no_fuse_head)
     ndist.shutdown()
     if rank == 0:
         print(json.dumps(out))

@@ -156,11 +156,70 @@ def bench_n3():
     row("  (encode alone, features to HBM)", timeit(encode_only), None, N * (12 + 1024 + 128))
 
 
+def bench_n3_train():
+    """Training step through encoder + density decoder: forward, loss, backward to the LoTD tables and the decoder weights."""
+    from nr3d_lib_b200.bindings import _lotd
+    from nr3d_lib_b200.fused import fused_density
+    from nr3d_lib_b200.lotd import LoTDFunction
+    res = (16 * 1.382 ** np.arange(16)).astype(int).tolist()
+    meta = _lotd.LoDMeta(3, res, [2] * 16, ["Dense" if r ** 3 <= 2 ** 19 else "Hash" for r in res], 2 ** 19)
+    N = 4 * 2 ** 20
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    xs = [torch.rand(N, 3, device=dev, generator=g).clamp(1e-6, 1 - 1e-6) for _ in range(2)]   # alternating point sets: every step sorts
+    params = ((torch.rand(meta.n_params, device=dev, generator=g) * 2 - 1) * 1e-1).requires_grad_(True)
+    w1 = (torch.randn(64, 32, device=dev, generator=g) * 0.3).requires_grad_(True)
+    b1 = (torch.randn(64, device=dev, generator=g) * 0.1).requires_grad_(True)
+    w2 = (torch.randn(1, 64, device=dev, generator=g) * 0.05).requires_grad_(True)
+    b2 = (torch.randn(1, device=dev, generator=g) * 0.1).requires_grad_(True)
+    target = torch.rand(N, device=dev, generator=g)
+    leaves = [params, w1, b1, w2, b2]
+    k = [0]
+
+    def zero():
+        for t in leaves:
+            t.grad = None
+        k[0] ^= 1
+        return xs[k[0]]
+
+    def step_fused():
+        x = zero()
+        sigma, _ = fused_density(x, params, w1, b1, w2, b2, meta, activation="softplus")
+        ((sigma - target) ** 2).mean().backward()
+
+    def step_unfused(mlp_dtype):
+        x = zero()
+        h = LoTDFunction.apply(meta, x, params, None, None, 0, 1.0, None).to(mlp_dtype)
+        out = torch.relu(h @ w1.to(mlp_dtype).t() + b1.to(mlp_dtype)) @ w2.to(mlp_dtype).t() + b2.to(mlp_dtype)
+        sigma = torch.nn.functional.softplus(out[:, 0].float())
+        ((sigma - target) ** 2).mean().backward()
+
+    step_fused(); gf = [t.grad.clone() for t in leaves]
+    k[0] ^= 1
+    step_unfused(torch.float32); gu = [t.grad.clone() for t in leaves]
+    errs = [((a - b).abs().max() / b.abs().max()).item() for a, b in zip(gf, gu)]
+    print(f"# n3 training step on {N} points (16-level NGP LoTD + MLP 32-64-1, softplus, MSE): fused vs fp32 autograd max rel err of "
+          f"dparams / dW1 / db1 / dW2 / db2 = " + " / ".join(f"{e:.1e}" for e in errs))
+    t_f = timeit(step_fused, warm=3, it=10)
+    row("fused fwd + bwd (tcgen05, 2 kernels + sort)", t_f, timeit(lambda: step_unfused(torch.float32), warm=3, it=10))
+    row("  vs unfused with bf16 MLP (cuBLAS)", t_f, timeit(lambda: step_unfused(torch.bfloat16), warm=3, it=10))
+
+    def enc_only():
+        x = zero()
+        y, _ = _lotd.lod_fwd(meta, x, params.detach(), need_input_grad=False)
+        _lotd.lod_bwd(meta, y, x, params.detach(), None, need_input_grad=False, need_param_grad=True)
+    row("  (encoder fwd + bwd alone, features in HBM)", timeit(enc_only, warm=3, it=10), None)
+
+
 if __name__ == "__main__":
     print(f"# {torch.cuda.get_device_name(0)}")
     if len(sys.argv) > 1 and sys.argv[1] == "n3":
         bench_n3()
+        bench_n3_train()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "n3train":
+        bench_n3_train()
         sys.exit(0)
     bench_n1()
     bench_n2()
     bench_n3()
+    bench_n3_train()

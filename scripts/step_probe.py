@@ -56,8 +56,12 @@ def main():
             for k, v in (("sort", t_sort), ("fwd", t_fwd), ("bwd", t_bwd), ("step", t_step)):
                 res[k].append(v)
     out = {k: float(np.median(v)) for k, v in res.items()}
+    # checksums of one forward / backward: the same for every build of the library up to fp32 summation order
+    y, _ = _lotd.lod_fwd(meta, xs[0], params, need_input_grad=False)
+    _, g = _lotd.lod_bwd(meta, dL_dy, xs[0], params, None, need_input_grad=False, need_param_grad=True)
+    out["checksum_y"], out["checksum_grad"] = float(y.double().abs().sum()), float(g.double().abs().sum())
     out.update(tag=args.tag or os.path.basename(_lib.LIB_PATH), half=args.half, msamples_per_s=N / out["step"] / 1e3,
-               note="fwd / bwd include the verify pass (records reused); step = fwd (with sort of new points) + bwd")
+               note="fwd = lod_fwd of new points (sort + gather), bwd = lod_bwd (fingerprint check + scatter), step = fwd + bwd back to back")
     print(json.dumps(out))
 
 

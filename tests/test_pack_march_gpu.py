@@ -91,6 +91,61 @@ def test_pack_vs_reference_build(seed, P, max_len, C, dev):
         _close(got[k], v, tol=3e-5 if ("cum" in k or "sum" in k) else 1e-5, what=f"ref:{k}")
 
 
+@pytest.mark.parametrize("P,max_len,min_len", [(20000, 230, 1), (33, 5000, 2000), (4097, 40, 0)])
+def test_staged_composite_bit_exact_vs_reference_build(P, max_len, min_len, dev):
+    """The staged thread-per-pack kernels (csrc/pack_staged.cu) walk every pack in the reference thread's order: fp32 weights, selectors,
+    counts, dL/dalpha and the one-channel pack sum are BIT-identical to the reference's CUDA build (and to the sequential numpy oracle)."""
+    from oracle import pack_oracle as PO
+    d = pack_inputs(P=P, max_len=max_len, C=1, seed=P, min_len=max(min_len, 1))
+    if min_len == 0:      # zero-length packs in between (undefined in the reference: oracle only)
+        n = d["n"].copy(); n[::7] = 0
+        d["pack_infos"] = np.stack([np.cumsum(n) - n, n], 1)
+        d["S"] = int(n.sum())
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    pi, al, gw = t(d["pack_infos"]), t(d["alphas"][: max(d["S"], 1)]), t(d["grad_w"][: max(d["S"], 1)])
+    mine = _pk()
+    ref = load_ref("_pack_ops") if min_len else None
+    for eps, thre in ((1e-4, 0.0), (0.3, 0.01), (0.0, 0.0)):
+        w, _, _ = mine.packed_alpha_to_vw_forward(al, pi, eps, thre, False)
+        _, cpi, sel = mine.packed_alpha_to_vw_forward(al, pi, eps, thre, True)
+        ga = mine.packed_alpha_to_vw_backward(w, gw, al, pi, eps, thre)
+        sm = mine.packed_sum(w, pi)
+        w_o, cnt_o, sel_o = PO.alpha_to_vw_forward(al.cpu().numpy(), d["pack_infos"], eps, thre)
+        assert np.array_equal(w.cpu().numpy(), w_o) and np.array_equal(sel.cpu().numpy().astype(bool), sel_o.astype(bool))
+        assert np.array_equal(cpi.cpu().numpy()[:, 1], cnt_o)
+        if ref is not None:
+            w_r, _, _ = ref.packed_alpha_to_vw_forward(al, pi, eps, thre, False)
+            _, cpi_r, sel_r = ref.packed_alpha_to_vw_forward(al, pi, eps, thre, True)
+            ga_r = ref.packed_alpha_to_vw_backward(w_r, gw, al, pi, eps, thre)
+            assert torch.equal(w, w_r) and torch.equal(sel, sel_r) and torch.equal(cpi, cpi_r)
+            assert torch.equal(ga, ga_r), f"dL/dalpha not bit-exact: max diff {(ga - ga_r).abs().max().item()}"
+            assert torch.equal(sm, ref.packed_sum(w_r, pi)), "pack sum not bit-exact"
+
+
+def test_staged_composite_untiled_packs(dev):
+    """pack_infos that do not tile one span (gaps, reversed order, overlapping packs): the staged kernels fall back to one pack per span and
+    still reproduce the sequential oracle bit for bit; entries outside every pack keep the caller's zeros."""
+    from oracle import pack_oracle as PO
+    rs = np.random.RandomState(5)
+    S = 9000
+    al = np.clip(rs.rand(S) ** 2 * 0.6, 0, 0.999).astype(np.float32)
+    begins = np.sort(rs.choice(S - 200, size=70, replace=False)).astype(np.int64)
+    lens = np.minimum(rs.randint(0, 120, size=70), np.diff(np.append(begins, S))).astype(np.int64)     # disjoint, with gaps
+    order = rs.permutation(70)
+    pinf = np.stack([begins, lens], 1)[order]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    mine = _pk()
+    w, _, _ = mine.packed_alpha_to_vw_forward(t(al), t(pinf), 1e-3, 0.0, False)
+    w_o, _, _ = PO.alpha_to_vw_forward(al, pinf, 1e-3, 0.0)
+    assert np.array_equal(w.cpu().numpy(), w_o)
+    gw = rs.randn(S).astype(np.float32)
+    ga = mine.packed_alpha_to_vw_backward(w, t(gw), t(al), t(pinf), 1e-3, 0.0)
+    ga_o = PO.alpha_to_vw_backward(w_o, gw, al, pinf, 1e-3, 0.0)
+    _close(ga, ga_o, 1e-6, "untiled alpha bwd")
+    assert np.array_equal(mine.packed_sum(t(al), t(pinf)).cpu().numpy(), np.array([al[b:b + n].astype(np.float32).cumsum(dtype=np.float32)[-1] if n else 0.0
+                                                                                     for b, n in pinf], dtype=np.float32))
+
+
 def test_pack_vs_oracle_with_empty_packs(dev):
     """oracle comparison incl. zero-length packs (undefined behaviour in the reference, defined as no-ops here)."""
     from oracle import pack_oracle as PO
