@@ -171,6 +171,11 @@ int nr3d_lotd_forest_bwd_bwd_dx(const nr3d_lotd_meta* meta, const nr3d_forest_me
  * params / dL_dparam must be 16-byte aligned; n_scenes * n_params < 2^32. */
 int nr3d_lotd_sort_points(uint64_t N, const float* x, const int64_t* batch_inds, uint32_t batch_data_size, uint32_t n_scenes, int32_t force,
                           void* xs, uint16_t* scenes, void* ws, uint64_t* ws_bytes, void* stream);
+/* Same, with a coordinate map applied on the fly: the records hold x' = fma(x, scale, shift), clamped to [1e-6, 1 - 1e-6] when clamp01 != 0
+ * (ray samples in [-1, 1]^3 -> scale = shift = 0.5: replaces the `x * 0.5 + 0.5` and `clamp` passes of LoTDEncoding.forward /
+ * LoTD.forward, lotd_encoding.py:162, lotd.py:211).  The map is part of the records' fingerprint. */
+int nr3d_lotd_sort_points_mapped(uint64_t N, const float* x, const int64_t* batch_inds, uint32_t batch_data_size, uint32_t n_scenes, int32_t force,
+                                 float scale, float shift, int32_t clamp01, void* xs, uint16_t* scenes, void* ws, uint64_t* ws_bytes, void* stream);
 int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
                          const void* params, int32_t max_level, void* y, int64_t y_stride_n, int64_t y_stride_f, void* stream);
 int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
@@ -344,6 +349,14 @@ int nr3d_pack_alpha_to_vw_fwd(int32_t dtype, uint64_t P, uint64_t S, const void*
 int nr3d_pack_alpha_to_vw_bwd(int32_t dtype, uint64_t P, uint64_t S, const void* weights, const void* grad_weights,
                               const void* alphas, const int64_t* pack_infos, float early_stop_eps, float alpha_thre,
                               void* grad_alphas, void* stream);
+/* Accumulated opacity and expected depth of every pack in one pass (no reference export; replaces acc = packed_sum(w), depth = packed_sum(w * t)
+ * of the render step, nr3d_lib/graphics/nerf/nerf_ray_query.py:182-188, and their autograd chain).  Values are bit-identical to that
+ * composition (sequential sums, product rounded before the add).  S = samples in `weights` / `depths` (f32 [S], 16-byte aligned).
+ * Backward: grad_weights [S] (elements outside every pack keep the caller's zeros) = grad_depth[p] * depths + grad_acc[p]; either grad may be NULL. */
+int nr3d_pack_weighted_sums_fwd(uint64_t P, uint64_t S, const float* weights, const float* depths, const int64_t* pack_infos, float* acc, float* depth,
+                                void* stream);
+int nr3d_pack_weighted_sums_bwd(uint64_t P, uint64_t S, const float* depths, const int64_t* pack_infos, const float* grad_acc, const float* grad_depth,
+                                float* grad_weights, void* stream);
 /* int64 exclusive scan helper: pack_infos[P,2] = (exclusive cumsum(n), n); total[0] = sum.  Replaces the
  * `cumsum` + `stack` + `.item()` idiom (pack_ops_cuda.cu:579-581,1874-1875). */
 int nr3d_pack_infos_from_counts(uint64_t P, const int64_t* counts, int64_t* pack_infos, int64_t* total,

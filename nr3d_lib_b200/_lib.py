@@ -71,6 +71,7 @@ SIGNATURES = {
     "nr3d_lotd_forest_bwd_param": [_meta_p, _forest_p, _i32, _i32, _u64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp],
     "nr3d_lotd_forest_bwd_bwd_dx": [_meta_p, _forest_p, _i32, _i32, _u64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp],
     "nr3d_lotd_sort_points": [_u64, _vp, _vp, _u32, _u32, _i32, _vp, _vp, _vp, _u64_p, _vp],
+    "nr3d_lotd_sort_points_mapped": [_u64, _vp, _vp, _u32, _u32, _i32, _f32, _f32, _i32, _vp, _vp, _vp, _u64_p, _vp],
     "nr3d_lotd_fwd_sorted": [_meta_p, _i32, _u64, _vp, _vp, _u32, _vp, _i32, _vp, _i64, _i64, _vp],
     "nr3d_lotd_bwd_param_sorted": [_meta_p, _i32, _u64, _vp, _vp, _u32, _vp, _i64, _i64, _i32, _u32, _u32, _vp, _vp],
     "nr3d_lotd_fwd_dydx_sorted": [_meta_p, _i32, _u64, _vp, _vp, _u32, _vp, _i32, _vp, _vp, _vp],
@@ -95,6 +96,8 @@ SIGNATURES = {
     "nr3d_pack_diff": [_i32, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp],
     "nr3d_pack_backward_diff": [_i32, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp],
     "nr3d_pack_binary": [_i32, _i32, _u64, _u32, _vp, _vp, _vp, _vp, _vp],
+    "nr3d_pack_weighted_sums_fwd": [_u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "nr3d_pack_weighted_sums_bwd": [_u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp],
     "nr3d_pack_alpha_to_vw_fwd": [_i32, _u64, _u64, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp],
     "nr3d_pack_alpha_to_vw_bwd": [_i32, _u64, _u64, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp],
     "nr3d_pack_infos_from_counts": [_u64, _vp, _vp, _vp, _vp, _u64_p, _vp],

@@ -250,11 +250,14 @@ def _sorted_eligible(meta, input, params, batch_inds, batch_offsets, bds):
     return True
 
 
-def _sorted_points(x: torch.Tensor, batch_inds: Optional[torch.Tensor] = None, bds: int = 0, n_scenes: int = 1, expect_new: bool = False):
+def _sorted_points(x: torch.Tensor, batch_inds: Optional[torch.Tensor] = None, bds: int = 0, n_scenes: int = 1, expect_new: bool = False,
+                   coord_map=None):
     """(xs, scenes): float4 records (x, y, z, original index) in (scene, cell) order and -- for batched calls -- the uint16 scene of every
     record.  Sorts on the current stream unless the device-side fingerprint says the cached records belong to these very points.
     `expect_new` (forward calls: a step brings new points): sort unconditionally and take the fingerprint inside the histogram pass, which
-    saves the separate fingerprint pass; the backward of the step then finds the records current."""
+    saves the separate fingerprint pass; the backward of the step then finds the records current.
+    `coord_map = (scale, shift, clamp01)`: the records hold fma(x, scale, shift) (clamped to [1e-6, 1 - 1e-6] if clamp01) -- for callers whose
+    points live in another box (ray samples in [-1, 1]^3) and who would otherwise spend two passes over [N, 3] on the conversion."""
     dev = x.device
     lib = _lib.get_lib()
     N = x.shape[0]
@@ -277,8 +280,9 @@ def _sorted_points(x: torch.Tensor, batch_inds: Optional[torch.Tensor] = None, b
             force = 1
         _, xs, scenes, ws, nb = ent
         nbytes = ctypes.c_uint64(nb)
-        _lib.check(lib.nr3d_lotd_sort_points(N, x.data_ptr(), _lib.ptr(batch_inds), int(bds), ns, force, xs.data_ptr(), _lib.ptr(scenes),
-                                             ws.data_ptr(), ctypes.byref(nbytes), st))
+        sc, sh, cl = (1.0, 0.0, 0) if coord_map is None else (float(coord_map[0]), float(coord_map[1]), int(bool(coord_map[2])))
+        _lib.check(lib.nr3d_lotd_sort_points_mapped(N, x.data_ptr(), _lib.ptr(batch_inds), int(bds), ns, force, sc, sh, cl, xs.data_ptr(),
+                                                    _lib.ptr(scenes), ws.data_ptr(), ctypes.byref(nbytes), st))
     return xs, scenes
 
 

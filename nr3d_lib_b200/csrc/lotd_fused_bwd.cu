@@ -99,6 +99,9 @@ __device__ __forceinline__ void scatter_level(const LevelDesc& L, uint32_t gfo, 
     }
 }
 
+// OUT16: an upstream gradient for all 16 decoder outputs is given (a.d_out16); otherwise only dL/dsigma feeds column 0 and the bias
+// gradient db2 needs one register instead of eight (the kernel is compiled for 64 registers per thread: 4 CTAs / SM).
+template <bool OUT16>
 __global__ void __launch_bounds__(kBwThreads, kBwCtasPerSm)
 lotd_fused_density_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, const FusedBwd a) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -137,9 +140,10 @@ lotd_fused_density_bwd_kernel(const __grid_constant__ LotdTable tab, const FastI
     const float* params = reinterpret_cast<const float*>(in.params);
     uint32_t phase = 0;        // parity of the next barrier completion
     bool first_tile = true;
-    float db2_acc[8];          // this lane's eight dL/dout columns (side * 8 + j), summed over the CTA's tiles
+    constexpr int NB2 = OUT16 ? 8 : 1;
+    float db2_acc[NB2];        // this lane's dL/dout columns (side * 8 + j), summed over the CTA's tiles
 #pragma unroll
-    for (int j = 0; j < 8; ++j) db2_acc[j] = 0.f;
+    for (int j = 0; j < NB2; ++j) db2_acc[j] = 0.f;
     const uint32_t quad = warp & 3, half = warp >> 2;     // TMEM lanes 32 quad .. +31, column half
     const uint32_t erow = quad * 32 + lane;               // tile row this thread owns in the epilogues
 
@@ -177,7 +181,7 @@ lotd_fused_density_bwd_kernel(const __grid_constant__ LotdTable tab, const FastI
 #pragma unroll
             for (int j = 0; j < 8; ++j) gv[j] = 0.f;
             if (active) {
-                if (a.d_out16) {
+                if (OUT16) {
                     const float4* src = reinterpret_cast<const float4*>(a.d_out16 + (uint64_t)i * 16 + side * 8);
                     const float4 u0 = __ldcs(src), u1 = __ldcs(src + 1);
                     gv[0] = u0.x; gv[1] = u0.y; gv[2] = u0.z; gv[3] = u0.w; gv[4] = u1.x; gv[5] = u1.y; gv[6] = u1.z; gv[7] = u1.w;
@@ -193,7 +197,7 @@ lotd_fused_density_bwd_kernel(const __grid_constant__ LotdTable tab, const FastI
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) db2_acc[j] += gv[j];
+            for (int j = 0; j < NB2; ++j) db2_acc[j] += gv[j];
             *reinterpret_cast<uint4*>(smem + kBoG + side * 2048 + (m >> 3) * 128 + (m & 7) * 16) =
                 make_uint4(pack_bf16(gv[0], gv[1]), pack_bf16(gv[2], gv[3]), pack_bf16(gv[4], gv[5]), pack_bf16(gv[6], gv[7]));
         }
@@ -350,11 +354,11 @@ lotd_fused_density_bwd_kernel(const __grid_constant__ LotdTable tab, const FastI
         }
         // db2: sum this lane's eight columns over the lanes of the same side, then over the CTA through HBM atomics
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < NB2; ++j) {
             float s = db2_acc[j];
 #pragma unroll
             for (int mm = 2; mm < 32; mm <<= 1) s += __shfl_xor_sync(0xffffffffu, s, mm);
-            if (lane < 2) atomicAdd(a.db2 + side * 8 + j, s);
+            if (lane < 2 && (OUT16 || side == 0)) atomicAdd(a.db2 + side * 8 + j, s);
         }
     }
     tc_fence_before();
@@ -391,13 +395,15 @@ extern "C" int nr3d_lotd_fused_density_bwd(const nr3d_lotd_meta* meta, uint64_t 
                sigma, d_sigma, d_out16, activation, dL_dparam, dW1, db1, dW2, db2};
     static bool configured = false;
     if (!configured) {
-        NR3D_CHECK(cudaFuncSetAttribute(lotd_fused_density_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwSmem) == cudaSuccess,
+        NR3D_CHECK(cudaFuncSetAttribute(lotd_fused_density_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwSmem) == cudaSuccess &&
+                   cudaFuncSetAttribute(lotd_fused_density_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwSmem) == cudaSuccess,
                    "fused_density_bwd: cannot reserve %d bytes of shared memory", (int)kBwSmem);
         configured = true;
     }
     const uint64_t n_tiles = div_up<uint64_t>(N, 128);
     const unsigned grid = (unsigned)(n_tiles < (uint64_t)kSMs * kBwCtasPerSm ? n_tiles : (uint64_t)kSMs * kBwCtasPerSm);
-    lotd_fused_density_bwd_kernel<<<grid, kBwThreads, kBwSmem, (cudaStream_t)stream>>>(tab, in, a);
+    if (d_out16) lotd_fused_density_bwd_kernel<true><<<grid, kBwThreads, kBwSmem, (cudaStream_t)stream>>>(tab, in, a);
+    else lotd_fused_density_bwd_kernel<false><<<grid, kBwThreads, kBwSmem, (cudaStream_t)stream>>>(tab, in, a);
     NR3D_LAUNCH_CHECK("lotd_fused_density_bwd");
     return 0;
 }

@@ -14,6 +14,7 @@
 //   scan     1 launch   decoupled look-back exclusive scan of the bin counters; zeroes the counters for the next call
 //   scatter  1 launch   16-byte records (x, y, z, original index) [+ uint16 scene] written at offsets[key] + rank
 #include "lotd_pair.cuh"
+#include <string.h>
 
 namespace nr3d {
 
@@ -46,6 +47,18 @@ static inline uint32_t bin_res_for(uint64_t N, uint32_t n_scenes) {
     if (per >= (192ull << 10)) return 64u;
     return 32u;
 }
+
+// Optional map applied to every coordinate before binning and before it is stored in the record: x' = clamp(fma(x, scale, shift)), so that
+// callers holding points in another box (ray samples in [-1, 1]^3: scale = shift = 0.5) need no separate passes over the [N, 3] array
+// (reference: LoTDEncoding.forward normalises, lotd_encoding.py:162, LoTD.forward clamps, lotd.py:211).  Identity: scale 1, shift 0, no clamp.
+struct SortMap {
+    float scale, shift;
+    int32_t clamp01;   // 1: clamp to [1e-6, 1 - 1e-6] like `x.clamp(1e-6, 1 - 1e-6)` (same float32 constants)
+    __device__ __forceinline__ float operator()(float v) const {
+        v = fmaf(v, scale, shift);
+        return clamp01 ? fminf(fmaxf(v, 1.0e-6f), (float)(1.0 - 1.0e-6)) : v;
+    }
+};
 
 __device__ __forceinline__ uint32_t bin_key(float x, float y, float z, uint32_t res) {
     const uint32_t bx = min(res - 1, (uint32_t)fmaxf(x * (float)res, 0.f));
@@ -81,7 +94,7 @@ __device__ __forceinline__ unsigned long long point_hash(const float* __restrict
 // Block-level end of a fingerprint pass: adds the block's partial sums to the header; the LAST block compares with the stored fingerprint,
 // stores the new one, sets `skip` and re-arms the scan state.  Returns (to every thread of the last block) whether it was the last block.
 __device__ __forceinline__ bool fingerprint_finish(unsigned long long sum, unsigned long long xr, uint64_t N, uint32_t n_scenes, uint32_t res, int force,
-                                                   SortHeader* __restrict__ hdr, unsigned long long* __restrict__ status, uint32_t n_tiles) {
+                                                   SortHeader* __restrict__ hdr, unsigned long long* __restrict__ status, uint32_t n_tiles, uint32_t map_tag) {
     __shared__ unsigned long long s_sum, s_xor;
     __shared__ bool s_last, s_same;
     if (threadIdx.x == 0) { s_sum = 0; s_xor = 0; }
@@ -104,7 +117,8 @@ __device__ __forceinline__ bool fingerprint_finish(unsigned long long sum, unsig
     __threadfence();
     if (threadIdx.x == 0) {
         const unsigned long long fs = atomicAdd(&hdr->acc_sum, 0ull), fx = atomicAdd(&hdr->acc_xor, 0ull);
-        const unsigned long long fn = N ^ ((unsigned long long)n_scenes << 40) ^ ((unsigned long long)res << 52);
+        // (the records also depend on the coordinate map they were built with)
+        const unsigned long long fn = N ^ ((unsigned long long)n_scenes << 40) ^ ((unsigned long long)res << 52) ^ mix64((unsigned long long)map_tag);
         const bool same = !force && fs == hdr->fp_sum && fx == hdr->fp_xor && fn == hdr->fp_n;
         hdr->fp_sum = fs; hdr->fp_xor = fx; hdr->fp_n = fn;
         hdr->skip = same ? 1u : 0u;
@@ -119,13 +133,13 @@ __device__ __forceinline__ bool fingerprint_finish(unsigned long long sum, unsig
 
 __global__ void __launch_bounds__(256) sort_verify_kernel(uint64_t N, const float* __restrict__ x, const int64_t* __restrict__ batch_inds, uint32_t bds,
                                                           uint32_t n_scenes, uint32_t res, int force, SortHeader* __restrict__ hdr,
-                                                          unsigned long long* __restrict__ status, uint32_t n_tiles) {
+                                                          unsigned long long* __restrict__ status, uint32_t n_tiles, uint32_t map_tag) {
     unsigned long long sum = 0, xr = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
         const unsigned long long h = point_hash(x, i, scene_of(i, batch_inds, bds, n_scenes));
         sum += h; xr ^= h;
     }
-    fingerprint_finish(sum, xr, N, n_scenes, res, force, hdr, status, n_tiles);
+    fingerprint_finish(sum, xr, N, n_scenes, res, force, hdr, status, n_tiles, map_tag);
 }
 
 // pass 1: rank of the point inside its bin (the rank makes the scatter pass atomic-free)
@@ -135,17 +149,17 @@ template <bool FP>
 __global__ void __launch_bounds__(256) sort_hist_kernel(uint64_t N, uint32_t res, uint32_t n_scenes, const float* __restrict__ x,
                                                         const int64_t* __restrict__ batch_inds, uint32_t bds, SortHeader* __restrict__ hdr,
                                                         uint32_t* __restrict__ hist, uint32_t* __restrict__ rank,
-                                                        unsigned long long* __restrict__ status, uint32_t n_tiles) {
+                                                        unsigned long long* __restrict__ status, uint32_t n_tiles, const SortMap map, uint32_t map_tag) {
     if (!FP && hdr->skip) return;
     const uint32_t bins = res * res * res;
     unsigned long long sum = 0, xr = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t sc = scene_of(i, batch_inds, bds, n_scenes);
-        const uint32_t k = sc == 0xffffu ? n_scenes * bins : sc * bins + bin_key(x[i * 3], x[i * 3 + 1], x[i * 3 + 2], res);
+        const uint32_t k = sc == 0xffffu ? n_scenes * bins : sc * bins + bin_key(map(x[i * 3]), map(x[i * 3 + 1]), map(x[i * 3 + 2]), res);
         rank[i] = atomicAdd(hist + k, 1u);
         if (FP) { const unsigned long long h = point_hash(x, i, sc); sum += h; xr ^= h; }
     }
-    if (FP) fingerprint_finish(sum, xr, N, n_scenes, res, /*force=*/1, hdr, status, n_tiles);
+    if (FP) fingerprint_finish(sum, xr, N, n_scenes, res, /*force=*/1, hdr, status, n_tiles, map_tag);
 }
 
 // single-pass exclusive scan (decoupled look-back): hist -> offsets; the counters are zeroed on the way for the next call
@@ -226,11 +240,11 @@ __global__ void __launch_bounds__(kScanThreads) sort_scan_kernel(uint32_t n, Sor
 __global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t N, uint32_t res, uint32_t n_scenes, const float* __restrict__ x,
                                                            const int64_t* __restrict__ batch_inds, uint32_t bds, const SortHeader* __restrict__ hdr,
                                                            const uint32_t* __restrict__ rank, const uint32_t* __restrict__ offsets,
-                                                           float4* __restrict__ xs, uint16_t* __restrict__ scenes) {
+                                                           float4* __restrict__ xs, uint16_t* __restrict__ scenes, const SortMap map) {
     if (hdr->skip) return;
     const uint32_t bins = res * res * res;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
-        const float px = x[i * 3], py = x[i * 3 + 1], pz = x[i * 3 + 2];
+        const float px = map(x[i * 3]), py = map(x[i * 3 + 1]), pz = map(x[i * 3 + 2]);
         const uint32_t sc = scene_of(i, batch_inds, bds, n_scenes);
         const uint32_t k = sc == 0xffffu ? n_scenes * bins : sc * bins + bin_key(px, py, pz, res);
         const uint32_t pos = __ldg(offsets + k) + __ldcs(rank + i);
@@ -245,8 +259,13 @@ using namespace nr3d;
 
 extern "C" {
 
-int nr3d_lotd_sort_points(uint64_t N, const float* x, const int64_t* batch_inds, uint32_t batch_data_size, uint32_t n_scenes, int32_t force,
-                          void* xs /* float4 [N] */, uint16_t* scenes /* [N] or NULL */, void* ws, uint64_t* ws_bytes, void* stream) {
+int nr3d_lotd_sort_points_mapped(uint64_t N, const float* x, const int64_t* batch_inds, uint32_t batch_data_size, uint32_t n_scenes, int32_t force,
+                                 float scale, float shift, int32_t clamp01, void* xs /* float4 [N] */, uint16_t* scenes /* [N] or NULL */, void* ws,
+                                 uint64_t* ws_bytes, void* stream) {
+    const SortMap map{scale, shift, clamp01};
+    uint32_t su, hu;
+    memcpy(&su, &scale, 4); memcpy(&hu, &shift, 4);
+    const uint32_t map_tag = (su * 0x9E3779B1u) ^ (hu * 0x85EBCA77u) ^ (clamp01 ? 0x27D4EB2Fu : 0u);
     if (n_scenes == 0) n_scenes = 1;
     NR3D_CHECK(n_scenes < 0xffffu, "sort_points: at most 65534 scenes");
     const uint32_t res = bin_res_for(N, n_scenes);
@@ -280,18 +299,23 @@ int nr3d_lotd_sort_points(uint64_t N, const float* x, const int64_t* batch_inds,
     const uint64_t vwant = div_up<uint64_t>(N, 256 * 8);
     const unsigned vgrid = (unsigned)(vwant < (uint64_t)kSMs * 8 ? vwant : (uint64_t)kSMs * 8);
     if (force) {   // new points (forward calls, first use of the buffers): sort unconditionally, the fingerprint is taken inside the histogram pass
-        sort_hist_kernel<true><<<grid, 256, 0, st>>>(N, res, n_scenes, x, batch_inds, batch_data_size, hdr, hist, rank, status, n_tiles);
+        sort_hist_kernel<true><<<grid, 256, 0, st>>>(N, res, n_scenes, x, batch_inds, batch_data_size, hdr, hist, rank, status, n_tiles, map, map_tag);
     } else {       // probably the points of the previous call (the backward of a step): fingerprint first, the sort kernels return at once on a match
-        sort_verify_kernel<<<vgrid, 256, 0, st>>>(N, x, batch_inds, batch_data_size, n_scenes, res, 0, hdr, status, n_tiles);
+        sort_verify_kernel<<<vgrid, 256, 0, st>>>(N, x, batch_inds, batch_data_size, n_scenes, res, 0, hdr, status, n_tiles, map_tag);
         NR3D_LAUNCH_CHECK("sort_verify");
-        sort_hist_kernel<false><<<grid, 256, 0, st>>>(N, res, n_scenes, x, batch_inds, batch_data_size, hdr, hist, rank, status, n_tiles);
+        sort_hist_kernel<false><<<grid, 256, 0, st>>>(N, res, n_scenes, x, batch_inds, batch_data_size, hdr, hist, rank, status, n_tiles, map, map_tag);
     }
     NR3D_LAUNCH_CHECK("sort_hist");
     sort_scan_kernel<<<n_tiles, kScanThreads, 0, st>>>(n_cnt, hdr, hist, offsets, status);
     NR3D_LAUNCH_CHECK("sort_scan");
-    sort_scatter_kernel<<<grid, 256, 0, st>>>(N, res, n_scenes, x, batch_inds, batch_data_size, hdr, rank, offsets, reinterpret_cast<float4*>(xs), scenes);
+    sort_scatter_kernel<<<grid, 256, 0, st>>>(N, res, n_scenes, x, batch_inds, batch_data_size, hdr, rank, offsets, reinterpret_cast<float4*>(xs), scenes, map);
     NR3D_LAUNCH_CHECK("sort_scatter");
     return 0;
+}
+
+int nr3d_lotd_sort_points(uint64_t N, const float* x, const int64_t* batch_inds, uint32_t batch_data_size, uint32_t n_scenes, int32_t force,
+                          void* xs /* float4 [N] */, uint16_t* scenes /* [N] or NULL */, void* ws, uint64_t* ws_bytes, void* stream) {
+    return nr3d_lotd_sort_points_mapped(N, x, batch_inds, batch_data_size, n_scenes, force, 1.0f, 0.0f, 0, xs, scenes, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

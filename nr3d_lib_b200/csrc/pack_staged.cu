@@ -16,11 +16,18 @@
 //      the state (transmittance, counters) stays in registers from window to window;
 //   3. the CTA writes the window's outputs back with coalesced stores (every element of the span is written, zeros included).
 // Packs that do not tile a span (gaps, overlaps, arbitrary order) are handled one pack per span through the same code.
+//
+// Sizing (measured on B200, 262144 packs x 115 samples, profiles/r2_pack_march_bench*.txt and the ncu capture next to them): the chain is
+// latency bound (one dependent step every ~40 clocks per thread), so what counts is (a) how many lanes of a warp have work in a window and
+// (b) how many warps per SM are inside a chain at once.  256-thread CTAs with 4096-sample windows had 36 of 256 threads busy per window and
+// ran 1.15 waves (154 us forward); ONE-WARP CTAs whose window covers the whole span of their 32 packs keep every lane busy, need no
+// block barrier, and 8192 small CTAs balance themselves over the SMs.  The chain is unrolled by four with the loads hoisted above the
+// stores of the same shared array (the compiler must otherwise order every load behind the previous store).
 #include "common.cuh"
 
 namespace nr3d {
 
-constexpr int kCtThreads = 256;               // packs per CTA
+constexpr int kCtThreads = 32;                // packs per CTA: ONE WARP -- see the sizing note below
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
 __device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a > b ? a : b; }
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -167,15 +174,31 @@ alpha_to_vw_fwd_cta_kernel(uint64_t P, uint64_t total, const T* __restrict__ alp
                 // this thread's part of the window (empty -- lo >= hi -- when its pack lies before or after it)
                 const uint64_t lo = umax64(sp.begin, w0), hi = umin64(sp.begin + sp.len, w0 + n);
                 const uint32_t t1 = lo < hi ? (uint32_t)(hi - w.a0) : 0u;
-                for (uint32_t t = lo < hi ? (uint32_t)(lo - w.a0) : 0u; t < t1; ++t) {   // == the reference thread's loop body, branch-free
-                    const W a = AR::up(buf[t]);
+                uint32_t t = lo < hi ? (uint32_t)(lo - w.a0) : 0u;
+                auto step = [&](W a, W& wv, uint8_t& sv) {   // == the reference thread's loop body, branch-free
                     stopped = stopped || (Tr < eps);
                     const bool live = !stopped && !(a <= thre);
-                    const W wv = live ? AR::mul(a, Tr) : AR::cast(0.f);
+                    wv = live ? AR::mul(a, Tr) : AR::cast(0.f);
                     Tr = live ? AR::mul(Tr, AR::one_minus(a)) : Tr;
-                    buf[t] = AR::down(wv);
-                    sel_s[t] = live ? 1 : 0;
+                    sv = live ? 1 : 0;
                     cnt += live ? 1 : 0;
+                };
+                for (; t + 4 <= t1; t += 4) {
+                    W a[4], wv[4];
+                    uint8_t sv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) a[u] = AR::up(buf[t + u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) step(a[u], wv[u], sv[u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { buf[t + u] = AR::down(wv[u]); sel_s[t + u] = sv[u]; }
+                }
+                for (; t < t1; ++t) {
+                    W wv;
+                    uint8_t sv;
+                    step(AR::up(buf[t]), wv, sv);
+                    buf[t] = AR::down(wv);
+                    sel_s[t] = sv;
                 }
             }
             __syncthreads();
@@ -263,16 +286,26 @@ alpha_to_vw_bwd_cta_kernel(uint64_t P, uint64_t total, const T* __restrict__ alp
                 // this thread's part of the window (empty -- lo >= hi -- when its pack lies before or after it)
                 const uint64_t lo = umax64(sp.begin, w0), hi = umin64(sp.begin + sp.len, w0 + n);
                 const uint32_t t1 = lo < hi ? (uint32_t)(hi - w.a0) : 0u;
-                for (uint32_t t = lo < hi ? (uint32_t)(lo - w.a0) : 0u; t < t1; ++t) {
-                    const T a = a_s[t], gw = g_s[t];
+                uint32_t t = lo < hi ? (uint32_t)(lo - w.a0) : 0u;
+                auto step = [&](T a, T gw, T wv) -> T {
                     stopped = stopped || (Tr < eps);
                     const bool live = !stopped && !(a < thre);   // `<` here, `<=` in the forward pass (reference quirk, kept)
                     const T om = (T)(1.f) - a;
                     const T out = fma_t<T>(gw, Tr, -accum) / (T)fmaxf((float)om, 1e-10f);
-                    a_s[t] = live ? out : (T)0;
-                    accum = live ? fma_t<T>(-gw, w_s[t], accum) : accum;
+                    accum = live ? fma_t<T>(-gw, wv, accum) : accum;
                     Tr = live ? Tr * om : Tr;
+                    return live ? out : (T)0;
+                };
+                for (; t + 4 <= t1; t += 4) {
+                    T a[4], gw[4], wv[4], o[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { a[u] = a_s[t + u]; gw[u] = g_s[t + u]; wv[u] = w_s[t + u]; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) o[u] = step(a[u], gw[u], wv[u]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) a_s[t + u] = o[u];
                 }
+                for (; t < t1; ++t) a_s[t] = step(a_s[t], g_s[t], w_s[t]);
             }
             __syncthreads();
             const uint32_t off = (uint32_t)(w0 - w.a0);
@@ -326,6 +359,103 @@ pack_sum_cta_kernel(uint64_t P, uint64_t total, const T* __restrict__ in, const 
     if (p0 + tid < P) out[p0 + tid] = acc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two per-pack reductions of the render step in one pass (no reference export; replaces the composition
+//   acc = packed_sum(w, pack_infos);  depth = packed_sum(w * t, pack_infos)         (nerf_ray_query.py:182-188: weights -> accumulated
+// opacity and expected depth) and its autograd chain.  Forward: sequential sums like the reference's packed_sum thread, the product w * t
+// rounded before it is added (what the separate torch `mul` kernel produces).  Backward: dL/dw[j] = fl(fl(g_depth[p] * t[j]) + g_acc[p]).
+// ------------------------------------------------------------------------------------------------
+template <int WIN>
+__global__ void __launch_bounds__(kCtThreads)
+pack_wsum_fwd_cta_kernel(uint64_t P, uint64_t total, const float* __restrict__ w_in, const float* __restrict__ t_in, const int64_t* __restrict__ pack_infos,
+                         float* __restrict__ acc_out, float* __restrict__ dep_out) {
+    constexpr int A = 4;
+    __shared__ __align__(128) float w_s[WIN + A];
+    __shared__ __align__(128) float t_s[WIN + A];
+    __shared__ uint64_t s_b[kCtThreads + 1], s_e[kCtThreads];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x;
+    const uint64_t p0 = (uint64_t)blockIdx.x * kCtThreads;
+    const uint32_t bar = smem_addr(&s_bar);
+    if (tid == 0) mbar_init(bar);
+    const CtaSpan sp = load_cta_span(pack_infos, P, p0, tid, s_b, s_e);
+    float acc = 0.f, dep = 0.f;
+    uint32_t parity = 0;
+    const int n_spans = sp.tiled ? 1 : sp.last + 1;
+    for (int s = 0; s < n_spans; ++s) {
+        const uint64_t sb = sp.tiled ? sp.sb : s_b[s], se = sp.tiled ? sp.se : s_e[s];
+        const bool mine = sp.tiled ? tid <= sp.last : tid == s;
+        for (uint64_t w0 = sb; w0 < se; w0 += WIN) {
+            const uint32_t n = (uint32_t)umin64((uint64_t)WIN, se - w0);
+            const Win<float> w(w0, n, total);
+            if (tid == 0 && w.bytes) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar, 2 * w.bytes);
+                bulk_g2s(smem_addr(w_s), w_in + w.a0, w.bytes, bar);
+                bulk_g2s(smem_addr(t_s), t_in + w.a0, w.bytes, bar);
+            }
+            stage_tail(w_s, w_in, w, w0, n, tid);
+            stage_tail(t_s, t_in, w, w0, n, tid);
+            if (w.bytes) { mbar_wait_parity(bar, parity); parity ^= 1u; }
+            __syncthreads();
+            if (mine) {
+                const uint64_t lo = umax64(sp.begin, w0), hi = umin64(sp.begin + sp.len, w0 + n);
+                const uint32_t t1 = lo < hi ? (uint32_t)(hi - w.a0) : 0u;
+                for (uint32_t t = lo < hi ? (uint32_t)(lo - w.a0) : 0u; t < t1; ++t) {
+                    const float wv = w_s[t];
+                    acc += wv;
+                    dep = __fadd_rn(dep, __fmul_rn(wv, t_s[t]));
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (p0 + tid < P) { acc_out[p0 + tid] = acc; dep_out[p0 + tid] = dep; }
+}
+
+template <int WIN>
+__global__ void __launch_bounds__(kCtThreads)
+pack_wsum_bwd_cta_kernel(uint64_t P, uint64_t total, const float* __restrict__ t_in, const int64_t* __restrict__ pack_infos, const float* __restrict__ g_acc,
+                         const float* __restrict__ g_dep, float* __restrict__ grad_w) {
+    constexpr int A = 4;
+    __shared__ __align__(128) float t_s[WIN + A];      // depths in, dL/dw out (in place)
+    __shared__ uint64_t s_b[kCtThreads + 1], s_e[kCtThreads];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x;
+    const uint64_t p0 = (uint64_t)blockIdx.x * kCtThreads;
+    const uint32_t bar = smem_addr(&s_bar);
+    if (tid == 0) mbar_init(bar);
+    const CtaSpan sp = load_cta_span(pack_infos, P, p0, tid, s_b, s_e);
+    const float ga = (p0 + tid < P && g_acc) ? __ldg(g_acc + p0 + tid) : 0.f, gd = (p0 + tid < P && g_dep) ? __ldg(g_dep + p0 + tid) : 0.f;
+    uint32_t parity = 0;
+    const int n_spans = sp.tiled ? 1 : sp.last + 1;
+    for (int s = 0; s < n_spans; ++s) {
+        const uint64_t sb = sp.tiled ? sp.sb : s_b[s], se = sp.tiled ? sp.se : s_e[s];
+        const bool mine = sp.tiled ? tid <= sp.last : tid == s;
+        for (uint64_t w0 = sb; w0 < se; w0 += WIN) {
+            const uint32_t n = (uint32_t)umin64((uint64_t)WIN, se - w0);
+            const Win<float> w(w0, n, total);
+            if (tid == 0 && w.bytes) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar, w.bytes);
+                bulk_g2s(smem_addr(t_s), t_in + w.a0, w.bytes, bar);
+            }
+            stage_tail(t_s, t_in, w, w0, n, tid);
+            if (w.bytes) { mbar_wait_parity(bar, parity); parity ^= 1u; }
+            __syncthreads();
+            if (mine) {
+                const uint64_t lo = umax64(sp.begin, w0), hi = umin64(sp.begin + sp.len, w0 + n);
+                const uint32_t t1 = lo < hi ? (uint32_t)(hi - w.a0) : 0u;
+                for (uint32_t t = lo < hi ? (uint32_t)(lo - w.a0) : 0u; t < t1; ++t) t_s[t] = __fadd_rn(__fmul_rn(gd, t_s[t]), ga);
+            }
+            __syncthreads();
+            const uint32_t off = (uint32_t)(w0 - w.a0);
+            for (uint32_t t = tid; t < n; t += kCtThreads) grad_w[w0 + t] = t_s[off + t];
+            __syncthreads();
+        }
+    }
+}
+
 static inline unsigned ct_grid(uint64_t P) { return (unsigned)div_up<uint64_t>(P, (uint64_t)kCtThreads); }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -363,3 +493,29 @@ int staged_pack_sum(int32_t dtype, uint64_t P, uint64_t total, const void* in, c
 }
 
 }  // namespace nr3d
+
+using namespace nr3d;
+
+extern "C" {
+
+int nr3d_pack_weighted_sums_fwd(uint64_t P, uint64_t S, const float* weights, const float* depths, const int64_t* pack_infos, float* acc, float* depth,
+                                void* stream) {
+    if (P == 0) return 0;
+    NR3D_CHECK(weights && depths && pack_infos && acc && depth, "packed_weighted_sums: null argument");
+    NR3D_CHECK(aligned16(weights) && aligned16(depths), "packed_weighted_sums: weights / depths must be 16-byte aligned");
+    pack_wsum_fwd_cta_kernel<4096><<<ct_grid(P), kCtThreads, 0, (cudaStream_t)stream>>>(P, S, weights, depths, pack_infos, acc, depth);
+    NR3D_LAUNCH_CHECK("packed_weighted_sums");
+    return 0;
+}
+
+int nr3d_pack_weighted_sums_bwd(uint64_t P, uint64_t S, const float* depths, const int64_t* pack_infos, const float* grad_acc, const float* grad_depth,
+                                float* grad_weights, void* stream) {
+    if (P == 0) return 0;
+    NR3D_CHECK(depths && pack_infos && grad_weights && (grad_acc || grad_depth), "packed_weighted_sums backward: null argument");
+    NR3D_CHECK(aligned16(depths), "packed_weighted_sums backward: depths must be 16-byte aligned");
+    pack_wsum_bwd_cta_kernel<4096><<<ct_grid(P), kCtThreads, 0, (cudaStream_t)stream>>>(P, S, depths, pack_infos, grad_acc, grad_depth, grad_weights);
+    NR3D_LAUNCH_CHECK("packed_weighted_sums backward");
+    return 0;
+}
+
+}  // extern "C"

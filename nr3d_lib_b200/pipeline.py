@@ -83,12 +83,15 @@ class _EncodeDensityAlpha(torch.autograd.Function):
     order of the features (tests/test_pipeline_gpu.py).  Differentiable w.r.t. `params` through alpha."""
 
     @staticmethod
-    def forward(ctx, meta, x01, params, deltas, gain, max_level):
+    def forward(ctx, meta, x01, params, deltas, gain, max_level, from_ndc=False):
         import ctypes
         from . import _lib
         from .bindings import _lotd
         dev = _lib.require_cuda(x01, params, deltas, who="encode_density_alpha")
-        x = x01.detach().clamp(1.0e-6, 1.0 - 1.0e-6).contiguous()          # as LoTDFunction does (reference lotd.py:211)
+        # LoTDFunction clamps the points (reference lotd.py:211) and LoTDEncoding maps [-1, 1] -> [0, 1] (lotd_encoding.py:162): both happen
+        # inside the point sort here, so no pass over [S, 3] is spent on them
+        x = x01.detach().contiguous()
+        cmap = (0.5, 0.5, True) if from_ndc else (1.0, 0.0, True)
         deltas = deltas.detach().float().contiguous().flatten()
         N = x.shape[0]
         ml = meta.n_levels if max_level is None else int(max_level)
@@ -96,12 +99,12 @@ class _EncodeDensityAlpha(torch.autograd.Function):
             sigma = torch.empty(N, dtype=torch.float32, device=dev)
             alpha = torch.empty(N, dtype=torch.float32, device=dev)
             if N:
-                xs, scenes = _lotd._sorted_points(x, expect_new=True)
+                xs, scenes = _lotd._sorted_points(x, expect_new=True, coord_map=cmap)
                 _lib.check(_lib.get_lib().nr3d_lotd_density_head_fwd_sorted(
                     ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), _lib.ptr(scenes), 1, params.data_ptr(), ml,
                     deltas.data_ptr(), float(gain), sigma.data_ptr(), alpha.data_ptr(), _lib.stream_of(dev)))
         ctx.save_for_backward(x, sigma, alpha, deltas)
-        ctx.meta, ctx.gain, ctx.ml, ctx.pshape, ctx.pdtype = meta, float(gain), ml, params.shape, params.dtype
+        ctx.meta, ctx.gain, ctx.ml, ctx.pshape, ctx.pdtype, ctx.cmap = meta, float(gain), ml, params.shape, params.dtype, cmap
         ctx.mark_non_differentiable(sigma)
         return alpha, sigma
 
@@ -113,28 +116,74 @@ class _EncodeDensityAlpha(torch.autograd.Function):
         from .bindings import _lotd
         x, sigma, alpha, deltas = ctx.saved_tensors
         if d_alpha is None or not ctx.needs_input_grad[2]:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         d_alpha = d_alpha.float().contiguous()
         dev, N = x.device, x.shape[0]
         with torch.cuda.device(dev):
             g = torch.zeros(ctx.pshape, dtype=ctx.pdtype, device=dev)
             if N:
-                xs, scenes = _lotd._sorted_points(x)      # the forward's records unless other points were sorted on this stream in between
+                xs, scenes = _lotd._sorted_points(x, coord_map=ctx.cmap)      # the forward's records unless other points were sorted on this stream in between
                 _lib.check(_lib.get_lib().nr3d_lotd_density_head_bwd_sorted(
                     ctypes.byref(ctx.meta._c), _lib.dtype_code(ctx.pdtype), N, xs.data_ptr(), _lib.ptr(scenes), 1, d_alpha.data_ptr(), sigma.data_ptr(),
                     alpha.data_ptr(), deltas.data_ptr(), ctx.gain, ctx.ml, g.data_ptr(), _lib.stream_of(dev)))
-        return None, None, g, None, None, None
+        return None, None, g, None, None, None, None
 
 
-def encode_density_alpha(encoder: LoTD, x01: torch.Tensor, params: torch.Tensor, deltas: torch.Tensor, gain: float = 20.0, max_level=None):
+def encode_density_alpha(encoder: LoTD, x01: torch.Tensor, params: torch.Tensor, deltas: torch.Tensor, gain: float = 20.0, max_level=None,
+                         from_ndc: bool = False):
     """(alpha, sigma) of the stand-in density head applied to the LoTD features of `x01`; one fused kernel each way when the encoder is
-    eligible for the cell-sorted fast path (Dense/Hash, D = 3, single scene), the two-kernel composition otherwise."""
+    eligible for the cell-sorted fast path (Dense/Hash, D = 3, single scene), the two-kernel composition otherwise.
+    `from_ndc`: the points are given in [-1, 1]^3 (ray samples) and mapped to the unit cube on the fly."""
     from .bindings import _lotd
     meta = encoder.meta
     p = params.to(encoder.dtype)
     if _lotd._sorted_eligible(meta, x01, p, None, None, 0) and x01.dim() == 2 and p.shape[0] == meta.n_params:
-        return _EncodeDensityAlpha.apply(meta, x01, p, deltas, gain, max_level)
+        return _EncodeDensityAlpha.apply(meta, x01, p, deltas, gain, max_level, from_ndc)
+    if from_ndc:
+        x01 = x01 * 0.5 + 0.5
     return density_alpha(encoder(x01, params, max_level=max_level).float(), deltas, gain)
+
+
+class _PackedWeightedSums(torch.autograd.Function):
+    """(acc, depth) = (packed_sum(w), packed_sum(w * t)) in one pass each way (csrc/pack_staged.cu); bit-identical to the composition."""
+
+    @staticmethod
+    def forward(ctx, w, t, pack_infos):
+        from . import _lib
+        dev = _lib.require_cuda(w, t, pack_infos, who="packed_weighted_sums")
+        if w.dtype != torch.float32 or t.dtype != torch.float32 or w.dim() != 1 or w.shape != t.shape:
+            raise RuntimeError("packed_weighted_sums: weights / depths must be float32 [S] tensors of the same size")
+        if pack_infos.dim() != 2 or pack_infos.shape[1] != 2 or pack_infos.dtype != torch.int64:
+            raise RuntimeError("packed_weighted_sums: pack_infos must be int64 [P, 2]")
+        w, t, pack_infos = w.contiguous(), t.detach().contiguous(), pack_infos.contiguous()
+        P, S = pack_infos.shape[0], w.shape[0]
+        with torch.cuda.device(dev):
+            out = torch.empty([2, P], dtype=torch.float32, device=dev)
+            _lib.check(_lib.get_lib().nr3d_pack_weighted_sums_fwd(P, S, w.data_ptr(), t.data_ptr(), pack_infos.data_ptr(), out[0].data_ptr(),
+                                                                  out[1].data_ptr(), _lib.stream_of(dev)))
+        ctx.save_for_backward(t, pack_infos)
+        return out[0], out[1]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_acc, g_depth):
+        from . import _lib
+        t, pack_infos = ctx.saved_tensors
+        if g_acc is None and g_depth is None:
+            return None, None, None
+        dev, P, S = t.device, pack_infos.shape[0], t.shape[0]
+        ga = None if g_acc is None else g_acc.float().contiguous()
+        gd = None if g_depth is None else g_depth.float().contiguous()
+        with torch.cuda.device(dev):
+            gw = torch.zeros([S], dtype=torch.float32, device=dev)
+            _lib.check(_lib.get_lib().nr3d_pack_weighted_sums_bwd(P, S, t.data_ptr(), pack_infos.data_ptr(), _lib.ptr(ga), _lib.ptr(gd), gw.data_ptr(),
+                                                                  _lib.stream_of(dev)))
+        return gw, None, None
+
+
+def packed_weighted_sums(weights: torch.Tensor, depths: torch.Tensor, pack_infos: torch.Tensor):
+    """(accumulated opacity, expected depth) of every pack: == (packed_sum(w, pi), packed_sum(w * depths, pi)), differentiable w.r.t. `weights`."""
+    return _PackedWeightedSums.apply(weights, depths, pack_infos)
 
 
 def march_encode_composite(encoder: LoTD, params: torch.Tensor, occ_grid: torch.Tensor, rays_o: torch.Tensor, rays_d: torch.Tensor,
@@ -145,15 +194,19 @@ def march_encode_composite(encoder: LoTD, params: torch.Tensor, occ_grid: torch.
     ret = occgrid_raymarch(occ_grid, rays_o, rays_d, near, far, step_size=step_size, max_steps=max_steps)
     if ret.num_hit_rays == 0:
         return RenderOut(ret, None, None, None)
-    x01 = ret.samples * 0.5 + 0.5                      # [-1,1] -> [0,1]  (LoTDEncoding.forward, lotd_encoding.py:162)
     if fuse_head:
-        alpha, _sigma = encode_density_alpha(encoder, x01, params, ret.deltas, gain)
+        # [-1,1] -> [0,1] (LoTDEncoding.forward, lotd_encoding.py:162) and the clamp happen inside the point sort
+        alpha, _sigma = encode_density_alpha(encoder, ret.samples, params, ret.deltas, gain, from_ndc=True)
     else:
+        x01 = ret.samples * 0.5 + 0.5
         h = encoder(x01, params)                       # [S, n_enc]
         alpha, _sigma = density_alpha(h.float(), ret.deltas, gain)   # softplus head + (1 - exp(-sigma * delta)), nerf_ray_query.py:182
     w = packed_alpha_to_vw(alpha, ret.pack_infos, early_stop_eps, alpha_thre)
-    depth = packed_sum(w * ret.depth_samples, ret.pack_infos)
-    acc = packed_sum(w, ret.pack_infos)
+    if fuse_head:
+        acc, depth = packed_weighted_sums(w, ret.depth_samples.reshape(-1), ret.pack_infos)     # one pass each way, same values as below
+    else:
+        depth = packed_sum(w * ret.depth_samples, ret.pack_infos)
+        acc = packed_sum(w, ret.pack_infos)
     return RenderOut(ret, depth, acc, w)
 
 

@@ -158,6 +158,44 @@ def test_fused_density_head_matches_composition(pdtype, dev):
 
 
 @pytest.mark.gpu
+def test_packed_weighted_sums_bit_identical_to_composition(dev):
+    """(acc, depth) in one pass each way == packed_sum(w), packed_sum(w * t) and their autograd, bit for bit."""
+    from nr3d_lib_b200.pack_ops import packed_sum
+    from nr3d_lib_b200.pipeline import packed_weighted_sums
+    from tests.util import pack_inputs
+    for P, max_len, min_len in ((5000, 300, 1), (700, 40, 0), (3, 9000, 5000)):
+        d = pack_inputs(P=P, max_len=max_len, C=1, seed=P, min_len=max(min_len, 1))
+        n = d["n"].copy()
+        if min_len == 0:
+            n[::5] = 0
+        pi = torch.from_numpy(np.stack([np.cumsum(n) - n, n], 1)).to(dev)
+        S = int(n.sum())
+        g = torch.Generator().manual_seed(P)
+        t = (torch.rand(S, generator=g) * 6).to(dev)
+        w0 = torch.rand(S, generator=g).to(dev)
+        ca, cd = torch.randn(P, generator=g).to(dev), torch.randn(P, generator=g).to(dev)
+        wa = w0.clone().requires_grad_(True)
+        acc, dep = packed_weighted_sums(wa, t, pi)
+        ((acc * ca).sum() + (dep * cd).sum()).backward()
+        wb = w0.clone().requires_grad_(True)
+        acc_r, dep_r = packed_sum(wb, pi), packed_sum(wb * t, pi)
+        ((acc_r * ca).sum() + (dep_r * cd).sum()).backward()
+        assert torch.equal(acc, acc_r) and torch.equal(dep, dep_r)
+        assert torch.equal(wa.grad, wb.grad)
+    # the coordinate map of the point sort: sorting x in [-1, 1] with (0.5, 0.5, clamp) == sorting clamp(x * 0.5 + 0.5)
+    from nr3d_lib_b200.bindings import _lotd
+    x = (torch.rand(50000, 3, generator=g) * 2.2 - 1.1).to(dev)
+    by_index = lambda r: r[r[:, 3].contiguous().view(torch.int32).argsort()]      # (the order inside a bin is not deterministic)
+    xs_a, _ = _lotd._sorted_points(x, expect_new=True, coord_map=(0.5, 0.5, True))
+    xs_a = by_index(xs_a.clone())
+    xs_b, _ = _lotd._sorted_points((x * 0.5 + 0.5).clamp(1e-6, 1 - 1e-6), expect_new=True)
+    assert torch.equal(xs_a, by_index(xs_b))
+    assert torch.equal(xs_a[:, :3], (x * 0.5 + 0.5).clamp(1e-6, 1 - 1e-6))
+    xs_c, _ = _lotd._sorted_points(x)                      # same tensor, other map: must NOT reuse the mapped records
+    assert torch.equal(by_index(xs_c)[:, :3], x)
+
+
+@pytest.mark.gpu
 def test_march_samples_bit_identical_to_torch(dev):
     from nr3d_lib_b200.bindings import _occ_grid
     g = torch.Generator().manual_seed(6)
