@@ -42,8 +42,8 @@ BYTES_FWD, BYTES_BWD, BYTES_TABLE = 12 + 1024 + 128, 12 + 128 + 1024, 23
 BYTES_PER_SAMPLE = BYTES_FWD + BYTES_BWD + BYTES_TABLE   # 2351
 BYTES_PER_SAMPLE_F16 = (12 + 512 + 64) + (12 + 64 + 512) + 12   # 1188 (SURVEY.md 8d, fp16 parameter tables)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the two dominant kernels at this workload, from the committed
-# `ncu --set full` capture profiles/r1_s2_pair_ncu_summary.txt (4 Mi points): the table is L2 resident, DRAM only sees x / y / dL_dy
-NCU_DRAM_BYTES = {"lod_bwd (dL/dparam scatter)": 672.2e6 + 36.2e6, "lod_fwd (corner gather)": 151.2e6 + 500.4e6}
+# `ncu --set full` capture profiles/r2_pair_ncu_summary.txt (4 Mi points): the table is L2 resident, DRAM only sees x / y / dL_dy
+NCU_DRAM_BYTES = {"lotd_pair_bwd_kernel (dL/dparam scatter)": 673.9e6 + 41.5e6, "lotd_pair_fwd_kernel (corner gather)": 153.7e6 + 499.4e6}
 
 
 def ngp_cfg(min_res=16, n_levels=16, scale=1.382, log2_T=19, F=2):
@@ -272,6 +272,7 @@ def main():
 
     # per-kernel durations for the roofline block: CUDA events on the launch stream around each call, inside this run
     def kernel_ms(fn, iters):
+        fn()                                   # untimed warm-up
         torch.cuda.synchronize(dev)
         ts = []
         for _ in range(iters):
@@ -288,14 +289,29 @@ def main():
     ms_fwd = kernel_ms(fwd_with_sort, it)      # includes the per-step point sort of the fast path
     ms_bwd = kernel_ms(lambda: _lotd.lod_bwd(meta, dL_dy, xs[flip[0]], params, None, need_input_grad=False, need_param_grad=True), it)   # fingerprint (hit) + scatter
     peak, peak_src = measured_peak_gbs()
-    dom = "lod_bwd (dL/dparam scatter)" if ms_bwd >= ms_fwd else "lod_fwd (corner gather)"
-    dom_ms, dom_bytes = (ms_bwd, BYTES_BWD + BYTES_TABLE) if ms_bwd >= ms_fwd else (ms_fwd, BYTES_FWD)
+    # the two dominant KERNELS on their own (no sort, no fingerprint check): the C-ABI entry points called directly on the sorted records
+    import ctypes
+    lib = _lib.get_lib()
+    recs, _ = _lotd._sorted_points(xs[0], expect_new=True)
+    y_tmp = torch.empty(N, meta.n_encoded_dims, device=dev)
+    g_tmp = torch.zeros(meta.n_params, device=dev)
+    E, P_ = meta.n_encoded_dims, meta.n_pseudo_levels
+    k_fwd = kernel_ms(lambda: _lib.check(lib.nr3d_lotd_fwd_sorted(ctypes.byref(meta._c), _lib.dtype_code(torch.float32), N, recs.data_ptr(), None, 1,
+                                                                  params.data_ptr(), meta.n_levels, y_tmp.data_ptr(), E, 1, stream.cuda_stream)), it)
+    k_bwd = kernel_ms(lambda: _lib.check(lib.nr3d_lotd_bwd_param_sorted(ctypes.byref(meta._c), _lib.dtype_code(torch.float32), N, recs.data_ptr(), None, 1,
+                                                                        dL_dy.data_ptr(), E, 1, meta.n_levels, 0, P_, g_tmp.data_ptr(), stream.cuda_stream)), it)
+    del y_tmp, g_tmp
+    dom = "lotd_pair_bwd_kernel (dL/dparam scatter)" if k_bwd >= k_fwd else "lotd_pair_fwd_kernel (corner gather)"
+    dom_ms, dom_bytes = (k_bwd, BYTES_BWD + BYTES_TABLE) if k_bwd >= k_fwd else (k_fwd, BYTES_FWD)
     achieved = N * dom_bytes / (dom_ms * 1e-3) / 1e9
     whole = value * 1e6 / n_gpus * BYTES_PER_SAMPLE / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES[dom],
-                "traffic_source": "ncu --set full capture of this kernel at this workload, profiles/r1_s2_pair_ncu_summary.txt (bytes per launch)",
+                "traffic_source": "ncu --set full capture of this kernel at this workload, profiles/r2_pair_ncu_summary.txt (bytes per launch)",
                 "peak_source": peak_src, "algorithmic_bytes_per_sample": {"fwd": BYTES_FWD, "bwd": BYTES_BWD, "table": BYTES_TABLE},
-                "ms": {"lod_fwd": ms_fwd, "lod_bwd": ms_bwd},
+                "kernel_ms": {"lotd_pair_fwd_kernel": k_fwd, "lotd_pair_bwd_kernel": k_bwd},
+                "ms": {"lod_fwd (sort + gather)": ms_fwd, "lod_bwd (fingerprint check + memset + scatter)": ms_bwd},
+                "note": "86 % of the algorithmic bytes are gathers / reductions that hit the L2-resident 48.5 MB table: the binding resources are the L1 line "
+                        "rate (forward, 91 % of peak in the ncu capture) and the L2 reduction-unit packet rate (backward), DRAM carries 0.65 - 0.72 GB per launch",
                 "whole_step": {"achieved": whole, "frac": whole / peak, "bytes_per_sample": BYTES_PER_SAMPLE}}
 
     # secondary number of metric M1: the same step with fp16 parameter tables (y, dL_dy and dL/dparams in half)

@@ -324,10 +324,12 @@ int nr3d_occ_query(uint64_t N, const float* pts, const int64_t* bidx, uint64_t b
 int nr3d_pack_sum(int32_t dtype, uint64_t P, uint32_t C, uint64_t S, const void* feats, const int64_t* pack_infos, void* out, void* stream);
 /* == packed_cumsum / packed_cumprod, pack_ops_cuda.cu:864-1095.  out [S, C] must be zero-filled where elements
  * are not covered by any pack. exclusive cumprod implements the DOCUMENTED semantics (leading 1,
- * nr3d_lib/graphics/pack_ops/pack_ops.py:149); bug_compat=1 reproduces the reference CUDA output (all zeros). */
-int nr3d_pack_cumsum(int32_t dtype, uint64_t P, uint32_t C, const void* feats, const int64_t* pack_infos,
+ * nr3d_lib/graphics/pack_ops/pack_ops.py:149); bug_compat=1 reproduces the reference CUDA output (all zeros).
+ * S = rows of `feats` (see nr3d_pack_sum): one-channel fp32 / fp64 calls run the staged sequential kernels (bit-identical to the reference's
+ * per-thread loops for sums and inclusive products); other calls use warp scans (fp32 reassociation, tolerance 3e-5 on long packs). */
+int nr3d_pack_cumsum(int32_t dtype, uint64_t P, uint32_t C, uint64_t S, const void* feats, const int64_t* pack_infos,
                      int32_t exclusive, int32_t reverse, void* out, void* stream);
-int nr3d_pack_cumprod(int32_t dtype, uint64_t P, uint32_t C, const void* feats, const int64_t* pack_infos,
+int nr3d_pack_cumprod(int32_t dtype, uint64_t P, uint32_t C, uint64_t S, const void* feats, const int64_t* pack_infos,
                       int32_t exclusive, int32_t reverse, int32_t bug_compat, void* out, void* stream);
 /* == packed_diff / packed_backward_diff, pack_ops_cuda.cu:1098-1334. edge / fill: [P, C] nullable, at most one. */
 int nr3d_pack_diff(int32_t dtype, uint64_t P, uint32_t C, const void* feats, const int64_t* pack_infos,

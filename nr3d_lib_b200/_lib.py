@@ -91,8 +91,8 @@ SIGNATURES = {
     "nr3d_density_alpha_fwd": [_u64, _u32, _vp, _i64, _vp, _f32, _vp, _vp, _vp],
     "nr3d_density_alpha_bwd": [_u64, _u32, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp],
     "nr3d_pack_sum": [_i32, _u64, _u32, _u64, _vp, _vp, _vp, _vp],
-    "nr3d_pack_cumsum": [_i32, _u64, _u32, _vp, _vp, _i32, _i32, _vp, _vp],
-    "nr3d_pack_cumprod": [_i32, _u64, _u32, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
+    "nr3d_pack_cumsum": [_i32, _u64, _u32, _u64, _vp, _vp, _i32, _i32, _vp, _vp],
+    "nr3d_pack_cumprod": [_i32, _u64, _u32, _u64, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
     "nr3d_pack_diff": [_i32, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp],
     "nr3d_pack_backward_diff": [_i32, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp],
     "nr3d_pack_binary": [_i32, _i32, _u64, _u32, _vp, _vp, _vp, _vp, _vp],

@@ -69,7 +69,7 @@ def _scan(fn_name, cfun, feats, pack_infos, exclusive, reverse, extra=()):
     dev, P, C = _check_feats(fn_name, feats, pack_infos)
     with torch.cuda.device(dev):
         out = torch.zeros_like(feats)
-        _lib.check(cfun(_lib.dtype_code(feats.dtype), P, C, feats.data_ptr(), pack_infos.data_ptr(), int(bool(exclusive)),
+        _lib.check(cfun(_lib.dtype_code(feats.dtype), P, C, feats.shape[0], feats.data_ptr(), pack_infos.data_ptr(), int(bool(exclusive)),
                         int(bool(reverse)), *extra, out.data_ptr(), _lib.stream_of(dev)))
     return out
 

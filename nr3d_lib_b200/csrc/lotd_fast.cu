@@ -33,6 +33,9 @@ namespace nr3d {
 #ifndef NR3D_FWD_THREADS
 #define NR3D_FWD_THREADS 256
 #endif
+#ifndef NR3D_FWD_OCC          // resident threads per SM the F = 2 forward is compiled for (register cap through __launch_bounds__)
+#define NR3D_FWD_OCC 1536     // A/B on B200 (profiles/r2_ab_tunables.txt): 2048 (30 registers, +21 % instructions) 0.873 ms, 1536 (39 registers) 0.843 ms, 1280 0.861 ms
+#endif
 #ifndef NR3D_BWD_THREADS      // 256 threads = 128 points per CTA: about one 8 x 4 x 2 brick of sort bins
 #define NR3D_BWD_THREADS 256
 #endif
@@ -88,7 +91,7 @@ struct HeadBwd { const float* d_alpha; const float* sigma; const float* alpha; c
 __device__ __forceinline__ float softplus_head(float v) { return v > 20.0f ? v : log1pf(expf(v)); }   // == F.softplus (beta 1, threshold 20)
 
 template <typename PT, int F, bool HEAD = false>
-__global__ void __launch_bounds__(kFastThreads, F == 2 ? 2048 / kFastThreads : 1)
+__global__ void __launch_bounds__(kFastThreads, F == 2 ? NR3D_FWD_OCC / kFastThreads : 1)
 lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT* __restrict__ y, int64_t ys_n, int64_t ys_f, const HeadFwd hd) {
     using C = Cvt<PT>;
     constexpr int H = F / 2;   // features of a pseudo level that one lane of the pair writes out

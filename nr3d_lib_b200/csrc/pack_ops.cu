@@ -479,6 +479,8 @@ int staged_alpha_fwd(int32_t dtype, uint64_t P, uint64_t total, const void* alph
 int staged_alpha_bwd(int32_t dtype, uint64_t P, uint64_t total, const void* alphas, const void* weights, const void* grad_weights,
                      const int64_t* pack_infos, float eps, float thre, void* grad_alphas, cudaStream_t st);
 int staged_pack_sum(int32_t dtype, uint64_t P, uint64_t total, const void* in, const int64_t* pack_infos, void* out, cudaStream_t st);
+int staged_pack_scan(int32_t dtype, bool prod, uint64_t P, uint64_t total, const void* in, const int64_t* pack_infos, bool exclusive, bool reverse, void* out,
+                     cudaStream_t st);
 
 #ifndef NR3D_PACK_STAGED      // 0: the warp-per-pack kernels of this file serve every call (A/B runs)
 #define NR3D_PACK_STAGED 1
@@ -521,21 +523,29 @@ int nr3d_pack_sum(int32_t dtype, uint64_t P, uint32_t C, uint64_t S, const void*
     return 0;
 }
 
-int nr3d_pack_cumsum(int32_t dtype, uint64_t P, uint32_t C, const void* feats, const int64_t* pack_infos, int32_t exclusive,
+int nr3d_pack_cumsum(int32_t dtype, uint64_t P, uint32_t C, uint64_t S, const void* feats, const int64_t* pack_infos, int32_t exclusive,
                      int32_t reverse, void* out, void* stream) {
     if (P == 0) return 0;
     NR3D_CHECK(feats && pack_infos && out && C > 0, "packed_cumsum: null argument");
+    if (NR3D_PACK_STAGED && C == 1 && S > 0 && staged_pack_scan(dtype, false, P, S, feats, pack_infos, exclusive != 0, reverse != 0, out, (cudaStream_t)stream) == 0) {
+        NR3D_LAUNCH_CHECK("packed_cumsum");
+        return 0;
+    }
     NR3D_PACK_DISPATCH(dtype, "packed_cumsum",
         (pack_scan_kernel<T, false><<<warp_grid(P * C), kPackThreads, 0, (cudaStream_t)stream>>>(P, C, (const T*)feats, pack_infos, exclusive != 0, reverse != 0, (T*)out)));
     NR3D_LAUNCH_CHECK("packed_cumsum");
     return 0;
 }
 
-int nr3d_pack_cumprod(int32_t dtype, uint64_t P, uint32_t C, const void* feats, const int64_t* pack_infos, int32_t exclusive,
+int nr3d_pack_cumprod(int32_t dtype, uint64_t P, uint32_t C, uint64_t S, const void* feats, const int64_t* pack_infos, int32_t exclusive,
                       int32_t reverse, int32_t bug_compat, void* out, void* stream) {
     if (P == 0) return 0;
     NR3D_CHECK(feats && pack_infos && out && C > 0, "packed_cumprod: null argument");
     if (exclusive && bug_compat) return 0;  // reference CUDA output: the zero-initialised tensor
+    if (NR3D_PACK_STAGED && C == 1 && S > 0 && staged_pack_scan(dtype, true, P, S, feats, pack_infos, exclusive != 0, reverse != 0, out, (cudaStream_t)stream) == 0) {
+        NR3D_LAUNCH_CHECK("packed_cumprod");
+        return 0;
+    }
     NR3D_PACK_DISPATCH(dtype, "packed_cumprod",
         (pack_scan_kernel<T, true><<<warp_grid(P * C), kPackThreads, 0, (cudaStream_t)stream>>>(P, C, (const T*)feats, pack_infos, exclusive != 0, reverse != 0, (T*)out)));
     NR3D_LAUNCH_CHECK("packed_cumprod");

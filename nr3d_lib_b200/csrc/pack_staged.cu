@@ -360,6 +360,92 @@ pack_sum_cta_kernel(uint64_t P, uint64_t total, const T* __restrict__ in, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// packed_cumsum / packed_cumprod, one channel (pack_ops_cuda.cu:864-1095): out[i] = in[i - offset] (op) out[i - 1] walked sequentially like
+// the reference thread, forwards or backwards -- bit-identical to the reference for sums and inclusive products; the exclusive product
+// follows the documented semantics (leading 1; pack_ops.cu handles the reference's all-zeros quirk before this is reached).
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool PROD, int WIN>
+__global__ void __launch_bounds__(kCtThreads)
+pack_scan_cta_kernel(uint64_t P, uint64_t total, const T* __restrict__ in, const int64_t* __restrict__ pack_infos, bool exclusive, bool reverse,
+                     T* __restrict__ out) {
+    constexpr int A = 16 / sizeof(T);
+    __shared__ __align__(128) T buf[WIN + A];
+    __shared__ uint64_t s_b[kCtThreads + 1], s_e[kCtThreads];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x;
+    const uint64_t p0 = (uint64_t)blockIdx.x * kCtThreads;
+    const uint32_t bar = smem_addr(&s_bar);
+    if (tid == 0) mbar_init(bar);
+    const CtaSpan sp = load_cta_span(pack_infos, P, p0, tid, s_b, s_e);
+    const T ident = PROD ? (T)1 : (T)0;
+    T acc = ident, prev = ident;
+    bool started = false;
+    uint32_t parity = 0;
+    auto step = [&](T v) -> T {
+        T o;
+        if (!started) { started = true; o = exclusive ? ident : v; }
+        else { const T a = exclusive ? prev : v; o = PROD ? (T)(a * acc) : (T)(a + acc); }
+        acc = o;
+        prev = v;
+        return o;
+    };
+    const int n_spans = sp.tiled ? 1 : sp.last + 1;
+    for (int s = 0; s < n_spans; ++s) {
+        const uint64_t sb = sp.tiled ? sp.sb : s_b[s], se = sp.tiled ? sp.se : s_e[s];
+        const bool mine = sp.tiled ? tid <= sp.last : tid == s;
+        const uint64_t n_win = (se - sb + WIN - 1) / WIN;
+        for (uint64_t k = 0; k < n_win; ++k) {
+            const uint64_t w0 = sb + (reverse ? n_win - 1 - k : k) * WIN;
+            const uint32_t n = (uint32_t)umin64((uint64_t)WIN, se - w0);
+            const Win<T> w(w0, n, total);
+            if (tid == 0 && w.bytes) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar, w.bytes);
+                bulk_g2s(smem_addr(buf), in + w.a0, w.bytes, bar);
+            }
+            stage_tail(buf, in, w, w0, n, tid);
+            if (w.bytes) { mbar_wait_parity(bar, parity); parity ^= 1u; }
+            __syncthreads();
+            if (mine) {
+                const uint64_t lo = umax64(sp.begin, w0), hi = umin64(sp.begin + sp.len, w0 + n);
+                if (lo < hi) {
+                    const uint32_t t0 = (uint32_t)(lo - w.a0), t1 = (uint32_t)(hi - w.a0);
+                    if (!reverse) {
+                        uint32_t t = t0;
+                        for (; t + 4 <= t1; t += 4) {
+                            T v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) v[u] = buf[t + u];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) v[u] = step(v[u]);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) buf[t + u] = v[u];
+                        }
+                        for (; t < t1; ++t) buf[t] = step(buf[t]);
+                    } else {
+                        uint32_t t = t1;
+                        for (; t >= t0 + 4; t -= 4) {
+                            T v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) v[u] = buf[t - 1 - u];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) v[u] = step(v[u]);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) buf[t - 1 - u] = v[u];
+                        }
+                        for (; t > t0; --t) buf[t - 1] = step(buf[t - 1]);
+                    }
+                }
+            }
+            __syncthreads();
+            const uint32_t off = (uint32_t)(w0 - w.a0);
+            for (uint32_t t = tid; t < n; t += kCtThreads) out[w0 + t] = buf[off + t];
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Two per-pack reductions of the render step in one pass (no reference export; replaces the composition
 //   acc = packed_sum(w, pack_infos);  depth = packed_sum(w * t, pack_infos)         (nerf_ray_query.py:182-188: weights -> accumulated
 // opacity and expected depth) and its autograd chain.  Forward: sequential sums like the reference's packed_sum thread, the product w * t
@@ -481,6 +567,22 @@ int staged_alpha_bwd(int32_t dtype, uint64_t P, uint64_t total, const void* alph
     case NR3D_F64: alpha_to_vw_bwd_cta_kernel<double, 1024><<<ct_grid(P), kCtThreads, 0, st>>>(P, total, (const double*)alphas, (const double*)weights, (const double*)grad_weights, pack_infos, eps, thre, (double*)grad_alphas); return 0;
     default: return 1;
     }
+}
+
+int staged_pack_scan(int32_t dtype, bool prod, uint64_t P, uint64_t total, const void* in, const int64_t* pack_infos, bool exclusive, bool reverse, void* out,
+                     cudaStream_t st) {
+    if (!aligned16(in)) return 1;
+    if (dtype == NR3D_F32) {
+        if (prod) pack_scan_cta_kernel<float, true, 4096><<<ct_grid(P), kCtThreads, 0, st>>>(P, total, (const float*)in, pack_infos, exclusive, reverse, (float*)out);
+        else pack_scan_cta_kernel<float, false, 4096><<<ct_grid(P), kCtThreads, 0, st>>>(P, total, (const float*)in, pack_infos, exclusive, reverse, (float*)out);
+        return 0;
+    }
+    if (dtype == NR3D_F64) {
+        if (prod) pack_scan_cta_kernel<double, true, 2048><<<ct_grid(P), kCtThreads, 0, st>>>(P, total, (const double*)in, pack_infos, exclusive, reverse, (double*)out);
+        else pack_scan_cta_kernel<double, false, 2048><<<ct_grid(P), kCtThreads, 0, st>>>(P, total, (const double*)in, pack_infos, exclusive, reverse, (double*)out);
+        return 0;
+    }
+    return 1;
 }
 
 int staged_pack_sum(int32_t dtype, uint64_t P, uint64_t total, const void* in, const int64_t* pack_infos, void* out, cudaStream_t st) {

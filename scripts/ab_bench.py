@@ -14,6 +14,9 @@ VARIANTS = {
     "tiles_brick": ["NR3D_BWD_TILES=1", "NR3D_BIN_ORDER=2", "NR3D_BWD_OCC=0"],
     "brick": ["NR3D_BIN_ORDER=2"],
     # round-2 A/B of TMA staging for the Dense levels of the forward (profiles/r2_ab_fwd_tma.txt)
+    "fwd_occ1536": ["NR3D_FWD_OCC=1536"],
+    "fwd_occ1280": ["NR3D_FWD_OCC=1280"],
+    "fwd_occ1536_u2": ["NR3D_FWD_OCC=1536", "NR3D_FWD_UNROLL=2"],
     "fwd_tma": ["NR3D_FWD_TMA=1"],
     "fwd_tma_12k": ["NR3D_FWD_TMA=1", "NR3D_FWD_TMA_FLOATS=3072"],
     "fwd_tma_brick": ["NR3D_FWD_TMA=1", "NR3D_BIN_ORDER=2"],

@@ -76,7 +76,24 @@ def run_m2(dev, rank, world, rays=1024 * 1024, chunk=262144, grid_kind="random",
     ms = ndist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
     ndist.barrier()
     total_samples = ndist.sum_over_ranks(float(n_samples), dev)
-    return {"metric": "full march+encode+composite fwd+bwd Mrays/s", "value": world * rays / ms / 1e3, "unit": "Mrays/s",
+    # Roofline of the whole step against the measured HBM copy bandwidth.  Algorithmic bytes per sample (fp32, fused density head; the 48.5 MB
+    # table itself is L2 resident, its corner traffic is counted like SURVEY.md 8d counts it for M1):
+    #   march 16 (t_start, t_end, ray id, voxel id written)            march_samples 28 (3 reads, position + delta written)
+    #   point sort 48 (x twice, rank, 16-byte record)                   encode + head forward 1052 (record, 1024 corner bytes, delta, sigma, alpha)
+    #   composite forward 8, per-pack sums forward 8                    per-pack sums backward 8, composite backward 16
+    #   encode + head backward 1080 (x fingerprint 12, record 16, 4 scalars, 1024 scatter bytes), table zero-init / reduce 3
+    bytes_per_sample = 16 + 28 + 48 + 1052 + 8 + 8 + 8 + 16 + 1080 + 3
+    peak = 6553.9
+    try:
+        peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    achieved = total_samples / world * bytes_per_sample / (ms * 1e-3) / 1e9      # per GPU
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_sample": bytes_per_sample,
+                "note": "whole M2 step per GPU; 93 % of the bytes are LoTD corner gathers / scatters that hit the L2-resident table, so -- as for M1 -- "
+                        "the binding resource is the L1 line rate (forward) and the L2 reduction rate (backward), not DRAM"}
+    return {"roofline": roofline, "metric": "full march+encode+composite fwd+bwd Mrays/s", "value": world * rays / ms / 1e3, "unit": "Mrays/s",
             "n_gpus": world, "ms_per_step": ms, "rays_per_gpu": rays, "samples_per_ray": total_samples / (world * rays),
             "Msamples_per_s": total_samples / ms / 1e3, "grid": grid_kind, "chunk": chunk, "steps": steps, "warmup": warmup,
             "sort_points": sort_points, "fuse_head": bool(fuse_head and sort_points), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,

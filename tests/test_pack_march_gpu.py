@@ -120,6 +120,13 @@ def test_staged_composite_bit_exact_vs_reference_build(P, max_len, min_len, dev)
             assert torch.equal(w, w_r) and torch.equal(sel, sel_r) and torch.equal(cpi, cpi_r)
             assert torch.equal(ga, ga_r), f"dL/dalpha not bit-exact: max diff {(ga - ga_r).abs().max().item()}"
             assert torch.equal(sm, ref.packed_sum(w_r, pi)), "pack sum not bit-exact"
+    if ref is not None:     # one-channel scans walk the pack like the reference thread: bit-identical (the exclusive product differs by design, Q2)
+        pr = t((1.0 + 0.2 * np.random.RandomState(P).randn(max(d["S"], 1))).astype(np.float32))
+        for ex in (False, True):
+            for rv in (False, True):
+                assert torch.equal(mine.packed_cumsum(gw, pi, ex, rv), ref.packed_cumsum(gw, pi, ex, rv)), ("cumsum", ex, rv)
+                if not ex:
+                    assert torch.equal(mine.packed_cumprod(pr, pi, ex, rv), ref.packed_cumprod(pr, pi, ex, rv)), ("cumprod", ex, rv)
 
 
 def test_staged_composite_untiled_packs(dev):
