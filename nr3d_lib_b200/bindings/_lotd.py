@@ -351,27 +351,33 @@ def lod_fwd(lod_meta, input: torch.Tensor, params: torch.Tensor, batch_inds: Opt
                 ctypes.byref(meta._c), _lib.dtype_code(params.dtype), N, xs.data_ptr(), _lib.ptr(scenes), ns, params.data_ptr(), max_level,
                 y.data_ptr(), dy_dx.data_ptr(), _lib.stream_of(dev)))
             return y, dy_dx
+        if input.dtype == torch.float16 and params.dtype != torch.float16:
+            raise RuntimeError("LoTDEncoding: Input type combination not supported. Supported types are: "
+                               "<input,param> -> (half, half), (float, half), (float, float)")
+        # the kernels write dy_dx in fp32; half points (the <half, half, half> combination) get it converted afterwards (same strides)
         if meta.c_hash_only:
             # feature-major storage returned through a transposed view (lotd_torch_api.cu:303,317)
             y_store = torch.empty([E, N], dtype=params.dtype, device=dev)
             y, ys_n, ys_f = y_store.t(), 1, N
             if need_input_grad:
                 if meta.c_permute_dydx:
-                    store = torch.empty([E, N, D], dtype=input.dtype, device=dev)
+                    store = torch.empty([E, N, D], dtype=torch.float32, device=dev)
                     dy_dx, ds_n, ds_f = store.permute(1, 0, 2), D, N * D
                 else:
-                    dy_dx = torch.empty([N, E * D], dtype=input.dtype, device=dev)
+                    dy_dx = torch.empty([N, E * D], dtype=torch.float32, device=dev)
                     ds_n, ds_f = E * D, D
         else:
             y = torch.empty([N, E], dtype=params.dtype, device=dev)
             ys_n, ys_f = E, 1
             if need_input_grad:
-                dy_dx = torch.empty([N, E * D], dtype=input.dtype, device=dev)
+                dy_dx = torch.empty([N, E * D], dtype=torch.float32, device=dev)
                 ds_n, ds_f = E * D, D
         _lib.check(_lib.get_lib().nr3d_lotd_fwd(
             ctypes.byref(meta._c), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, _lib.ptr(input), _lib.ptr(params),
             _lib.ptr(batch_inds), _lib.ptr(batch_offsets), bds, max_level, y.data_ptr(), ys_n, ys_f,
             _lib.ptr(dy_dx), ds_n, ds_f, _lib.stream_of(dev)))
+        if dy_dx is not None and input.dtype != torch.float32:
+            dy_dx = dy_dx.to(input.dtype)
     return y, dy_dx
 
 
@@ -399,14 +405,15 @@ def lod_bwd(lod_meta, dL_dy: torch.Tensor, input: torch.Tensor, params: torch.Te
         if need_input_grad:
             if dy_dx is None:
                 raise RuntimeError("LoTDEncoding::bwd: need `dy_dx` to comput `dL_dx`.")
-            dL_dx = torch.zeros([N, D], dtype=input.dtype, device=dev) if max_level <= -1 else torch.empty([N, D], dtype=input.dtype, device=dev)
+            # (fp32 inside; half points get dL_dx converted on return)
+            dL_dx = torch.zeros([N, D], dtype=torch.float32, device=dev) if max_level <= -1 else torch.empty([N, D], dtype=torch.float32, device=dev)
         if need_param_grad:
             dL_dparam = torch.zeros([params.shape[0]], dtype=params.dtype, device=dev)
         if max_level <= -1:
-            return dL_dx, dL_dparam
+            return (None if dL_dx is None else dL_dx.to(input.dtype)), dL_dparam
         st = _lib.stream_of(dev)
         if need_input_grad:
-            dv, ds_n, ds_f = _dydx_view(dy_dx, N, meta)
+            dv, ds_n, ds_f = _dydx_view(dy_dx if dy_dx.dtype == torch.float32 else dy_dx.float(), N, meta)
             _lib.check(lib.nr3d_lotd_bwd_input(
                 ctypes.byref(meta._c), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, dL_dy.data_ptr(),
                 dL_dy.stride(0), dL_dy.stride(1), dv.data_ptr(), ds_n, ds_f, dL_dx.data_ptr(), st))

@@ -27,12 +27,9 @@ int build_launch(const nr3d_lotd_meta* m, int32_t input_dtype, int32_t param_dty
                         const void* params, const int64_t* batch_inds, const int64_t* batch_offsets,
                         uint32_t batch_data_size, int32_t max_level, void* stream, LotdLaunch& L) {
     NR3D_CHECK(m != nullptr, "LoTDEncoding: null meta");
-    NR3D_CHECK(input_dtype == NR3D_F32,
-               "LoTDEncoding: Input type combination not supported by the B200 build. Supported types are: "
-               "<input,param> -> (float, half), (float, float)");
-    NR3D_CHECK(param_dtype == NR3D_F32 || param_dtype == NR3D_F16,
+    NR3D_CHECK((input_dtype == NR3D_F32 && (param_dtype == NR3D_F32 || param_dtype == NR3D_F16)) || (input_dtype == NR3D_F16 && param_dtype == NR3D_F16),
                "LoTDEncoding: Input type combination not supported. Supported types are: "
-               "<input,param> -> (float, half), (float, float)");
+               "<input,param> -> (half, half), (float, half), (float, float)");
     NR3D_CHECK(m->n_levels <= NR3D_MAX_LEVELS && m->n_pseudo_levels <= NR3D_MAX_PSEUDO_LEVELS, "LoTDEncoding: corrupt meta");
     NR3D_CHECK(N < (1ull << 32), "LoTDEncoding: batch_size must be < 2^32");
     memset(&L.tab, 0, sizeof(L.tab));
@@ -56,6 +53,7 @@ int build_launch(const nr3d_lotd_meta* m, int32_t input_dtype, int32_t param_dty
     L.tab.fpl = m->n_feat_per_pseudo_lvl;
     L.in.N = N;
     L.in.x = (const float*)x;
+    L.in.x_half = input_dtype == NR3D_F16 ? 1u : 0u;
     L.in.params = params;
     L.in.batch_inds = batch_inds;
     L.in.batch_offsets = batch_offsets;
@@ -261,7 +259,7 @@ int nr3d_lotd_grid_index(const nr3d_lotd_meta* meta, int32_t input_dtype, uint64
                          const int64_t* batch_offsets, uint32_t batch_data_size, int32_t max_level, int64_t* out, void* stream) {
     if (N == 0) return 0;
     LotdLaunch L;
-    if (int rc = build_launch(meta, input_dtype, NR3D_F32, N, x, nullptr, batch_inds, batch_offsets, batch_data_size, max_level, stream, L)) return rc;
+    if (int rc = build_launch(meta, input_dtype, input_dtype == NR3D_F16 ? NR3D_F16 : NR3D_F32, N, x, nullptr, batch_inds, batch_offsets, batch_data_size, max_level, stream, L)) return rc;
     for (uint32_t l = 0; l < meta->n_levels; ++l)
         NR3D_CHECK(meta->level_types[l] == NR3D_LOD_DENSE || meta->level_types[l] == NR3D_LOD_HASH,
                    "LoTDEncoding::get_grid_index: Only support Dense/Hash type.");

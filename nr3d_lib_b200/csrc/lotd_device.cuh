@@ -32,6 +32,7 @@ struct LotdIn {
     uint32_t batch_data_size;
     int32_t max_level;
     uint32_t vec_ok;  // 1: level base pointers are 8-byte aligned (no user-supplied batch_offsets)
+    uint32_t x_half;  // 1: `x` points at __half coordinates (the reference's <half, half, half> combination, lotd_hash_only.h:776)
 };
 
 template <int D>
@@ -71,10 +72,24 @@ __device__ __forceinline__ bool lotd_setup(const LotdTable& tab, const LotdIn& i
     for (int d = 0; d < D; ++d) {
         c.res[d] = L.res[d];
         c.scale[d] = (float)(c.res[d] - 2u);
-        float v = xp[d] * c.scale[d] + 0.5f;
-        const float fl = floorf(v);
-        c.cell[d] = (uint32_t)fl;
-        v -= (float)c.cell[d];
+        float v;
+        if (in.x_half) {
+            // half points: the reference computes position, cell and fraction in HALF precision (COMPUTE_T = __half, lotd_cuda.h:959-977:
+            // val = x * scale + 0.5 with two roundings, cell = floor(val), val -= cell) -- reproduced so that the cells are the reference's;
+            // the interpolation weights are then formed in fp32 from that half fraction (the reference multiplies them out in half)
+            const __half xh = reinterpret_cast<const __half*>(in.x)[i * D + d];
+            const __half sc = __uint2half_rn(c.res[d] - 2u);
+            const __half val = __hadd(__hmul(xh, sc), __float2half_rn(0.5f));
+            const float fl = floorf(__half2float(val));
+            c.cell[d] = (uint32_t)fl;
+            c.scale[d] = __half2float(sc);
+            v = __half2float(__hsub(val, __uint2half_rn(c.cell[d])));
+        } else {
+            v = xp[d] * c.scale[d] + 0.5f;
+            const float fl = floorf(v);
+            c.cell[d] = (uint32_t)fl;
+            v -= (float)c.cell[d];
+        }
         if (smooth) {
             c.p[d] = v * v * (3.0f - 2.0f * v);
             c.dp[d] = 6.0f * v * (1.0f - v);

@@ -316,6 +316,7 @@ static int forest_prepare(const nr3d_lotd_meta* meta, const nr3d_forest_meta* fo
                           const void* x, const void* params, const int64_t* batch_inds, const int64_t* batch_offsets, uint32_t batch_data_size,
                           int32_t max_level, void* stream, LotdLaunch& L, ForestRef& fr) {
     NR3D_CHECK(forest != nullptr, "LoTDEncoding: null forest meta");
+    NR3D_CHECK(input_dtype == NR3D_F32, "LoTDEncoding: lotd-forest needs fp32 points (<input,param> -> (float, half), (float, float))");
     NR3D_CHECK(meta != nullptr && meta->n_dims_to_encode == 3, "LoTDEncoding::fwd: lotd-forest only supports `n_dims_to_encode`==3");
     NR3D_CHECK(forest->octree && forest->exsum && forest->block_ks, "LoTDEncoding: forest.octree / forest.exsum / forest.block_ks must be given");
     NR3D_CHECK(forest->level <= 15, "LoTDEncoding: forest level must be <= 15 (block coordinates are int16)");
