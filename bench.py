@@ -10,7 +10,7 @@ One step  = lod_fwd(need_input_grad=False) + lod_bwd(need_param_grad=True) throu
             point sets alternate), so every forward sorts and every backward reuses the forward's records after the on-device check.
 `value`   = whole-job samples/s with x and dL_dy already resident in HBM (device-timed, max over ranks).
 `e2e`     = the same step driven from HOST buffers: x comes from pinned host memory every step (H2D inside the timed
-            region), dL_dy is derived on the device from the step's own output y (stand-in for the decoder's backward),
+            region), dL_dy is the step's own output y (loss = |y|^2 / 2: stand-in for the decoder's backward, costs no extra pass over [N, 32]),
             and the step's result dL/dparams is read back to the host (D2H inside the timed region).
 `--impl reference` times the CPU port of the reference's algorithm (oracle/lotd_port.c, plain C, fp32, OpenMP over all host threads) on a
             bounded sample of the same workload -- the reference has no CPU implementation of this path.
@@ -151,7 +151,7 @@ def workload_config(n_gpus):
     return {"workload": "configs[1]: 16-level Hash LoTD (NGP gen_ngp_cfg: res 16..2049, 6 Dense + 10 Hash levels, T=2^19, F=2), "
                         "4Mi uniform points per GPU, lod_fwd + lod_bwd(dL/dparam)",
             "points_per_gpu": N_POINTS, "n_params": 12131648, "param_dtype": "f32", "parallelism": f"dp{n_gpus} (points sharded, params replicated, "
-                                                                                                 "1 NCCL all-reduce of dL/dparams per step)",
+                                                                                                 "1 all-reduce of dL/dparams per step)",
             "l2_policy": "inputs larger than L2 (x 48 MB + dL_dy 512 MB + y 512 MB per step >> 126 MB); the 48.5 MB parameter table is "
                          "L2-resident by nature of the workload"}
 
@@ -169,8 +169,10 @@ def main():
     ap.add_argument("--e2e-serial", action="store_true", help="e2e leg without copy/compute overlap (single stream)")
     ap.add_argument("--no-sort", action="store_true", help="use the generic (unsorted, feature-major) kernels instead of lotd_fast.cu")
     ap.add_argument("--no-m2", action="store_true", help="skip the secondary M2 block (march + encode + composite rays/s)")
-    ap.add_argument("--allreduce", default="allreduce", choices=["bucketed", "allreduce"],
-                    help="N > 1: how dL/dparams is summed (dist.GradReducer): one NCCL all-reduce after the scatter (default), or fine levels first "
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "symm", "bucketed", "allreduce"],
+                    help="N > 1: how dL/dparams is summed (dist.GradReducer): one all-reduce after the scatter -- on a symmetric-memory buffer with NVSwitch "
+                         "multicast (`symm`; measured 2.165 vs 2.226 ms / step at 8 GPUs but 2.46 vs 2.12 at 2) or plain NCCL (`allreduce`); `auto` (default) "
+                         "takes symm from 8 ranks on --, or fine levels first "
                          "with their all-reduce overlapping the coarse levels' scatter (measured slower: 2.47 vs 2.15 ms / step at 2 GPUs, "
                          "profiles/r2_bench_2gpu_*.json)")
     ap.add_argument("--no-extras", action="store_true", help="skip the informational legs (reference CUDA build, generic path, torch CPU baselines)")
@@ -208,7 +210,8 @@ def main():
     xs_host = [x.cpu().pin_memory() for x in xs]
     grad_host = torch.empty(meta.n_params, dtype=torch.float32).pin_memory()
     stream = torch.cuda.current_stream(dev)
-    reducer = ndist.GradReducer(meta, n_gpus, dev, mode=args.allreduce)
+    ar_mode = args.allreduce if args.allreduce != "auto" else ("symm" if n_gpus >= 8 else "allreduce")
+    reducer = ndist.GradReducer(meta, n_gpus, dev, mode=ar_mode)
     step_no = [0]
 
     def step_resident(m=meta, p=params, gy=dL_dy):
@@ -224,14 +227,14 @@ def main():
     # steps overlap the kernels (3 streams, double buffers).  `--e2e-serial` issues everything on one stream instead.
     from nr3d_lib_b200.pipeline import HostFedLoTDStep
     grad_host2 = [grad_host, torch.empty(meta.n_params, dtype=torch.float32).pin_memory()]
-    pipe = HostFedLoTDStep(meta, params, N, dev, grad_of_y=lambda y: y * 1.0e-4, world=n_gpus, rank=rank)   # y * 1e-4: stand-in for the decoder's backward
+    pipe = HostFedLoTDStep(meta, params, N, dev, grad_of_y=lambda y: y, world=n_gpus, rank=rank)   # dL/dy = y (loss = |y|^2 / 2): stand-in for the decoder's backward, no extra pass
 
     def run_e2e(steps):
         if args.e2e_serial:
             for k in range(steps):
                 xd = xs_host[k & 1].to(dev, non_blocking=True)
                 y, _ = _lotd.lod_fwd(meta, xd, params, need_input_grad=False)
-                _, g = _lotd.lod_bwd(meta, y * 1.0e-4, xd, params, None, need_input_grad=False, need_param_grad=True)
+                _, g = _lotd.lod_bwd(meta, y, xd, params, None, need_input_grad=False, need_param_grad=True)
                 out = pipe.reducer.reduce(g)
                 lo, hi = pipe.reducer.slice_range(g.shape[0], rank) if n_gpus > 1 else (0, g.shape[0])
                 grad_host2[k % 2][lo:hi].copy_(out[: hi - lo], non_blocking=True)
@@ -384,11 +387,15 @@ def main():
             "config": workload_config(n_gpus), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(xs_host[0].numel() * 4) * n_gpus,
                     "d2h_bytes_per_step": int(grad_host.numel() * 4),
-                    "note": "whole-job bytes per step: every rank feeds its own 4 Mi points from pinned host memory, dL_dy is derived on device "
-                            "from the step's y, the summed dL/dparams (one reduce-scatter) is read back to the host once -- each rank returns its 1/N slice; "
+                    "note": "whole-job bytes per step: every rank feeds its own 4 Mi points from pinned host memory, dL_dy is the step's own y on the device "
+                            "(loss |y|^2 / 2), the summed dL/dparams (one reduce-scatter) is read back to the host once -- each rank returns its 1/N slice; "
                             + ("single stream" if args.e2e_serial else "copies of neighbouring steps overlap the kernels (pipeline.HostFedLoTDStep)")},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "fp16_params": fp16_block, "m2": m2_block,
-            "collective": (None if n_gpus == 1 else {"value_leg": ("bucketed: all-reduce of levels 8-15 overlaps the scatter of levels 0-7" if args.allreduce == "bucketed" else "one NCCL all-reduce (sum) of the 48.5 MB fp32 dL/dparams after the scatter, on the step's stream"),
+            "collective": (None if n_gpus == 1 else {"value_leg": {"bucketed": "bucketed: NCCL all-reduce of levels 8-15 overlaps the scatter of levels 0-7",
+                                                                    "allreduce": "one NCCL all-reduce (sum) of the 48.5 MB fp32 dL/dparams after the scatter, on the step's stream",
+                                                                    "symm": "one all-reduce (sum) of the 48.5 MB fp32 dL/dparams after the scatter: torch symmetric memory, NVSwitch "
+                                                                            "multicast / in-switch reduction (torch.ops.symm_mem.multimem_all_reduce_) after a 48.5 MB device copy into the symmetric buffer"}[reducer.mode],
+                                                     "requested": args.allreduce, "fallback_reason": reducer.fallback_reason,
                                                      "e2e_leg": "reduce-scatter, each rank returns its slice"}),
             "numa": numa, "generic_path": generic_block, "ref_cuda_build": ref_cuda_block, "torch_cpu_baselines": torch_cpu}
     sys.stdout.flush()

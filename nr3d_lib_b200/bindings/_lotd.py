@@ -301,6 +301,17 @@ def set_grad_bucket_hook(fn, split: Optional[int] = None):
         _grad_bucket_split = int(split)
 
 
+# Second multi-GPU hook: who allocates dL/dparams.  `fn(numel, dtype, device)` must return a ZEROED contiguous 1-D tensor; a reducer that owns a
+# symmetric-memory (NVLS multicast) buffer hands it out here so that the scatter writes straight into the buffer the all-reduce runs on
+# (nr3d_lib_b200.dist.GradReducer(mode="symm")).  None: torch.zeros.
+_param_grad_allocator = None
+
+
+def set_param_grad_allocator(fn):
+    global _param_grad_allocator
+    _param_grad_allocator = fn
+
+
 def _dydx_view(dy_dx, N, meta):
     """[N, n_enc, D] view of a dy_dx tensor in either reference layout; returns (tensor, stride_n, stride_j)."""
     D, E = meta.n_dims_to_encode, meta.n_encoded_dims
@@ -408,7 +419,11 @@ def lod_bwd(lod_meta, dL_dy: torch.Tensor, input: torch.Tensor, params: torch.Te
             # (fp32 inside; half points get dL_dx converted on return)
             dL_dx = torch.zeros([N, D], dtype=torch.float32, device=dev) if max_level <= -1 else torch.empty([N, D], dtype=torch.float32, device=dev)
         if need_param_grad:
-            dL_dparam = torch.zeros([params.shape[0]], dtype=params.dtype, device=dev)
+            dL_dparam = None
+            if _param_grad_allocator is not None:
+                dL_dparam = _param_grad_allocator(params.shape[0], params.dtype, dev)
+            if dL_dparam is None:
+                dL_dparam = torch.zeros([params.shape[0]], dtype=params.dtype, device=dev)
         if max_level <= -1:
             return (None if dL_dx is None else dL_dx.to(input.dtype)), dL_dparam
         st = _lib.stream_of(dev)
@@ -443,6 +458,8 @@ def lod_bwd(lod_meta, dL_dy: torch.Tensor, input: torch.Tensor, params: torch.Te
                 ctypes.byref(meta._c), _lib.dtype_code(input.dtype), _lib.dtype_code(params.dtype), N, dL_dy.data_ptr(),
                 dL_dy.stride(0), dL_dy.stride(1), None, input.data_ptr(), params.data_ptr(), _lib.ptr(batch_inds),
                 _lib.ptr(batch_offsets), bds, params.shape[0] // meta.n_params, max_level, dL_dparam.data_ptr(), st))
+    if dL_dx is not None and dL_dx.dtype != input.dtype:
+        dL_dx = dL_dx.to(input.dtype)
     return dL_dx, dL_dparam
 
 

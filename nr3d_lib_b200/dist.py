@@ -63,19 +63,54 @@ class GradReducer:
       "scatter"    reduce-scatter: every rank ends with ITS contiguous 1/world slice of the summed table (what a sharded optimizer or the
                    host-fed driver needs: pipeline.HostFedLoTDStep returns each slice to the host from its own rank) -- half the NVLink bytes
 
-    Usage per step:  (lod_bwd runs, the hook fires)  ->  out = reducer.reduce(grad)   # "scatter": out is the rank's slice, else `grad`.
-    The hook is installed with `bindings._lotd.set_grad_bucket_hook`; call close() to remove it."""
+      "symm"       the all-reduce runs on a torch symmetric-memory buffer with the NVSwitch multicast / in-switch reduction
+                   (`torch.ops.symm_mem.multimem_all_reduce_`): 0.131 ms instead of NCCL's 0.220 ms for the 48.5 MB table on 8 B200s
+                   (profiles/r2_allreduce_probe_8gpu.json).  The reducer owns the buffer; the gradient is copied into it (48.5 MB, ~15 us) --
+                   letting the scatter write straight into the symmetric buffer (`symm_direct=True`, through
+                   `bindings._lotd.set_param_grad_allocator`) was measured SLOWER (2 GPUs: 2.44 vs 2.12 ms per step: the L2 reductions of
+                   the scatter do not like the multicast-mapped allocation).  The returned gradient IS the symmetric buffer -- consume it
+                   (optimizer step) before the next reduce.  Falls back to "allreduce" when symmetric memory or multicast is not
+                   available (`self.mode` then says so).
 
-    def __init__(self, meta, world: int, device, mode: str = "allreduce"):
+    Usage per step:  (lod_bwd runs, the hook fires)  ->  out = reducer.reduce(grad)   # "scatter": out is the rank's slice, else `grad`.
+    The hooks are installed with `bindings._lotd.set_grad_bucket_hook` / `set_param_grad_allocator`; call close() to remove them."""
+
+    def __init__(self, meta, world: int, device, mode: str = "allreduce", symm_direct: bool = False):
         from .bindings import _lotd
         self._lotd, self.meta, self.world, self.mode, self.device = _lotd, meta, int(world), mode, device
         self.pending = []
         self.active = self.world > 1 and dist.is_available() and dist.is_initialized()
-        if mode not in ("allreduce", "bucketed", "scatter"):
+        if mode not in ("allreduce", "bucketed", "scatter", "symm"):
             raise RuntimeError(f"GradReducer: unknown mode {mode!r}")
         if self.active and mode == "bucketed":
             _lotd.set_grad_bucket_hook(self._on_part)
         self._slice = None
+        self._symm_buf = self._symm_op = self._symm_group = None
+        self.fallback_reason = None
+        if self.active and mode == "symm":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                self._symm_group = dist.group.WORLD.group_name
+                n = int(meta.n_params)
+                buf = symm.empty(n, dtype=torch.float32, device=torch.device(device))
+                symm.rendezvous(buf, self._symm_group)
+                op = torch.ops.symm_mem.multimem_all_reduce_
+                buf.zero_()
+                op(buf, "sum", self._symm_group)           # first use: fails here, not inside a step, when multicast is unavailable
+                torch.cuda.synchronize(torch.device(device))
+                self._symm_buf, self._symm_op = buf, op
+                if symm_direct:
+                    _lotd.set_param_grad_allocator(self._alloc)
+            except Exception as e:      # no symmetric memory / no NVLS on this box: plain NCCL all-reduce
+                self.fallback_reason = str(e)[:200]
+                self.mode = "allreduce"
+
+    def _alloc(self, numel, dtype, device):
+        buf = self._symm_buf
+        if buf is None or numel != buf.numel() or dtype != buf.dtype or torch.device(device) != buf.device:
+            return None
+        buf.zero_()
+        return buf
 
     def _on_part(self, grad, lo, hi):
         # issued on NCCL's stream behind everything already queued on the current stream: overlaps what the caller launches next
@@ -101,6 +136,14 @@ class GradReducer:
                 w.wait()                    # the current stream waits for the collective; the host does not block
             self.pending = []
             return grad
+        if self.mode == "symm":
+            if grad.data_ptr() != self._symm_buf.data_ptr():      # a gradient that did not come from our allocator (generic path, other sizes)
+                if grad.numel() != self._symm_buf.numel() or grad.dtype != self._symm_buf.dtype:
+                    dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+                    return grad
+                self._symm_buf.copy_(grad)
+            self._symm_op(self._symm_buf, "sum", self._symm_group)
+            return self._symm_buf
         if self.mode == "scatter":
             n = grad.shape[0]
             per = (n + self.world - 1) // self.world
@@ -123,6 +166,8 @@ class GradReducer:
     def close(self):
         if self.active and self.mode == "bucketed":
             self._lotd.set_grad_bucket_hook(None)
+        if self._symm_buf is not None:
+            self._lotd.set_param_grad_allocator(None)
 
 
 def bind_to_gpu_numa(local_rank: int) -> dict:
