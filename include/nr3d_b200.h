@@ -176,6 +176,9 @@ int nr3d_lotd_sort_points(uint64_t N, const float* x, const int64_t* batch_inds,
  * LoTD.forward, lotd_encoding.py:162, lotd.py:211).  The map is part of the records' fingerprint. */
 int nr3d_lotd_sort_points_mapped(uint64_t N, const float* x, const int64_t* batch_inds, uint32_t batch_data_size, uint32_t n_scenes, int32_t force,
                                  float scale, float shift, int32_t clamp01, void* xs, uint16_t* scenes, void* ws, uint64_t* ws_bytes, void* stream);
+/* Test / A-B knob: point count from which single-scene calls take the two-level (coarse partition + fine) sort; 0 restores the default (12 Mi).
+ * The workspace size of a given N depends on it: query it again afterwards. */
+int nr3d_lotd_sort_set_two_level_min(uint64_t n_points);
 int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,
                          const void* params, int32_t max_level, void* y, int64_t y_stride_n, int64_t y_stride_f, void* stream);
 int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64_t N, const void* xs, const uint16_t* scenes, uint32_t n_scenes,

@@ -11,13 +11,13 @@
 //     from different SMs serialise in the L2 slice (coarse levels: up to 4.5x slower).
 // So the levers are (1) lanes of one instruction sharing lines / sectors, (2) merging same-address contributions before they
 // reach L2, (3) fewer instructions.  This file implements them:
-//   1. points are binned once per step by (scene, cell bin) with a counting sort (lotd_sort.cu; bricks of 8 x 4 x 2 bins, x fastest
-//      inside); forward and backward walk the points in that order, so coarse and middle levels hit few lines per warp;
+//   1. points are binned once per step by (scene, cell bin) with a counting sort (lotd_sort.cu; x-fastest bins -- brick-ordered bins lost
+//      their A/B); forward and backward walk the points in that order, so coarse and middle levels hit few lines per warp;
 //   2. TWO ADJACENT LANES share one point (see "pair layout" below): the x-neighbour corners of a Hash level (z-neighbours
 //      of a Dense level) are fetched / scattered by the two lanes of a pair in the same instruction and coalesce in hardware;
-//   3. in the backward pass, runs of points in the same cell sum their corner contributions with a segmented shuffle reduction, and the
-//      CTA (128 points = about one brick of bins) sums what is left per table entry in SHARED-MEMORY TILES -- one tile per level whose corner
-//      bounding box fits -- that are flushed with ONE reduction per touched entry (scripts/sim_tiles.py: 55.6 -> 38.3 L2 packets per point);
+//   3. in the backward pass, runs of points in the same cell sum their corner contributions with a segmented shuffle reduction and the run's
+//      head issues one reduction per corner.  (A CTA-level stage -- shared-memory tiles that sum what is left per table entry -- is kept behind
+//      -DNR3D_BWD_TILES=1: it removes 31 % of the L2 packets and is 2x slower, because fp32 adds into shared memory are CAS loops on sm_100a.)
 //   4. y and dL_dy are accessed as [N, n_enc] rows staged through shared memory (one coalesced 128-byte access per point),
 //      so the sort permutation costs no partial-sector traffic.
 // Results are identical to the generic kernels up to fp32 summation order (same index functions, same weights).

@@ -253,6 +253,128 @@ __global__ void __launch_bounds__(256) sort_scatter_kernel(uint64_t N, uint32_t 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Two-level variant for large single-scene calls (>= kTwoLevelMin points: the ray-sample chunks of the M2 workload, 30 Mi samples over 256^3
+// bins).  There the one-level sort is bound by RANDOM traffic: the histogram's atomics and the scatter's offset gathers miss L2 in a 64 MB
+// counter table, and the 16-byte records land on random sectors of a 480 MB array (partial-sector writes: DRAM read-modify-write).
+// Level 1 partitions the points into 16^3 coarse buckets with CTA-local staging -- a tile of 4096 points counts its buckets in shared
+// memory, reserves ONE range per (tile, bucket) with a single global atomic and writes each bucket's records back to back (ray samples:
+// runs of ~12 records) --, level 2 runs the fine sort over that coarse-sorted copy, where consecutive records share their counter lines and
+// their output segments, so atomics, gathers and record writes all combine in L2.  The final order is the same x-fastest bin order.
+// ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kCoarse = 16, kCoarseN = kCoarse * kCoarse * kCoarse;
+constexpr int kCoarseTile = 4096;            // points per tile (256 threads x 16)
+static uint64_t g_two_level_min = 12ull << 20;
+
+__device__ __forceinline__ uint32_t coarse_key(float x, float y, float z, uint32_t res) {   // (x, y, z) already mapped; res is a multiple of 16
+    const uint32_t per = res / kCoarse;
+    const uint32_t bx = min(res - 1, (uint32_t)fmaxf(x * (float)res, 0.f)) / per;
+    const uint32_t by = min(res - 1, (uint32_t)fmaxf(y * (float)res, 0.f)) / per;
+    const uint32_t bz = min(res - 1, (uint32_t)fmaxf(z * (float)res, 0.f)) / per;
+    return (bz * kCoarse + by) * kCoarse + bx;
+}
+
+template <bool FP>
+__global__ void __launch_bounds__(256) sort_coarse_count_kernel(uint64_t N, uint32_t res, const float* __restrict__ x, SortHeader* __restrict__ hdr,
+                                                                uint32_t* __restrict__ coarse_cnt, unsigned long long* __restrict__ status, uint32_t n_tiles,
+                                                                const SortMap map, uint32_t map_tag) {
+    if (!FP && hdr->skip) return;
+    __shared__ uint32_t sh[kCoarseN];
+    unsigned long long sum = 0, xr = 0;
+    const uint64_t tiles = (N + kCoarseTile - 1) / kCoarseTile;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (uint32_t b = threadIdx.x; b < kCoarseN; b += 256) sh[b] = 0;
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < kCoarseTile / 256; ++j) {
+            const uint64_t i = tile * kCoarseTile + (uint64_t)j * 256 + threadIdx.x;
+            if (i < N) {
+                atomicAdd(&sh[coarse_key(map(x[i * 3]), map(x[i * 3 + 1]), map(x[i * 3 + 2]), res)], 1u);
+                if (FP) { const unsigned long long h = point_hash(x, i, 0u); sum += h; xr ^= h; }
+            }
+        }
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < kCoarseN; b += 256) { const uint32_t c = sh[b]; if (c) atomicAdd(coarse_cnt + b, c); }
+        __syncthreads();
+    }
+    if (FP) fingerprint_finish(sum, xr, N, 1u, res, /*force=*/1, hdr, status, n_tiles, map_tag);
+}
+
+// exclusive scan of the 4096 bucket sizes -> first record of every bucket (also the running cursor of the partition pass); re-zeroes the sizes
+__global__ void __launch_bounds__(1024) sort_coarse_scan_kernel(const SortHeader* __restrict__ hdr, uint32_t* __restrict__ coarse_cnt, uint32_t* __restrict__ cursor) {
+    if (hdr->skip) return;
+    __shared__ uint32_t ws[32];
+    const uint32_t t = threadIdx.x;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = coarse_cnt[t * 4 + k]; coarse_cnt[t * 4 + k] = 0; }
+    const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+    uint32_t s = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, s, d); if ((t & 31) >= (uint32_t)d) s += u; }
+    if ((t & 31) == 31) ws[t >> 5] = s;
+    __syncthreads();
+    if (t < 32) {
+        uint32_t w = ws[t];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, w, d); if (t >= (uint32_t)d) w += u; }
+        ws[t] = w;
+    }
+    __syncthreads();
+    uint32_t o = ((t >> 5) ? ws[(t >> 5) - 1] : 0u) + s - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { cursor[t * 4 + k] = o; o += v[k]; }
+}
+
+__global__ void __launch_bounds__(256) sort_coarse_partition_kernel(uint64_t N, uint32_t res, const float* __restrict__ x, const SortHeader* __restrict__ hdr,
+                                                                    uint32_t* __restrict__ cursor, float4* __restrict__ tmp, const SortMap map) {
+    if (hdr->skip) return;
+    __shared__ uint32_t cnt[kCoarseN], base[kCoarseN];
+    const uint64_t tiles = (N + kCoarseTile - 1) / kCoarseTile;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (uint32_t b = threadIdx.x; b < kCoarseN; b += 256) cnt[b] = 0;
+        __syncthreads();
+        uint32_t kr[kCoarseTile / 256];      // (bucket << 16) | rank inside (tile, bucket)   -- a tile holds 4096 points: 12 bits suffice for both
+#pragma unroll
+        for (int j = 0; j < kCoarseTile / 256; ++j) {
+            const uint64_t i = tile * kCoarseTile + (uint64_t)j * 256 + threadIdx.x;
+            kr[j] = 0xffffffffu;
+            if (i < N) {
+                const uint32_t ck = coarse_key(map(x[i * 3]), map(x[i * 3 + 1]), map(x[i * 3 + 2]), res);
+                kr[j] = (ck << 16) | atomicAdd(&cnt[ck], 1u);
+            }
+        }
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < kCoarseN; b += 256) { const uint32_t c = cnt[b]; if (c) base[b] = atomicAdd(cursor + b, c); }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kCoarseTile / 256; ++j) {
+            const uint64_t i = tile * kCoarseTile + (uint64_t)j * 256 + threadIdx.x;
+            if (kr[j] != 0xffffffffu)
+                tmp[base[kr[j] >> 16] + (kr[j] & 0xffffu)] = make_float4(map(x[i * 3]), map(x[i * 3 + 1]), map(x[i * 3 + 2]), __uint_as_float((uint32_t)i));
+        }
+        __syncthreads();
+    }
+}
+
+// level 2 over the coarse-sorted records (coordinates already mapped)
+__global__ void __launch_bounds__(256) sort_hist_rec_kernel(uint64_t N, uint32_t res, const float4* __restrict__ tmp, const SortHeader* __restrict__ hdr,
+                                                            uint32_t* __restrict__ hist, uint32_t* __restrict__ rank) {
+    if (hdr->skip) return;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 r = tmp[i];
+        rank[i] = atomicAdd(hist + bin_key(r.x, r.y, r.z, res), 1u);
+    }
+}
+__global__ void __launch_bounds__(256) sort_scatter_rec_kernel(uint64_t N, uint32_t res, const float4* __restrict__ tmp, const SortHeader* __restrict__ hdr,
+                                                               const uint32_t* __restrict__ rank, const uint32_t* __restrict__ offsets, float4* __restrict__ xs) {
+    if (hdr->skip) return;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 r = __ldcs(tmp + i);
+        xs[__ldg(offsets + bin_key(r.x, r.y, r.z, res)) + __ldcs(rank + i)] = r;
+    }
+}
+
 }  // namespace nr3d
 
 using namespace nr3d;
@@ -274,7 +396,9 @@ int nr3d_lotd_sort_points_mapped(uint64_t N, const float* x, const int64_t* batc
     const uint32_t n_cnt = (uint32_t)n_cnt64;
     const uint32_t n_tiles = div_up<uint32_t>(n_cnt, kScanTile);
     const uint64_t cnt_bytes = div_up<uint64_t>((uint64_t)n_cnt * 4, 256) * 256;
-    const uint64_t need = kHeaderBytes + (uint64_t)kMaxTiles * 8 + 2 * cnt_bytes + div_up<uint64_t>(N * 4, 256) * 256;
+    const bool two_level = N >= g_two_level_min && n_scenes == 1 && batch_inds == nullptr && batch_data_size == 0 && (res % kCoarse) == 0;
+    const uint64_t rank_bytes = div_up<uint64_t>(N * 4, 256) * 256;
+    const uint64_t need = kHeaderBytes + (uint64_t)kMaxTiles * 8 + 2 * cnt_bytes + rank_bytes + (two_level ? N * 16 + 2 * kCoarseN * 4 : 0);
     if (ws == nullptr) {
         NR3D_CHECK(ws_bytes != nullptr, "sort_points: null ws_bytes");
         *ws_bytes = need;
@@ -298,6 +422,32 @@ int nr3d_lotd_sort_points_mapped(uint64_t N, const float* x, const int64_t* batc
     const unsigned grid = (unsigned)(gwant < (uint64_t)kSMs * 16 ? gwant : (uint64_t)kSMs * 16);
     const uint64_t vwant = div_up<uint64_t>(N, 256 * 8);
     const unsigned vgrid = (unsigned)(vwant < (uint64_t)kSMs * 8 ? vwant : (uint64_t)kSMs * 8);
+    if (two_level) {
+        float4* tmp = reinterpret_cast<float4*>(reinterpret_cast<char*>(rank) + rank_bytes);
+        uint32_t* coarse_cnt = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(tmp) + N * 16);
+        uint32_t* cursor = coarse_cnt + kCoarseN;
+        const uint64_t twant = div_up<uint64_t>(N, kCoarseTile);
+        const unsigned tgrid = (unsigned)(twant < (uint64_t)kSMs * 6 ? twant : (uint64_t)kSMs * 6);
+        if (force) {
+            sort_coarse_count_kernel<true><<<tgrid, 256, 0, st>>>(N, res, x, hdr, coarse_cnt, status, n_tiles, map, map_tag);
+        } else {
+            sort_verify_kernel<<<vgrid, 256, 0, st>>>(N, x, nullptr, 0, 1u, res, 0, hdr, status, n_tiles, map_tag);
+            NR3D_LAUNCH_CHECK("sort_verify");
+            sort_coarse_count_kernel<false><<<tgrid, 256, 0, st>>>(N, res, x, hdr, coarse_cnt, status, n_tiles, map, map_tag);
+        }
+        NR3D_LAUNCH_CHECK("sort_coarse_count");
+        sort_coarse_scan_kernel<<<1, 1024, 0, st>>>(hdr, coarse_cnt, cursor);
+        NR3D_LAUNCH_CHECK("sort_coarse_scan");
+        sort_coarse_partition_kernel<<<tgrid, 256, 0, st>>>(N, res, x, hdr, cursor, tmp, map);
+        NR3D_LAUNCH_CHECK("sort_coarse_partition");
+        sort_hist_rec_kernel<<<grid, 256, 0, st>>>(N, res, tmp, hdr, hist, rank);
+        NR3D_LAUNCH_CHECK("sort_hist_rec");
+        sort_scan_kernel<<<n_tiles, kScanThreads, 0, st>>>(n_cnt, hdr, hist, offsets, status);
+        NR3D_LAUNCH_CHECK("sort_scan");
+        sort_scatter_rec_kernel<<<grid, 256, 0, st>>>(N, res, tmp, hdr, rank, offsets, reinterpret_cast<float4*>(xs));
+        NR3D_LAUNCH_CHECK("sort_scatter_rec");
+        return 0;
+    }
     if (force) {   // new points (forward calls, first use of the buffers): sort unconditionally, the fingerprint is taken inside the histogram pass
         sort_hist_kernel<true><<<grid, 256, 0, st>>>(N, res, n_scenes, x, batch_inds, batch_data_size, hdr, hist, rank, status, n_tiles, map, map_tag);
     } else {       // probably the points of the previous call (the backward of a step): fingerprint first, the sort kernels return at once on a match
@@ -310,6 +460,13 @@ int nr3d_lotd_sort_points_mapped(uint64_t N, const float* x, const int64_t* batc
     NR3D_LAUNCH_CHECK("sort_scan");
     sort_scatter_kernel<<<grid, 256, 0, st>>>(N, res, n_scenes, x, batch_inds, batch_data_size, hdr, rank, offsets, reinterpret_cast<float4*>(xs), scenes, map);
     NR3D_LAUNCH_CHECK("sort_scatter");
+    return 0;
+}
+
+// test / A-B knob: point count from which single-scene calls take the two-level sort (0 restores the default of 12 Mi).  Changing it changes the
+// workspace size of a given N: drop cached workspaces afterwards (bindings._lotd.clear_sort_cache()).
+int nr3d_lotd_sort_set_two_level_min(uint64_t n_points) {
+    g_two_level_min = n_points ? n_points : (12ull << 20);
     return 0;
 }
 

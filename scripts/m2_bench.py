@@ -116,6 +116,9 @@ def main():
     rank, world, local = ndist.init_from_env("nccl")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    if os.environ.get("NR3D_M2_TWO_LEVEL_OFF"):      # A/B: force the one-level point sort for every size
+        from nr3d_lib_b200 import _lib
+        _lib.check(_lib.get_lib().nr3d_lotd_sort_set_two_level_min(1 << 40))
     out = run_m2(dev, rank, world, args.rays, args.chunk, args.grid, args.steps, args.warmup, not args.no_sort, not args.no_fuse_head)
     ndist.shutdown()
     if rank == 0:

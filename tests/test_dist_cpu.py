@@ -50,6 +50,22 @@ def _worker(rank, world, port, out_dir):
     host[lo:hi] = gp_local[lo:hi]
     torch.distributed.all_reduce(host)                                                  # (stands for the shared pinned host buffer)
     assert torch.equal(host, gp_local)
+    # GradReducer modes on this backend: plain all-reduce, reduce-scatter (each rank keeps its slice), and the symmetric-memory mode, which
+    # has no multicast here and must fall back to the plain all-reduce (and say so) instead of failing
+    import types
+    fake_meta = types.SimpleNamespace(n_params=meta.n_params)
+    _, gp_mine = O.bwd(meta, dLdy[b:e], x[b:e], p)
+    for mode in ("allreduce", "symm", "scatter"):
+        red = nd.GradReducer(fake_meta, w, "cpu", mode=mode)
+        out = red.reduce(gp_mine.clone())
+        if mode == "scatter":
+            slo, shi = red.slice_range(meta.n_params, r)
+            assert torch.allclose(out[: shi - slo], gp_full[slo:shi], rtol=1e-12, atol=1e-12)
+        else:
+            assert torch.allclose(out, gp_full, rtol=1e-12, atol=1e-12)
+        if mode == "symm":
+            assert red.mode == "allreduce" and red.fallback_reason
+        red.close()
     nd.barrier()
     np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([1]))
     torch.distributed.destroy_process_group()

@@ -309,3 +309,56 @@ def test_sorted_path_streams_and_sizes(dev):
     torch.cuda.synchronize()
     for k, ref_k in (("a", "a"), ("b", "b"), ("c", "c"), ("a2", "a"), ("b2", "b")):
         assert rel_err(got[k].cpu(), want[ref_k].cpu()) < 1e-6, k
+
+
+def test_two_level_sort_matches_one_level(dev):
+    """The two-level sort (coarse partition with CTA-local staging + fine sort, csrc/lotd_sort.cu; default from 12 Mi points) forced at small
+    sizes: the records are a permutation of the points, non-decreasing in the x-fastest bin key, the fingerprint path reuses them, and the
+    encoder gives the same values as on the one-level records."""
+    from nr3d_lib_b200 import _lib
+    from nr3d_lib_b200.bindings import _lotd
+    lib = _lib.get_lib()
+    cfg = LOTD_CONFIGS["ngp8"]
+    meta = _lotd.LoDMeta(*meta_args(cfg))
+    g = torch.Generator().manual_seed(21)
+    by_index = lambda r: r[r[:, 3].contiguous().view(torch.int32).argsort()]
+
+    def bin_keys(r, res):
+        b = (r[:, :3] * float(res)).clamp_min(0).floor().clamp_max(res - 1).long()
+        return (b[:, 2] * res + b[:, 1]) * res + b[:, 0]
+
+    try:
+        for N, res in ((5000, 32), (300000, 64), (2500000, 128)):
+            # ray-like input: short runs of neighbouring points, like the samples of the marcher
+            base = torch.rand((N + 15) // 16, 1, 3, generator=g)
+            x = (base + torch.arange(16).view(1, 16, 1) * 0.004 * torch.randn((N + 15) // 16, 1, 3, generator=g)).reshape(-1, 3)[:N]
+            x = x.clamp(1e-6, 1 - 1e-6).contiguous().to(dev)
+            x0 = x.clone()
+            _lib.check(lib.nr3d_lotd_sort_set_two_level_min(1000))
+            _lotd.clear_sort_cache()
+            xs2, _ = _lotd._sorted_points(x, expect_new=True)
+            k2 = bin_keys(xs2, res)
+            assert torch.equal(by_index(xs2)[:, :3], x), N
+            assert bool((k2[1:] >= k2[:-1]).all()), N
+            ptr = xs2.data_ptr()
+            xs2b, _ = _lotd._sorted_points(x)                        # fingerprint check: same records, nothing re-sorted
+            assert xs2b.data_ptr() == ptr and torch.equal(bin_keys(xs2b, res), k2)
+            p = (torch.rand(meta.n_params, generator=g) - 0.5).to(dev)
+            y2, _ = _lotd.lod_fwd(meta, x, p, need_input_grad=False)
+            _, g2 = _lotd.lod_bwd(meta, y2, x, p, None, need_input_grad=False, need_param_grad=True)
+            x.mul_(0.999)                                            # new points through the verify path of the two-level sort
+            _, g2n = _lotd.lod_bwd(meta, y2, x, p, None, need_input_grad=False, need_param_grad=True)
+            _lib.check(lib.nr3d_lotd_sort_set_two_level_min(0))
+            _lotd.clear_sort_cache()
+            xs1, _ = _lotd._sorted_points(x, expect_new=True)
+            k1 = bin_keys(xs1, res)
+            assert bool((k1[1:] >= k1[:-1]).all())
+            _, g1n = _lotd.lod_bwd(meta, y2, x, p, None, need_input_grad=False, need_param_grad=True)
+            assert rel_err(g2n.cpu(), g1n.cpu()) < 2e-5
+            y1, _ = _lotd.lod_fwd(meta, x0, p, need_input_grad=False)
+            assert rel_err(y2.cpu(), y1.cpu()) < 1e-5
+            _, g1 = _lotd.lod_bwd(meta, y2, x0, p, None, need_input_grad=False, need_param_grad=True)
+            assert rel_err(g2.cpu(), g1.cpu()) < 2e-5
+    finally:
+        _lib.check(lib.nr3d_lotd_sort_set_two_level_min(0))
+        _lotd.clear_sort_cache()
