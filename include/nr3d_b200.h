@@ -255,6 +255,19 @@ int nr3d_march_fill(uint64_t n_rays, const float* rays_o, const float* rays_d, c
                     const int32_t* packed_info, float* t_starts, float* t_ends, int32_t* ridx, int32_t* bidx,
                     int32_t* gidx, void* stream);
 
+/* Single-pass variant of the two passes above (same outputs, the ray loop runs ONCE): nr3d_march_record counts like nr3d_march_count and
+ * parks every sample as a 16-byte record (t_start, t_end, voxel id) in records[j * n_rays + ray] (16-byte aligned scratch of at least
+ * n_rays * max_steps * 16 bytes); after nr3d_march_pack, nr3d_march_compact moves the records to their packed positions (ridx / bidx are
+ * regenerated from the ray index and batch_inds / batch_data_size).  Callers choose it when the scratch fits their budget. */
+int nr3d_march_record(uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                      const int32_t* batch_inds, uint32_t batch_data_size, int32_t n_batches,
+                      const float* roi, const uint8_t* grid, int32_t rx, int32_t ry, int32_t rz, int32_t contraction,
+                      float step_size, float max_step_size, float dt_gamma, uint32_t max_steps,
+                      int32_t* num_steps, void* records, uint64_t records_bytes, void* stream);
+int nr3d_march_compact(uint64_t n_rays, const int32_t* batch_inds, uint32_t batch_data_size, const void* records,
+                       const int32_t* packed_info, float* t_starts, float* t_ends, int32_t* ridx, int32_t* bidx, int32_t* gidx,
+                       void* stream);
+
 /* Forest (multi-block) marcher, SURVEY.md section 8f row n4: == forest_ray_marching (csrc/occ_grid/src/forest_marching.cu:27-303,
  * bound as nr3d_lib.bindings._occ_grid.forest_ray_marching, occ_grid.cpp:32).  Every ray owns a pack of block segments
  * (seg_pack_infos int32 [R,2] -> seg_block_inds int32 / seg_entries f32 / seg_exits f32 [n_segments]) from the octree ray

@@ -84,6 +84,9 @@ SIGNATURES = {
     "nr3d_march_pack": [_u64, _vp, _vp, _vp, _vp, _u64_p, _vp],
     "nr3d_march_fill": [_u64, _vp, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _u32,
                         _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "nr3d_march_record": [_u64, _vp, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _u32,
+                          _vp, _vp, _u64, _vp],
+    "nr3d_march_compact": [_u64, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "nr3d_forest_march_count": [_u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32_3, _f32_3, _vp, _i32, _i32, _i32, _f32, _f32, _f32,
                                 _u32, _vp, _vp],
     "nr3d_forest_march_fill": [_u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32_3, _f32_3, _vp, _i32, _i32, _i32, _f32, _f32, _f32,

@@ -2,11 +2,13 @@
 
 ``ray_marching`` / ``batched_ray_marching`` keep the reference's signature and return list
 (``[packed_info i32[R,2], t_starts f32[S,1], t_ends f32[S,1], ridx i32[S], (bidx i32[S],) gidx i32[S] | None]``).
-Both passes and the exclusive scan between them run on the device; the only host synchronisation is the single
-read of the total sample count that sizes the outputs (the reference also needs it, ray_marching.cu:209).
+The march and the exclusive scan run on the device; the only host synchronisation is the single read of the total sample
+count that sizes the outputs (the reference also needs it, ray_marching.cu:209).  Calls whose scratch fits MARCH_SCRATCH_BYTES
+march every ray once (record + compact) instead of twice (count + fill).
 """
 import ctypes
 import enum
+import os
 from typing import List, Optional
 
 import torch
@@ -34,6 +36,11 @@ def _check(name, t, dim, dtype=None):
         raise RuntimeError(f"expected scalar type {dtype} for {name} but found {t.dtype}")
 
 
+# Scratch budget of the single-pass marcher (16 bytes per ray and step of `max_steps`): calls that fit march every ray ONCE (record + compact),
+# larger ones take the reference's two passes (count + fill).  Same outputs either way.  NR3D_B200_MARCH_SCRATCH_GB=0 forces the two passes.
+MARCH_SCRATCH_BYTES = int(float(os.environ.get("NR3D_B200_MARCH_SCRATCH_GB", "4")) * 2 ** 30)
+
+
 def _march(rays_o, rays_d, t_min, t_max, batch_inds, batch_data_size, n_batches, roi, grid, res, type_, step_size, max_step_size,
            dt_gamma, max_steps, return_gidx, batched):
     dev = _lib.require_cuda(rays_o, rays_d, t_min, t_max, batch_inds, roi, grid, who="ray_marching")
@@ -50,7 +57,12 @@ def _march(rays_o, rays_d, t_min, t_max, batch_inds, batch_data_size, n_batches,
         num_steps = torch.empty([R], dtype=torch.int32, device=dev)
         packed_info = torch.empty([R, 2], dtype=torch.int32, device=dev)
         total = torch.zeros([1], dtype=torch.int64, device=dev)
-        if R > 0:
+        rec_bytes = R * int(max_steps) * 16
+        records = None
+        if 0 < rec_bytes <= MARCH_SCRATCH_BYTES:
+            records = torch.empty([rec_bytes], dtype=torch.uint8, device=dev)
+            _lib.check(lib.nr3d_march_record(*common, num_steps.data_ptr(), records.data_ptr(), rec_bytes, st))
+        elif R > 0:
             _lib.check(lib.nr3d_march_count(*common, num_steps.data_ptr(), st))
         nbytes = ctypes.c_uint64(0)
         _lib.check(lib.nr3d_march_pack(R, None, None, None, None, ctypes.byref(nbytes), None))
@@ -64,7 +76,10 @@ def _march(rays_o, rays_d, t_min, t_max, batch_inds, batch_data_size, n_batches,
         ridx = torch.empty([S], dtype=torch.int32, device=dev)
         bidx = torch.empty([S], dtype=torch.int32, device=dev) if batched else None
         gidx = torch.empty([S], dtype=torch.int32, device=dev) if return_gidx else None
-        if R > 0 and S > 0:
+        if R > 0 and S > 0 and records is not None:
+            _lib.check(lib.nr3d_march_compact(R, _lib.ptr(batch_inds), int(batch_data_size), records.data_ptr(), packed_info.data_ptr(),
+                                              t_starts.data_ptr(), t_ends.data_ptr(), ridx.data_ptr(), _lib.ptr(bidx), _lib.ptr(gidx), st))
+        elif R > 0 and S > 0:
             _lib.check(lib.nr3d_march_fill(*common, packed_info.data_ptr(), t_starts.data_ptr(), t_ends.data_ptr(), ridx.data_ptr(),
                                            _lib.ptr(bidx), _lib.ptr(gidx), st))
     if batched:

@@ -23,6 +23,7 @@
 // Results are identical to the generic kernels up to fp32 summation order (same index functions, same weights).
 #include "lotd_pair.cuh"
 #include <string.h>
+#include <math.h>
 
 namespace nr3d {
 
@@ -50,6 +51,19 @@ namespace nr3d {
 #endif
 #ifndef NR3D_BWD_OCC          // resident threads per SM the F = 2 backward is compiled for (register cap through __launch_bounds__), 0: no cap
 #define NR3D_BWD_OCC 1536
+#endif
+#ifndef NR3D_BWD_MERGE        // how same-cell points of a warp are merged before the scatter: 0 contiguous runs only (round 1), 1 any lanes of the warp (match.any),
+                              // 2 lanes linked over at most NR3D_LINK_DIST points (shuffles); 1 and 2 sum by pointer jumping
+#define NR3D_BWD_MERGE 1
+#endif
+#ifndef NR3D_LINK_DIST        // NR3D_BWD_MERGE == 2: how many points ahead a lane looks for the next point of its cell
+#define NR3D_LINK_DIST 3
+#endif
+#ifndef NR3D_BWD_NEIGH        // 1: on Hash levels the side-0 head of cell (X, y, z) hands its four sums to the side-1 head of cell (X - 1, y, z) (same entries)
+#define NR3D_BWD_NEIGH 0
+#endif
+#ifndef NR3D_MERGE_DENSITY    // levels with res^3 <= NR3D_MERGE_DENSITY * (points per scene) try to merge; finer levels hold less than one point per cell
+#define NR3D_MERGE_DENSITY 16 // (0: every level whose cell key fits 10 bits per axis, the round-1 rule)
 #endif
 constexpr int kFastThreads = NR3D_FWD_THREADS;
 constexpr int kBwdThreads = NR3D_BWD_THREADS;
@@ -425,8 +439,10 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
     float gx[3] = {0.f, 0.f, 0.f};
     if (SECOND && live) { gx[0] = __ldg(ddx + i * 3); gx[1] = __ldg(ddx + i * 3 + 1); gx[2] = __ldg(ddx + i * 3 + 2); }
     // a point starts a new run on every level when its scene differs from the previous point's
+#if !NR3D_BWD_MERGE
     const uint32_t scene_prev = __shfl_up_sync(0xffffffffu, scene, 2);
     const bool scene_break = scene != scene_prev;
+#endif
 
 #if NR3D_BWD_TILES
     // ---- CTA bounding box of the live points (in unit-cube coordinates: 6 reductions instead of 6 per level) and the tile plan ----
@@ -526,12 +542,89 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
         for (int q = 0; q < 4; ++q)
 #pragma unroll
             for (int f = 0; f < F; ++f) cx[q][f] = g.w[q] * gv[f];
-        // Points of one run (consecutive points of the warp in the same cell of this level) merge their contributions before they leave the
-        // warp: the hardware merges different entries of a sector, not lanes that hit the same entry.  The cell key holds 10 bits per axis;
-        // finer levels have no runs worth merging (less than one point per cell).
+        // Points of the warp in the same cell of this level merge their contributions before they leave the warp: the hardware merges different
+        // entries of a sector, not lanes that hit the same entry.  The cell key holds 10 bits per axis; levels finer than in.merge_res hold less
+        // than one point per cell and skip the attempt (it costs issue slots the kernel does not have: 76 % busy in the round-2 ncu capture).
         bool issue = live;   // this lane issues its four contributions
-        const bool can_key = L.res[0] <= 1024u && L.res[1] <= 1024u && L.res[2] <= 1024u;
+        const bool can_key = max(L.res[0], max(L.res[1], L.res[2])) <= in.merge_res;
+#if NR3D_BWD_MERGE
         if (can_key) {
+            // ANY lanes of the warp with the same (cell, side, scene) form a group -- not only neighbours: the sort orders the points by bin, and a
+            // cell boundary that cuts a bin leaves its points interleaved (A B A B: four "runs", two cells).  scripts/sim_sectors.py: 55.6 -> 51.2
+            // packets per point.  Every lane learns its successor in the group (`next`, 32: none) and whether it is the group's first lane; the sums
+            // then travel towards the first lane by pointer jumping (after step t a lane holds the sum over itself and its 2^t - 1 successors, `next`
+            // points 2^t members ahead).
+            int next = 32;
+            bool first = true;
+#if NR3D_BWD_MERGE == 1   // groups from match.any
+            // (match.any costs about as much as it finds DISTINCT values -- measured, profiles/r2_ab_merge.txt -- so the key leaves the side out: the
+            // two lanes of a point fall into one group that the parity mask splits again, and all idle lanes share one sentinel)
+            const uint32_t mkey = live ? g.key : 0x80000000u;
+            const uint32_t smask = in.scenes ? __match_any_sync(0xffffffffu, scene) : 0xffffffffu;   // lanes of my scene (recomputed per level: one register less)
+            const uint32_t same_cell = __match_any_sync(0xffffffffu, mkey);   // (every lane of the warp executes the match)
+            const uint32_t grp = live ? (same_cell & smask & (0x55555555u << side)) : (1u << lane);
+            {
+                const uint32_t above = grp & ~((2u << lane) - 1u);
+                if (above) next = __ffs(above) - 1;
+                first = (grp & ((1u << lane) - 1u)) == 0u;
+            }
+#else                     // links to the nearest same-cell point at most NR3D_LINK_DIST points away (three shuffles instead of a match)
+            const uint32_t mkey = live ? (g.key | (side << 30)) : (0x80000000u | (uint32_t)lane);
+#pragma unroll
+            for (int d = NR3D_LINK_DIST; d >= 1; --d) {
+                const uint32_t kd = __shfl_down_sync(0xffffffffu, mkey, 2 * d);
+                bool same = lane + 2 * d < 32 && kd == mkey;
+                if (in.scenes) same = same && __shfl_down_sync(0xffffffffu, scene, 2 * d) == scene;
+                if (same) next = lane + 2 * d;   // the nearest one wins (d runs downwards)
+                const uint32_t b = __ballot_sync(0xffffffffu, same);   // bit l: lane l has a same-cell successor d points on, so lane l + 2 d is not a first lane
+                if (lane >= 2 * d && ((b >> (lane - 2 * d)) & 1u)) first = false;
+            }
+#endif
+            if (__any_sync(0xffffffffu, next < 32)) {
+#pragma unroll
+                for (int d = 1; d < 16; d <<= 1) {
+                    if (d > 1 && !__any_sync(0xffffffffu, next < 32)) break;   // warp uniform
+                    const bool take = next < 32;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int f = 0; f < F; ++f) {
+                            const float u = __shfl_sync(0xffffffffu, cx[q][f], next);
+                            if (take) cx[q][f] += u;
+                        }
+                    const int nn = __shfl_sync(0xffffffffu, next, next);
+                    next = take ? nn : 32;
+                }
+                issue = live && first;
+            }
+#if NR3D_BWD_NEIGH
+            if (L.type != NR3D_LOD_DENSE) {   // warp uniform
+                // The side-1 head of cell (X - 1, y, z) and the side-0 head of cell (X, y, z) address the same four entries (X ^ h(y + dy, z + dz)):
+                // the lower lane of such a pair takes the other's sums.
+                const uint32_t nkey = issue ? (g.key + side) : 0x80000000u;   // x coordinate of my corners (<= res - 1: no carry into y)
+#if NR3D_BWD_MERGE != 1
+                const uint32_t smask = in.scenes ? __match_any_sync(0xffffffffu, scene) : 0xffffffffu;
+#endif
+                const uint32_t pairm = __match_any_sync(0xffffffffu, nkey) & smask;
+                const uint32_t other = (issue && __popc(pairm) == 2) ? (pairm ^ (1u << lane)) : 0u;   // (link merging can leave several heads per cell: those keep their sums)
+                if (__any_sync(0xffffffffu, other != 0u)) {
+                    const int ol = other ? (__ffs(other) - 1) : lane;
+                    const bool recv = other != 0u && lane < ol;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int f = 0; f < F; ++f) {
+                            const float u = __shfl_sync(0xffffffffu, cx[q][f], ol);
+                            if (recv) cx[q][f] += u;
+                        }
+                    if (other != 0u && !recv) issue = false;
+                }
+            }
+#endif
+        }
+#else
+        if (can_key) {
+            // (round-1 rule) runs = CONSECUTIVE points of the warp in the same cell
             const uint32_t key = live ? g.key : (0xffffffffu - (uint32_t)k);
             const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 2);
             const uint32_t hmask = __ballot_sync(0xffffffffu, k == 0 || key != prev || scene_break) & 0x55555555u;  // bit 2k set: point k starts a run
@@ -560,6 +653,7 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
                 issue = live && j == 0;
             }
         }
+#endif
 #if NR3D_BWD_TILES
         const int32_t toff = pl < kMaxTiledLevels ? plan.off[pl] : -1;   // CTA uniform
         if (toff >= 0) {
@@ -742,6 +836,15 @@ static int check_fast(const nr3d_lotd_meta* m, int32_t param_dtype, uint64_t N, 
     return 0;
 }
 
+// Finest resolution whose cells still hold about one point each (res^3 <= NR3D_MERGE_DENSITY * points per scene): the backward tries to merge
+// same-cell points up to there.  The cell key has 10 bits per axis, so never beyond 1024.
+static uint32_t merge_res_for(uint64_t N, uint32_t n_scenes) {
+    if (NR3D_MERGE_DENSITY == 0) return 1024u;
+    const double cells = (double)NR3D_MERGE_DENSITY * (double)N / (double)(n_scenes ? n_scenes : 1);
+    const double r = cbrt(cells);
+    return r >= 1024.0 ? 1024u : (uint32_t)r;
+}
+
 // shared memory of the backward kernel: CTA tiles + one staged [16, 32] row tile per warp
 constexpr size_t kBwdSmem = sizeof(float) * ((NR3D_BWD_TILES ? kTileFloats : 0) + kBwdWarps * 16 * kPairRowStride);
 
@@ -835,7 +938,7 @@ int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, 
     LotdTable tab;
     make_table(meta, tab);
     const uint32_t pl_stop = (pl_end < meta->n_pseudo_levels) ? pl_end : meta->n_pseudo_levels;
-    FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, nullptr, max_level, meta->n_params, pl_begin, pl_stop};
+    FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, nullptr, max_level, meta->n_params, pl_begin, pl_stop, merge_res_for(N, n_scenes)};
     int rc = 0;
     NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl,
                        (rc = launch_bwd<PT, F, false>(tab, in, dL_dy, dLdy_stride_n, dLdy_stride_f, nullptr, dL_dparam, (cudaStream_t)stream)));
@@ -864,7 +967,7 @@ int nr3d_lotd_density_head_bwd_sorted(const nr3d_lotd_meta* meta, int32_t param_
     NR3D_CHECK(xs && d_alpha && sigma && alpha && deltas && dL_dparam, "LoTDEncoding::density_head_bwd_sorted: null argument");
     LotdTable tab;
     make_table(meta, tab);
-    FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, nullptr, max_level, meta->n_params, 0u, meta->n_pseudo_levels};
+    FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, nullptr, max_level, meta->n_params, 0u, meta->n_pseudo_levels, merge_res_for(N, n_scenes)};
     const HeadBwd hd{d_alpha, sigma, alpha, deltas, gain};
     int rc = 0;
     NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl,
@@ -895,7 +998,7 @@ int nr3d_lotd_bwd_param2_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype,
     LotdTable tab;
     make_table(meta, tab);
     const uint32_t pl_stop = (pl_end < meta->n_pseudo_levels) ? pl_end : meta->n_pseudo_levels;
-    FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, nullptr, max_level, meta->n_params, pl_begin, pl_stop};
+    FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, nullptr, max_level, meta->n_params, pl_begin, pl_stop, merge_res_for(N, n_scenes)};
     int rc = 0;
     NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl,
                        (rc = launch_bwd<PT, F, true>(tab, in, dL_dy, dLdy_stride_n, dLdy_stride_f, dL_ddLdx, dL_dparam, (cudaStream_t)stream)));

@@ -33,6 +33,7 @@ struct FastIn {
     int32_t max_level;
     uint32_t n_params;        // elements per scene
     uint32_t pl_begin, pl_end;  // pseudo levels [pl_begin, pl_end) to process (backward only: level groups whose all-reduce starts early)
+    uint32_t merge_res;       // backward only: levels up to this resolution merge same-cell points inside a warp before the scatter (0: none)
 };
 
 struct Geo2 {

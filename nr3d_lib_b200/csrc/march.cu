@@ -87,10 +87,16 @@ struct MarchArgs {
     uint32_t max_steps;
 };
 
-template <bool FILL>
+// MODE 0: count pass (num_steps).  MODE 1: fill pass with thread-per-ray stores (A/B only, the staged fill kernel below is used).
+// MODE 2: RECORD pass of the single-pass marcher: counts like MODE 0 and parks every sample as one 16-byte record (t_start, t_end, voxel id)
+// in rec[j * n_rays + ray] -- sample-major, so the 32 rays of a warp fill one 512-byte row per sample index and the rows are complete by the
+// time L2 writes them back.  march_compact_kernel then moves the records to their packed positions; the ray is marched ONCE instead of twice.
+template <int MODE>
 __global__ void __launch_bounds__(256)
 march_kernel(const MarchArgs a, const int32_t* __restrict__ packed_info, int32_t* __restrict__ num_steps, float* __restrict__ t_starts,
-             float* __restrict__ t_ends, int32_t* __restrict__ ridx_out, int32_t* __restrict__ bidx_out, int32_t* __restrict__ gidx_out) {
+             float* __restrict__ t_ends, int32_t* __restrict__ ridx_out, int32_t* __restrict__ bidx_out, int32_t* __restrict__ gidx_out,
+             float4* __restrict__ rec) {
+    constexpr bool FILL = MODE == 1;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_rays) return;
     uint32_t batch_ind = 0;
@@ -144,6 +150,7 @@ march_kernel(const MarchArgs a, const int32_t* __restrict__ packed_info, int32_t
                 if (bidx_out) bidx_out[base + j] = (int32_t)batch_ind;
                 if (gidx_out) gidx_out[base + j] = grid_idx + (int32_t)grid_offset;
             }
+            if (MODE == 2) __stcg(rec + (uint64_t)j * a.n_rays + i, make_float4(t0, t1, __int_as_float(grid_idx + (int32_t)grid_offset), 0.f));
             ++j;
             t0 = t1;
             t1 = t0 + calc_dt(t0, a.dt_gamma, dt_min, dt_max);
@@ -160,6 +167,55 @@ march_kernel(const MarchArgs a, const int32_t* __restrict__ packed_info, int32_t
         }
     }
     if (!FILL) num_steps[i] = (int32_t)j;
+}
+
+// Second half of the single-pass marcher: records rec[j * n_rays + ray] (written by march_kernel<2>) -> packed outputs.  One warp owns 32
+// consecutive rays, whose samples form ONE contiguous span of the outputs.  Per round of 32 sample indices: 32 coalesced 512-byte row reads
+// into a padded shared-memory tile (conflict-free both ways), then ray after ray the warp writes 32 consecutive samples of that ray
+// (consecutive lanes -> consecutive addresses).  Rows beyond a ray's own count hold stale bytes that are read and never used.
+constexpr int kCompactThreads = 64;
+__global__ void __launch_bounds__(kCompactThreads)
+march_compact_kernel(uint64_t n_rays, const int32_t* __restrict__ batch_inds, uint32_t batch_data_size, const float4* __restrict__ rec,
+                     const int32_t* __restrict__ packed_info, float* __restrict__ t_starts, float* __restrict__ t_ends,
+                     int32_t* __restrict__ ridx_out, int32_t* __restrict__ bidx_out, int32_t* __restrict__ gidx_out) {
+    __shared__ float s_t0[kCompactThreads / 32][32 * 33];
+    __shared__ float s_t1[kCompactThreads / 32][32 * 33];
+    __shared__ int32_t s_g[kCompactThreads / 32][32 * 33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * (kCompactThreads / 32) + wid) * 32;
+    if (i0 >= n_rays) return;   // whole warp
+    const uint64_t i = i0 + lane;
+    const bool have = i < n_rays;
+    const int32_t base = have ? packed_info[i * 2] : 0, cnt = have ? packed_info[i * 2 + 1] : 0;
+    int32_t bat = 0;
+    if (have && bidx_out) bat = batch_inds ? batch_inds[i] : (batch_data_size ? (int32_t)(i / batch_data_size) : 0);
+    const int32_t maxc = __reduce_max_sync(0xffffffffu, cnt);
+    float* t0s = s_t0[wid]; float* t1s = s_t1[wid]; int32_t* gs = s_g[wid];
+    for (int32_t j0 = 0; j0 < maxc; j0 += 32) {
+        const int rows = min(32, maxc - j0);   // warp uniform
+        if (have) {
+#pragma unroll 8
+            for (int jj = 0; jj < rows; ++jj) {
+                const float4 v = __ldcs(rec + (uint64_t)(j0 + jj) * n_rays + i);
+                t0s[jj * 33 + lane] = v.x; t1s[jj * 33 + lane] = v.y; gs[jj * 33 + lane] = __float_as_int(v.z);
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < 32; ++r) {
+            const int32_t c = __shfl_sync(0xffffffffu, cnt, r) - j0;     // samples of ray r left from this round on
+            if (c <= 0) continue;                                        // warp uniform
+            const int64_t b = (int64_t)__shfl_sync(0xffffffffu, base, r) + j0;
+            const int32_t br = __shfl_sync(0xffffffffu, bat, r);
+            if (lane < c) {
+                t_starts[b + lane] = t0s[lane * 33 + r];
+                t_ends[b + lane] = t1s[lane * 33 + r];
+                ridx_out[b + lane] = (int32_t)(i0 + r);
+                if (bidx_out) bidx_out[b + lane] = br;
+                if (gidx_out) gidx_out[b + lane] = gs[lane * 33 + r];
+            }
+        }
+        __syncwarp();
+    }
 }
 
 // Fill pass with coalesced output.  One thread per ray writes t_starts[base + j] etc. with a different base per lane: every store
@@ -412,8 +468,38 @@ int nr3d_march_count(uint64_t n_rays, const float* rays_o, const float* rays_d, 
     if (int rc = fill_args(a, n_rays, rays_o, rays_d, t_min, t_max, batch_inds, batch_data_size, n_batches, roi, grid, rx, ry, rz,
                            contraction, step_size, max_step_size, dt_gamma, max_steps)) return rc;
     NR3D_CHECK(num_steps != nullptr, "ray_marching: null num_steps");
-    march_kernel<false><<<(unsigned)div_up<uint64_t>(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(a, nullptr, num_steps, nullptr, nullptr, nullptr, nullptr, nullptr);
+    march_kernel<0><<<(unsigned)div_up<uint64_t>(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(a, nullptr, num_steps, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     NR3D_LAUNCH_CHECK("ray_marching(count)");
+    return 0;
+}
+
+int nr3d_march_record(uint64_t n_rays, const float* rays_o, const float* rays_d, const float* t_min, const float* t_max,
+                      const int32_t* batch_inds, uint32_t batch_data_size, int32_t n_batches, const float* roi, const uint8_t* grid,
+                      int32_t rx, int32_t ry, int32_t rz, int32_t contraction, float step_size, float max_step_size, float dt_gamma,
+                      uint32_t max_steps, int32_t* num_steps, void* records, uint64_t records_bytes, void* stream) {
+    if (n_rays == 0) return 0;
+    MarchArgs a;
+    if (int rc = fill_args(a, n_rays, rays_o, rays_d, t_min, t_max, batch_inds, batch_data_size, n_batches, roi, grid, rx, ry, rz,
+                           contraction, step_size, max_step_size, dt_gamma, max_steps)) return rc;
+    NR3D_CHECK(num_steps != nullptr && records != nullptr, "ray_marching: null num_steps / records");
+    NR3D_CHECK((reinterpret_cast<uintptr_t>(records) & 15u) == 0, "ray_marching: records must be 16-byte aligned");
+    NR3D_CHECK(records_bytes / 16 / n_rays >= (uint64_t)max_steps, "ray_marching: records buffer too small (%llu bytes for %llu rays x %u steps)",
+               (unsigned long long)records_bytes, (unsigned long long)n_rays, max_steps);
+    march_kernel<2><<<(unsigned)div_up<uint64_t>(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(a, nullptr, num_steps, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                                             reinterpret_cast<float4*>(records));
+    NR3D_LAUNCH_CHECK("ray_marching(record)");
+    return 0;
+}
+
+int nr3d_march_compact(uint64_t n_rays, const int32_t* batch_inds, uint32_t batch_data_size, const void* records, const int32_t* packed_info,
+                       float* t_starts, float* t_ends, int32_t* ridx, int32_t* bidx, int32_t* gidx, void* stream) {
+    if (n_rays == 0) return 0;
+    NR3D_CHECK(records && packed_info && t_starts && t_ends && ridx, "ray_marching(compact): null argument");
+    NR3D_CHECK(n_rays < (1ull << 31), "ray_marching: n_rays must be < 2^31");
+    constexpr int rays_per_cta = kCompactThreads;   // 32 rays per warp
+    march_compact_kernel<<<(unsigned)div_up<uint64_t>(n_rays, rays_per_cta), kCompactThreads, 0, (cudaStream_t)stream>>>(
+        n_rays, batch_inds, batch_data_size, reinterpret_cast<const float4*>(records), packed_info, t_starts, t_ends, ridx, bidx, gidx);
+    NR3D_LAUNCH_CHECK("ray_marching(compact)");
     return 0;
 }
 
@@ -432,7 +518,7 @@ int nr3d_march_fill(uint64_t n_rays, const float* rays_o, const float* rays_d, c
                            contraction, step_size, max_step_size, dt_gamma, max_steps)) return rc;
     NR3D_CHECK(packed_info && t_starts && t_ends && ridx, "ray_marching: null output");
 #ifdef NR3D_MARCH_FILL_UNSTAGED   // thread-per-ray stores (kept for A/B runs)
-    march_kernel<true><<<(unsigned)div_up<uint64_t>(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(a, packed_info, nullptr, t_starts, t_ends, ridx, bidx, gidx);
+    march_kernel<1><<<(unsigned)div_up<uint64_t>(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(a, packed_info, nullptr, t_starts, t_ends, ridx, bidx, gidx, nullptr);
 #else
     march_fill_staged_kernel<<<(unsigned)div_up<uint64_t>(n_rays, kFillThreads), kFillThreads, 0, (cudaStream_t)stream>>>(a, packed_info, t_starts, t_ends, ridx, bidx, gidx);
 #endif

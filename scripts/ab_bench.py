@@ -20,18 +20,30 @@ VARIANTS = {
     "fwd_tma": ["NR3D_FWD_TMA=1"],
     "fwd_tma_12k": ["NR3D_FWD_TMA=1", "NR3D_FWD_TMA_FLOATS=3072"],
     "fwd_tma_brick": ["NR3D_FWD_TMA=1", "NR3D_BIN_ORDER=2"],
+    # round-2 (late) A/B of the warp-level merge in the backward (profiles/r2_ab_merge.txt): contiguous runs (round 1) vs any lanes of the warp
+    # (match.any / shuffle links + pointer jumping), Hash-level neighbour hand-over, and up to which level merging is attempted
+    "runs_all": ["NR3D_BWD_MERGE=0", "NR3D_MERGE_DENSITY=0"],          # the round-1 / early round-2 kernel
+    "any_d1": ["NR3D_BWD_MERGE=1", "NR3D_BWD_NEIGH=0", "NR3D_MERGE_DENSITY=1"],
+    "any_d2": ["NR3D_BWD_MERGE=1", "NR3D_BWD_NEIGH=0", "NR3D_MERGE_DENSITY=2"],
+    "any_d4": ["NR3D_BWD_MERGE=1", "NR3D_BWD_NEIGH=0", "NR3D_MERGE_DENSITY=4"],
+    "any_d8": ["NR3D_BWD_MERGE=1", "NR3D_BWD_NEIGH=0", "NR3D_MERGE_DENSITY=8"],
+    "any_d16": ["NR3D_BWD_MERGE=1", "NR3D_BWD_NEIGH=0", "NR3D_MERGE_DENSITY=16"],
+    "any_neigh_d4": ["NR3D_BWD_MERGE=1", "NR3D_BWD_NEIGH=1", "NR3D_MERGE_DENSITY=4"],
+    "link3_d8": ["NR3D_BWD_MERGE=2", "NR3D_BWD_NEIGH=0", "NR3D_MERGE_DENSITY=8"],
 }
 if sys.argv[1] == "build":
     from nr3d_lib_b200.csrc import build as B
     B.build()
     for n, d in VARIANTS.items():
+        if len(sys.argv) > 2 and n not in sys.argv[2].split(","):
+            continue
         print(n, B.build_variant(n, d))
 else:
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     names = sys.argv[2].split(",") if len(sys.argv) > 2 else list(VARIANTS)
     for n in names:
         env = dict(os.environ, NR3D_B200_LIB=os.path.join(root, "nr3d_lib_b200", "lib", "variants", n + ".so"))
-        for extra in ([], ["--half"]):
+        for extra in ([], ["--half"]) if not os.environ.get("NR3D_AB_FP32_ONLY") else ([],):
             r = subprocess.run([sys.executable, os.path.join(root, "scripts", "step_probe.py"), "--tag", n] + extra, env=env, capture_output=True, text=True)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ("FAILED " + r.stderr[-400:])
             print(line, flush=True)

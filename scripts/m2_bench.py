@@ -67,12 +67,14 @@ def run_m2(dev, rank, world, rays=1024 * 1024, chunk=262144, grid_kind="random",
         step()
     ndist.barrier()
     torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for k in range(steps):
         step()
-    e1.record()
+        evs[k + 1].record()
     torch.cuda.synchronize(dev)
+    e0, e1 = evs[0], evs[-1]
+    step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(steps)]      # this rank's steps one by one (spread = how noisy the box is)
     ms = ndist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
     ndist.barrier()
     total_samples = ndist.sum_over_ranks(float(n_samples), dev)
@@ -94,7 +96,7 @@ def run_m2(dev, rank, world, rays=1024 * 1024, chunk=262144, grid_kind="random",
                 "note": "whole M2 step per GPU; 93 % of the bytes are LoTD corner gathers / scatters that hit the L2-resident table, so -- as for M1 -- "
                         "the binding resource is the L1 line rate (forward) and the L2 reduction rate (backward), not DRAM"}
     return {"roofline": roofline, "metric": "full march+encode+composite fwd+bwd Mrays/s", "value": world * rays / ms / 1e3, "unit": "Mrays/s",
-            "n_gpus": world, "ms_per_step": ms, "rays_per_gpu": rays, "samples_per_ray": total_samples / (world * rays),
+            "n_gpus": world, "ms_per_step": ms, "step_ms": [round(t, 3) for t in step_ms], "rays_per_gpu": rays, "samples_per_ray": total_samples / (world * rays),
             "Msamples_per_s": total_samples / ms / 1e3, "grid": grid_kind, "chunk": chunk, "steps": steps, "warmup": warmup,
             "sort_points": sort_points, "fuse_head": bool(fuse_head and sort_points), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
             "workload": ("configs[4] (4096^2 rays over 8 GPUs)" if world * rays == 4096 * 4096 else "configs[2] shape (1024^2 rays per GPU)") +

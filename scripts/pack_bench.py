@@ -73,13 +73,17 @@ def main():
     CT = _occ_grid.ContractionType.AABB
     r = _occ_grid.ray_marching(o, d, near, far, roi, grid, CT, 0.01, 1e10, 0.0, 512, True)
     Sm = int(r[1].shape[0])
-    row(f"ray_marching ({Sm / P:.0f} samples/ray)", Sm * 16 + P * 40,
+    row(f"ray_marching ({Sm / P:.0f} samples/ray), record + compact", Sm * 16 + P * 40,
         lambda: _occ_grid.ray_marching(o, d, near, far, roi, grid, CT, 0.01, 1e10, 0.0, 512, True),
         (lambda: ref_o.ray_marching(o, d, near, far, roi, grid, ref_o.ContractionType.AABB, 0.01, 1e10, 0.0, 512, True)) if ref_o else None)
+    budget, _occ_grid.MARCH_SCRATCH_BYTES = _occ_grid.MARCH_SCRATCH_BYTES, 0
+    row("ray_marching, count + fill (two passes)", Sm * 16 + P * 40,
+        lambda: _occ_grid.ray_marching(o, d, near, far, roi, grid, CT, 0.01, 1e10, 0.0, 512, True), None)
+    _occ_grid.MARCH_SCRATCH_BYTES = budget
     print(f"# {P} packs / rays, {S} samples ({S / P:.0f} per pack), fp32, B200; peak = {peak:.0f} GB/s (MEASURED_PEAKS.json)")
-    print(f"{'op':48s} {'ours ms':>9s} {'ref build ms':>13s} {'speed-up':>9s} {'GB/s':>8s} {'of HBM':>7s}")
+    print(f"{'op':58s} {'ours ms':>9s} {'ref build ms':>13s} {'speed-up':>9s} {'GB/s':>8s} {'of HBM':>7s}")
     for name, tm, tr, gbs, frac in rows:
-        print(f"{name:48s} {tm:9.3f} {tr:13.3f} {tr / tm:9.2f} {gbs:8.0f} {frac:7.2f}")
+        print(f"{name:58s} {tm:9.3f} {tr:13.3f} {tr / tm:9.2f} {gbs:8.0f} {frac:7.2f}")
 
 
 if __name__ == "__main__":

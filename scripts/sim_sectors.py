@@ -6,11 +6,15 @@ Cost model (scripts/ubench_redgroup.cu, profiles/r1_s2_ubench_redgroup.txt): lan
 32-byte sector share one packet, lanes that hit the SAME entry need one packet each.  Columns, in packets per point and level:
   no merge          every lane issues its reduction
   runs >= 4 merged  the shared-memory run merge (consecutive points in one cell) for runs of four and more  -- the build that ncu saw
-  all runs merged   + runs of two and three points through shuffles                                        -- the shipped build
+  all runs merged   + runs of two and three points through shuffles                                        -- the build shipped until late round 2
+  any lanes merged  every point of the warp in the same cell merged, neighbours or not (match.any + pointer jumping) -- the shipped build on the
+                    levels it merges (res^3 <= 4 N); a cell boundary that cuts a sort bin leaves the bin's points interleaved, which "runs" cannot see
+  + x neighbours    additionally, on Hash levels, the side-0 head of cell (X, y, z) hands its sums to the side-1 head of cell (X - 1, y, z): this
+                    reaches the floor of the Hash levels and still loses on the GPU (a second match.any, profiles/r2_ab_merge.txt)
   distinct sectors  the floor if every repeated entry inside an instruction were merged for free
 Measured (ncu, profiles/r1_s2_pair_ncu_summary.txt): 260.8 M packets / 4 194 304 points = 62.2 for the "runs >= 4" build.
 
-    python scripts/sim_sectors.py > profiles/r1_s2_sector_simulation.txt
+    python scripts/sim_sectors.py > profiles/r2_sector_simulation.txt     (round 1: profiles/r1_s2_sector_simulation.txt)
 """
 import numpy as np
 
@@ -45,8 +49,8 @@ def packets(ent, valid):
 
 
 print(f"# {N} uniform points, 16-level NGP LoTD (T = 2^19, F = 2), sorted by 128^3 bins (x fastest); L2 reduction packets per point")
-print("# level   res  type | no merge | runs >= 4 merged | all runs merged | distinct sectors")
-tot = np.zeros(4)
+print("# level   res  type | no merge | runs >= 4 merged | all runs merged | any lanes merged | + x neighbours | distinct sectors")
+tot = np.zeros(6)
 for li, R in enumerate(res_list):
     dense = R ** 3 <= T
     c = np.floor(xs * np.float32(R - 2) + np.float32(0.5)).astype(np.int64)
@@ -58,7 +62,17 @@ for li, R in enumerate(res_list):
     for r in range(1, 17):
         m = run_id == r
         rl += m * m.sum(1, keepdims=True)
-    res = np.zeros(4)
+    head_any = np.ones((W, 16), bool)      # first point of its cell in the warp
+    for k in range(1, 16):
+        head_any[:, k] = ~(key[:, :k] == key[:, k:k + 1]).any(1)
+    valid_any = np.repeat(head_any, 2, axis=1)
+    valid_nb = valid_any.copy()
+    if not dense:
+        keym1 = ((c[:, 0] - 1) | (c[:, 1] << 10) | (c[:, 2] << 20)).reshape(W, 16)
+        for k in range(16):
+            has = ((key == keym1[:, k:k + 1]) & head_any).any(1) & head_any[:, k]
+            valid_nb[:, 2 * k] &= ~has
+    res = np.zeros(6)
     for q in range(4):
         ents = []
         for side in range(2):
@@ -74,11 +88,15 @@ for li, R in enumerate(res_list):
         res[0] += packets(ent, np.ones((W, 32), bool))
         res[1] += packets(ent, np.repeat(head | (rl < 4), 2, axis=1))
         res[2] += packets(ent, np.repeat(head, 2, axis=1))
+        res[3] += packets(ent, valid_any)
+        res[4] += packets(ent, valid_nb)
         s = np.sort(ent >> 2, axis=1)
-        res[3] += (np.diff(s, axis=1) != 0).sum() + W
+        res[5] += (np.diff(s, axis=1) != 0).sum() + W
     res /= N
     tot += res
-    print(f"  L{li:<2d}  {R:5d}  {'Dense' if dense else 'Hash '} | {res[0]:8.3f} | {res[1]:16.3f} | {res[2]:15.3f} | {res[3]:16.3f}")
-print(f"  total               | {tot[0]:8.3f} | {tot[1]:16.3f} | {tot[2]:15.3f} | {tot[3]:16.3f}")
-print("# measured on B200: 62.2 packets per point at 212 G/s for the 'runs >= 4' build (backward 1.268 ms); the shipped 'all runs' build runs the")
-print("# backward in 1.148 ms -- the time follows the packet count (61.6 -> 55.6 = -9.7 %, time -9.5 %): the kernel is bound by the L2 reduction unit.")
+    print(f"  L{li:<2d}  {R:5d}  {'Dense' if dense else 'Hash '} | {res[0]:8.3f} | {res[1]:16.3f} | {res[2]:15.3f} | {res[3]:16.3f} | {res[4]:14.3f} | {res[5]:16.3f}", flush=True)
+print(f"  total               | {tot[0]:8.3f} | {tot[1]:16.3f} | {tot[2]:15.3f} | {tot[3]:16.3f} | {tot[4]:14.3f} | {tot[5]:16.3f}")
+print("# measured on B200: 62.2 packets per point at 212 G/s for the 'runs >= 4' build (backward 1.268 ms); the 'all runs' build runs the backward")
+print("# in 1.148 ms -- the time followed the packet count (61.6 -> 55.6 = -9.7 %, time -9.5 %).  'any lanes' on the levels up to res 406 (shipped,")
+print("# profiles/r2_ab_merge.txt): 1.200 -> 1.169 ms; by now the kernel also sits on its issue slots, and every match.any costs about as much as")
+print("# it finds distinct values, so the last 3 packets ('+ x neighbours') cost more than they save.")

@@ -60,6 +60,14 @@ def main():
     y, _ = _lotd.lod_fwd(meta, xs[0], params, need_input_grad=False)
     _, g = _lotd.lod_bwd(meta, dL_dy, xs[0], params, None, need_input_grad=False, need_param_grad=True)
     out["checksum_y"], out["checksum_grad"] = float(y.double().abs().sum()), float(g.double().abs().sum())
+    # the gradient table of the first build that runs is kept; later builds (A/B variants in the same gpurun call) report their distance to it
+    ref_file = os.path.join(os.environ.get("NR3D_AB_REF_DIR", "/tmp"), f"ab_ref_grad_{'f16' if args.half else 'f32'}_{N}.pt")
+    if os.path.exists(ref_file):
+        ref = torch.load(ref_file, map_location=dev)
+        out["grad_max_abs_diff_vs_first"] = float((g.double() - ref.double()).abs().max())
+        out["grad_max_abs"] = float(ref.double().abs().max())
+    else:
+        torch.save(g, ref_file)
     out.update(tag=args.tag or os.path.basename(_lib.LIB_PATH), half=args.half, msamples_per_s=N / out["step"] / 1e3,
                note="fwd = lod_fwd of new points (sort + gather), bwd = lod_bwd (fingerprint check + scatter), step = fwd + bwd back to back")
     print(json.dumps(out))

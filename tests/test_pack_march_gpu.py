@@ -239,8 +239,16 @@ def _march_equal(got, want, what, exact_float=True):
 MARCH_GOLDEN = ["aabb", "aabb_gamma", "aabb_shell", "aabb_maxsteps", "sphere", "tanh", "batched_inds", "batched_size"]
 
 
+@pytest.fixture(params=["single_pass", "two_pass"])
+def march_mode(request, monkeypatch):
+    """Both marchers: record + compact (every ray marched once; default when the scratch fits) and count + fill (the reference's two passes)."""
+    if request.param == "two_pass":
+        monkeypatch.setattr(_og(), "MARCH_SCRATCH_BYTES", 0)
+    return request.param
+
+
 @pytest.mark.parametrize("name", MARCH_GOLDEN)
-def test_march_vs_golden(name, dev):
+def test_march_vs_golden(name, dev, march_mode):
     g = golden("march_" + name)
     if g is None:
         pytest.skip("golden fixture not generated yet")
@@ -251,8 +259,8 @@ def test_march_vs_golden(name, dev):
     _march_equal(got, g, "golden:" + name)
 
 
-@pytest.mark.parametrize("R,res,B", [(20000, 64, 1), (8192, 32, 4)])
-def test_march_vs_reference_build_and_oracle(R, res, B, dev):
+@pytest.mark.parametrize("R,res,B", [(20000, 64, 1), (8192, 32, 4), (33, 32, 1)])
+def test_march_vs_reference_build_and_oracle(R, res, B, dev, march_mode):
     from oracle import march_oracle as MO
     d = march_inputs(R=R, res=res, seed=21, B=B)
     got = _march(_og(), d, dev, 0, 0.005, 1e10, 0.0, 512)
