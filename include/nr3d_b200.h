@@ -176,6 +176,11 @@ int nr3d_lotd_sort_points(uint64_t N, const float* x, const int64_t* batch_inds,
  * LoTD.forward, lotd_encoding.py:162, lotd.py:211).  The map is part of the records' fingerprint. */
 int nr3d_lotd_sort_points_mapped(uint64_t N, const float* x, const int64_t* batch_inds, uint32_t batch_data_size, uint32_t n_scenes, int32_t force,
                                  float scale, float shift, int32_t clamp01, void* xs, uint16_t* scenes, void* ws, uint64_t* ws_bytes, void* stream);
+/* Puts the stateful parts of a sort workspace (header, histogram counters, coarse bucket sizes: a few tens of MB) into their initial all-zero
+ * state for calls with this configuration, on `stream`; has_batch_inds = whether those calls pass batch_inds.  Callers whose point count changes
+ * from call to call (ray samples) keep ONE workspace of sufficient size and call this whenever (N, batching) changes, instead of allocating
+ * and zero-filling a new one (the rank / record scratch behind the counters needs no initialisation). */
+int nr3d_lotd_sort_ws_reset(uint64_t N, int32_t has_batch_inds, uint32_t batch_data_size, uint32_t n_scenes, void* ws, uint64_t ws_bytes, void* stream);
 /* Test / A-B knob: point count from which single-scene calls take the two-level (coarse partition + fine) sort; 0 restores the default (12 Mi).
  * The workspace size of a given N depends on it: query it again afterwards. */
 int nr3d_lotd_sort_set_two_level_min(uint64_t n_points);

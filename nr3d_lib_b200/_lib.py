@@ -72,6 +72,7 @@ SIGNATURES = {
     "nr3d_lotd_forest_bwd_bwd_dx": [_meta_p, _forest_p, _i32, _i32, _u64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp],
     "nr3d_lotd_sort_points": [_u64, _vp, _vp, _u32, _u32, _i32, _vp, _vp, _vp, _u64_p, _vp],
     "nr3d_lotd_sort_set_two_level_min": [_u64],
+    "nr3d_lotd_sort_ws_reset": [_u64, _i32, _u32, _u32, _vp, _u64, _vp],
     "nr3d_lotd_sort_points_mapped": [_u64, _vp, _vp, _u32, _u32, _i32, _f32, _f32, _i32, _vp, _vp, _vp, _u64_p, _vp],
     "nr3d_lotd_fwd_sorted": [_meta_p, _i32, _u64, _vp, _vp, _u32, _vp, _i32, _vp, _i64, _i64, _vp],
     "nr3d_lotd_bwd_param_sorted": [_meta_p, _i32, _u64, _vp, _vp, _u32, _vp, _i64, _i64, _i32, _u32, _u32, _vp, _vp],

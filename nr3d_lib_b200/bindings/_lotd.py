@@ -225,12 +225,15 @@ def _check_common(fn, meta: LoDMeta, input, params, batch_inds, batch_offsets, b
 # stream that produced them.  Memory held: 16 B + 4 B per point and 2 x 4 B per sort bin per (device, stream); clear_sort_cache() frees it.
 _sort_cache = {}
 _sort_lock = threading.Lock()
+_sort_calls = {}     # (device, stream) -> number of _sorted_points calls so far: any of them may have re-sorted the slot's records
 
 
 def clear_sort_cache():
     """Free the sorted-record buffers (the next call sorts unconditionally)."""
     with _sort_lock:
         _sort_cache.clear()
+        for k in _sort_calls:
+            _sort_calls[k] += 1
 
 
 def _n_scenes(meta, params):
@@ -270,12 +273,19 @@ def _sorted_points(x: torch.Tensor, batch_inds: Optional[torch.Tensor] = None, b
         ent = _sort_cache.get(key)
         force = 1 if expect_new else 0
         if ent is None or ent[0] != cfg:
+            # New configuration (ray samples: every call has its own point count).  The workspace is kept while it is large enough -- only its
+            # stateful head (header + counters) is put back to zero, not the hundreds of MB of rank / record scratch behind it.
             nbytes = ctypes.c_uint64(0)
-            _lib.check(lib.nr3d_lotd_sort_points(N, None, None, int(bds), ns, 1, None, None, None, ctypes.byref(nbytes), None))
+            _lib.check(lib.nr3d_lotd_sort_points(N, None, _lib.ptr(batch_inds), int(bds), ns, 1, None, None, None, ctypes.byref(nbytes), None))
             xs = torch.empty([N, 4], dtype=torch.float32, device=dev)      # (x, y, z, original index bits) per sorted point
             scenes = torch.empty([N], dtype=torch.int16, device=dev) if batched else None
-            ws = torch.zeros([nbytes.value], dtype=torch.uint8, device=dev)   # stateful: zero before first use
-            ent = (cfg, xs, scenes, ws, nbytes.value)
+            ws = ent[3] if ent is not None else None
+            if ws is None or ws.numel() < nbytes.value:
+                ws = None                                                     # (release the old one first)
+                _sort_cache.pop(key, None)
+                ws = torch.empty([nbytes.value + nbytes.value // 8], dtype=torch.uint8, device=dev)   # 1/8 headroom for slightly larger calls
+            _lib.check(lib.nr3d_lotd_sort_ws_reset(N, 1 if batch_inds is not None else 0, int(bds), ns, ws.data_ptr(), ws.numel(), st))
+            ent = (cfg, xs, scenes, ws, ws.numel())
             _sort_cache[key] = ent
             force = 1
         _, xs, scenes, ws, nb = ent
@@ -283,7 +293,32 @@ def _sorted_points(x: torch.Tensor, batch_inds: Optional[torch.Tensor] = None, b
         sc, sh, cl = (1.0, 0.0, 0) if coord_map is None else (float(coord_map[0]), float(coord_map[1]), int(bool(coord_map[2])))
         _lib.check(lib.nr3d_lotd_sort_points_mapped(N, x.data_ptr(), _lib.ptr(batch_inds), int(bds), ns, force, sc, sh, cl, xs.data_ptr(),
                                                     _lib.ptr(scenes), ws.data_ptr(), ctypes.byref(nbytes), st))
+        _sort_calls[key] = _sort_calls.get(key, 0) + 1
     return xs, scenes
+
+
+def _records_token(x: torch.Tensor):
+    """Token of the records the LAST _sorted_points call on x's device / current stream produced (take it right after that call)."""
+    key = (x.device.index, int(_lib.stream_of(x.device) or 0))
+    with _sort_lock:
+        ent = _sort_cache.get(key)
+        return None if ent is None else (key, _sort_calls.get(key, 0), ent[1].data_ptr())
+
+
+def _records_if_untouched(token, dev):
+    """(xs, scenes) of a token if the current stream of `dev` is the one the records were made on and NO sort call has been made on that
+    (device, stream) slot since -- the records are then the token's for certain and a caller that owns its points (pipeline.
+    _EncodeDensityAlpha: forward and backward of one autograd node) can skip the fingerprint pass.  None otherwise: call _sorted_points again."""
+    if token is None:
+        return None
+    key, calls, ptr = token
+    if key != (dev.index, int(_lib.stream_of(dev) or 0)):
+        return None
+    with _sort_lock:
+        ent = _sort_cache.get(key)
+        if ent is None or _sort_calls.get(key, 0) != calls or ent[1].data_ptr() != ptr:
+            return None
+        return ent[1], ent[2]
 
 
 # Multi-GPU hook (no reference counterpart; the reference's DDP support is "discarded", nr3d_lib/config.py:74-75).  When set, an eligible

@@ -51,6 +51,14 @@ __device__ __forceinline__ void st_cs(__half* p, __half v) {
     asm volatile("st.global.cs.b16 [%0], %1;" ::"l"(p), "h"(*reinterpret_cast<unsigned short*>(&v)) : "memory");
 }
 
+// predicated forms (one instruction, no branch / reconvergence bookkeeping around a store that only some lanes of a warp perform)
+__device__ __forceinline__ void st_cs_if(bool on, float* p, float v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.cs.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((int)on) : "memory");
+}
+__device__ __forceinline__ void st_cs_if(bool on, __half* p, __half v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.cs.b16 [%0], %1;\n\t}" ::"l"(p), "h"(*reinterpret_cast<unsigned short*>(&v)), "r"((int)on) : "memory");
+}
+
 template <typename T> struct Cvt;
 template <> struct Cvt<float> {
     static __device__ __forceinline__ float to_f(float v) { return v; }

@@ -125,6 +125,7 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT*
     const uint64_t i = __float_as_uint(rec.w);
     const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
     const bool staged = (ys_f == 1);
+    const uint32_t itag = active ? (uint32_t)i : 0xffffffffu;   // (N < 2^32, so no point has index 2^32 - 1)
     uint32_t chunk_base = 0;
     float hsum = 0.f;   // HEAD: sum of the point's features, level after level
     constexpr int kFwdUnroll = NR3D_FWD_UNROLL;
@@ -136,10 +137,10 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT*
         for (int f = 0; f < F; ++f) r[f] = 0.f;
         if ((int32_t)level <= in.max_level) {
             Geo2 g;
-            pair_geo(tab.lv[level], (uint32_t)tab.map_cnt[pl] * F, smooth, x, yv, z, side, g);
+            pair_geo(tab.lv[level], in.fl[level], (uint32_t)tab.map_cnt[pl] * F, pbase, smooth, x, yv, z, side, g);
             float v[4][F];  // all four loads are issued before the first use
 #pragma unroll
-            for (int q = 0; q < 4; ++q) load_feats<PT, F>(params + pbase + g.e[q], v[q]);
+            for (int q = 0; q < 4; ++q) load_feats<PT, F>(params + g.e[q], v[q]);
             if constexpr (std::is_same<PT, __half>::value) {
                 // fp16 tables: every product is rounded to half and accumulated in half like the reference (linear_interpolate.cuh:118);
                 // two features per packed instruction (cvt.rn.f16x2.f32 + HADD2) -- same values as the scalar chain, a third of the issue slots
@@ -179,14 +180,13 @@ lotd_pair_fwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, PT*
 #pragma unroll
             for (int j = 0; j < H; ++j) myrows[k * kPairRowStride + c + side * H + j] = mine[j];
             const bool last = (pl + 1 == tab.n_pseudo);
-            if (c + F == 32 || last) {  // flush the chunk: one coalesced row store per point of the warp
-                const uint32_t width = c + F;
+            if (c + F == 32 || last) {  // flush the chunk: one coalesced row store per point of the warp (predicated: no branch per row)
+                const bool inw = (uint32_t)lane < c + F;
                 __syncwarp();
 #pragma unroll 4
                 for (int rr = 0; rr < 16; ++rr) {
-                    const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * rr);
-                    const bool ok = __shfl_sync(0xffffffffu, (int)active, 2 * rr);
-                    if (ok && (uint32_t)lane < width) st_cs(y + (int64_t)ir * ys_n + chunk_base + lane, C::from_f(myrows[rr * kPairRowStride + lane]));
+                    const uint32_t ir = __shfl_sync(0xffffffffu, itag, 2 * rr);   // original index of point rr, 0xffffffff: no such point
+                    st_cs_if(inw && ir != 0xffffffffu, y + (int64_t)ir * ys_n + chunk_base + lane, C::from_f(myrows[rr * kPairRowStride + lane]));
                 }
                 __syncwarp();
                 chunk_base += 32;
@@ -331,7 +331,7 @@ lotd_pair_fwd_tma_kernel(const __grid_constant__ LotdTable tab, const FastIn in,
         if ((int32_t)level <= in.max_level) {
             const LevelDesc& L = tab.lv[level];
             Geo2 g;
-            pair_geo(L, (uint32_t)tab.map_cnt[pl] * F, smooth, x, yv, z, side, g);
+            pair_geo(L, in.fl[level], (uint32_t)tab.map_cnt[pl] * F, 0u, smooth, x, yv, z, side, g);
             float2 v[4];
             const int32_t off = pl < (uint32_t)kTmaLevels ? plan.off[pl] : -1;
             if (off >= 0) {
@@ -429,6 +429,7 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
     const PT* grow = dLdy + (int64_t)i * gs_n;
     const bool smooth = tab.interp == NR3D_INTERP_SMOOTHSTEP;
     const bool staged = !HEAD && (gs_f == 1);
+    const uint32_t ltag = live ? (uint32_t)i : 0xffffffffu;   // (N < 2^32, so no point has index 2^32 - 1)
     float ghead = 0.f;
     if (HEAD && live) {
         // alpha = 1 - exp(-sigma * delta): d alpha / d sigma = delta * (1 - alpha);  sigma = softplus(gain * s): d sigma / d s = gain * (1 - exp(-sigma))
@@ -505,14 +506,13 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
             const uint32_t want_base = (pl * (uint32_t)F) / 32u * 32u;
             if (want_base != chunk_base) {  // stage the next (up to) 32 features of the warp's 16 rows: one coalesced row read per point
                 const uint32_t width = min(32u, tab.n_enc - want_base);
+                // (a level-group launch only touches the sectors of its own features)
+                const bool inw = (uint32_t)lane < width && want_base + lane >= in.pl_begin * F && want_base + lane < in.pl_end * F;
                 __syncwarp();
 #pragma unroll 4
-                for (int rr = 0; rr < 16; ++rr) {
-                    const uint64_t ir = __shfl_sync(0xffffffffu, (uint32_t)i, 2 * rr);
-                    const bool ok = __shfl_sync(0xffffffffu, (int)live, 2 * rr);
-                    // (a level-group launch only touches the sectors of its own features)
-                    if (ok && (uint32_t)lane < width && want_base + lane >= in.pl_begin * F && want_base + lane < in.pl_end * F)
-                        myrows[rr * kPairRowStride + lane] = ldcs_f<PT>(dLdy + (int64_t)ir * gs_n + want_base + lane);
+                for (int rr = 0; rr < 16; ++rr) {   // predicated loads (0 for absent points / columns, never used): no branch per row
+                    const uint32_t ir = __shfl_sync(0xffffffffu, ltag, 2 * rr);
+                    myrows[rr * kPairRowStride + lane] = ldcs_f_if<PT>(inw && ir != 0xffffffffu, dLdy + (int64_t)ir * gs_n + want_base + lane);
                 }
                 __syncwarp();
             }
@@ -530,11 +530,11 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
         Geo2 g;
         if (SECOND) {
             float dw[3][4];
-            pair_geo_d(L, (uint32_t)tab.map_cnt[pl] * F, smooth, x, yv, z, side, g, dw);
+            pair_geo_d(L, in.fl[level], (uint32_t)tab.map_cnt[pl] * F, pbase, smooth, x, yv, z, side, g, dw);
 #pragma unroll
             for (int q = 0; q < 4; ++q) g.w[q] = gx[0] * dw[0][q] + gx[1] * dw[1][q] + gx[2] * dw[2][q];
         } else {
-            pair_geo(L, (uint32_t)tab.map_cnt[pl] * F, smooth, x, yv, z, side, g);
+            pair_geo(L, in.fl[level], (uint32_t)tab.map_cnt[pl] * F, pbase, smooth, x, yv, z, side, g);
         }
         // every lane holds four contributions (entry g.e[q], F values)
         float cx[4][F];
@@ -677,7 +677,7 @@ lotd_pair_bwd_kernel(const __grid_constant__ LotdTable tab, const FastIn in, con
 #endif
         if (issue) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) red_feats<PT, F>(grad + pbase + g.e[q], cx[q]);
+            for (int q = 0; q < 4; ++q) red_feats<PT, F>(grad + g.e[q], cx[q]);
         }
     }
 
@@ -760,10 +760,10 @@ lotd_pair_fwd_dydx_kernel(const __grid_constant__ LotdTable tab, const FastIn in
         if ((int32_t)level <= in.max_level) {
             Geo2 g;
             float dw[3][4];
-            pair_geo_d(tab.lv[level], (uint32_t)tab.map_cnt[pl] * F, smooth, x, yv, z, side, g, dw);
+            pair_geo_d(tab.lv[level], in.fl[level], (uint32_t)tab.map_cnt[pl] * F, pbase, smooth, x, yv, z, side, g, dw);
             float v[4][F];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) load_feats<PT, F>(params + pbase + g.e[q], v[q]);
+            for (int q = 0; q < 4; ++q) load_feats<PT, F>(params + g.e[q], v[q]);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -923,6 +923,7 @@ int nr3d_lotd_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, uint64
     LotdTable tab;
     make_table(meta, tab);
     FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, params, max_level, meta->n_params, 0u, meta->n_pseudo_levels};
+    fast_levels(meta, in);
     int rc = 0;
     NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl, (rc = launch_fwd<PT, F>(tab, in, y, y_stride_n, y_stride_f, (cudaStream_t)stream)));
     return rc;
@@ -939,6 +940,7 @@ int nr3d_lotd_bwd_param_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, 
     make_table(meta, tab);
     const uint32_t pl_stop = (pl_end < meta->n_pseudo_levels) ? pl_end : meta->n_pseudo_levels;
     FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, nullptr, max_level, meta->n_params, pl_begin, pl_stop, merge_res_for(N, n_scenes)};
+    fast_levels(meta, in);
     int rc = 0;
     NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl,
                        (rc = launch_bwd<PT, F, false>(tab, in, dL_dy, dLdy_stride_n, dLdy_stride_f, nullptr, dL_dparam, (cudaStream_t)stream)));
@@ -953,6 +955,7 @@ int nr3d_lotd_density_head_fwd_sorted(const nr3d_lotd_meta* meta, int32_t param_
     LotdTable tab;
     make_table(meta, tab);
     FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, params, max_level, meta->n_params, 0u, meta->n_pseudo_levels};
+    fast_levels(meta, in);
     const HeadFwd hd{deltas, gain, sigma, alpha};
     int rc = 0;
     NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl, (rc = launch_fwd_head<PT, F>(tab, in, hd, (cudaStream_t)stream)));
@@ -968,6 +971,7 @@ int nr3d_lotd_density_head_bwd_sorted(const nr3d_lotd_meta* meta, int32_t param_
     LotdTable tab;
     make_table(meta, tab);
     FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, nullptr, max_level, meta->n_params, 0u, meta->n_pseudo_levels, merge_res_for(N, n_scenes)};
+    fast_levels(meta, in);
     const HeadBwd hd{d_alpha, sigma, alpha, deltas, gain};
     int rc = 0;
     NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl,
@@ -983,6 +987,7 @@ int nr3d_lotd_fwd_dydx_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype, u
     LotdTable tab;
     make_table(meta, tab);
     FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, params, max_level, meta->n_params, 0u, meta->n_pseudo_levels};
+    fast_levels(meta, in);
     int rc = 0;
     NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl, (rc = launch_fwd_dydx<PT, F>(tab, in, y, (float*)dy_dx, (cudaStream_t)stream)));
     return rc;
@@ -999,6 +1004,7 @@ int nr3d_lotd_bwd_param2_sorted(const nr3d_lotd_meta* meta, int32_t param_dtype,
     make_table(meta, tab);
     const uint32_t pl_stop = (pl_end < meta->n_pseudo_levels) ? pl_end : meta->n_pseudo_levels;
     FastIn in{N, reinterpret_cast<const float4*>(xs), scenes, nullptr, max_level, meta->n_params, pl_begin, pl_stop, merge_res_for(N, n_scenes)};
+    fast_levels(meta, in);
     int rc = 0;
     NR3D_DISPATCH_PT_F(param_dtype, meta->n_feat_per_pseudo_lvl,
                        (rc = launch_bwd<PT, F, true>(tab, in, dL_dy, dLdy_stride_n, dLdy_stride_f, dL_ddLdx, dL_dparam, (cudaStream_t)stream)));

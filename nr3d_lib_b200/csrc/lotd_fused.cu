@@ -92,7 +92,7 @@ lotd_fused_density_kernel(const __grid_constant__ LotdTable tab, const FastIn in
         float r0 = 0.f, r1 = 0.f;
         if (active && (int32_t)level <= in.max_level) {
             Geo2 g;
-            pair_geo(tab.lv[level], (uint32_t)tab.map_cnt[pl] * 2u, smooth, rec.x, rec.y, rec.z, side, g);
+            pair_geo(tab.lv[level], in.fl[level], (uint32_t)tab.map_cnt[pl] * 2u, 0u, smooth, rec.x, rec.y, rec.z, side, g);
             float2 v[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float2*>(params + g.e[q]));
@@ -205,6 +205,7 @@ extern "C" int nr3d_lotd_fused_density_fwd(const nr3d_lotd_meta* meta, uint64_t 
     LotdTable tab;
     make_table_public(meta, tab);
     FastIn in{N, reinterpret_cast<const float4*>(xs), nullptr, params, max_level, meta->n_params, 0u, meta->n_pseudo_levels};
+    fast_levels(meta, in);
     FusedDec dec{reinterpret_cast<const uint4*>(w1_packed), reinterpret_cast<const uint4*>(w2_packed), b1, b2, activation};
     const uint64_t n_tiles = div_up<uint64_t>(N, 128);
     const unsigned grid = (unsigned)(n_tiles < (uint64_t)kSMs * kFusedCtasPerSm ? n_tiles : (uint64_t)kSMs * kFusedCtasPerSm);

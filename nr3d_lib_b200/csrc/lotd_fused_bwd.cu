@@ -59,10 +59,10 @@ struct FusedBwd {
 };
 
 // run-merged scatter of one pseudo level (F = 2, fp32 tables): the backward loop body of lotd_pair_bwd_kernel (lotd_fast.cu)
-__device__ __forceinline__ void scatter_level(const LevelDesc& L, uint32_t gfo, bool smooth, float x, float y, float z, uint32_t side, int k,
+__device__ __forceinline__ void scatter_level(const LevelDesc& L, const FastLevel& X, uint32_t gfo, bool smooth, float x, float y, float z, uint32_t side, int k,
                                               bool live, float g0, float g1, float* __restrict__ grad) {
     Geo2 g;
-    pair_geo(L, gfo, smooth, x, y, z, side, g);
+    pair_geo(L, X, gfo, 0u, smooth, x, y, z, side, g);
     float cx[4][2];
 #pragma unroll
     for (int q = 0; q < 4; ++q) { cx[q][0] = g.w[q] * g0; cx[q][1] = g.w[q] * g1; }
@@ -162,7 +162,7 @@ lotd_fused_density_bwd_kernel(const __grid_constant__ LotdTable tab, const FastI
             float r0 = 0.f, r1 = 0.f;
             if (active && (int32_t)level <= in.max_level) {
                 Geo2 g;
-                pair_geo(tab.lv[level], (uint32_t)tab.map_cnt[pl] * 2u, smooth, rec.x, rec.y, rec.z, side, g);
+                pair_geo(tab.lv[level], in.fl[level], (uint32_t)tab.map_cnt[pl] * 2u, 0u, smooth, rec.x, rec.y, rec.z, side, g);
                 float2 v[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float2*>(params + g.e[q]));
@@ -315,7 +315,7 @@ lotd_fused_density_bwd_kernel(const __grid_constant__ LotdTable tab, const FastI
                 const uint32_t level = tab.map_level[pl];
                 if ((int32_t)level > in.max_level) continue;   // uniform
                 const float g0 = live ? df_s[m * kDfStride + 2 * pl] : 0.f, g1 = live ? df_s[m * kDfStride + 2 * pl + 1] : 0.f;
-                scatter_level(tab.lv[level], (uint32_t)tab.map_cnt[pl] * 2u, smooth, x, y, z, side, k, live, g0, g1, a.dparams);
+                scatter_level(tab.lv[level], in.fl[level], (uint32_t)tab.map_cnt[pl] * 2u, smooth, x, y, z, side, k, live, g0, g1, a.dparams);
             }
         }
         __syncthreads();   // the dF rows / idx are free for the next tile's F and G
@@ -391,6 +391,7 @@ extern "C" int nr3d_lotd_fused_density_bwd(const nr3d_lotd_meta* meta, uint64_t 
     LotdTable tab;
     make_table_public(meta, tab);
     FastIn in{N, reinterpret_cast<const float4*>(xs), nullptr, params, max_level, meta->n_params, 0u, meta->n_pseudo_levels};
+    fast_levels(meta, in);
     FusedBwd a{reinterpret_cast<const uint4*>(w1_packed), reinterpret_cast<const uint4*>(w2t_packed), reinterpret_cast<const uint4*>(w1t_packed), b1,
                sigma, d_sigma, d_out16, activation, dL_dparam, dW1, db1, dW2, db2};
     static bool configured = false;

@@ -375,11 +375,53 @@ __global__ void __launch_bounds__(256) sort_scatter_rec_kernel(uint64_t N, uint3
     }
 }
 
+// Workspace layout of a call: [header | scan status | hist | offsets | rank | (two-level: tmp records | coarse sizes | coarse cursors)].
+// The header, the histogram counters and the coarse bucket sizes are STATE: every call expects them zero and leaves them zero.
+struct SortLayout {
+    uint32_t res, n_cnt, n_tiles;
+    uint64_t cnt_bytes, rank_bytes, need;
+    bool two_level;
+};
+
+static int sort_layout(uint64_t N, bool has_batch_inds, uint32_t batch_data_size, uint32_t n_scenes, SortLayout& l) {
+    NR3D_CHECK(n_scenes < 0xffffu, "sort_points: at most 65534 scenes");
+    l.res = bin_res_for(N, n_scenes);
+    const uint64_t n_cnt64 = (uint64_t)n_scenes * l.res * l.res * l.res + 1;   // one extra bucket for skipped points
+    NR3D_CHECK(n_cnt64 <= (uint64_t)kMaxTiles * kScanTile, "sort_points: too many scenes for the bin grid (%llu counters)", (unsigned long long)n_cnt64);
+    l.n_cnt = (uint32_t)n_cnt64;
+    l.n_tiles = div_up<uint32_t>(l.n_cnt, kScanTile);
+    l.cnt_bytes = div_up<uint64_t>((uint64_t)l.n_cnt * 4, 256) * 256;
+    l.two_level = N >= g_two_level_min && n_scenes == 1 && !has_batch_inds && batch_data_size == 0 && (l.res % kCoarse) == 0;
+    l.rank_bytes = div_up<uint64_t>(N * 4, 256) * 256;
+    l.need = kHeaderBytes + (uint64_t)kMaxTiles * 8 + 2 * l.cnt_bytes + l.rank_bytes + (l.two_level ? N * 16 + 2 * kCoarseN * 4 : 0);
+    return 0;
+}
+
 }  // namespace nr3d
 
 using namespace nr3d;
 
 extern "C" {
+
+// Puts the stateful parts of a workspace into their initial (all-zero) state for calls with this (N, batching) configuration, on `stream`:
+// what `zero-fill before the first use` asks for, without touching the hundreds of megabytes of rank / record scratch behind them.  Callers
+// that keep ONE buffer for point counts that change from call to call (ray samples: every step has its own count) call it whenever the
+// configuration changes instead of allocating and zero-filling a new workspace.
+int nr3d_lotd_sort_ws_reset(uint64_t N, int32_t has_batch_inds, uint32_t batch_data_size, uint32_t n_scenes, void* ws, uint64_t ws_bytes, void* stream) {
+    if (n_scenes == 0) n_scenes = 1;
+    SortLayout l;
+    if (int rc = sort_layout(N, has_batch_inds != 0, batch_data_size, n_scenes, l)) return rc;
+    NR3D_CHECK(ws != nullptr && ws_bytes >= l.need, "sort_points: workspace too small");
+    NR3D_CHECK((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "sort_points: ws must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w = reinterpret_cast<char*>(ws);
+    NR3D_CHECK(cudaMemsetAsync(w, 0, kHeaderBytes + (uint64_t)kMaxTiles * 8 + l.cnt_bytes, st) == cudaSuccess, "sort_points: memset failed");
+    if (l.two_level) {
+        char* coarse = w + kHeaderBytes + (uint64_t)kMaxTiles * 8 + 2 * l.cnt_bytes + l.rank_bytes + N * 16;
+        NR3D_CHECK(cudaMemsetAsync(coarse, 0, 2 * kCoarseN * 4, st) == cudaSuccess, "sort_points: memset failed");
+    }
+    return 0;
+}
 
 int nr3d_lotd_sort_points_mapped(uint64_t N, const float* x, const int64_t* batch_inds, uint32_t batch_data_size, uint32_t n_scenes, int32_t force,
                                  float scale, float shift, int32_t clamp01, void* xs /* float4 [N] */, uint16_t* scenes /* [N] or NULL */, void* ws,
@@ -389,16 +431,11 @@ int nr3d_lotd_sort_points_mapped(uint64_t N, const float* x, const int64_t* batc
     memcpy(&su, &scale, 4); memcpy(&hu, &shift, 4);
     const uint32_t map_tag = (su * 0x9E3779B1u) ^ (hu * 0x85EBCA77u) ^ (clamp01 ? 0x27D4EB2Fu : 0u);
     if (n_scenes == 0) n_scenes = 1;
-    NR3D_CHECK(n_scenes < 0xffffu, "sort_points: at most 65534 scenes");
-    const uint32_t res = bin_res_for(N, n_scenes);
-    const uint64_t n_cnt64 = (uint64_t)n_scenes * res * res * res + 1;   // one extra bucket for skipped points
-    NR3D_CHECK(n_cnt64 <= (uint64_t)kMaxTiles * kScanTile, "sort_points: too many scenes for the bin grid (%llu counters)", (unsigned long long)n_cnt64);
-    const uint32_t n_cnt = (uint32_t)n_cnt64;
-    const uint32_t n_tiles = div_up<uint32_t>(n_cnt, kScanTile);
-    const uint64_t cnt_bytes = div_up<uint64_t>((uint64_t)n_cnt * 4, 256) * 256;
-    const bool two_level = N >= g_two_level_min && n_scenes == 1 && batch_inds == nullptr && batch_data_size == 0 && (res % kCoarse) == 0;
-    const uint64_t rank_bytes = div_up<uint64_t>(N * 4, 256) * 256;
-    const uint64_t need = kHeaderBytes + (uint64_t)kMaxTiles * 8 + 2 * cnt_bytes + rank_bytes + (two_level ? N * 16 + 2 * kCoarseN * 4 : 0);
+    SortLayout l;
+    if (int rc = sort_layout(N, batch_inds != nullptr, batch_data_size, n_scenes, l)) return rc;
+    const uint32_t res = l.res, n_cnt = l.n_cnt, n_tiles = l.n_tiles;
+    const uint64_t cnt_bytes = l.cnt_bytes, rank_bytes = l.rank_bytes, need = l.need;
+    const bool two_level = l.two_level;
     if (ws == nullptr) {
         NR3D_CHECK(ws_bytes != nullptr, "sort_points: null ws_bytes");
         *ws_bytes = need;

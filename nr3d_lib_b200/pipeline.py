@@ -105,6 +105,7 @@ class _EncodeDensityAlpha(torch.autograd.Function):
                     deltas.data_ptr(), float(gain), sigma.data_ptr(), alpha.data_ptr(), _lib.stream_of(dev)))
         ctx.save_for_backward(x, sigma, alpha, deltas)
         ctx.meta, ctx.gain, ctx.ml, ctx.pshape, ctx.pdtype, ctx.cmap = meta, float(gain), ml, params.shape, params.dtype, cmap
+        ctx.records = _lotd._records_token(x) if N else None
         ctx.mark_non_differentiable(sigma)
         return alpha, sigma
 
@@ -122,7 +123,10 @@ class _EncodeDensityAlpha(torch.autograd.Function):
         with torch.cuda.device(dev):
             g = torch.zeros(ctx.pshape, dtype=ctx.pdtype, device=dev)
             if N:
-                xs, scenes = _lotd._sorted_points(x, coord_map=ctx.cmap)      # the forward's records unless other points were sorted on this stream in between
+                # the forward's records: for certain when no other sort ran on this stream since (x is saved for backward, so autograd has
+                # checked that nobody wrote to it) -- otherwise the fingerprint pass decides and re-sorts if it must
+                cur = _lotd._records_if_untouched(ctx.records, dev)
+                xs, scenes = cur if cur is not None else _lotd._sorted_points(x, coord_map=ctx.cmap)
                 _lib.check(_lib.get_lib().nr3d_lotd_density_head_bwd_sorted(
                     ctypes.byref(ctx.meta._c), _lib.dtype_code(ctx.pdtype), N, xs.data_ptr(), _lib.ptr(scenes), 1, d_alpha.data_ptr(), sigma.data_ptr(),
                     alpha.data_ptr(), deltas.data_ptr(), ctx.gain, ctx.ml, g.data_ptr(), _lib.stream_of(dev)))

@@ -158,6 +158,51 @@ def test_fused_density_head_matches_composition(pdtype, dev):
 
 
 @pytest.mark.gpu
+def test_fused_density_head_records_across_interleaved_calls(dev):
+    """The fused head keeps a token of the sorted records for its backward.  Two point sets of DIFFERENT sizes share the one record slot and the
+    one sort workspace of the stream (re-armed, not re-allocated, when the point count changes): forward A, forward B, backward A (records
+    overwritten -> re-sorted behind the fingerprint), backward B (re-sorted again), then A alone (token valid -> no fingerprint pass)."""
+    from nr3d_lib_b200 import _lib
+    from nr3d_lib_b200.bindings import _lotd
+    from nr3d_lib_b200.lotd import LoTD
+    from nr3d_lib_b200.pipeline import encode_density_alpha
+    cfg = _ngp()
+    enc = LoTD(dtype=torch.float32, **cfg)
+    g = torch.Generator().manual_seed(5)
+    p_host = torch.randn(enc.n_params, generator=g) * 0.05
+    sets = []
+    for S in (20011, 7001, 26003):       # smaller, then larger than the first: the workspace is reused, then grown
+        sets.append((torch.rand(S, 3, generator=g).to(dev), (torch.rand(S, generator=g) * 0.05).to(dev), torch.randn(S, generator=g).to(dev)))
+
+    def alone(k):
+        _lotd.clear_sort_cache()
+        p = p_host.to(dev).requires_grad_(True)
+        x, d, w = sets[k]
+        a, _ = encode_density_alpha(enc, x, p, d, 2.0)
+        (a * w).sum().backward()
+        return a.detach(), p.grad.clone()
+
+    ref = [alone(k) for k in range(3)]
+    _lotd.clear_sort_cache()
+    p = p_host.to(dev).requires_grad_(True)
+    outs = [encode_density_alpha(enc, x, p, d, 2.0)[0] for x, d, _ in sets]            # three forwards back to back: one slot, three sizes
+    assert len(_lotd._sort_cache) == 1
+    for k in (0, 2, 1):                                                                 # backwards in another order
+        p.grad = None
+        (outs[k] * sets[k][2]).sum().backward(retain_graph=True)
+        assert torch.equal(outs[k].detach(), ref[k][0])
+        assert rel_err(p.grad, ref[k][1]) < 2e-5, k
+    # a forward directly followed by its backward: the token is still valid, the backward launches no sort kernels at all
+    p.grad = None
+    a, _ = encode_density_alpha(enc, sets[1][0], p, sets[1][1], 2.0)
+    n0 = _lib.launch_count()
+    (a * sets[1][2]).sum().backward()
+    assert _lib.launch_count() - n0 == 1                                                # the head backward kernel
+    assert rel_err(p.grad, ref[1][1]) < 2e-5
+    _lotd.clear_sort_cache()
+
+
+@pytest.mark.gpu
 def test_packed_weighted_sums_bit_identical_to_composition(dev):
     """(acc, depth) in one pass each way == packed_sum(w), packed_sum(w * t) and their autograd, bit for bit."""
     from nr3d_lib_b200.pack_ops import packed_sum
