@@ -43,7 +43,7 @@ BYTES_PER_SAMPLE = BYTES_FWD + BYTES_BWD + BYTES_TABLE   # 2351
 BYTES_PER_SAMPLE_F16 = (12 + 512 + 64) + (12 + 64 + 512) + 12   # 1188 (SURVEY.md 8d, fp16 parameter tables)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the two dominant kernels at this workload, from the committed
 # `ncu --set full` capture profiles/r2_pair_ncu_summary.txt (4 Mi points): the table is L2 resident, DRAM only sees x / y / dL_dy
-NCU_DRAM_BYTES = {"lotd_pair_bwd_kernel (dL/dparam scatter)": 673.9e6 + 41.5e6, "lotd_pair_fwd_kernel (corner gather)": 153.7e6 + 499.4e6}
+NCU_DRAM_BYTES = {"lotd_pair_bwd_kernel (dL/dparam scatter)": 672.3e6 + 36.0e6, "lotd_pair_fwd_kernel (corner gather)": 153.6e6 + 499.6e6}
 
 
 def ngp_cfg(min_res=16, n_levels=16, scale=1.382, log2_T=19, F=2):
@@ -314,7 +314,7 @@ def main():
                 "kernel_ms": {"lotd_pair_fwd_kernel": k_fwd, "lotd_pair_bwd_kernel": k_bwd},
                 "ms": {"lod_fwd (sort + gather)": ms_fwd, "lod_bwd (fingerprint check + memset + scatter)": ms_bwd},
                 "note": "86 % of the algorithmic bytes are gathers / reductions that hit the L2-resident 48.5 MB table: the binding resources are the L1 line "
-                        "rate (forward, 91 % of peak in the ncu capture) and the L2 reduction-unit packet rate (backward), DRAM carries 0.65 - 0.72 GB per launch",
+                        "rate (forward, 97 % of peak in the ncu capture) and the L2 reduction-unit packet rate + issue slots (backward: 88 % / 79 %), DRAM carries 0.65 - 0.71 GB per launch",
                 "whole_step": {"achieved": whole, "frac": whole / peak, "bytes_per_sample": BYTES_PER_SAMPLE}}
 
     # secondary number of metric M1: the same step with fp16 parameter tables (y, dL_dy and dL/dparams in half)
