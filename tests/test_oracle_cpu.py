@@ -312,3 +312,29 @@ def test_lotd_port_vs_golden_and_oracle(name):
     assert abs(float((y2.astype(np.float64) * inp["dL_dy"].numpy()).sum() - (inp["params"].numpy().astype(np.float64) * gp2).sum())) < 1e-3   # adjoint
     with pytest.raises(ValueError):
         P.fwd(O.OracleMeta(*meta_args(LOTD_CONFIGS["mixed"])), g["x"], g["params"])
+
+
+def test_fast_path_hash_arithmetic_matches_oracle():
+    """The fast kernels (csrc/lotd_pair.cuh:pair_geo) derive the four Hash corners of a lane from TWO products and two additions -- the product of the
+    +1 corner is the product of the cell plus the prime, in uint32 arithmetic -- and reduce with a mask for power-of-two tables (host-side
+    `fast_levels`: hmask = size - 1 for size > 1, else modulo).  Restated here in numpy uint32 and held against the oracle's index function
+    (lotd_cuda.h hash: x * 1 ^ y * 2654435761 ^ z * 805459861, mod size) for every corner, power-of-two and odd table sizes, cells up to 2^11."""
+    rs = np.random.RandomState(0)
+    c = rs.randint(0, 2049, size=(20000, 3)).astype(np.uint32)
+    P1, P2 = np.uint32(2654435761), np.uint32(805459861)
+    with np.errstate(over="ignore"):
+        y0 = c[:, 1] * P1
+        y1 = y0 + P1
+        z0 = c[:, 2] * P2
+        z1 = z0 + P2
+    for size in (1, 2, 4096, 2 ** 19, 2 ** 19 - 1, 300007, 2 ** 24):
+        hmask = np.uint32(size - 1) if (size > 1 and size & (size - 1) == 0) else np.uint32(0)
+        for side in (0, 1):
+            hx = c[:, 0] + np.uint32(side)
+            for q in range(4):
+                dy, dz = q & 1, q >> 1
+                h = hx ^ (y1 if dy else y0) ^ (z1 if dz else z0)
+                mine = (h & hmask) if hmask else (h % np.uint32(size))
+                pos = torch.from_numpy(np.stack([c[:, 0] + side, c[:, 1] + dy, c[:, 2] + dz], -1).astype(np.int64))
+                want = O._idx_hash(pos, size).numpy().astype(np.uint32)
+                assert np.array_equal(mine, want), (size, side, q)
