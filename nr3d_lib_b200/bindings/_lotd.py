@@ -281,7 +281,7 @@ def _sorted_points(x: torch.Tensor, batch_inds: Optional[torch.Tensor] = None, b
             scenes = torch.empty([N], dtype=torch.int16, device=dev) if batched else None
             ws = ent[3] if ent is not None else None
             if ws is None or ws.numel() < nbytes.value:
-                ws = None                                                     # (release the old one first)
+                ws = ent = None                                               # (release the old one first)
                 _sort_cache.pop(key, None)
                 ws = torch.empty([nbytes.value + nbytes.value // 8], dtype=torch.uint8, device=dev)   # 1/8 headroom for slightly larger calls
             _lib.check(lib.nr3d_lotd_sort_ws_reset(N, 1 if batch_inds is not None else 0, int(bds), ns, ws.data_ptr(), ws.numel(), st))
