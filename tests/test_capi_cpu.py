@@ -147,3 +147,39 @@ def test_sort_points_flag_default_and_env(monkeypatch):
     assert m.c_sort_points is True
     monkeypatch.setenv("NR3D_B200_SORT_POINTS", "1")
     assert _lotd.LoDMeta(*args).c_sort_points is True
+
+
+def test_sort_workspace_sizes_and_scratch_validation_without_gpu():
+    """Host-side logic of the two scratch buffers added late in round 2, exercised through the C-ABI without a GPU (argument checks precede every
+    CUDA call): the sort workspace layout (size query; two-level scratch only for large single-scene calls without batch indices) and the
+    single-pass marcher's record buffer."""
+    from nr3d_lib_b200 import _lib
+    lib = _lib.get_lib()
+
+    def need(N, has_inds=False, bds=0, ns=1):
+        nb = ctypes.c_uint64(0)
+        fake = ctypes.c_void_p(256) if has_inds else None          # only tested for NULL-ness by the size query
+        _lib.check(lib.nr3d_lotd_sort_points(N, None, fake, bds, ns, 1, None, None, None, ctypes.byref(nb), None))
+        return nb.value
+
+    n4, n30 = need(4 << 20), need(30 << 20)
+    head = 256 + 8192 * 8
+    cnt = -(-(128 ** 3 + 1) * 4 // 256) * 256
+    assert n4 == head + 2 * cnt + (4 << 20) * 4                            # header + scan status + 2 counter tables (128^3 bins + 1) + rank
+    assert n30 - ((30 << 20) * 16) > head + (30 << 20) * 4                 # two-level: + one 16-byte record per point (+ 256^3 counters)
+    assert need(30 << 20, has_inds=True) < n30 - (30 << 20) * 16 + 4096    # batch indices -> one-level sort, no record scratch
+    assert need(30 << 20, bds=1 << 20, ns=30) < n30                        # batched by data size: one-level as well
+    assert need(8 << 20) > n4 and need(1000) < n4                          # monotone in the point count
+    # ws_reset refuses a workspace that is too small for the configuration (before touching the device)
+    rc = lib.nr3d_lotd_sort_ws_reset(4 << 20, 0, 0, 1, ctypes.c_void_p(256), 1024, None)
+    assert rc != 0 and b"workspace too small" in lib.nr3d_last_error()
+    rc = lib.nr3d_lotd_sort_ws_reset(4 << 20, 0, 0, 1, ctypes.c_void_p(128), n4, None)
+    assert rc != 0 and b"256-byte aligned" in lib.nr3d_last_error()
+    # marcher record pass: scratch smaller than n_rays * max_steps * 16 bytes is an error, so is a misaligned one
+    p = ctypes.c_void_p(4096)
+    common = (1000, p, p, p, p, None, 0, 1, p, p, 8, 8, 8, 0, 0.01, 1e10, 0.0, 64)
+    rc = lib.nr3d_march_record(*common, p, p, 1000 * 64 * 16 - 16, None)
+    assert rc != 0 and b"records buffer too small" in lib.nr3d_last_error()
+    rc = lib.nr3d_march_record(*common, p, ctypes.c_void_p(4104), 1000 * 64 * 16, None)
+    assert rc != 0 and b"16-byte aligned" in lib.nr3d_last_error()
+    assert lib.nr3d_march_compact(0, None, 0, None, None, None, None, None, None, None, None) == 0      # nothing to do for zero rays
