@@ -15,11 +15,14 @@
 //      their A/B); forward and backward walk the points in that order, so coarse and middle levels hit few lines per warp;
 //   2. TWO ADJACENT LANES share one point (see "pair layout" below): the x-neighbour corners of a Hash level (z-neighbours
 //      of a Dense level) are fetched / scattered by the two lanes of a pair in the same instruction and coalesce in hardware;
-//   3. in the backward pass, runs of points in the same cell sum their corner contributions with a segmented shuffle reduction and the run's
-//      head issues one reduction per corner.  (A CTA-level stage -- shared-memory tiles that sum what is left per table entry -- is kept behind
-//      -DNR3D_BWD_TILES=1: it removes 31 % of the L2 packets and is 2x slower, because fp32 adds into shared memory are CAS loops on sm_100a.)
+//   3. in the backward pass, the points of a warp that fall into the same cell -- neighbours or not: groups from one match.any per level -- sum
+//      their corner contributions by pointer jumping and the group's first lane issues one reduction per corner (profiles/r2_ab_merge.txt).
+//      (A CTA-level stage -- shared-memory tiles that sum what is left per table entry -- is kept behind -DNR3D_BWD_TILES=1: it removes 31 % of
+//      the L2 packets and is 2x slower, because fp32 adds into shared memory are CAS loops on sm_100a.)
 //   4. y and dL_dy are accessed as [N, n_enc] rows staged through shared memory (one coalesced 128-byte access per point),
 //      so the sort permutation costs no partial-sector traffic.
+//   5. both kernels are issue-slot bound as much as memory bound, so everything that does not depend on the point is derived on the host
+//      (FastLevel, lotd_pair.cuh), offsets are 32-bit and the row staging is predicated.
 // Results are identical to the generic kernels up to fp32 summation order (same index functions, same weights).
 #include "lotd_pair.cuh"
 #include <string.h>
